@@ -1,0 +1,205 @@
+"""Pin the oracle against the unmodified reference and write tests/golden/*.npz.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+For every case: build the reference SlaterJastrow on a fixture molecule, sample
+walkers with the reference Metropolis, evaluate the hot path with the reference,
+assert oracle/sj_oracle.py agrees, and store inputs + reference outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+import ref_shim  # noqa: E402
+
+ref_shim.load_reference()
+
+from qmctorch.wavefunction import SlaterJastrow  # noqa: E402
+from qmctorch.sampler import Metropolis  # noqa: E402
+from qmctorch.solver import Solver  # noqa: E402
+from qmctorch.wavefunction.jastrows.elec_elec import (  # noqa: E402
+    JastrowFactor as JastrowEE, PadeJastrowKernel as PadeEE)
+from qmctorch.wavefunction.jastrows.elec_nuclei import (  # noqa: E402
+    JastrowFactor as JastrowEN, PadeJastrowKernel as PadeEN)
+
+import sj_oracle as orc  # noqa: E402
+from qmctorch_b200.molecules import fixture_molecule  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+# name, molecule key, configs, jastrow, nwalkers, thermalisation steps, step size, init
+CASES = [
+    ("h2_single22", "h2", "single(2,2)", "ee", 256, 200, 0.5, "normal"),
+    ("h2_ground", "h2", "ground_state", "ee", 128, 100, 0.5, "normal"),
+    ("lih_ground", "lih", "ground_state", "ee", 512, 200, 0.3, "normal"),
+    ("lih_nojastrow", "lih", "ground_state", None, 64, 100, 0.3, "normal"),
+    ("lih_sd22", "lih", "single_double(2,2)", "ee", 128, 100, 0.3, "normal"),
+    ("lih_cas24", "lih", "cas(2,4)", "ee", 128, 100, 0.3, "normal"),
+    ("lih_een", "lih", "ground_state", "ee+en", 128, 100, 0.3, "normal"),
+    ("h2o_ground", "h2o", "ground_state", "ee", 96, 100, 0.15, "atomic"),
+    ("h2o_cas44", "h2o", "cas(4,4)", "ee+en", 48, 100, 0.15, "atomic"),
+    ("c4h6_ground", "c4h6", "ground_state", "ee", 16, 60, 0.05, "atomic"),
+]
+
+
+def rel(a, b):
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    return float(((a - b).abs() / b.abs().clamp(min=1e-300)).max())
+
+
+def relmax(a, b):
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-300))
+
+
+def build(case):
+    name, key, configs, jast, nw, ntherm, step, init = case
+    mol = fixture_molecule(key)
+    if jast == "ee":
+        j = "default"
+    elif jast is None:
+        j = None
+    else:
+        j = [JastrowEE(mol, PadeEE), JastrowEN(mol, PadeEN)]
+    wf = SlaterJastrow(mol, configs=configs, jastrow=j, include_all_mo=True)
+    return mol, wf
+
+
+def main(only=None):
+    os.makedirs(OUT, exist_ok=True)
+    for case in CASES:
+        name, key, configs, jast, nw, ntherm, step, init = case
+        if only and name not in only:
+            continue
+        torch.manual_seed(1234)
+        np.random.seed(1234)
+        mol, wf = build(case)
+        sampler = Metropolis(nwalkers=nw, nstep=ntherm, step_size=step, nelec=wf.nelec,
+                             ndim=3, init=mol.domain(init),
+                             move={"type": "all-elec", "proba": "normal"})
+        pos = sampler(wf.pdf, with_tqdm=False).detach().clone()
+        # perturb the trainable parameters so gradients/values are not at a symmetric point
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            wf.mo.mo_modifier.mul_(1 + 0.05 * (torch.rand(wf.mo.mo_modifier.shape, generator=g) - 0.5))
+            if wf.nci > 1:
+                wf.fc.weight.add_(0.2 * (torch.rand(wf.fc.weight.shape, generator=g) - 0.5))
+            if jast == "ee":
+                wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+            elif jast == "ee+en":
+                wf.jastrow.jastrow_terms[0].jastrow_kernel.weight.fill_(0.8)
+                wf.jastrow.jastrow_terms[1].jastrow_kernel.weight.data.fill_(1.3)
+
+        P = orc.make_params(mol, wf.configs,
+                            jastrow_weight=None if jast is None else 0.8,
+                            en_weight=1.3 if jast == "ee+en" else None)
+        P.mo_modifier = wf.mo.mo_modifier.detach().clone()
+        P.ci = wf.fc.weight.detach().clone()
+
+        out = dict(pos=pos.numpy(), mo_modifier=P.mo_modifier.numpy(), ci=P.ci.numpy(),
+                   cfg_up=wf.configs[0].numpy(), cfg_down=wf.configs[1].numpy(),
+                   jw=np.array([0.8 if jast else np.nan]),
+                   enw=np.array([1.3 if jast == "ee+en" else np.nan]))
+        need_grad = jast == "ee+en"   # CombineJastrow flags requires_autograd
+        with torch.no_grad():
+            ao, dao, d2ao = wf.ao(pos, derivative=[0, 1, 2])
+            psi = wf(pos)
+            if jast is not None:
+                J, dJ, d2J = wf.jastrow(pos, derivative=[0, 1, 2], sum_grad=False)
+            ekin = wf.kinetic_energy(pos)
+            eloc = wf.local_energy(pos)
+            gpsi = wf.gradients_jacobi(pos)
+            gpdf = wf.gradients_jacobi(pos, pdf=True)
+        # --- oracle vs reference
+        o_ao, o_dao, o_d2ao = orc.ao_all(P, pos)
+        o_psi = orc.psi(P, pos)
+        o_ekin = orc.kinetic_energy(P, pos)
+        o_eloc = orc.local_energy(P, pos)
+        o_g = orc.grad_psi(P, pos)
+        o_gp = orc.grad_psi(P, pos, pdf=True)
+        errs = dict(ao=relmax(o_ao, ao), dao=relmax(o_dao, dao), d2ao=relmax(o_d2ao, d2ao),
+                    psi=rel(o_psi, psi), ekin=rel(o_ekin, ekin), eloc=rel(o_eloc, eloc),
+                    gpsi=relmax(o_g, gpsi), gpdf=relmax(o_gp, gpdf))
+        if jast is not None:
+            oJ, odJ, od2J = orc.jastrow_all(P, pos)
+            errs.update(J=rel(oJ, J), dJ=relmax(odJ, dJ), d2J=relmax(od2J, d2J))
+            out.update(J=J.numpy(), dJ=dJ.numpy(), d2J=d2J.numpy())
+        # keep AO tensors only for a slice (size)
+        ns = min(8, pos.shape[0])
+        out.update(ao=ao[:ns].numpy(), dao=dao[:ns].numpy(), d2ao=d2ao[:ns].numpy(),
+                   psi=psi.numpy(), ekin=ekin.numpy(), eloc=eloc.numpy(),
+                   gpsi=gpsi.numpy(), gpdf=gpdf.numpy())
+
+        # --- parameter gradients through the reference solver (grad="manual")
+        opt = torch.optim.SGD(wf.parameters(), lr=0.0)
+        solver = Solver(wf=wf, sampler=sampler, optimizer=opt)
+        solver.configure(track=["local_energy"], loss="energy", grad="manual")
+        opt.zero_grad()
+        solver.evaluate_grad_manual(pos.clone())
+        ref_g = dict(mo_modifier=wf.mo.mo_modifier.grad.clone(), ci=wf.fc.weight.grad.clone(),
+                     bas_exp=wf.ao.bas_exp.grad.clone(), bas_coeffs=wf.ao.bas_coeffs.grad.clone())
+        if jast == "ee":
+            ref_g["jastrow_weight"] = wf.jastrow.jastrow_kernel.weight.grad.clone()
+        elif jast == "ee+en":
+            ref_g["jastrow_weight"] = wf.jastrow.jastrow_terms[0].jastrow_kernel.weight.grad.clone()
+        names = tuple(ref_g.keys()) + (("en_weight",) if jast == "ee+en" else ())
+        og, _ = orc.param_grads(P, pos, names=names)
+        for k, v in ref_g.items():
+            if k == "ci" and wf.nci == 1:
+                continue
+            # (sum_w (E_L - <E_L>) = 0 makes the single-determinant ci gradient pure rounding noise)
+            errs["g_" + k] = float((og[k] - v).abs().max() / max(float(v.abs().max()), 1e-6))
+            out["grad_" + k] = v.numpy()
+        if "en_weight" in og:
+            out["grad_en_weight"] = og["en_weight"].numpy()   # reference keeps this one off the graph
+
+        # --- Metropolis decisions, teacher forced, injected draws
+        with torch.no_grad():
+            gen = torch.Generator().manual_seed(99)
+            sig = orc.proposal_sigma(step)
+            nstep = 4
+            cur = pos.clone()
+            fx = wf.pdf(cur)
+            fx[fx == 0] = 1e-16
+            tr_disp, tr_tau, tr_acc, tr_fxn, tr_pos = [], [], [], [], [cur.numpy().copy()]
+            ofx = (orc.psi(P, cur) ** 2).reshape(-1)
+            for it in range(nstep):
+                disp = torch.randn(cur.shape, generator=gen, dtype=torch.float64) * np.sqrt(sig)
+                xn = cur + disp
+                fxn = wf.pdf(xn)
+                fxn[fxn == 0.0] = 1e-16
+                df = fxn / fx
+                torch.manual_seed(1000 + it)
+                idx = sampler._accept(df.clone())
+                torch.manual_seed(1000 + it)
+                tau = torch.rand_like(df)
+                # oracle from the same state
+                npos, nfx, oacc, ofxn = orc.metropolis_step(P, cur, fx.clone(), disp, tau)
+                assert bool((oacc == idx).all()), "oracle accept mismatch"
+                errs["mh_fxn"] = max(errs.get("mh_fxn", 0.0), rel(ofxn, fxn))
+                cur[idx, :] = xn[idx, :]
+                fx[idx] = fxn[idx]
+                fx[fx == 0] = 1e-16
+                assert torch.equal(npos, cur)
+                tr_disp.append(disp.numpy()); tr_tau.append(tau.numpy())
+                tr_acc.append(idx.numpy()); tr_fxn.append(fxn.numpy())
+                tr_pos.append(cur.numpy().copy())
+            out.update(mh_disp=np.stack(tr_disp), mh_tau=np.stack(tr_tau), mh_acc=np.stack(tr_acc),
+                       mh_fxn=np.stack(tr_fxn), mh_pos=np.stack(tr_pos))
+        out["meta"] = np.array([name, key, configs, str(jast), str(step)])
+        print("%-14s W=%4d " % (name, pos.shape[0])
+              + " ".join("%s=%.1e" % kv for kv in errs.items()))
+        bad = {k: v for k, v in errs.items() if not v < 5e-11}
+        assert not bad, "oracle does not reproduce the reference: %r" % bad
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
