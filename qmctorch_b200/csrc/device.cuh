@@ -1,0 +1,370 @@
+// Device-side building blocks shared by the fused and the operator-level kernels:
+// shared-memory table staging, shell evaluation (radial x cartesian harmonic),
+// Jastrow/potential terms per electron, small dense determinants/inverses.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "plan.h"
+
+#define QMCB_EPS 1e-16
+
+struct Tab {
+  const double *atoms, *alpha, *coef, *pn, *cscale, *mow, *ci;
+  const int *ash, *spo, *sco, *ck, *cao, *used, *ucu, *ucd, *ciu, *cid, *pfo, *pflat;
+};
+
+// Copies both blobs into shared memory (all threads), returns the first free double slot.
+__device__ __forceinline__ double *stage_tables(const DevSys &S, double *smem, Tab &T) {
+  double *sd = smem;
+  int *si = reinterpret_cast<int *>(smem + S.ndbl);
+  for (int i = threadIdx.x; i < S.ndbl; i += blockDim.x) sd[i] = S.dblob[i];
+  for (int i = threadIdx.x; i < S.nint; i += blockDim.x) si[i] = S.iblob[i];
+  T.atoms = sd + S.o_atoms; T.alpha = sd + S.o_alpha; T.coef = sd + S.o_coef; T.pn = sd + S.o_pn;
+  T.cscale = sd + S.o_cscale; T.mow = sd + S.o_mow; T.ci = sd + S.o_ci;
+  T.ash = si + S.o_ash; T.spo = si + S.o_spo; T.sco = si + S.o_sco; T.ck = si + S.o_ck;
+  T.cao = si + S.o_cao; T.used = si + S.o_used; T.ucu = si + S.o_ucu; T.ucd = si + S.o_ucd;
+  T.ciu = si + S.o_ciu; T.cid = si + S.o_cid; T.pfo = si + S.o_pfo; T.pflat = si + S.o_pflat;
+  return smem + S.ndbl + S.nint / 2;
+}
+
+__host__ __device__ inline int table_doubles(const DevSys &S) { return S.ndbl + S.nint / 2; }
+
+__device__ __forceinline__ double ipow(double x, int k) {
+  switch (k) {
+    case 0: return 1.0;
+    case 1: return x;
+    case 2: return x * x;
+    default: {
+      double r = x * x;
+      for (int i = 2; i < k; ++i) r *= x;
+      return r;
+    }
+  }
+}
+
+// r^m for m >= -2 given r and 1/r
+__device__ __forceinline__ double rpow(double r, double rinv, int m) {
+  if (m >= 0) return ipow(r, m);
+  return m == -1 ? rinv : rinv * rinv;
+}
+
+// ---------------------------------------------------------------------------------------
+// Shell evaluation.  For every shell the radial part is contracted first:
+//   R(r) = S0,  grad R = S1 * (x,y,z),  lap R = S2        (spherically symmetric)
+// then each cartesian component Y = x^kx y^ky z^kz (degree L) gives
+//   ao = R Y,  grad ao = S1 Y (x,y,z) + R grad Y,  lap ao = (S2 + 2 L S1) Y + R lap Y
+// (Euler: (x,y,z).grad Y = L Y).  Restates atomic_orbitals.py:578-669,
+// radial_functions.py:6-406, spherical_harmonics.py:102-199.
+// Sink::emit(ao_index, v[NCH]) consumes the values: v[0]=ao, v[1..3]=grad, v[4]=lap.
+// ---------------------------------------------------------------------------------------
+template <int NCH>
+__device__ __forceinline__ void radial_sums(const DevSys &S, const Tab &T, int s, double r2, double r,
+                                            double rinv, double &S0, double &S1, double &S2) {
+  S0 = 0.0; S1 = 0.0; S2 = 0.0;
+  const int p1 = T.spo[s + 1];
+  if (S.radial_type == QMCB_GTO_PURE) {
+    for (int p = T.spo[s]; p < p1; ++p) {
+      const double a = T.alpha[p];
+      const double ce = T.coef[p] * exp(-a * r2);
+      S0 += ce;
+      if (NCH > 1) {
+        const double t = a * ce;
+        S1 -= 2.0 * t;
+        S2 += t * (4.0 * a * r2 - 6.0);
+      }
+    }
+  } else if (S.radial_type == QMCB_STO_PURE) {
+    for (int p = T.spo[s]; p < p1; ++p) {
+      const double a = T.alpha[p];
+      const double ce = T.coef[p] * exp(-a * r);
+      S0 += ce;
+      if (NCH > 1) {
+        const double t = a * ce;
+        S1 -= t * rinv;
+        S2 += t * (a - 2.0 * rinv);
+      }
+    }
+  } else {
+    const bool gto = S.radial_type == QMCB_GTO;
+    for (int p = T.spo[s]; p < p1; ++p) {
+      const double a = T.alpha[p];
+      const int n = (int)T.pn[p];
+      const double ce = T.coef[p] * exp(gto ? -a * r2 : -a * r);
+      const double rn = ipow(r, n);
+      S0 += ce * rn;
+      if (NCH > 1) {
+        const double nrnm2 = n == 0 ? 0.0 : n * rpow(r, rinv, n - 2);
+        if (gto) {
+          S1 += ce * (nrnm2 - 2.0 * a * rn);
+          S2 += ce * (nrnm2 * (n + 1) - 4.0 * a * n * rn + a * rn * (4.0 * a * r2 - 6.0));
+        } else {
+          S1 += ce * (nrnm2 - a * rn * rinv);
+          S2 += ce * (nrnm2 * (n + 1) - 2.0 * a * nrnm2 * r + a * rn * (a - 2.0 * rinv));
+        }
+      }
+    }
+  }
+}
+
+template <int NCH>
+__device__ __forceinline__ void component_values(int kk, double sc, double x, double y, double z,
+                                                 double S0, double S1, double S2, double (&v)[NCH]) {
+  const int kx = kk & 255, ky = (kk >> 8) & 255, kz = (kk >> 16) & 255;
+  const int L = kx + ky + kz;
+  if (L == 0) {
+    v[0] = S0 * sc;
+    if (NCH > 1) {
+      const double t = S1 * sc;
+      v[1] = t * x; v[2] = t * y; v[3] = t * z;
+      v[4] = S2 * sc;
+    }
+  } else if (L == 1) {
+    const double c = kx ? x : (ky ? y : z);
+    const double R = S0 * sc;
+    v[0] = R * c;
+    if (NCH > 1) {
+      const double t = S1 * sc * c;
+      v[1] = t * x + (kx ? R : 0.0);
+      v[2] = t * y + (ky ? R : 0.0);
+      v[3] = t * z + (kz ? R : 0.0);
+      v[4] = (S2 + 2.0 * S1) * sc * c;
+    }
+  } else {
+    const double px = ipow(x, kx), py = ipow(y, ky), pz = ipow(z, kz);
+    const double Y = px * py * pz;
+    const double R = S0 * sc;
+    v[0] = R * Y;
+    if (NCH > 1) {
+      const double dYx = kx ? kx * ipow(x, kx - 1) * py * pz : 0.0;
+      const double dYy = ky ? ky * px * ipow(y, ky - 1) * pz : 0.0;
+      const double dYz = kz ? kz * px * py * ipow(z, kz - 1) : 0.0;
+      double lapY = 0.0;
+      if (kx > 1) lapY += kx * (kx - 1) * ipow(x, kx - 2) * py * pz;
+      if (ky > 1) lapY += ky * (ky - 1) * px * ipow(y, ky - 2) * pz;
+      if (kz > 1) lapY += kz * (kz - 1) * px * py * ipow(z, kz - 2);
+      const double t = S1 * sc * Y;
+      v[1] = t * x + R * dYx;
+      v[2] = t * y + R * dYy;
+      v[3] = t * z + R * dYz;
+      v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
+    }
+  }
+}
+
+template <int NCH, class Sink>
+__device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double ex, double ey, double ez,
+                                         Sink &sink) {
+  for (int A = 0; A < S.natom; ++A) {
+    const double x = ex - T.atoms[4 * A], y = ey - T.atoms[4 * A + 1], z = ez - T.atoms[4 * A + 2];
+    const double r2 = x * x + y * y + z * z;
+    double r = 0.0, rinv = 0.0;
+    if (S.radial_type != QMCB_GTO_PURE) { r = sqrt(r2); rinv = 1.0 / r; }
+    const int s1 = T.ash[A + 1];
+    for (int s = T.ash[A]; s < s1; ++s) {
+      double S0, S1, S2;
+      radial_sums<NCH>(S, T, s, r2, r, rinv, S0, S1, S2);
+      const int k1 = T.sco[s + 1];
+      for (int k = T.sco[s]; k < k1; ++k) {
+        double v[NCH];
+        component_values<NCH>(T.ck[k], T.cscale[k], x, y, z, S0, S1, S2, v);
+        sink.emit(T.cao[k], v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-electron Jastrow / potential terms.  sp = this walker's positions [3*nelec] (shared).
+// Output: g[3] = grad_e ln J, lap = (lap_e J)/J, ks = this electron's share of ln J
+// (pairs j>e, all nuclei), ven, vee (pairs j>e).
+// e-e: jastrow_factor_electron_electron.py:124-260, kernels/pade_jastrow_kernel.py:34-153,
+//      distance/electron_electron_distance.py:47-190 (Gram-form r_ij reproduced exactly);
+// e-n: jastrow_factor_electron_nuclei.py:60-161, kernels/pade_jastrow_kernel.py:36-116,
+//      distance/electron_nuclei_distance.py:53-162;  product rule: combine_jastrow.py:116-195;
+// potentials: wf_base.py:49-95.
+// ---------------------------------------------------------------------------------------
+struct ElecTerms {
+  double gx, gy, gz, lap, ks, ven, vee;
+};
+
+template <bool DERIV>
+__device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, const double *sp, int e,
+                                               ElecTerms &o) {
+  const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
+  double gx = 0, gy = 0, gz = 0, h = 0, ks = 0, ven = 0, vee = 0;
+  const double ni = __dadd_rn(__dadd_rn(__dmul_rn(xi, xi), __dmul_rn(yi, yi)), __dmul_rn(zi, zi));
+  const bool up_i = e < S.nup;
+  const double w = S.jee_w;
+  for (int j = 0; j < S.nelec; ++j) {
+    if (j == e) continue;
+    const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
+    const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    const double s2 = dx * dx + dy * dy + dz * dz;
+    if (j > e) vee += 1.0 / sqrt(s2);
+    if (S.use_jee) {
+      const double nj = __dadd_rn(__dadd_rn(__dmul_rn(xj, xj), __dmul_rn(yj, yj)), __dmul_rn(zj, zj));
+      double dot;
+      if (S.gram_fma) dot = __fma_rn(zi, zj, __fma_rn(yi, yj, __dmul_rn(xi, xj)));
+      else dot = __dadd_rn(__dadd_rn(__dmul_rn(xi, xj), __dmul_rn(yi, yj)), __dmul_rn(zi, zj));
+      const double d2 = __dsub_rn(__dadd_rn(ni, nj), __dmul_rn(2.0, dot));
+      const double r = sqrt(d2);
+      const double w0 = (up_i == (j < S.nup)) ? 0.25 : 0.5;
+      const double den = 1.0 / (1.0 + w * r);
+      if (j > e) ks += w0 * r * den;
+      if (DERIV) {
+        const double rinv = 1.0 / r;
+        const double kp = w0 * den * den * rinv;
+        gx += kp * dx; gy += kp * dy; gz += kp * dz;
+        h += 2.0 * kp * den * (s2 * rinv * rinv);
+      }
+    }
+  }
+  double gnx = 0, gny = 0, gnz = 0;
+  for (int A = 0; A < S.natom; ++A) {
+    const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+    const double dx = xi - xa, dy = yi - ya, dz = zi - za;
+    const double s2 = dx * dx + dy * dy + dz * dz;
+    ven -= T.atoms[4 * A + 3] / sqrt(s2);
+    if (S.use_jen) {
+      const double wn = S.jen_w;
+      const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));
+      const double dot = __fma_rn(zi, za, __fma_rn(yi, ya, __dmul_rn(xi, xa)));
+      const double r = sqrt(__dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot)));
+      const double den = 1.0 / (1.0 + wn * r);
+      ks += r * den;
+      if (DERIV) {
+        const double invr = 1.0 / (r + QMCB_EPS);
+        const double invr3 = 1.0 / (r * r * r + QMCB_EPS);
+        const double kp = den * den * invr;
+        gnx += kp * dx; gny += kp * dy; gnz += kp * dz;
+        const double sdr2 = s2 * invr * invr;   // sum_c dr_c^2
+        const double sd2r = 2.0 * s2 * invr3;   // sum_c d2r_c
+        const double den2 = den * den;
+        h += den * sd2r - 2.0 * wn * den2 * sdr2 - wn * r * den2 * sd2r +
+             2.0 * wn * wn * r * den2 * den * sdr2;
+      }
+    }
+  }
+  gx += gnx; gy += gny; gz += gnz;
+  o.gx = gx; o.gy = gy; o.gz = gz;
+  o.lap = h + gx * gx + gy * gy + gz * gz;
+  o.ks = ks; o.ven = ven; o.vee = vee;
+}
+
+// ---------------------------------------------------------------------------------------
+// Small dense LU-type kernels on one spin block (n x n), one thread per matrix.
+// A(i,j) = mo[row0+i][cols[j]], B likewise.  Closed forms for n<=3; Gauss-Jordan with
+// partial pivoting on an interleaved shared scratch otherwise (element stride `es`).
+// Replaces torch.det / torch.inverse / btrace in slater_pooling.py:96-111,348-387,827-849.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void det_trace_small(int n, const double *A, const double *B, int ld,
+                                                const int *cols, bool with_b, double &det, double &tr) {
+  if (n == 1) {
+    det = A[cols[0]];
+    tr = with_b ? B[cols[0]] / det : 0.0;
+  } else if (n == 2) {
+    const double a00 = A[cols[0]], a01 = A[cols[1]], a10 = A[ld + cols[0]], a11 = A[ld + cols[1]];
+    det = a00 * a11 - a01 * a10;
+    if (with_b) {
+      const double b00 = B[cols[0]], b01 = B[cols[1]], b10 = B[ld + cols[0]], b11 = B[ld + cols[1]];
+      tr = (a11 * b00 - a01 * b10 - a10 * b01 + a00 * b11) / det;
+    } else tr = 0.0;
+  } else {  // n == 3
+    double a[3][3], c[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) a[i][j] = A[i * ld + cols[j]];
+    c[0][0] = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+    c[0][1] = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+    c[0][2] = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+    c[1][0] = a[0][2] * a[2][1] - a[0][1] * a[2][2];
+    c[1][1] = a[0][0] * a[2][2] - a[0][2] * a[2][0];
+    c[1][2] = a[0][1] * a[2][0] - a[0][0] * a[2][1];
+    c[2][0] = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+    c[2][1] = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+    c[2][2] = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+    det = a[0][0] * c[0][0] + a[0][1] * c[0][1] + a[0][2] * c[0][2];
+    tr = 0.0;
+    if (with_b) {
+      // inv(A)[j][i] = c[i][j]/det ; Tr(inv(A) B) = sum_ij inv[j][i] B[i][j] = sum_ij c[i][j] B[i][j]/det
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t += c[i][j] * B[i * ld + cols[j]];
+      tr = t / det;
+    }
+  }
+}
+
+// inverse for n<=3 written to inv[i*n+j] (row-major), returns det
+__device__ __forceinline__ double inverse_small(int n, const double *A, int ld, const int *cols, double *inv,
+                                                int es) {
+  if (n == 1) {
+    const double d = A[cols[0]];
+    inv[0] = 1.0 / d;
+    return d;
+  }
+  if (n == 2) {
+    const double a00 = A[cols[0]], a01 = A[cols[1]], a10 = A[ld + cols[0]], a11 = A[ld + cols[1]];
+    const double det = a00 * a11 - a01 * a10, id = 1.0 / det;
+    inv[0] = a11 * id; inv[es] = -a01 * id; inv[2 * es] = -a10 * id; inv[3 * es] = a00 * id;
+    return det;
+  }
+  double a[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[i][j] = A[i * ld + cols[j]];
+  const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+  const double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+  const double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+  const double det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02, id = 1.0 / det;
+  inv[0 * es] = c00 * id;
+  inv[1 * es] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id;
+  inv[2 * es] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+  inv[3 * es] = c01 * id;
+  inv[4 * es] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id;
+  inv[5 * es] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+  inv[6 * es] = c02 * id;
+  inv[7 * es] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id;
+  inv[8 * es] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+  return det;
+}
+
+// Gauss-Jordan with partial pivoting on [A | R] (n x (n+nr)), scratch element (i,j) at
+// scr[(i*(n+nr)+j)*es].  On exit the right block holds inv(A) R.  Returns det(A).
+__device__ inline double gauss_jordan(int n, int nr, double *scr, int es) {
+  const int ldw = n + nr;
+  double det = 1.0;
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = fabs(scr[(k * ldw + k) * es]);
+    for (int i = k + 1; i < n; ++i) {
+      const double v = fabs(scr[(i * ldw + k) * es]);
+      if (v > best) { best = v; piv = i; }
+    }
+    if (piv != k) {
+      for (int j = 0; j < ldw; ++j) {
+        const double t = scr[(k * ldw + j) * es];
+        scr[(k * ldw + j) * es] = scr[(piv * ldw + j) * es];
+        scr[(piv * ldw + j) * es] = t;
+      }
+      det = -det;
+    }
+    const double pv = scr[(k * ldw + k) * es];
+    det *= pv;
+    const double ip = 1.0 / pv;
+    for (int j = k + 1; j < ldw; ++j) scr[(k * ldw + j) * es] *= ip;
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = scr[(i * ldw + k) * es];
+      if (f != 0.0)
+        for (int j = k + 1; j < ldw; ++j) scr[(i * ldw + j) * es] -= f * scr[(k * ldw + j) * es];
+    }
+  }
+  return det;
+}

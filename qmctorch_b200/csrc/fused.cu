@@ -1,0 +1,453 @@
+// The fused walker-tile kernel: psi, local energy, grad psi and the Metropolis step.
+//
+// One CTA owns TW walkers at a time (persistent, grid-stride over tiles) and stages the
+// basis / MO / configuration tables in shared memory once.  Per tile:
+//   P0  coalesced load of the walker coordinates (optionally + proposal) -> smem
+//   P1  thread (walker, electron): Jastrow gradient/Laplacian terms + potentials
+//   P2  thread (walker, MO block, electron): shells -> AO value/grad/lap in registers,
+//       contracted on the fly against the MO columns some configuration occupies;
+//       B_kin row assembled in registers; only mo and B_kin (or grad mo) go to smem
+//   P3  thread (walker, spin, unique occupation): det, inverse / Tr(A^-1 B)
+//   P4  thread (walker): CI sum, psi, E_kin, E_L  (or accept/reject + in-place update)
+// Nothing but pos in and psi/E_L out touches HBM.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "device.cuh"
+#include "philox.cuh"
+
+enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3 };
+
+struct FusedArgs {
+  const double *pos;   // [W,3Ne]   (MH: updated in place through pos_rw)
+  double *pos_rw;
+  int64_t W;
+  double *out0;        // psi [W]           | eloc [W]      | grad [W,3Ne] | fx [W] (in/out)
+  double *out1;        // -                 | psi or null   | -            | -
+  double *out2;        // -                 | ekin or null  | -            | -
+  int pdf;             // GRAD: return grad psi^2
+  // Metropolis
+  const double *disp;  // [W,3Ne] or null
+  const double *tau;   // [W] or null
+  const int *elec_index;
+  int move_elec, proba_normal;
+  double scale, eps;
+  uint64_t seed, offset;
+  uint8_t *accept;
+  unsigned long long *naccept;
+};
+
+template <int NCH, int MB>
+struct MoSink {
+  double acc[NCH][MB];
+  const double *w;
+  int nmup;
+  __device__ __forceinline__ void init(const double *w_, int nmup_) {
+    w = w_; nmup = nmup_;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < MB; ++j) acc[c][j] = 0.0;
+  }
+  __device__ __forceinline__ void emit(int ao, const double (&v)[NCH]) {
+    const double *wr = w + ao * nmup;
+#pragma unroll
+    for (int j = 0; j < MB; ++j) {
+      const double wj = wr[j];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc[c][j] = fma(v[c], wj, acc[c][j]);
+    }
+  }
+};
+
+// shared-memory plan per CTA (doubles), after the tables:
+//   spos [TW][3Ne] | jv [TW][Ne][8] | mo [NCHS][TW][Ne][nmup] | dets [TW][nuu+nud] | trs [TW][nuu+nud]
+//   | wsum [TW][4] | scratch
+template <int MODE>
+__host__ __device__ constexpr int nchs() { return MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1); }
+
+__host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode) {
+  const int n = S.nup > S.ndown ? S.nup : S.ndown;
+  if (mode == MODE_GRAD) return n <= 3 ? n * n : 2 * n * n;   // inverse kept ([A|I] for n>3)
+  if (n <= 3) return 0;
+  return mode == MODE_ELOC ? 2 * n * n : n * n;            // [A|B] or A
+}
+
+template <int MODE, int MB>
+__global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedArgs a, const int TW,
+                                                    const int NBLK, const int lu_conc) {
+  constexpr int NCH = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? 5 : 1;
+  constexpr int NCHS = nchs<MODE>();
+  extern __shared__ double smem[];
+  Tab T;
+  double *ws = stage_tables(S, smem, T);
+  const int Ne = S.nelec, ne3 = 3 * Ne, nmup = S.nmup;
+  const int nun = S.nuu + S.nud;
+  double *spos = ws;
+  double *jv = spos + TW * ne3;
+  double *smo = jv + TW * Ne * 8;
+  double *sdet = smo + (size_t)NCHS * TW * Ne * nmup;
+  double *str = sdet + TW * nun;
+  double *wsum = str + TW * nun;
+  double *scr = wsum + TW * 4;
+  const int tid = threadIdx.x;
+  const int64_t ntile = (a.W + TW - 1) / TW;
+  __syncthreads();
+
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t w0 = tile * TW;
+    const int tw = (int)((a.W - w0) < TW ? (a.W - w0) : TW);
+    // ---- P0: coordinates
+    for (int i = tid; i < tw * ne3; i += blockDim.x) {
+      double v = a.pos[w0 * ne3 + i];
+      if (MODE == MODE_MH) {
+        const int wl = i / ne3, c = i - wl * ne3, e = c / 3;
+        int me = a.move_elec;
+        if (me == -2) {
+          if (a.elec_index) me = a.elec_index[w0 + wl];
+          else me = (int)(philox_u32(a.seed, a.offset, (uint64_t)(w0 + wl), 2u) % (unsigned)Ne);
+        }
+        if (me < 0 || me == e) {
+          double d;
+          if (a.disp) d = a.disp[w0 * ne3 + i];
+          else if (a.proba_normal) d = a.scale * philox_normal(a.seed, a.offset, (uint64_t)(w0 * ne3 + i));
+          else d = a.scale * (2.0 * philox_uniform(a.seed, a.offset, (uint64_t)(w0 * ne3 + i), 0u) - 1.0);
+          v += d;
+        }
+      }
+      spos[i] = v;
+    }
+    __syncthreads();
+    // ---- P1: Jastrow + potentials, thread (wl, e)
+    for (int it = tid; it < tw * Ne; it += blockDim.x) {
+      const int wl = it / Ne, e = it - wl * Ne;
+      ElecTerms o;
+      electron_terms<(NCH > 1)>(S, T, spos + wl * ne3, e, o);
+      double *q = jv + (size_t)it * 8;
+      q[0] = o.gx; q[1] = o.gy; q[2] = o.gz; q[3] = o.lap; q[4] = o.ks; q[5] = o.ven; q[6] = o.vee;
+    }
+    __syncthreads();
+    // ---- P2: AO -> MO rows, thread (wl, blk, e)
+    for (int it = tid; it < tw * NBLK * Ne; it += blockDim.x) {
+      const int wl = it / (NBLK * Ne), rem = it - wl * NBLK * Ne;
+      const int blk = rem / Ne, e = rem - blk * Ne;
+      const double *sp = spos + wl * ne3 + 3 * e;
+      MoSink<NCH, MB> sink;
+      sink.init(T.mow + blk * MB, nmup);
+      eval_aos<NCH>(S, T, sp[0], sp[1], sp[2], sink);
+      const size_t chs = (size_t)TW * Ne * nmup;
+      double *dst = smo + ((size_t)wl * Ne + e) * nmup + blk * MB;
+      if (MODE == MODE_ELOC) {
+        const double *q = jv + ((size_t)wl * Ne + e) * 8;
+        const double gx = q[0], gy = q[1], gz = q[2], lp = q[3];
+        const bool uj = S.use_jee || S.use_jen;
+#pragma unroll
+        for (int j = 0; j < MB; ++j) {
+          double b = sink.acc[4][j];
+          if (uj) b += 2.0 * (gx * sink.acc[1][j] + gy * sink.acc[2][j] + gz * sink.acc[3][j]) + lp * sink.acc[0][j];
+          dst[j] = sink.acc[0][j];
+          dst[chs + j] = -0.5 * b;
+        }
+      } else if (MODE == MODE_GRAD) {
+#pragma unroll
+        for (int j = 0; j < MB; ++j) {
+          dst[j] = sink.acc[0][j];
+          dst[chs + j] = sink.acc[1][j];
+          dst[2 * chs + j] = sink.acc[2][j];
+          dst[3 * chs + j] = sink.acc[3][j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < MB; ++j) dst[j] = sink.acc[0][j];
+      }
+    }
+    __syncthreads();
+    // ---- P3: determinants (and traces / inverses) per (wl, unique occupation)
+    {
+      const int nitem = tw * nun;
+      const int per = lu_scratch_per_item(S, MODE);
+      // scratch slot: GRAD keeps every inverse resident (slot = item); otherwise one slot
+      // per participating thread, reused across rounds
+      const int conc = per ? lu_conc : blockDim.x;
+      const int stride = (MODE == MODE_GRAD) ? blockDim.x : (conc < (int)blockDim.x ? conc : blockDim.x);
+      const size_t chs = (size_t)TW * Ne * nmup;
+      if (tid < stride) {
+        for (int it = tid; it < nitem; it += stride) {
+          const int wl = it / nun, u = it - wl * nun;
+          const bool up = u < S.nuu;
+          const int n = up ? S.nup : S.ndown;
+          const int *cols = up ? T.ucu + u * S.nup : T.ucd + (u - S.nuu) * S.ndown;
+          const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
+          double det = 1.0, tr = 0.0;
+          if (n == 0) {
+            det = 1.0; tr = 0.0;
+          } else if (MODE == MODE_GRAD) {
+            double *m = scr + it;   // element stride = conc
+            if (n <= 3) det = inverse_small(n, A, nmup, cols, m, conc);
+            else {
+              const int ldw = 2 * n;
+              for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                  m[(i * ldw + j) * conc] = A[i * nmup + cols[j]];
+                  m[(i * ldw + n + j) * conc] = i == j ? 1.0 : 0.0;
+                }
+              det = gauss_jordan(n, n, m, conc);
+            }
+          } else if (n <= 3) {
+            det_trace_small(n, A, A + chs, nmup, cols, MODE == MODE_ELOC, det, tr);
+          } else {
+            double *m = scr + tid;
+            const int nr = MODE == MODE_ELOC ? n : 0;
+            const int ldw = n + nr;
+            for (int i = 0; i < n; ++i)
+              for (int j = 0; j < n; ++j) {
+                m[(i * ldw + j) * conc] = A[i * nmup + cols[j]];
+                if (nr) m[(i * ldw + n + j) * conc] = A[chs + i * nmup + cols[j]];
+              }
+            det = gauss_jordan(n, nr, m, conc);
+            if (nr)
+              for (int i = 0; i < n; ++i) tr += m[(i * ldw + n + i) * conc];
+          }
+          sdet[wl * nun + u] = det;
+          str[wl * nun + u] = tr;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- P4: per-walker epilogue
+    if (tid < tw) {
+      const int wl = tid;
+      const double *dd = sdet + wl * nun, *tt = str + wl * nun;
+      double sig = 0.0, ksig = 0.0;
+      for (int c = 0; c < S.nconf; ++c) {
+        const int iu = T.ciu[c], id = S.nuu + T.cid[c];
+        const double d = T.ci[c] * dd[iu] * dd[id];
+        sig += d;
+        if (MODE == MODE_ELOC) ksig += d * (tt[iu] + tt[id]);
+      }
+      double ks = 0.0, ven = 0.0, vee = 0.0;
+      for (int e = 0; e < Ne; ++e) {
+        const double *q = jv + ((size_t)wl * Ne + e) * 8;
+        ks += q[4]; ven += q[5]; vee += q[6];
+      }
+      const double J = (S.use_jee || S.use_jen) ? exp(ks) : 1.0;
+      const double psi = J * sig;
+      if (MODE == MODE_PSI) {
+        a.out0[w0 + wl] = psi;
+      } else if (MODE == MODE_ELOC) {
+        const double ekin = ksig / sig;
+        a.out0[w0 + wl] = ekin + ven + vee + S.vnn;
+        if (a.out1) a.out1[w0 + wl] = psi;
+        if (a.out2) a.out2[w0 + wl] = ekin;
+      } else if (MODE == MODE_MH) {
+        double fxn = psi * psi;
+        if (fxn == 0.0) fxn = a.eps;
+        const double fx = a.out0[w0 + wl];
+        double df = fxn / fx;
+        if (df > 1.0) df = 1.0;
+        const double tau = a.tau ? a.tau[w0 + wl]
+                                 : philox_uniform(a.seed, a.offset, (uint64_t)(w0 + wl), 1u);
+        const bool acc = (df - tau) >= 0.0;
+        wsum[wl * 4] = acc ? 1.0 : 0.0;
+        if (acc) a.out0[w0 + wl] = fxn;   // fxn is never 0 here
+        if (a.accept) a.accept[w0 + wl] = acc ? 1 : 0;
+      } else {
+        wsum[wl * 4] = J;
+        wsum[wl * 4 + 1] = sig;
+      }
+    }
+    if (MODE == MODE_MH) {
+      __syncthreads();
+      int cnt = 0;
+      for (int i = tid; i < tw * ne3; i += blockDim.x) {
+        const int wl = i / ne3;
+        if (wsum[wl * 4] != 0.0) {
+          a.pos_rw[w0 * ne3 + i] = spos[i];
+          if (i == wl * ne3) ++cnt;
+        }
+      }
+      if (a.naccept) {
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((tid & 31) == 0 && cnt) atomicAdd(a.naccept, (unsigned long long)cnt);
+      }
+    }
+    if (MODE == MODE_GRAD) {
+      __syncthreads();
+      // d psi / d r_{e,c} = J [ sum_u C_u sum_j inv_u[j][e] dmo_c[e][cols_u[j]] + g_{e,c} Sigma ]
+      // (slater_jastrow.py:346-447), C_u = D_u * sum_{n: occ_s(n)=u} c_n D_other(n)
+      const size_t chs = (size_t)TW * Ne * nmup;
+      const int conc = lu_conc;
+      for (int it = tid; it < tw * Ne; it += blockDim.x) {
+        const int wl = it / Ne, e = it - wl * Ne;
+        const bool up = e < S.nup;
+        const int n = up ? S.nup : S.ndown;
+        const int el = up ? e : e - S.nup;
+        const double *dd = sdet + wl * nun;
+        const double *row = smo + ((size_t)wl * Ne + e) * nmup;
+        double gsx = 0, gsy = 0, gsz = 0;
+        const int nu = up ? S.nuu : S.nud;
+        for (int u = 0; u < nu; ++u) {
+          double cu = 0.0;
+          for (int c = 0; c < S.nconf; ++c) {
+            if ((up ? T.ciu[c] : T.cid[c]) != u) continue;
+            cu += T.ci[c] * dd[up ? S.nuu + T.cid[c] : T.ciu[c]];
+          }
+          cu *= dd[up ? u : S.nuu + u];
+          if (cu == 0.0) continue;
+          const int item = wl * nun + (up ? u : S.nuu + u);
+          const double *inv = scr + item;   // thread `item` wrote it (single round)
+          const int *cols = up ? T.ucu + u * S.nup : T.ucd + u * S.ndown;
+          double tx = 0, ty = 0, tz = 0;
+          const int ild = n <= 3 ? n : 2 * n, ioff = n <= 3 ? 0 : n;
+          for (int j = 0; j < n; ++j) {
+            const double iv = inv[(j * ild + ioff + el) * conc];
+            tx += iv * row[chs + cols[j]];
+            ty += iv * row[2 * chs + cols[j]];
+            tz += iv * row[3 * chs + cols[j]];
+          }
+          gsx += cu * tx; gsy += cu * ty; gsz += cu * tz;
+        }
+        const double J = wsum[wl * 4], sig = wsum[wl * 4 + 1];
+        const double *q = jv + (size_t)it * 8;
+        double ox = J * (gsx + q[0] * sig), oy = J * (gsy + q[1] * sig), oz = J * (gsz + q[2] * sig);
+        if (a.pdf) {
+          const double f = 2.0 * sig * J;
+          ox *= f; oy *= f; oz *= f;
+        }
+        double *g = a.out0 + (w0 + wl) * ne3 + 3 * e;
+        g[0] = ox; g[1] = oy; g[2] = oz;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static size_t fused_smem_bytes(const DevSys &S, int mode, int tw, int lu_conc) {
+  const int nchs_ = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
+  const int nun = S.nuu + S.nud;
+  size_t d = table_doubles(S);
+  d += (size_t)tw * 3 * S.nelec + (size_t)tw * S.nelec * 8 + (size_t)nchs_ * tw * S.nelec * S.nmup;
+  d += 2 * (size_t)tw * nun + (size_t)tw * 4;
+  d += (size_t)lu_conc * lu_scratch_per_item(S, mode);
+  return d * sizeof(double);
+}
+
+static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
+  const DevSys &S = p->sys;
+  int mb = 1;
+  while (mb < S.nmu && mb < 8) mb *= 2;
+  c.mb = mb;
+  c.nblk = S.nmup / mb;
+  const int per_walker = S.nelec * c.nblk;
+  if (per_walker > 512) {
+    qmcb_set_error("qmcb: nelec * MO blocks exceeds one CTA");
+    return QMCB_ESMEM;
+  }
+  const int nun = S.nuu + S.nud;
+  const int per = lu_scratch_per_item(S, mode);
+  const int budget = p->smem_optin - 1024;
+  int tw = 512 / per_walker;
+  if (tw > 128) tw = 128;
+  for (; tw >= 1; --tw) {
+    int threads = ((tw * per_walker + 31) / 32) * 32;
+    if (threads > 512) continue;
+    int conc = 0;
+    if (per) {
+      conc = tw * nun;                                     // GRAD: every inverse stays resident
+      if (mode != MODE_GRAD && conc > threads) conc = threads;
+    }
+    size_t sm = fused_smem_bytes(S, mode, tw, conc);
+    // prefer two CTAs per SM when the tile is small
+    if ((int)sm <= budget) {
+      c.tw = tw; c.threads = threads; c.smem = (int)sm; c.lu_conc = conc;
+      return 0;
+    }
+  }
+  qmcb_set_error("qmcb: system does not fit the shared-memory tiling");
+  return QMCB_ESMEM;
+}
+
+int qmcb_choose_launch(qmcb_plan *p) {
+  int rc = choose(p, MODE_PSI, p->cfg_psi);
+  if (!rc) rc = choose(p, MODE_ELOC, p->cfg_eloc);
+  if (!rc) rc = choose(p, MODE_GRAD, p->cfg_grad);
+  return rc;
+}
+
+template <int MODE, int MB>
+static int launch_t(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
+  auto k = fused_kernel<MODE, MB>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t ntile = (a.W + c.tw - 1) / c.tw;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, c.threads, c.smem);
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)p->sm_count * occ;
+  if (grid > ntile) grid = ntile;
+  if (grid < 1) grid = 1;
+  k<<<(unsigned)grid, c.threads, c.smem, st>>>(p->sys, a, c.tw, c.nblk, c.lu_conc);
+  return (int)cudaGetLastError();
+}
+
+template <int MODE>
+static int launch(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
+  switch (c.mb) {
+    case 1: return launch_t<MODE, 1>(p, c, a, st);
+    case 2: return launch_t<MODE, 2>(p, c, a, st);
+    case 4: return launch_t<MODE, 4>(p, c, a, st);
+    default: return launch_t<MODE, 8>(p, c, a, st);
+  }
+}
+
+static int check(const qmcb_plan *p, const void *pos, int64_t W) {
+  if (!p || !p->d_dbl) { qmcb_set_error("qmcb: plan has no device tables"); return QMCB_EINVAL; }
+  if (W < 0 || (W > 0 && !pos)) { qmcb_set_error("qmcb: bad walker array"); return QMCB_EINVAL; }
+  return 0;
+}
+
+extern "C" int qmcb_psi(const qmcb_plan *p, const double *pos, int64_t W, double *psi, void *stream) {
+  int rc = check(p, pos, W);
+  if (rc || W == 0) return rc;
+  FusedArgs a{};
+  a.pos = pos; a.W = W; a.out0 = psi;
+  return launch<MODE_PSI>(p, p->cfg_psi, a, (cudaStream_t)stream);
+}
+
+extern "C" int qmcb_local_energy(const qmcb_plan *p, const double *pos, int64_t W, double *eloc,
+                                 double *psi, double *ekin, void *stream) {
+  int rc = check(p, pos, W);
+  if (rc || W == 0) return rc;
+  FusedArgs a{};
+  a.pos = pos; a.W = W; a.out0 = eloc; a.out1 = psi; a.out2 = ekin;
+  return launch<MODE_ELOC>(p, p->cfg_eloc, a, (cudaStream_t)stream);
+}
+
+extern "C" int qmcb_grad_psi(const qmcb_plan *p, const double *pos, int64_t W, int pdf, double *grad,
+                             void *stream) {
+  int rc = check(p, pos, W);
+  if (rc || W == 0) return rc;
+  FusedArgs a{};
+  a.pos = pos; a.W = W; a.out0 = grad; a.pdf = pdf;
+  return launch<MODE_GRAD>(p, p->cfg_grad, a, (cudaStream_t)stream);
+}
+
+extern "C" int qmcb_metropolis_step(const qmcb_plan *p, double *pos, double *fx, int64_t W,
+                                    const double *disp, const double *tau, const int32_t *elec_index,
+                                    int move_elec, int proba_normal, double scale, double eps,
+                                    uint64_t seed, uint64_t offset, uint8_t *accept,
+                                    unsigned long long *naccept, void *stream) {
+  int rc = check(p, pos, W);
+  if (rc || W == 0) return rc;
+  if (move_elec >= p->sys.nelec || move_elec < -2) { qmcb_set_error("qmcb_metropolis_step: move_elec"); return QMCB_EINVAL; }
+  FusedArgs a{};
+  a.pos = pos; a.pos_rw = pos; a.W = W; a.out0 = fx;
+  a.disp = disp; a.tau = tau; a.elec_index = elec_index; a.move_elec = move_elec;
+  a.proba_normal = proba_normal; a.scale = scale; a.eps = eps; a.seed = seed; a.offset = offset;
+  a.accept = accept; a.naccept = naccept;
+  return launch<MODE_MH>(p, p->cfg_psi, a, (cudaStream_t)stream);
+}

@@ -1,0 +1,355 @@
+// Host side of the plan: regroup the reference's flat primitive list into shells
+// (one exp per (atom, exponent) shared by all cartesian components), collect the
+// MO columns that some configuration occupies, deduplicate spin occupations, and
+// choose the CTA tiling.  Reference data contract: atomic_orbitals.py:27-94,
+// molecular_orbitals.py:40-74, orbital_configurations.py:14-214, orbital_projector.py:29-51.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "plan.h"
+
+static thread_local std::string g_err;
+void qmcb_set_error(const std::string &msg) { g_err = msg; }
+extern "C" const char *qmcb_last_error(void) { return g_err.c_str(); }
+extern "C" int qmcb_abi_version(void) { return QMCB_ABI_VERSION; }
+
+namespace {
+
+struct AoDesc {
+  int atom, kx, ky, kz;
+  std::vector<double> alpha, pn, cn;   // per primitive
+  std::vector<int> flat;
+};
+
+struct ShellDesc {
+  int atom;
+  std::vector<double> alpha, pn, coef;
+  std::vector<int> comp_ao, comp_k;
+  std::vector<double> comp_scale;
+  std::vector<std::vector<int>> flat;  // [prim][comp]
+};
+
+bool proportional(const std::vector<double> &a, const std::vector<double> &ref, double *ratio) {
+  double r = 0.0;
+  bool have = false;
+  for (size_t i = 0; i < a.size(); ++i) {
+    if (ref[i] == 0.0) {
+      if (a[i] != 0.0) return false;
+      continue;
+    }
+    double q = a[i] / ref[i];
+    if (!have) { r = q; have = true; }
+    else if (std::fabs(q - r) > 1e-13 * std::fabs(r)) return false;
+  }
+  if (!have) r = 1.0;
+  *ratio = r;
+  return true;
+}
+
+}  // namespace
+
+int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
+  if (!s || s->nelec <= 0 || s->nup + s->ndown != s->nelec || s->natom <= 0 || s->nbas <= 0 ||
+      s->nao <= 0 || s->nmo <= 0 || s->nconf <= 0) {
+    qmcb_set_error("qmcb_plan: inconsistent sizes");
+    return QMCB_EINVAL;
+  }
+  if (s->radial_type < 0 || s->radial_type > 3) {
+    qmcb_set_error("qmcb_plan: unknown radial_type");
+    return QMCB_EINVAL;
+  }
+  // ---- AOs from flat primitives
+  std::vector<AoDesc> aos(s->nao);
+  std::vector<char> seen(s->nao, 0);
+  for (int i = 0; i < s->nbas; ++i) {
+    int a = s->index_ctr[i];
+    if (a < 0 || a >= s->nao) {
+      qmcb_set_error("qmcb_plan: index_ctr out of range");
+      return QMCB_EINVAL;
+    }
+    AoDesc &d = aos[a];
+    if (!seen[a]) {
+      seen[a] = 1;
+      d.atom = s->bas_atom[i];
+      d.kx = s->bas_kx[i]; d.ky = s->bas_ky[i]; d.kz = s->bas_kz[i];
+    } else if (d.atom != s->bas_atom[i] || d.kx != s->bas_kx[i] || d.ky != s->bas_ky[i] ||
+               d.kz != s->bas_kz[i]) {
+      qmcb_set_error("qmcb_plan: an AO mixes primitives of different centre/monomial (unsupported)");
+      return QMCB_EINVAL;
+    }
+    if (d.kx < 0 || d.ky < 0 || d.kz < 0 || d.kx > 15 || d.ky > 15 || d.kz > 15) {
+      qmcb_set_error("qmcb_plan: cartesian power out of range");
+      return QMCB_EINVAL;
+    }
+    double cg = s->bas_norm[i] * s->bas_coeffs[i];
+    double cv = s->contract ? cg : s->bas_norm[i];
+    if (cv != cg) {
+      // atomic_orbitals.py:236-249 drops bas_coeffs from values/laplacians when nothing is
+      // contracted while :344 keeps them in gradients; identical unless coeffs != 1.
+      qmcb_set_error("qmcb_plan: uncontracted basis with coefficients != 1 is not supported");
+      return QMCB_EINVAL;
+    }
+    d.alpha.push_back(s->bas_exp[i]);
+    d.pn.push_back((double)s->bas_kr[i]);
+    d.cn.push_back(cg);
+    d.flat.push_back(i);
+  }
+  for (int a = 0; a < s->nao; ++a)
+    if (!seen[a]) {
+      qmcb_set_error("qmcb_plan: AO without primitives");
+      return QMCB_EINVAL;
+    }
+  // ---- shells
+  std::vector<ShellDesc> shells;
+  for (int a = 0; a < s->nao; ++a) {
+    const AoDesc &d = aos[a];
+    bool placed = false;
+    for (auto &sh : shells) {
+      if (sh.atom != d.atom || sh.alpha != d.alpha || sh.pn != d.pn) continue;
+      double ratio;
+      if (!proportional(d.cn, sh.coef, &ratio)) continue;
+      sh.comp_ao.push_back(a);
+      sh.comp_k.push_back(d.kx | (d.ky << 8) | (d.kz << 16));
+      sh.comp_scale.push_back(ratio);
+      for (size_t q = 0; q < d.flat.size(); ++q) sh.flat[q].push_back(d.flat[q]);
+      placed = true;
+      break;
+    }
+    if (!placed) {
+      ShellDesc sh;
+      sh.atom = d.atom;
+      sh.alpha = d.alpha; sh.pn = d.pn; sh.coef = d.cn;
+      sh.comp_ao = {a};
+      sh.comp_k = {d.kx | (d.ky << 8) | (d.kz << 16)};
+      sh.comp_scale = {1.0};
+      sh.flat.resize(d.flat.size());
+      for (size_t q = 0; q < d.flat.size(); ++q) sh.flat[q] = {d.flat[q]};
+      shells.push_back(sh);
+    }
+  }
+  std::stable_sort(shells.begin(), shells.end(),
+                   [](const ShellDesc &x, const ShellDesc &y) { return x.atom < y.atom; });
+  // ---- used MO columns and unique spin occupations
+  std::vector<int> used;
+  for (int c = 0; c < s->nconf; ++c) {
+    for (int j = 0; j < s->nup; ++j) used.push_back(s->cfg_up[c * s->nup + j]);
+    for (int j = 0; j < s->ndown; ++j) used.push_back(s->cfg_down[c * s->ndown + j]);
+  }
+  std::sort(used.begin(), used.end());
+  used.erase(std::unique(used.begin(), used.end()), used.end());
+  for (int m : used)
+    if (m < 0 || m >= s->nmo) {
+      qmcb_set_error("qmcb_plan: configuration refers to an MO outside [0,nmo)");
+      return QMCB_EINVAL;
+    }
+  std::map<int, int> upos;
+  for (size_t i = 0; i < used.size(); ++i) upos[used[i]] = (int)i;
+  std::vector<std::vector<int>> uu, ud;
+  std::vector<int> ciu(s->nconf), cid(s->nconf);
+  for (int c = 0; c < s->nconf; ++c) {
+    std::vector<int> u(s->nup), d(s->ndown);
+    for (int j = 0; j < s->nup; ++j) u[j] = upos[s->cfg_up[c * s->nup + j]];
+    for (int j = 0; j < s->ndown; ++j) d[j] = upos[s->cfg_down[c * s->ndown + j]];
+    auto iu = std::find(uu.begin(), uu.end(), u);
+    if (iu == uu.end()) { uu.push_back(u); ciu[c] = (int)uu.size() - 1; }
+    else ciu[c] = (int)(iu - uu.begin());
+    auto id = std::find(ud.begin(), ud.end(), d);
+    if (id == ud.end()) { ud.push_back(d); cid[c] = (int)ud.size() - 1; }
+    else cid[c] = (int)(id - ud.begin());
+  }
+  // ---- sizes
+  DevSys &S = p->sys;
+  S = DevSys{};
+  S.nelec = s->nelec; S.nup = s->nup; S.ndown = s->ndown; S.natom = s->natom;
+  S.nshell = (int)shells.size();
+  S.nao = s->nao; S.nmo = s->nmo; S.nbas = s->nbas;
+  S.nmu = (int)used.size();
+  int mb = 1;
+  while (mb < S.nmu && mb < 8) mb *= 2;
+  S.nmup = ((S.nmu + mb - 1) / mb) * mb;
+  S.nconf = s->nconf; S.nuu = (int)uu.size(); S.nud = (int)ud.size();
+  S.radial_type = s->radial_type; S.use_jee = s->use_jee; S.use_jen = s->use_jen;
+  S.gram_fma = s->gram_fma;
+  S.jee_w = s->jee_w; S.jen_w = s->jen_w;
+  // nuclear repulsion, wf_base.py:97-116
+  double vnn = 0.0;
+  for (int a = 0; a < s->natom - 1; ++a)
+    for (int b = a + 1; b < s->natom; ++b) {
+      double dx = s->atom_coords[3 * a] - s->atom_coords[3 * b];
+      double dy = s->atom_coords[3 * a + 1] - s->atom_coords[3 * b + 1];
+      double dz = s->atom_coords[3 * a + 2] - s->atom_coords[3 * b + 2];
+      vnn += s->atomic_number[a] * s->atomic_number[b] / std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  S.vnn = vnn;
+  // ---- blobs
+  std::vector<double> &hd = p->hd;
+  std::vector<int> &hi = p->hi;
+  hd.clear(); hi.clear();
+  S.o_atoms = (int)hd.size();
+  for (int a = 0; a < s->natom; ++a) {
+    hd.push_back(s->atom_coords[3 * a]); hd.push_back(s->atom_coords[3 * a + 1]);
+    hd.push_back(s->atom_coords[3 * a + 2]); hd.push_back(s->atomic_number[a]);
+  }
+  S.o_alpha = (int)hd.size();
+  for (auto &sh : shells) hd.insert(hd.end(), sh.alpha.begin(), sh.alpha.end());
+  S.nprim = (int)hd.size() - S.o_alpha;
+  S.o_coef = (int)hd.size();
+  for (auto &sh : shells) hd.insert(hd.end(), sh.coef.begin(), sh.coef.end());
+  S.o_pn = (int)hd.size();
+  for (auto &sh : shells) hd.insert(hd.end(), sh.pn.begin(), sh.pn.end());
+  S.o_cscale = (int)hd.size();
+  for (auto &sh : shells) hd.insert(hd.end(), sh.comp_scale.begin(), sh.comp_scale.end());
+  S.ncomp = (int)hd.size() - S.o_cscale;
+  S.o_mow = (int)hd.size();
+  for (int a = 0; a < s->nao; ++a)
+    for (int j = 0; j < S.nmup; ++j)
+      hd.push_back(j < S.nmu ? s->mo[(size_t)a * s->nmo + used[j]] : 0.0);
+  S.o_ci = (int)hd.size();
+  for (int c = 0; c < s->nconf; ++c) hd.push_back(s->ci[c]);
+  S.ndbl = (int)hd.size();
+
+  S.o_ash = (int)hi.size();
+  {
+    int sidx = 0;
+    for (int a = 0; a < s->natom; ++a) {
+      hi.push_back(sidx);
+      while (sidx < S.nshell && shells[sidx].atom == a) ++sidx;
+    }
+    hi.push_back(sidx);
+    if (sidx != S.nshell) {
+      qmcb_set_error("qmcb_plan: bas_atom out of range");
+      return QMCB_EINVAL;
+    }
+  }
+  S.o_spo = (int)hi.size();
+  { int o = 0; for (auto &sh : shells) { hi.push_back(o); o += (int)sh.alpha.size(); } hi.push_back(o); }
+  S.o_sco = (int)hi.size();
+  { int o = 0; for (auto &sh : shells) { hi.push_back(o); o += (int)sh.comp_ao.size(); } hi.push_back(o); }
+  S.o_ck = (int)hi.size();
+  for (auto &sh : shells) hi.insert(hi.end(), sh.comp_k.begin(), sh.comp_k.end());
+  S.o_cao = (int)hi.size();
+  for (auto &sh : shells) hi.insert(hi.end(), sh.comp_ao.begin(), sh.comp_ao.end());
+  S.o_used = (int)hi.size();
+  hi.insert(hi.end(), used.begin(), used.end());
+  S.o_ucu = (int)hi.size();
+  for (auto &u : uu) hi.insert(hi.end(), u.begin(), u.end());
+  S.o_ucd = (int)hi.size();
+  for (auto &d : ud) hi.insert(hi.end(), d.begin(), d.end());
+  S.o_ciu = (int)hi.size();
+  hi.insert(hi.end(), ciu.begin(), ciu.end());
+  S.o_cid = (int)hi.size();
+  hi.insert(hi.end(), cid.begin(), cid.end());
+  S.o_pfo = (int)hi.size();
+  { int o = 0; for (auto &sh : shells) { hi.push_back(o); o += (int)(sh.alpha.size() * sh.comp_ao.size()); } hi.push_back(o); }
+  S.o_pflat = (int)hi.size();
+  for (auto &sh : shells)
+    for (size_t q = 0; q < sh.alpha.size(); ++q)
+      for (size_t k = 0; k < sh.comp_ao.size(); ++k) hi.push_back(sh.flat[q][k]);
+  if (hi.size() & 1) hi.push_back(0);
+  S.nint = (int)hi.size();
+
+  p->index_ctr.assign(s->index_ctr, s->index_ctr + s->nbas);
+  p->mo_full.assign(s->mo, s->mo + (size_t)s->nao * s->nmo);
+  return 0;
+}
+
+static int upload(qmcb_plan *p) {
+  cudaError_t e;
+  size_t nd = p->hd.size() * sizeof(double), ni = p->hi.size() * sizeof(int);
+  if (nd > p->cap_dbl) {
+    if (p->d_dbl) cudaFree(p->d_dbl);
+    if ((e = cudaMalloc(&p->d_dbl, nd)) != cudaSuccess) return (int)e;
+    p->cap_dbl = nd;
+  }
+  if (ni > p->cap_int) {
+    if (p->d_int) cudaFree(p->d_int);
+    if ((e = cudaMalloc(&p->d_int, ni)) != cudaSuccess) return (int)e;
+    p->cap_int = ni;
+  }
+  size_t nm = p->mo_full.size() * sizeof(double);
+  if (nm > p->cap_mo_full) {
+    if (p->d_mo_full) cudaFree(p->d_mo_full);
+    if ((e = cudaMalloc(&p->d_mo_full, nm)) != cudaSuccess) return (int)e;
+    p->cap_mo_full = nm;
+  }
+  // the default stream orders these copies before any later kernel on a blocking stream;
+  // callers on non-blocking streams get a full sync here as well.
+  if ((e = cudaMemcpy(p->d_dbl, p->hd.data(), nd, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpy(p->d_int, p->hi.data(), ni, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpy(p->d_mo_full, p->mo_full.data(), nm, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  p->sys.dblob = p->d_dbl;
+  p->sys.iblob = p->d_int;
+  return 0;
+}
+
+extern "C" int qmcb_plan_create(const qmcb_system *sys, int device, qmcb_plan **out) {
+  if (!out) return QMCB_EINVAL;
+  *out = nullptr;
+  // device < 0: host-only plan (tables + tiling, no upload) for CPU-side tests of the
+  // grouping logic; every compute call on it fails with QMCB_EINVAL.
+  if (device >= 0) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+      qmcb_set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  qmcb_plan *p = new qmcb_plan();
+  p->device = device;
+  if (device >= 0) {
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&p->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  }
+  int rc = qmcb_build_tables(sys, p);
+  if (rc == 0) rc = qmcb_choose_launch(p);
+  if (rc == 0 && device >= 0) {
+    rc = upload(p);
+    if (rc) qmcb_set_error(std::string("plan upload: ") + cudaGetErrorString((cudaError_t)rc));
+  }
+  if (rc) { qmcb_plan_destroy(p); return rc; }
+  *out = p;
+  return 0;
+}
+
+extern "C" int qmcb_plan_update(qmcb_plan *p, const qmcb_system *sys) {
+  if (!p) return QMCB_EINVAL;
+  if (p->device >= 0) cudaSetDevice(p->device);
+  int rc = qmcb_build_tables(sys, p);
+  if (rc == 0) rc = qmcb_choose_launch(p);
+  if (rc == 0 && p->device >= 0) {
+    rc = upload(p);
+    if (rc) qmcb_set_error(std::string("plan upload: ") + cudaGetErrorString((cudaError_t)rc));
+  }
+  return rc;
+}
+
+extern "C" void qmcb_plan_destroy(qmcb_plan *p) {
+  if (!p) return;
+  if (p->device >= 0) cudaSetDevice(p->device);
+  if (p->d_dbl) cudaFree(p->d_dbl);
+  if (p->d_int) cudaFree(p->d_int);
+  if (p->d_mo_full) cudaFree(p->d_mo_full);
+  delete p;
+}
+
+extern "C" int qmcb_plan_info(const qmcb_plan *p, int what) {
+  if (!p) return QMCB_EINVAL;
+  switch (what) {
+    case 0: return p->sys.nshell;
+    case 1: return p->sys.nprim;
+    case 2: return p->sys.ncomp;
+    case 3: return p->sys.nmu;
+    case 4: return p->sys.nuu;
+    case 5: return p->sys.nud;
+    case 6: return p->cfg_eloc.tw;
+    case 7: return p->cfg_eloc.threads;
+    case 8: return p->cfg_eloc.smem;
+    case 9: return p->cfg_psi.tw;
+    default: return QMCB_EINVAL;
+  }
+}

@@ -1,0 +1,77 @@
+// Host-side plan and the device table layout shared by all kernels.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qmcb.h"
+
+// Everything a kernel needs to know about the system, passed by value as a kernel
+// parameter.  The tables themselves live in one double blob + one int blob in global
+// memory; every CTA stages them in shared memory once.
+struct DevSys {
+  int nelec, nup, ndown, natom;
+  int nshell, nprim, ncomp;      // grouped basis: shells -> primitives / components
+  int nao, nmo;
+  int nmu, nmup;                 // MO columns used by some configuration; padded count
+  int nconf, nuu, nud;           // configurations; unique spin-up / spin-down occupations
+  int radial_type, use_jee, use_jen, gram_fma;
+  int nbas;                      // flat primitives (gradient outputs)
+  double jee_w, jen_w, vnn;
+  const double *dblob;
+  const int *iblob;
+  int ndbl, nint;
+  // offsets into dblob (doubles)
+  int o_atoms;   // [natom][4]  x y z Z
+  int o_alpha;   // [nprim]
+  int o_coef;    // [nprim]     coeff * norm of the first component
+  int o_pn;      // [nprim]     radial power n (gto/sto), as double
+  int o_cscale;  // [ncomp]     component scale relative to the shell's coef vector
+  int o_mow;     // [nao][nmup] MO weights of the used columns (zero padded)
+  int o_ci;      // [nconf]
+  // offsets into iblob (ints)
+  int o_ash;     // [natom+1]   first shell of each atom
+  int o_spo;     // [nshell+1]  first primitive of each shell
+  int o_sco;     // [nshell+1]  first component of each shell
+  int o_ck;      // [ncomp]     kx | ky<<8 | kz<<16
+  int o_cao;     // [ncomp]     AO index
+  int o_used;    // [nmu]       MO index of used column
+  int o_ucu;     // [nuu][nup]  unique up occupations, as positions in the used list
+  int o_ucd;     // [nud][ndown]
+  int o_ciu;     // [nconf]     unique-up index of each configuration
+  int o_cid;     // [nconf]
+  int o_pflat;   // per shell: [nprim_s][ncomp_s] flat primitive index; start at o_pfo[s]
+  int o_pfo;     // [nshell+1]
+};
+
+struct LaunchCfg {
+  int tw;        // walkers per CTA
+  int nblk;      // MO column blocks per electron
+  int mb;        // MO columns per block (template)
+  int threads;
+  int smem;      // dynamic shared memory bytes
+  int lu_conc;   // concurrent LU scratch slots (0: closed forms only)
+};
+
+struct qmcb_plan {
+  int device = 0;
+  DevSys sys{};
+  std::vector<double> hd;
+  std::vector<int> hi;
+  double *d_dbl = nullptr;
+  int *d_int = nullptr;
+  size_t cap_dbl = 0, cap_int = 0;
+  int sm_count = 148;
+  int smem_optin = 227 * 1024;
+  LaunchCfg cfg_psi{}, cfg_eloc{}, cfg_grad{};
+  // full MO matrix for the operator-level entry point
+  double *d_mo_full = nullptr;
+  size_t cap_mo_full = 0;
+  // host copy of flat data needed by backward post-processing
+  std::vector<int> index_ctr;
+  std::vector<double> mo_full;
+};
+
+void qmcb_set_error(const std::string &msg);
+int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p);   // host grouping -> hd/hi/sys
+int qmcb_choose_launch(qmcb_plan *p);

@@ -1,0 +1,392 @@
+"""Solver - drop-in for qmctorch.solver.Solver (qmctorch/solver/solver.py:15-431,
+solver_base.py:12-546): single-point energies and wave-function optimisation with the
+low-variance ("manual") energy-gradient estimator.
+
+Orchestration stays Python; ``wf.local_energy``, ``wf(pos)`` and its backward are the fused
+CUDA kernels.  Under torch.distributed every rank owns a shard of the walkers and the
+statistics / gradients are summed with one all-reduce each (solver/distributed.py).
+HDF5 dumps (utils/hdf5_utils.py) are outside the hot path: results are returned, not written.
+"""
+import os
+from math import ceil
+from time import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import _lib
+from . import distributed as D
+
+
+class Loss:
+    """Clipping mask of qmctorch/solver/loss.py:93-110 (energy loss only on this path)."""
+
+    def __init__(self, wf, method="energy", clip=False, clip_threshold=5):
+        if method not in ("energy", "weighted-energy"):
+            raise NotImplementedError(
+                "only the energy loss with the manual gradient estimator is on the CUDA path")
+        self.wf = wf
+        self.method = method
+        self.clip = clip
+        self.clip_num_std = clip_threshold
+        self.use_weight = False
+        self.weight = {"psi": None, "psi0": None}
+
+    def get_clipping_mask(self, eloc):
+        if not self.clip:
+            return torch.ones_like(eloc).type(torch.bool)
+        if D.is_distributed():
+            raise NotImplementedError("clip_loss needs a global median; keep it off under torch.distributed")
+        median = torch.median(eloc)
+        std = torch.std(eloc)
+        return torch.abs((eloc - median) / std) < self.clip_num_std
+
+
+class _Loader:
+    """utils/torch_utils.py:156-207 (batches are views; walkers stay where they are)."""
+
+    def __init__(self, data, batch_size):
+        self.dataset = data
+        self.batch_size = batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        for i in range(ceil(n / self.batch_size)):
+            yield self.dataset[i * self.batch_size: (i + 1) * self.batch_size]
+
+
+class Solver:
+    def __init__(self, wf=None, sampler=None, optimizer=None, scheduler=None, output=None, rank=0):
+        self.wf = wf
+        self.sampler = sampler
+        self.opt = optimizer
+        self.scheduler = scheduler
+        self.rank = rank
+        self.cuda = bool(wf.cuda)
+        self.device = wf.ao.atom_coords.device
+        self.dataloader = None
+        self.loss = None
+        self.obs_dict = None
+        self.qmctorch_version = "qmctorch_b200"
+        if self.opt is not None and "lpos_needed" not in self.opt.__dict__:
+            self.opt.lpos_needed = False
+        self.save_model = "model.pth"
+        if self.cuda:
+            self.sampler.cuda = True
+            self.sampler.walkers.cuda = True
+        self.hdf5file = output
+        if output is None:
+            base = os.path.basename(getattr(wf.mol, "hdf5file", "mol.hdf5")).split(".")[0]
+            self.hdf5file = base + "_QMCTorch.hdf5"
+        self._stats_ws = None
+        self.set_params_requires_grad()
+        self.configure(track=["local_energy"], freeze=None, loss="energy", grad="manual", ortho_mo=False,
+                       clip_loss=False,
+                       resampling={"mode": "update", "resample_every": 1, "nstep_update": 25})
+
+    # -- configuration (solver.py:50-178) ------------------------------------------------------
+    def configure(self, track=None, freeze=None, loss=None, grad=None, ortho_mo=None, clip_loss=False,
+                  clip_threshold=5, resampling=None):
+        self.set_params_requires_grad()
+        self.freeze_params_list = freeze
+        self.freeze_parameters(freeze)
+        if track is not None:
+            self.track_observable(track)
+        if grad is not None:
+            if grad != "manual":
+                raise NotImplementedError(
+                    "grad='auto' back-propagates through E_L (solver.py:352-370): second-order "
+                    "derivatives of the fused kernel are a later scope row (SURVEY.md 8f4)")
+            self.grad_method = grad
+            self.evaluate_gradient = self.evaluate_grad_manual
+        if resampling is not None:
+            self.configure_resampling(**resampling)
+        if loss is not None:
+            self.loss = Loss(self.wf, method=loss, clip=clip_loss, clip_threshold=clip_threshold)
+            self.loss.use_weight = self.resampling_options.resample_every > 1
+        self.ortho_mo = ortho_mo
+
+    def set_params_requires_grad(self, wf_params=True, geo_params=False):
+        self.wf.ao.bas_exp.requires_grad = wf_params
+        self.wf.ao.bas_coeffs.requires_grad = wf_params
+        for p in self.wf.mo.parameters():
+            p.requires_grad = wf_params
+        self.wf.fc.weight.requires_grad = wf_params
+        if getattr(self.wf, "jastrow", None) is not None:
+            for p in self.wf.jastrow.parameters():
+                p.requires_grad = wf_params
+        self.wf.ao.atom_coords.requires_grad = geo_params
+
+    def freeze_parameters(self, freeze):
+        if freeze is None:
+            return
+        if not isinstance(freeze, list):
+            freeze = [freeze]
+        for name in freeze:
+            low = name.lower()
+            if low == "ci":
+                self.wf.fc.weight.requires_grad = False
+            elif low == "mo":
+                for p in self.wf.mo.parameters():
+                    p.requires_grad = False
+            elif low == "ao":
+                self.wf.ao.bas_exp.requires_grad = False
+                self.wf.ao.bas_coeffs.requires_grad = False
+            elif low == "jastrow":
+                for p in self.wf.jastrow.parameters():
+                    p.requires_grad = False
+            elif low == "backflow":
+                pass
+            else:
+                raise ValueError("Valid arguments for freeze are :", ["ci", "mo", "ao", "jastrow", "backflow"])
+
+    def configure_resampling(self, mode="update", resample_every=1, nstep_update=25, ntherm_update=-1,
+                             increment={"every": None, "factor": None}):
+        if mode not in ["never", "full", "update"]:
+            raise ValueError(mode, "not a valid update method : ", ["never", "full", "update"])
+        self.resampling_options = SimpleNamespace(mode=mode, resample_every=resample_every,
+                                                  ntherm_update=ntherm_update, nstep_update=nstep_update,
+                                                  increment=increment)
+
+    def track_observable(self, obs_name):
+        if not isinstance(obs_name, list):
+            obs_name = list(obs_name)
+        valid = ["energy", "local_energy", "geometry", "parameters", "gradients"]
+        for name in obs_name:
+            if name not in valid and not hasattr(self.wf, name):
+                raise ValueError("Observable not recognized")
+        self.observable = SimpleNamespace()
+        self.observable.qmctorch_version = self.qmctorch_version
+        obs_name = list(obs_name)
+        for extra in ("energy", "geometry"):
+            if extra not in obs_name:
+                obs_name.append(extra)
+        for k in obs_name:
+            if k == "parameters":
+                for key, p in self.wf.named_parameters():
+                    if p.requires_grad:
+                        setattr(self.observable, key, [])
+            elif k == "gradients":
+                for key, p in self.wf.named_parameters():
+                    if p.requires_grad:
+                        setattr(self.observable, key + ".grad", [])
+            else:
+                setattr(self.observable, k, [])
+        self.observable.models = SimpleNamespace()
+
+    def store_observable(self, pos, local_energy=None, ibatch=None, **kwargs):
+        """solver_base.py:166-248."""
+        if pos.device != self.device:
+            pos = pos.to(self.device)
+        for obs in list(self.observable.__dict__.keys()):
+            if obs in ("qmctorch_version", "models"):
+                continue
+            if obs == "energy":
+                if local_energy is None:
+                    local_energy = self.wf.local_energy(pos)
+                m = float(local_energy.mean())
+                if ibatch is None or ibatch == 0:
+                    self.observable.energy.append(m)
+                else:
+                    self.observable.energy[-1] *= ibatch / (ibatch + 1)
+                    self.observable.energy[-1] += m / (ibatch + 1)
+            elif obs == "local_energy":
+                if local_energy is None:
+                    continue
+                data = local_energy.detach().cpu().numpy()
+                if ibatch is None or ibatch == 0:
+                    self.observable.local_energy.append(data)
+                else:
+                    self.observable.local_energy[-1] = np.append(self.observable.local_energy[-1], data)
+            elif obs.endswith(".grad"):
+                continue
+            elif obs in self.wf.state_dict():
+                p = dict(self.wf.named_parameters()).get(obs)
+                getattr(self.observable, obs).append(self.wf.state_dict()[obs].detach().cpu().numpy().copy())
+                if obs + ".grad" in self.observable.__dict__:
+                    g = p.grad if p is not None and p.grad is not None else torch.zeros_like(p.data)
+                    getattr(self.observable, obs + ".grad").append(g.detach().cpu().numpy().copy())
+            elif hasattr(self.wf, obs):
+                data = getattr(self.wf, obs)(pos)
+                if isinstance(data, torch.Tensor):
+                    data = data.detach().cpu().numpy()
+                if isinstance(data, list):
+                    data = np.array(data)
+                if ibatch is None or ibatch == 0:
+                    getattr(self.observable, obs).append(data)
+                else:
+                    getattr(self.observable, obs)[-1] = np.append(getattr(self.observable, obs)[-1], data)
+
+    # -- statistics -------------------------------------------------------------------------
+    def _stats(self, eloc):
+        """[sum, sum sq, n finite, n non-finite] on the device (qmcb_energy_stats), summed over
+        ranks -> mean, variance, error."""
+        L = _lib.lib()
+        dev = eloc.device
+        flat = eloc.detach().reshape(-1).contiguous()
+        if self._stats_ws is None or self._stats_ws.device != dev:
+            self._stats_ws = torch.empty(int(L.qmcb_stats_workspace_bytes(flat.numel())), dtype=torch.uint8,
+                                         device=dev)
+        out4 = torch.empty(4, dtype=torch.float64, device=dev)
+        _lib.check(L.qmcb_energy_stats(_lib.ptr(flat), flat.numel(), _lib.ptr(out4), _lib.ptr(self._stats_ws),
+                                       _lib.stream_ptr(dev)), "qmcb_energy_stats")
+        return D.global_stats(out4, None, None)
+
+    # -- single point (solver_base.py:316-387) -------------------------------------------------
+    def single_point(self, with_tqdm=True, batchsize=None, hdf5_group="single_point"):
+        with torch.no_grad():
+            pos = self.sampler(self.wf.pdf, with_tqdm=with_tqdm)
+            if pos.device != self.device:
+                pos = pos.to(self.device)
+            if batchsize is None:
+                eloc = self.wf.local_energy(pos)
+            else:
+                eloc = torch.cat([self.wf.local_energy(pos[i: i + batchsize])
+                                  for i in range(0, len(pos), batchsize)])
+            if D.is_distributed():
+                mean, var, err, n, nbad = self._stats(eloc)
+                dt = dict(dtype=torch.float64, device=eloc.device)
+                e, s, er = torch.tensor(mean, **dt), torch.tensor(var, **dt), torch.tensor(err, **dt)
+            else:
+                e, s, er = torch.mean(eloc), torch.var(eloc), self.wf.sampling_error(eloc)
+        return SimpleNamespace(pos=pos, local_energy=eloc, energy=e, variance=s, error=er)
+
+    # -- optimisation (solver.py:186-431) --------------------------------------------------------
+    def save_sampling_parameters(self):
+        self.sampler._nstep_save = self.sampler.nstep
+        self.sampler._ntherm_save = self.sampler.ntherm
+        if self.resampling_options.mode == "update":
+            self.sampler.ntherm = self.resampling_options.ntherm_update
+            self.sampler.nstep = self.resampling_options.nstep_update
+
+    def restore_sampling_parameters(self):
+        self.sampler.nstep = self.sampler._nstep_save
+        self.sampler.ntherm = self.sampler._ntherm_save
+
+    def run(self, nepoch, batchsize=None, hdf5_group="wf_opt", chkpt_every=None, tqdm=False):
+        self.prepare_optimization(batchsize, chkpt_every, tqdm)
+        self.run_epochs(nepoch)
+        self.restore_sampling_parameters()
+        self.observable.models.last = dict(self.wf.state_dict())
+        return self.observable
+
+    def prepare_optimization(self, batchsize, chkpt_every, tqdm=False):
+        pos = self.sampler(self.wf.pdf, with_tqdm=tqdm)
+        pos = pos.detach().to(self.device)
+        if batchsize is None:
+            batchsize = len(pos)
+        self.save_sampling_parameters()
+        self.dataloader = _Loader(pos, batchsize)
+        with torch.no_grad():
+            for ibatch, data in enumerate(self.dataloader):
+                self.store_observable(data, ibatch=ibatch)
+        self.chkpt_every = chkpt_every
+
+    def run_epochs(self, nepoch, with_tqdm=False, verbose=True):
+        cumulative_loss = 0
+        min_loss = 0
+        for n in range(nepoch):
+            tstart = time()
+            cumulative_loss = 0
+            self.opt.zero_grad()
+            self.wf.zero_grad()
+            for ibatch, data in enumerate(self.dataloader):
+                lpos = data.to(self.device)
+                loss, eloc = self.evaluate_gradient(lpos)
+                cumulative_loss += float(loss)
+                if torch.isnan(eloc).any():
+                    return cumulative_loss
+                self.store_observable(lpos, local_energy=eloc, ibatch=ibatch)
+            self.optimization_step(lpos)
+            if n == 0 or cumulative_loss < min_loss:
+                min_loss = cumulative_loss
+                self.observable.models.best = {k: v.clone() for k, v in self.wf.state_dict().items()}
+            if self.chkpt_every is not None and n > 0 and n % self.chkpt_every == 0:
+                self.save_checkpoint(n, cumulative_loss)
+            self.dataloader.dataset = self.resample(n, self.dataloader.dataset)
+            if self.scheduler is not None:
+                self.scheduler.step()
+            self.epoch_time = time() - tstart
+        return cumulative_loss
+
+    def evaluate_grad_manual(self, lpos):
+        """dE/dk = < (dpsi/dk)/psi (E_L - <E_L>) > * 2   (solver.py:372-431); the mean and the
+        normalisation are GLOBAL over all ranks, gradients are summed over ranks."""
+        if self.loss.method not in ["energy", "weighted-energy"]:
+            raise ValueError("Manual gradient only for energy minimization")
+        with torch.no_grad():
+            eloc = self.wf.local_energy(lpos)
+        psi = self.wf(lpos)
+        if D.is_distributed():
+            buf = torch.stack([eloc.sum(), torch.tensor(float(len(psi)), dtype=torch.float64, device=eloc.device)])
+            D.allreduce_sum_(buf)
+            ntot = float(buf[1])
+            mean = buf[0] / ntot
+        else:
+            ntot = float(len(psi))
+            mean = torch.mean(eloc)
+        weight = eloc.clone()
+        weight -= mean
+        weight /= psi.detach().clone()
+        weight *= 2.0 / ntot
+        mask = self.loss.get_clipping_mask(eloc)
+        if not bool(mask.all()):
+            weight = weight * mask
+        psi.backward(weight)
+        D.allreduce_gradients([p for p in self._trainable()])
+        return mean, eloc
+
+    def _trainable(self):
+        ps = [p for p in self.wf.parameters() if p.requires_grad]
+        if self.wf.ao.bas_coeffs.requires_grad:
+            ps.append(self.wf.ao.bas_coeffs)
+        return ps
+
+    def optimization_step(self, lpos):
+        if self.opt.lpos_needed:
+            self.opt.step(lpos)
+        else:
+            self.opt.step()
+
+    def resample(self, n, pos):
+        """solver_base.py:273-314 - walkers stay on the device between epochs."""
+        if self.resampling_options.mode != "never":
+            if n % self.resampling_options.resample_every == 0:
+                if self.resampling_options.mode == "update":
+                    pos = pos.clone().detach()[: self.sampler.walkers.nwalkers].to(self.device)
+                else:
+                    pos = None
+                inc = self.resampling_options.increment
+                if inc["every"] is not None and n % inc["every"] == 0:
+                    self.sampler.nstep += inc["factor"] * self.sampler.ndecor
+                pos = self.sampler(self.wf.pdf, pos=pos, with_tqdm=False).detach().to(self.device)
+                self.dataloader.dataset = pos
+            if self.loss.use_weight:
+                self.loss.weight["psi0"] = None
+        return pos
+
+    def sampling_traj(self, pos=None, with_tqdm=True, hdf5_group="sampling_trajectory"):
+        """solver_base.py:435-471."""
+        if pos is None:
+            pos = self.sampler(self.wf.pdf, with_tqdm=with_tqdm)
+        ndim = pos.shape[-1]
+        p = pos.view(-1, self.sampler.walkers.nwalkers, ndim)
+        el = []
+        with torch.no_grad():
+            for ip in p:
+                el.append(self.wf.local_energy(ip.to(self.device)).cpu().numpy())
+        el = np.array(el).squeeze(-1)
+        return SimpleNamespace(local_energy=el, pos=pos)
+
+    def save_checkpoint(self, epoch, loss):
+        """solver_base.py:389-405 (key spelling kept so checkpoints interchange)."""
+        torch.save({"epoch": epoch, "model_state_dict": self.wf.state_dict(),
+                    "optimzier_state_dict": self.opt.state_dict(), "loss": loss},
+                   "checkpoint_epoch%d.pth" % epoch)
+
+    def load_checkpoint(self, filename):
+        data = torch.load(filename)
+        self.wf.load_state_dict(data["model_state_dict"])
+        self.opt.load_state_dict(data["optimzier_state_dict"])
+        return data["epoch"], data["loss"]

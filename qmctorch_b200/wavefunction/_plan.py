@@ -1,0 +1,138 @@
+"""Host-side plan handle: flattens the modules' parameters into a ``qmcb_system`` and keeps
+the device tables of libqmcb.so in sync with them.
+
+The handle is shared by a SlaterJastrow and its sub-modules (``ao``, ``mo``, ``pool``,
+``jastrow``) so that operator-level calls and the fused path see the same tables.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _cpu(t):
+    return t.detach().to("cpu", torch.float64).contiguous().numpy()
+
+
+class PlanHandle:
+    def __init__(self, ao, mo=None, configs=None, fc=None, jastrow_ee=None, jastrow_en=None,
+                 nup=None, ndown=None, device=None):
+        self.ao = ao
+        self.mo = mo
+        self.configs = configs
+        self.fc = fc
+        self.jee = jastrow_ee
+        self.jen = jastrow_en
+        self.nup = ao.nup if nup is None else nup
+        self.ndown = ao.ndown if ndown is None else ndown
+        self.device = device
+        self._plan = C.c_void_p()
+        self._sig = None
+        self._arrays = None
+        self._finalizer = None
+
+    # -- parameters that feed the device tables
+    def _tracked(self):
+        ts = [self.ao.atom_coords, self.ao.bas_exp, self.ao.bas_coeffs]
+        if self.mo is not None:
+            ts += [self.mo.mo_modifier, self.mo.mo_scf]
+        if self.fc is not None:
+            ts.append(self.fc.weight)
+        if self.jee is not None:
+            ts.append(self.jee.jastrow_kernel.weight)
+        if self.jen is not None:
+            ts.append(self.jen.jastrow_kernel.weight)
+        return ts
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in self._tracked())
+
+    def _system(self):
+        ao = self.ao
+        nelec = self.nup + self.ndown
+        nao = ao.norb
+        if self.mo is not None:
+            w = _cpu(self.mo.mo_scf * self.mo.mo_modifier)
+        else:
+            w = np.eye(nao)
+        nmo = w.shape[1]
+        if self.configs is not None:
+            cu = np.asarray(self.configs[0].cpu().numpy(), dtype=np.int32).reshape(-1, max(self.nup, 0))
+            cd = np.asarray(self.configs[1].cpu().numpy(), dtype=np.int32).reshape(-1, max(self.ndown, 0))
+        else:
+            cu = np.arange(self.nup, dtype=np.int32)[None]
+            cd = np.arange(self.ndown, dtype=np.int32)[None]
+        nconf = cu.shape[0]
+        if self.fc is not None:
+            ci = _cpu(self.fc.weight).reshape(-1)
+        else:
+            ci = np.zeros(nconf)
+            ci[0] = 1.0
+        # Gram-form dot product: ATen's small-matrix bmm path (unfused) is taken when
+        # 3*Ne*Ne < 400, MKL (fma chain) otherwise - SURVEY.md section 7, hard part 1.
+        gram_fma = 0 if 3 * nelec * nelec < 400 else 1
+        return _lib.SystemArrays(
+            nelec=nelec, nup=self.nup, ndown=self.ndown, natom=ao.natoms, nbas=ao.nbas, nao=nao,
+            nmo=nmo, radial_type=_lib.RADIAL[ao.radial_type], contract=int(ao.contract),
+            atom_coords=_cpu(ao.atom_coords), atomic_number=np.asarray(ao.atomic_number, dtype=np.float64),
+            bas_atom=ao.bas_atom_np, bas_exp=_cpu(ao.bas_exp), bas_coeffs=_cpu(ao.bas_coeffs),
+            bas_norm=_cpu(ao.norm_cst), bas_kx=ao.bas_kx_np, bas_ky=ao.bas_ky_np, bas_kz=ao.bas_kz_np,
+            bas_kr=ao.bas_kr_np, index_ctr=ao.index_ctr_np, mo=w, nconf=nconf, cfg_up=cu, cfg_down=cd,
+            ci=ci,
+            use_jee=int(self.jee is not None),
+            jee_w=float(_cpu(self.jee.jastrow_kernel.weight)[0]) if self.jee is not None else 0.0,
+            use_jen=int(self.jen is not None),
+            jen_w=float(_cpu(self.jen.jastrow_kernel.weight)[0]) if self.jen is not None else 0.0,
+            gram_fma=gram_fma)
+
+    def plan(self):
+        """Returns the (up to date) ``qmcb_plan*``; rebuilds the tables if a parameter changed."""
+        dev = self.ao.atom_coords.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "qmctorch_b200 runs on CUDA devices only (construct the wave function with "
+                "cuda=True); there is no CPU path")
+        sig = self._signature()
+        if sig == self._sig:
+            return self._plan
+        L = _lib.lib()
+        arrays = self._system()
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if not self._plan:
+            # make sure the primary context exists before the library's runtime touches it
+            torch.cuda.current_stream(dev)
+            _lib.check(L.qmcb_plan_create(C.byref(arrays.struct), index, C.byref(self._plan)),
+                       "qmcb_plan_create")
+            handle = self._plan.value
+            self._finalizer = weakref.finalize(self, L.qmcb_plan_destroy, C.c_void_p(handle))
+        else:
+            torch.cuda.current_stream(dev).synchronize()
+            _lib.check(L.qmcb_plan_update(self._plan, C.byref(arrays.struct)), "qmcb_plan_update")
+        self._arrays = arrays
+        self._sig = sig
+        return self._plan
+
+    def host_plan_info(self):
+        """Host-only plan (no device) -> dict of grouping/tiling figures; used by CPU tests."""
+        L = _lib.lib()
+        arrays = self._system()
+        p = C.c_void_p()
+        _lib.check(L.qmcb_plan_create(C.byref(arrays.struct), -1, C.byref(p)), "qmcb_plan_create(host)")
+        names = ["nshell", "nprim", "ncomp", "nmo_used", "nuniq_up", "nuniq_down", "tw_eloc",
+                 "threads_eloc", "smem_eloc", "tw_psi"]
+        out = {n: L.qmcb_plan_info(p, i) for i, n in enumerate(names)}
+        L.qmcb_plan_destroy(p)
+        return out
+
+    def info(self, what):
+        return _lib.lib().qmcb_plan_info(self.plan(), what)
+
+
+def as_walkers(pos, ncols, device):
+    """Contiguous FP64 [W, ncols] tensor on the wave function's device (one H2D copy if needed)."""
+    if pos.dim() != 2 or pos.shape[1] != ncols:
+        raise ValueError("positions must have shape [nwalkers, %d], got %s" % (ncols, tuple(pos.shape)))
+    return pos.detach().to(device=device, dtype=torch.float64).contiguous()

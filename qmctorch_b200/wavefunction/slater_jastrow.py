@@ -1,0 +1,259 @@
+"""SlaterJastrow - drop-in for qmctorch.wavefunction.SlaterJastrow
+(qmctorch/wavefunction/slater_jastrow.py:30-482) on top of libqmcb.so.
+
+Same constructor, attributes, parameter names and method surface.  ``forward``,
+``local_energy``, ``kinetic_energy``, ``gradients_jacobi`` and ``pdf`` each run one fused
+sm_100a kernel per call; ``forward`` is differentiable w.r.t. the wave-function
+parameters (``psi.backward(weight)`` as used by ``Solver.evaluate_grad_manual``) through
+``qmcb_psi_backward``.
+"""
+import torch
+from torch import nn
+
+from .. import _lib
+from ._plan import PlanHandle, as_walkers
+from .jastrows import CombineJastrow, JastrowFactorElectronElectron, JastrowFactorElectronNuclei
+from .jastrows.elec_elec import PadeJastrowKernel
+from .orbitals import AtomicOrbitals, MolecularOrbitals
+from .pooling import OrbitalConfigurations, SlaterPooling
+from .wf_base import WaveFunction
+
+
+class _PsiFunction(torch.autograd.Function):
+    """psi(pos; theta) with analytic parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, wf, x, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w):
+        ctx.wf = wf
+        ctx.save_for_backward(x)
+        return wf._psi(x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        wf = ctx.wf
+        (x,) = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        g = wf._psi_backward(x, grad_out.reshape(-1).contiguous())
+        gx = None
+        if need[1]:
+            gx = wf._grad_psi(x, pdf=False) * grad_out.reshape(-1, 1)
+        return (None, gx,
+                g["bas_exp"] if need[2] else None,
+                g["bas_coeffs"] if need[3] else None,
+                g["mo_modifier"] if need[4] else None,
+                g["ci"] if need[5] else None,
+                g["jee_w"] if need[6] else None,
+                g["jen_w"] if need[7] else None)
+
+
+class SlaterJastrow(WaveFunction):
+    def __init__(self, mol, jastrow="default", backflow=None, configs="ground_state", kinetic="jacobi",
+                 cuda=False, include_all_mo=True, mix_mo=False, orthogonalize_mo=False):
+        super().__init__(mol.nelec, 3, kinetic, cuda)
+        if self.cuda and not torch.cuda.is_available():
+            raise ValueError("Cuda not available, use cuda=False")
+        if not include_all_mo and isinstance(configs, str) and configs.startswith("cas("):
+            raise ValueError("CAS calculation only possible with include_all_mo=True")
+        if backflow is not None:
+            raise NotImplementedError(
+                "backflow orbitals (slater_jastrow.py:484-580) are outside the fused hot path")
+        if kinetic != "jacobi":
+            raise NotImplementedError(
+                "kinetic='auto' (autograd Hessian, wf_base.py:142-182) is not provided; the CUDA "
+                "path implements the Jacobi formula")
+        self.mol = mol
+        self.atoms = mol.atoms
+        self.natom = mol.natom
+        # configurations (slater_jastrow.py:158-169)
+        self.orb_confs = OrbitalConfigurations(mol)
+        self.configs_method = configs if isinstance(configs, str) else "explicit"
+        self.configs = self.orb_confs.get_configs(configs)
+        self.nci = len(self.configs[0])
+        self.highest_occ_mo = int(max(self.configs[0].max(), self.configs[1].max())) + 1
+        # operators
+        self.use_backflow = False
+        self.ao = AtomicOrbitals(mol, cuda)
+        self.include_all_mo = include_all_mo
+        self.nmo_opt = mol.basis.nmo if include_all_mo else self.highest_occ_mo
+        self.mo = MolecularOrbitals(mol, include_all_mo, self.highest_occ_mo, mix_mo, orthogonalize_mo, cuda)
+        self.pool = SlaterPooling(self.configs_method, self.configs, mol, cuda)
+        self.fc = nn.Linear(self.nci, 1, bias=False).to(torch.float64)
+        self.fc.weight.data.fill_(0.0)
+        self.fc.weight.data[0][0] = 1.0
+        if self.cuda:
+            self.fc = self.fc.to(self.device)
+        self._init_jastrow(jastrow)
+        self.kinetic_method = kinetic
+        self.gradients = self.gradients_jacobi
+        self.kinetic_energy = self.kinetic_energy_jacobi
+        # shared device tables
+        self._handle = PlanHandle(self.ao, self.mo, self.configs, self.fc, self._jee, self._jen,
+                                  nup=mol.nup, ndown=mol.ndown)
+        for m in (self.ao, self.mo, self.pool, self._jee, self._jen,
+                  self.jastrow if isinstance(self.jastrow, CombineJastrow) else None):
+            if m is not None:
+                m._handle = self._handle
+        self._ws = {}
+
+    # -- construction helpers -------------------------------------------------------------
+    def _init_jastrow(self, jastrow):
+        """slater_jastrow.py:193-222."""
+        # plain attributes (not registered sub-modules: the parameters already live under
+        # ``jastrow.`` and state_dict names must match the reference)
+        self.__dict__["_jee"] = None
+        self.__dict__["_jen"] = None
+        if jastrow is None:
+            self.jastrow = None
+            self.use_jastrow = False
+            return
+        self.use_jastrow = True
+        if isinstance(jastrow, str) and jastrow == "default":
+            self.jastrow = JastrowFactorElectronElectron(self.mol, PadeJastrowKernel, cuda=self.cuda)
+        elif isinstance(jastrow, list):
+            self.jastrow = CombineJastrow(jastrow)
+        elif isinstance(jastrow, nn.Module):
+            self.jastrow = jastrow
+        else:
+            raise TypeError("Jastrow factor not supported.")
+        if isinstance(self.jastrow, JastrowFactorElectronElectron):
+            self.__dict__["_jee"] = self.jastrow
+        elif isinstance(self.jastrow, JastrowFactorElectronNuclei):
+            self.__dict__["_jen"] = self.jastrow
+        elif isinstance(self.jastrow, CombineJastrow):
+            self.__dict__["_jee"], self.__dict__["_jen"] = self.jastrow.ee, self.jastrow.en
+        else:
+            raise NotImplementedError(
+                "only the Pade e-e / e-n Jastrow factors (and their product) are fused into the CUDA path")
+        self.jastrow_type = self.jastrow.__repr__()
+        if self.cuda:
+            self.jastrow = self.jastrow.to(self.device)
+
+    def set_combined_jastrow(self, jastrow):
+        raise NotImplementedError("rebuild the wave function with jastrow=[...] instead")
+
+    # -- raw kernel calls -----------------------------------------------------------------
+    def _dev(self):
+        return self.ao.atom_coords.device
+
+    def _x(self, pos):
+        return as_walkers(pos, self.ndim_tot, self._dev())
+
+    def _psi(self, x):
+        W = x.shape[0]
+        out = torch.empty(W, 1, dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib().qmcb_psi(self._handle.plan(), _lib.ptr(x), W, _lib.ptr(out),
+                                       _lib.stream_ptr(x.device)), "qmcb_psi")
+        return out
+
+    def _eloc(self, x, want_psi=False, want_ekin=False):
+        W = x.shape[0]
+        e = torch.empty(W, 1, dtype=torch.float64, device=x.device)
+        p = torch.empty(W, 1, dtype=torch.float64, device=x.device) if want_psi else None
+        k = torch.empty(W, 1, dtype=torch.float64, device=x.device) if want_ekin else None
+        _lib.check(_lib.lib().qmcb_local_energy(self._handle.plan(), _lib.ptr(x), W, _lib.ptr(e), _lib.ptr(p),
+                                                _lib.ptr(k), _lib.stream_ptr(x.device)), "qmcb_local_energy")
+        return e, p, k
+
+    def _grad_psi(self, x, pdf):
+        W = x.shape[0]
+        g = torch.empty(W, self.ndim_tot, dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib().qmcb_grad_psi(self._handle.plan(), _lib.ptr(x), W, int(pdf), _lib.ptr(g),
+                                            _lib.stream_ptr(x.device)), "qmcb_grad_psi")
+        return g
+
+    def _psi_backward(self, x, weight):
+        L = _lib.lib()
+        plan = self._handle.plan()
+        dev = x.device
+        W = x.shape[0]
+        nao, nmo = self.mo.mo_scf.shape
+        nbas = self.ao.nbas
+        g_mo = torch.empty(nao, nmo, dtype=torch.float64, device=dev)
+        g_ci = torch.empty(1, self.nci, dtype=torch.float64, device=dev)
+        g_exp = torch.empty(nbas, dtype=torch.float64, device=dev)
+        g_cf = torch.empty(nbas, dtype=torch.float64, device=dev)
+        g_jee = torch.empty(1, dtype=torch.float64, device=dev)
+        g_jen = torch.empty(1, dtype=torch.float64, device=dev)
+        nbytes = L.qmcb_backward_workspace_bytes(plan, W)
+        ws = self._ws.get("bwd")
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
+            self._ws["bwd"] = ws
+        _lib.check(L.qmcb_psi_backward(plan, _lib.ptr(x), _lib.ptr(weight), W, _lib.ptr(g_mo), _lib.ptr(g_ci),
+                                       _lib.ptr(g_exp), _lib.ptr(g_cf), _lib.ptr(g_jee), _lib.ptr(g_jen),
+                                       _lib.ptr(ws), _lib.stream_ptr(dev)), "qmcb_psi_backward")
+        return {"mo_modifier": g_mo * self.mo.mo_scf, "ci": g_ci, "bas_exp": g_exp, "bas_coeffs": g_cf,
+                "jee_w": g_jee, "jen_w": g_jen}
+
+    # -- public API (reference signatures) ---------------------------------------------------
+    def forward(self, x, ao=None):
+        """psi(R) [W,1]  (slater_jastrow.py:243-286)."""
+        if ao is not None:
+            raise NotImplementedError("forward(x, ao=...) only serves the one-electron update sampler path")
+        xd = self._x(x)
+        jw = self._jee.jastrow_kernel.weight if self._jee is not None else None
+        nw = self._jen.jastrow_kernel.weight if self._jen is not None else None
+        leaves = [self.ao.bas_exp, self.ao.bas_coeffs, self.mo.mo_modifier, self.fc.weight, jw, nw]
+        track = torch.is_grad_enabled() and (
+            any(t is not None and t.requires_grad for t in leaves) or x.requires_grad)
+        if not track:
+            return self._psi(xd)
+        if x.requires_grad:
+            xd = x if (x.device == xd.device and x.dtype == torch.float64 and x.is_contiguous()) else \
+                x.to(device=xd.device, dtype=torch.float64).contiguous()
+        return _PsiFunction.apply(self, xd, *leaves)
+
+    def ao2mo(self, ao):
+        return self.mo(ao)
+
+    def pos2mo(self, x, derivative=0, sum_grad=True):
+        """slater_jastrow.py:292-310."""
+        return self.ao2mo(self.ao(x, derivative=derivative, sum_grad=sum_grad))
+
+    def local_energy(self, pos):
+        """E_L [W,1]  (wf_base.py:184-215 + slater_jastrow.py:312-344)."""
+        return self._eloc(self._x(pos))[0]
+
+    def kinetic_energy_jacobi(self, x, **kwargs):
+        """slater_jastrow.py:312-344."""
+        return self._eloc(self._x(x), want_ekin=True)[2]
+
+    def gradients_jacobi(self, x, sum_grad=False, pdf=False):
+        """slater_jastrow.py:346-447 -> [W, 3*nelec]."""
+        return self._grad_psi(self._x(x), pdf)
+
+    def get_kinetic_operator(self, x, ao, dao, d2ao, mo):
+        raise NotImplementedError("B_kin is formed inside the fused kernel and never materialised")
+
+    def nuclear_potential(self, pos):
+        """wf_base.py:72-95."""
+        x = self._x(pos).view(-1, self.nelec, 1, 3)
+        z = torch.as_tensor(self.ao.atomic_number, dtype=torch.float64, device=x.device)
+        r = (x - self.ao.atom_coords.detach()[None, None]).norm(dim=-1)
+        return (-z / r).sum((1, 2)).view(-1, 1)
+
+    def electronic_potential(self, pos):
+        """wf_base.py:49-70."""
+        x = self._x(pos).view(-1, self.nelec, 3)
+        iu = torch.triu_indices(self.nelec, self.nelec, 1, device=x.device)
+        r = (x[:, iu[0]] - x[:, iu[1]]).norm(dim=-1)
+        return (1.0 / r).sum(1).view(-1, 1)
+
+    def nuclear_repulsion(self):
+        """wf_base.py:97-116."""
+        c = self.ao.atom_coords.detach()
+        vnn = 0.0
+        for a in range(self.natom - 1):
+            for b in range(a + 1, self.natom):
+                vnn = vnn + self.ao.atomic_number[a] * self.ao.atomic_number[b] / (c[a] - c[b]).norm()
+        return vnn
+
+    def geometry(self, pos=None):
+        d = []
+        for iat in range(self.natom):
+            xyz = self.ao.atom_coords[iat, :].detach().cpu().numpy().tolist()
+            d.append(xyz)
+        return d
+
+    def log_data(self):
+        pass
