@@ -1,0 +1,90 @@
+"""CPU: the oracle (oracle/sj_oracle.py) against the committed golden vectors, which were
+produced by the unmodified reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import _cases as C
+import sj_oracle as orc
+
+TOL = 1e-11   # the oracle reproduced the reference to <= 1e-12 when the fixtures were made
+
+
+@pytest.mark.parametrize("name", C.CASES)
+def test_oracle_reproduces_reference(name):
+    g = C.load(name)
+    mol, P = C.oracle_params(g)
+    pos = torch.tensor(g["pos"])
+    assert C.rel_err(orc.psi(P, pos), g["psi"]) < TOL
+    assert C.rel_err(orc.kinetic_energy(P, pos), g["ekin"]) < TOL
+    assert C.rel_err(orc.local_energy(P, pos), g["eloc"]) < TOL
+    ns = g["ao"].shape[0]
+    ao, dao, d2ao = orc.ao_all(P, pos[:ns])
+    assert C.scaled_err(ao, g["ao"]) < TOL
+    assert C.scaled_err(dao, g["dao"]) < TOL
+    assert C.scaled_err(d2ao, g["d2ao"]) < TOL
+    if g["jastrow"] != "None":
+        J, dJ, d2J = orc.jastrow_all(P, pos)
+        assert C.rel_err(J, g["J"]) < TOL
+        assert C.scaled_err(dJ, g["dJ"]) < TOL
+        assert C.scaled_err(d2J, g["d2J"]) < TOL
+    assert C.scaled_err(orc.grad_psi(P, pos), g["gpsi"]) < TOL
+    assert C.scaled_err(orc.grad_psi(P, pos, pdf=True), g["gpdf"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "lih_cas24", "lih_een", "h2o_cas44"])
+def test_oracle_parameter_gradients(name):
+    g = C.load(name)
+    mol, P = C.oracle_params(g)
+    pos = torch.tensor(g["pos"])
+    names = [k[5:] for k in g if k.startswith("grad_")]
+    og, _ = orc.param_grads(P, pos, names=tuple(names))
+    for k in names:
+        if k == "ci" and g["ci"].shape[1] == 1:
+            continue   # sum_w (E_L - <E_L>) = 0: pure rounding noise
+        ref = torch.tensor(g["grad_" + k])
+        err = float((og[k] - ref).abs().max() / max(float(ref.abs().max()), 1e-6))
+        assert err < 1e-9, (k, err)
+
+
+@pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "h2o_cas44"])
+def test_oracle_metropolis_decisions_bit_exact(name):
+    g = C.load(name)
+    mol, P = C.oracle_params(g)
+    nstep = g["mh_disp"].shape[0]
+    for it in range(nstep):
+        cur = torch.tensor(g["mh_pos"][it])
+        fx = (orc.psi(P, cur) ** 2).reshape(-1)
+        fx[fx == 0] = 1e-16
+        npos, nfx, acc, fxn = orc.metropolis_step(P, cur, fx, torch.tensor(g["mh_disp"][it]),
+                                                  torch.tensor(g["mh_tau"][it]))
+        assert np.array_equal(acc.numpy(), g["mh_acc"][it])
+        assert np.array_equal(npos.numpy(), g["mh_pos"][it + 1])
+        assert C.rel_err(fxn, g["mh_fxn"][it]) < TOL
+
+
+def test_oracle_local_energy_matches_autograd_laplacian():
+    """The reference's own known-answer procedure (tests/wavefunction/base_test_cases.py:92-105):
+    Jacobi kinetic energy == autograd Laplacian."""
+    g = C.load("lih_ground")
+    mol, P = C.oracle_params(g)
+    pos = torch.tensor(g["pos"][:6]).requires_grad_(True)
+    val = orc.psi(P, pos)
+    (jac,) = torch.autograd.grad(val.sum(), pos, create_graph=True)
+    lap = torch.zeros(pos.shape[0], dtype=torch.float64)
+    for i in range(pos.shape[1]):
+        (h,) = torch.autograd.grad(jac[:, i].sum(), pos, retain_graph=True)
+        lap += h[:, i]
+    ekin_auto = -0.5 * lap.view(-1, 1) / val.detach()
+    assert torch.allclose(ekin_auto, orc.kinetic_energy(P, pos.detach()), rtol=1e-8, atol=1e-9)
+    assert torch.allclose(jac.detach(), orc.grad_psi(P, pos.detach()), rtol=1e-9, atol=1e-12)
+
+
+def test_oracle_antisymmetry():
+    """tests/wavefunction/base_test_cases.py:24-57."""
+    g = C.load("lih_ground")
+    mol, P = C.oracle_params(g)
+    pos = torch.tensor(g["pos"][:16])
+    swapped = pos.clone()
+    swapped[:, 0:3], swapped[:, 3:6] = pos[:, 3:6], pos[:, 0:3]     # two spin-up electrons
+    assert torch.allclose(orc.psi(P, pos), -orc.psi(P, swapped), rtol=1e-11, atol=0)
