@@ -178,7 +178,7 @@ def main():
     torch.manual_seed(1234 + rank)
     ens = []
     for b in range(NBUF):
-        s = Metropolis(nwalkers=wpg, nstep=25, step_size=step_size, nelec=wf.nelec, ndim=3,
+        s = Metropolis(nwalkers=wpg, nstep=100, step_size=step_size, nelec=wf.nelec, ndim=3,
                        init=mol.domain("normal"), move={"type": "all-elec", "proba": "normal"}, cuda=True,
                        seed=1000 * rank + b, keep_on_device=True)
         ens.append(s(wf.pdf, with_tqdm=False).detach().contiguous())

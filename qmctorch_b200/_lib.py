@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqmcb.so")
+LIB_PATH = os.environ.get("QMCB_LIB") or os.path.join(_HERE, "lib", "libqmcb.so")
 
 RADIAL = {"gto_pure": 0, "gto": 1, "sto_pure": 2, "sto": 3}
 

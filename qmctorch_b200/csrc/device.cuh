@@ -12,6 +12,7 @@
 
 struct Tab {
   const double *atoms, *alpha, *coef, *pn, *cscale, *mow, *ci;
+  const double2 *stream;
   const int *ash, *spo, *sco, *ck, *cao, *used, *ucu, *ucd, *ciu, *cid, *pfo, *pflat;
 };
 
@@ -23,6 +24,7 @@ __device__ __forceinline__ double *stage_tables(const DevSys &S, double *smem, T
   for (int i = threadIdx.x; i < S.nint; i += blockDim.x) si[i] = S.iblob[i];
   T.atoms = sd + S.o_atoms; T.alpha = sd + S.o_alpha; T.coef = sd + S.o_coef; T.pn = sd + S.o_pn;
   T.cscale = sd + S.o_cscale; T.mow = sd + S.o_mow; T.ci = sd + S.o_ci;
+  T.stream = reinterpret_cast<const double2 *>(sd + S.o_stream);
   T.ash = si + S.o_ash; T.spo = si + S.o_spo; T.sco = si + S.o_sco; T.ck = si + S.o_ck;
   T.cao = si + S.o_cao; T.used = si + S.o_used; T.ucu = si + S.o_ucu; T.ucd = si + S.o_ucd;
   T.ciu = si + S.o_ciu; T.cid = si + S.o_cid; T.pfo = si + S.o_pfo; T.pflat = si + S.o_pflat;
@@ -51,34 +53,85 @@ __device__ __forceinline__ double rpow(double r, double rinv, int m) {
 }
 
 // ---------------------------------------------------------------------------------------
+// exp(x) for x <= 0 (any x <= 709 works), ~1 ulp, NaN propagates, no branches:
+// x = k ln2 + r, |r| <= ln2/2; degree-11 Chebyshev-economised polynomial (max error 3.2e-18 on
+// the interval, coefficients from mpmath.chebyfit); 2^k built from the exponent bits.
+// Arguments below -708 are clamped (result 3e-308 instead of a denormal/0).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp_neg(double x) {
+  x = x < -708.0 ? -708.0 : x;
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -0x1.62e42fee00000p-1, x);
+  r = fma(kd, -0x1.a39ef35793c76p-33, r);
+  double p = 0x1.af631d0059becp-26;
+  p = fma(p, r, 0x1.28b4057f44145p-22);
+  p = fma(p, r, 0x1.71ddf5749d126p-19);
+  p = fma(p, r, 0x1.a01991ac8730ap-16);
+  p = fma(p, r, 0x1.a01a01b14378fp-13);
+  p = fma(p, r, 0x1.6c16c187fbe02p-10);
+  p = fma(p, r, 0x1.111111110f225p-7);
+  p = fma(p, r, 0x1.555555554f0cfp-5);
+  p = fma(p, r, 0x1.555555555555ap-3);
+  p = fma(p, r, 0x1.0000000000011p-1);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
+// ---------------------------------------------------------------------------------------
 // Shell evaluation.  For every shell the radial part is contracted first:
 //   R(r) = S0,  grad R = S1 * (x,y,z),  lap R = S2        (spherically symmetric)
 // then each cartesian component Y = x^kx y^ky z^kz (degree L) gives
 //   ao = R Y,  grad ao = S1 Y (x,y,z) + R grad Y,  lap ao = (S2 + 2 L S1) Y + R lap Y
 // (Euler: (x,y,z).grad Y = L Y).  Restates atomic_orbitals.py:578-669,
 // radial_functions.py:6-406, spherical_harmonics.py:102-199.
+// The basis is walked as a packed program of 16-byte records (plan.cu): no index tables,
+// one LDS.128 per primitive / component group.
 // Sink::emit(ao_index, v[NCH]) consumes the values: v[0]=ao, v[1..3]=grad, v[4]=lap.
+// RT = 0: gto_pure (compile-time fast path), RT = 1: radial type read from S at run time.
 // ---------------------------------------------------------------------------------------
 template <int NCH>
-__device__ __forceinline__ void radial_sums(const DevSys &S, const Tab &T, int s, double r2, double r,
-                                            double rinv, double &S0, double &S1, double &S2) {
+__device__ __forceinline__ void gto_pure_prim(double a, double c, double r2, double &S0, double &S1,
+                                              double &S2) {
+  const double ce = c * exp_neg(-a * r2);
+  S0 += ce;
+  if (NCH > 1) {
+    const double t = a * ce;
+    S1 = fma(-2.0, t, S1);
+    S2 = fma(t, fma(4.0 * a, r2, -6.0), S2);
+  }
+}
+
+template <int NCH, int RT>
+__device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const double2 *rec, int nprim, double r2,
+                                                      double r, double rinv, double &S0, double &S1,
+                                                      double &S2) {
   S0 = 0.0; S1 = 0.0; S2 = 0.0;
-  const int p1 = T.spo[s + 1];
-  if (S.radial_type == QMCB_GTO_PURE) {
-    for (int p = T.spo[s]; p < p1; ++p) {
-      const double a = T.alpha[p];
-      const double ce = T.coef[p] * exp(-a * r2);
-      S0 += ce;
-      if (NCH > 1) {
-        const double t = a * ce;
-        S1 -= 2.0 * t;
-        S2 += t * (4.0 * a * r2 - 6.0);
-      }
+  if (RT == 0) {
+    int i = 0;
+    double T0 = 0.0, T1 = 0.0, T2 = 0.0;      // second accumulator set: two independent chains
+    for (; i + 2 <= nprim; i += 2) {
+      const double2 p0 = rec[0], p1 = rec[1];
+      rec += 2;
+      gto_pure_prim<NCH>(p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(p1.x, p1.y, r2, T0, T1, T2);
     }
+    if (i < nprim) {
+      const double2 p0 = rec[0];
+      rec += 1;
+      gto_pure_prim<NCH>(p0.x, p0.y, r2, S0, S1, S2);
+    }
+    S0 += T0; S1 += T1; S2 += T2;
+    return rec;
+  }
+  if (S.radial_type == QMCB_GTO_PURE) {
+    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(rec->x, rec->y, r2, S0, S1, S2);
   } else if (S.radial_type == QMCB_STO_PURE) {
-    for (int p = T.spo[s]; p < p1; ++p) {
-      const double a = T.alpha[p];
-      const double ce = T.coef[p] * exp(-a * r);
+    for (int i = 0; i < nprim; ++i, ++rec) {
+      const double a = rec->x;
+      const double ce = rec->y * exp_neg(-a * r);
       S0 += ce;
       if (NCH > 1) {
         const double t = a * ce;
@@ -88,10 +141,10 @@ __device__ __forceinline__ void radial_sums(const DevSys &S, const Tab &T, int s
     }
   } else {
     const bool gto = S.radial_type == QMCB_GTO;
-    for (int p = T.spo[s]; p < p1; ++p) {
-      const double a = T.alpha[p];
-      const int n = (int)T.pn[p];
-      const double ce = T.coef[p] * exp(gto ? -a * r2 : -a * r);
+    for (int i = 0; i < nprim; ++i, rec += 2) {
+      const double a = rec[0].x;
+      const int n = (int)rec[1].x;
+      const double ce = rec[0].y * exp_neg(gto ? -a * r2 : -a * r);
       const double rn = ipow(r, n);
       S0 += ce * rn;
       if (NCH > 1) {
@@ -106,70 +159,83 @@ __device__ __forceinline__ void radial_sums(const DevSys &S, const Tab &T, int s
       }
     }
   }
+  return rec;
 }
 
 template <int NCH>
-__device__ __forceinline__ void component_values(int kk, double sc, double x, double y, double z,
-                                                 double S0, double S1, double S2, double (&v)[NCH]) {
+__device__ __forceinline__ void generic_component(int kk, double sc, double x, double y, double z, double S0,
+                                                  double S1, double S2, double (&v)[NCH]) {
   const int kx = kk & 255, ky = (kk >> 8) & 255, kz = (kk >> 16) & 255;
   const int L = kx + ky + kz;
-  if (L == 0) {
-    v[0] = S0 * sc;
-    if (NCH > 1) {
-      const double t = S1 * sc;
-      v[1] = t * x; v[2] = t * y; v[3] = t * z;
-      v[4] = S2 * sc;
-    }
-  } else if (L == 1) {
-    const double c = kx ? x : (ky ? y : z);
-    const double R = S0 * sc;
-    v[0] = R * c;
-    if (NCH > 1) {
-      const double t = S1 * sc * c;
-      v[1] = t * x + (kx ? R : 0.0);
-      v[2] = t * y + (ky ? R : 0.0);
-      v[3] = t * z + (kz ? R : 0.0);
-      v[4] = (S2 + 2.0 * S1) * sc * c;
-    }
-  } else {
-    const double px = ipow(x, kx), py = ipow(y, ky), pz = ipow(z, kz);
-    const double Y = px * py * pz;
-    const double R = S0 * sc;
-    v[0] = R * Y;
-    if (NCH > 1) {
-      const double dYx = kx ? kx * ipow(x, kx - 1) * py * pz : 0.0;
-      const double dYy = ky ? ky * px * ipow(y, ky - 1) * pz : 0.0;
-      const double dYz = kz ? kz * px * py * ipow(z, kz - 1) : 0.0;
-      double lapY = 0.0;
-      if (kx > 1) lapY += kx * (kx - 1) * ipow(x, kx - 2) * py * pz;
-      if (ky > 1) lapY += ky * (ky - 1) * px * ipow(y, ky - 2) * pz;
-      if (kz > 1) lapY += kz * (kz - 1) * px * py * ipow(z, kz - 2);
-      const double t = S1 * sc * Y;
-      v[1] = t * x + R * dYx;
-      v[2] = t * y + R * dYy;
-      v[3] = t * z + R * dYz;
-      v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
-    }
+  const double px = ipow(x, kx), py = ipow(y, ky), pz = ipow(z, kz);
+  const double Y = px * py * pz;
+  const double R = S0 * sc;
+  v[0] = R * Y;
+  if (NCH > 1) {
+    const double dYx = kx ? kx * ipow(x, kx - 1) * py * pz : 0.0;
+    const double dYy = ky ? ky * px * ipow(y, ky - 1) * pz : 0.0;
+    const double dYz = kz ? kz * px * py * ipow(z, kz - 1) : 0.0;
+    double lapY = 0.0;
+    if (kx > 1) lapY += kx * (kx - 1) * ipow(x, kx - 2) * py * pz;
+    if (ky > 1) lapY += ky * (ky - 1) * px * ipow(y, ky - 2) * pz;
+    if (kz > 1) lapY += kz * (kz - 1) * px * py * ipow(z, kz - 2);
+    const double t = S1 * sc * Y;
+    v[1] = t * x + R * dYx;
+    v[2] = t * y + R * dYy;
+    v[3] = t * z + R * dYz;
+    v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
   }
 }
 
-template <int NCH, class Sink>
+template <int NCH, int RT, class Sink>
 __device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double ex, double ey, double ez,
                                          Sink &sink) {
+  const double2 *rec = T.stream;
   for (int A = 0; A < S.natom; ++A) {
     const double x = ex - T.atoms[4 * A], y = ey - T.atoms[4 * A + 1], z = ez - T.atoms[4 * A + 2];
     const double r2 = x * x + y * y + z * z;
     double r = 0.0, rinv = 0.0;
-    if (S.radial_type != QMCB_GTO_PURE) { r = sqrt(r2); rinv = 1.0 / r; }
-    const int s1 = T.ash[A + 1];
-    for (int s = T.ash[A]; s < s1; ++s) {
+    if (RT != 0 && S.radial_type != QMCB_GTO_PURE) { r = sqrt(r2); rinv = 1.0 / r; }
+    const int ns = T.ash[A + 1] - T.ash[A];
+    for (int s = 0; s < ns; ++s) {
+      const double hdr = rec->x;
+      ++rec;
+      const int nprim = __double2loint(hdr), ngrp = __double2hiint(hdr);
       double S0, S1, S2;
-      radial_sums<NCH>(S, T, s, r2, r, rinv, S0, S1, S2);
-      const int k1 = T.sco[s + 1];
-      for (int k = T.sco[s]; k < k1; ++k) {
+      rec = radial_sums<NCH, RT>(S, rec, nprim, r2, r, rinv, S0, S1, S2);
+      for (int g = 0; g < ngrp; ++g, ++rec) {
+        const double2 gr = *rec;
+        const int kk = __double2loint(gr.x), ao = __double2hiint(gr.x);
+        const double sc = gr.y;
         double v[NCH];
-        component_values<NCH>(T.ck[k], T.cscale[k], x, y, z, S0, S1, S2, v);
-        sink.emit(T.cao[k], v);
+        if (kk == 0) {                       // s
+          v[0] = S0 * sc;
+          if (NCH > 1) {
+            const double t = S1 * sc;
+            v[1] = t * x; v[2] = t * y; v[3] = t * z;
+            v[4] = S2 * sc;
+          }
+          sink.emit(ao, v);
+        } else if (kk == (1 << 24)) {        // px, py, pz on consecutive AOs
+          const double R = S0 * sc;
+          if (NCH > 1) {
+            const double t = S1 * sc, lf = fma(2.0, S1, S2) * sc;
+            const double tx = t * x, ty = t * y, tz = t * z;
+            v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z; v[4] = lf * x;
+            sink.emit(ao, v);
+            v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z; v[4] = lf * y;
+            sink.emit(ao + 1, v);
+            v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R); v[4] = lf * z;
+            sink.emit(ao + 2, v);
+          } else {
+            v[0] = R * x; sink.emit(ao, v);
+            v[0] = R * y; sink.emit(ao + 1, v);
+            v[0] = R * z; sink.emit(ao + 2, v);
+          }
+        } else {
+          generic_component<NCH>(kk, sc, x, y, z, S0, S1, S2, v);
+          sink.emit(ao, v);
+        }
       }
     }
   }
@@ -202,19 +268,19 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
     const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
     const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
     const double s2 = dx * dx + dy * dy + dz * dz;
-    if (j > e) vee += 1.0 / sqrt(s2);
+    if (j > e) vee += rsqrt(s2);
     if (S.use_jee) {
       const double nj = __dadd_rn(__dadd_rn(__dmul_rn(xj, xj), __dmul_rn(yj, yj)), __dmul_rn(zj, zj));
       double dot;
       if (S.gram_fma) dot = __fma_rn(zi, zj, __fma_rn(yi, yj, __dmul_rn(xi, xj)));
       else dot = __dadd_rn(__dadd_rn(__dmul_rn(xi, xj), __dmul_rn(yi, yj)), __dmul_rn(zi, zj));
       const double d2 = __dsub_rn(__dadd_rn(ni, nj), __dmul_rn(2.0, dot));
-      const double r = sqrt(d2);
+      const double rinv = rsqrt(d2);
+      const double r = d2 * rinv;
       const double w0 = (up_i == (j < S.nup)) ? 0.25 : 0.5;
       const double den = 1.0 / (1.0 + w * r);
       if (j > e) ks += w0 * r * den;
       if (DERIV) {
-        const double rinv = 1.0 / r;
         const double kp = w0 * den * den * rinv;
         gx += kp * dx; gy += kp * dy; gz += kp * dz;
         h += 2.0 * kp * den * (s2 * rinv * rinv);
@@ -226,7 +292,7 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
     const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
     const double dx = xi - xa, dy = yi - ya, dz = zi - za;
     const double s2 = dx * dx + dy * dy + dz * dz;
-    ven -= T.atoms[4 * A + 3] / sqrt(s2);
+    ven -= T.atoms[4 * A + 3] * rsqrt(s2);
     if (S.use_jen) {
       const double wn = S.jen_w;
       const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));

@@ -14,6 +14,7 @@
 
 #include <cstdio>
 
+#pragma once
 #include "device.cuh"
 #include "philox.cuh"
 
@@ -74,16 +75,39 @@ __host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode) {
   return mode == MODE_ELOC ? 2 * n * n : n * n;            // [A|B] or A
 }
 
-template <int MODE, int MB>
-__global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedArgs a, const int TW,
-                                                    const int NBLK, const int lu_conc) {
+// Work area of one tile (doubles): spos [TW][3Ne] | jv [TW][Ne][8] | mo [NCHS][TW][Ne][nmup]
+// | dets [TW][nun] | trs [TW][nun] | wsum [TW][4] | LU scratch
+__host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw, int lu_conc) {
+  const int nchs_ = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
+  const int nun = S.nuu + S.nud;
+  size_t d = (size_t)tw * 3 * S.nelec + (size_t)tw * S.nelec * 8 + (size_t)nchs_ * tw * S.nelec * S.nmup;
+  d += 2 * (size_t)tw * nun + (size_t)tw * 4;
+  d += (size_t)lu_conc * lu_scratch_per_item(S, mode);
+  return (d + 1) & ~(size_t)1;
+}
+
+#ifndef QMCB_MINBLOCKS
+#define QMCB_MINBLOCKS 1
+#endif
+
+// WARP = true : a tile belongs to ONE WARP (Ne * NBLK divides 32); phases are separated by
+//               __syncwarp only, warps never wait for each other.
+// WARP = false: a tile belongs to the CTA; phases are separated by __syncthreads.
+template <int MODE, int MB, int RT, bool WARP>
+__global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
+    fused_kernel(const DevSys S, const FusedArgs a, const int TW, const int NBLK, const int lu_conc) {
   constexpr int NCH = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? 5 : 1;
   constexpr int NCHS = nchs<MODE>();
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   Tab T;
   double *ws = stage_tables(S, smem, T);
   const int Ne = S.nelec, ne3 = 3 * Ne, nmup = S.nmup;
   const int nun = S.nuu + S.nud;
+  const int nthr = WARP ? 32 : (int)blockDim.x;
+  const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int64_t unit = WARP ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
+  const int64_t nunit = WARP ? (int64_t)gridDim.x * (blockDim.x >> 5) : gridDim.x;
+  if (WARP) ws += (threadIdx.x >> 5) * tile_doubles(S, MODE, TW, lu_conc);
   double *spos = ws;
   double *jv = spos + TW * ne3;
   double *smo = jv + TW * Ne * 8;
@@ -91,15 +115,16 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
   double *str = sdet + TW * nun;
   double *wsum = str + TW * nun;
   double *scr = wsum + TW * 4;
-  const int tid = threadIdx.x;
   const int64_t ntile = (a.W + TW - 1) / TW;
+  const size_t chs = (size_t)TW * Ne * nmup;
   __syncthreads();
+#define TILE_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
 
-  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+  for (int64_t tile = unit; tile < ntile; tile += nunit) {
     const int64_t w0 = tile * TW;
     const int tw = (int)((a.W - w0) < TW ? (a.W - w0) : TW);
     // ---- P0: coordinates
-    for (int i = tid; i < tw * ne3; i += blockDim.x) {
+    for (int i = tid; i < tw * ne3; i += nthr) {
       double v = a.pos[w0 * ne3 + i];
       if (MODE == MODE_MH) {
         const int wl = i / ne3, c = i - wl * ne3, e = c / 3;
@@ -118,25 +143,24 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
       }
       spos[i] = v;
     }
-    __syncthreads();
+    TILE_SYNC();
     // ---- P1: Jastrow + potentials, thread (wl, e)
-    for (int it = tid; it < tw * Ne; it += blockDim.x) {
+    for (int it = tid; it < tw * Ne; it += nthr) {
       const int wl = it / Ne, e = it - wl * Ne;
       ElecTerms o;
       electron_terms<(NCH > 1)>(S, T, spos + wl * ne3, e, o);
       double *q = jv + (size_t)it * 8;
       q[0] = o.gx; q[1] = o.gy; q[2] = o.gz; q[3] = o.lap; q[4] = o.ks; q[5] = o.ven; q[6] = o.vee;
     }
-    __syncthreads();
+    if (NCH > 1) TILE_SYNC();   // P2 reads jv only when it assembles B_kin / the gradient
     // ---- P2: AO -> MO rows, thread (wl, blk, e)
-    for (int it = tid; it < tw * NBLK * Ne; it += blockDim.x) {
+    for (int it = tid; it < tw * NBLK * Ne; it += nthr) {
       const int wl = it / (NBLK * Ne), rem = it - wl * NBLK * Ne;
       const int blk = rem / Ne, e = rem - blk * Ne;
       const double *sp = spos + wl * ne3 + 3 * e;
       MoSink<NCH, MB> sink;
       sink.init(T.mow + blk * MB, nmup);
-      eval_aos<NCH>(S, T, sp[0], sp[1], sp[2], sink);
-      const size_t chs = (size_t)TW * Ne * nmup;
+      eval_aos<NCH, RT>(S, T, sp[0], sp[1], sp[2], sink);
       double *dst = smo + ((size_t)wl * Ne + e) * nmup + blk * MB;
       if (MODE == MODE_ELOC) {
         const double *q = jv + ((size_t)wl * Ne + e) * 8;
@@ -162,16 +186,15 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
         for (int j = 0; j < MB; ++j) dst[j] = sink.acc[0][j];
       }
     }
-    __syncthreads();
+    TILE_SYNC();
     // ---- P3: determinants (and traces / inverses) per (wl, unique occupation)
     {
       const int nitem = tw * nun;
       const int per = lu_scratch_per_item(S, MODE);
       // scratch slot: GRAD keeps every inverse resident (slot = item); otherwise one slot
       // per participating thread, reused across rounds
-      const int conc = per ? lu_conc : blockDim.x;
-      const int stride = (MODE == MODE_GRAD) ? blockDim.x : (conc < (int)blockDim.x ? conc : blockDim.x);
-      const size_t chs = (size_t)TW * Ne * nmup;
+      const int conc = per ? lu_conc : nthr;
+      const int stride = (MODE == MODE_GRAD) ? nthr : (conc < nthr ? conc : nthr);
       if (tid < stride) {
         for (int it = tid; it < nitem; it += stride) {
           const int wl = it / nun, u = it - wl * nun;
@@ -214,10 +237,9 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
         }
       }
     }
-    __syncthreads();
+    TILE_SYNC();
     // ---- P4: per-walker epilogue
-    if (tid < tw) {
-      const int wl = tid;
+    for (int wl = tid; wl < tw; wl += nthr) {
       const double *dd = sdet + wl * nun, *tt = str + wl * nun;
       double sig = 0.0, ksig = 0.0;
       for (int c = 0; c < S.nconf; ++c) {
@@ -258,9 +280,9 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
       }
     }
     if (MODE == MODE_MH) {
-      __syncthreads();
+      TILE_SYNC();
       int cnt = 0;
-      for (int i = tid; i < tw * ne3; i += blockDim.x) {
+      for (int i = tid; i < tw * ne3; i += nthr) {
         const int wl = i / ne3;
         if (wsum[wl * 4] != 0.0) {
           a.pos_rw[w0 * ne3 + i] = spos[i];
@@ -269,16 +291,15 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
       }
       if (a.naccept) {
         cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if ((tid & 31) == 0 && cnt) atomicAdd(a.naccept, (unsigned long long)cnt);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(a.naccept, (unsigned long long)cnt);
       }
     }
     if (MODE == MODE_GRAD) {
-      __syncthreads();
+      TILE_SYNC();
       // d psi / d r_{e,c} = J [ sum_u C_u sum_j inv_u[j][e] dmo_c[e][cols_u[j]] + g_{e,c} Sigma ]
       // (slater_jastrow.py:346-447), C_u = D_u * sum_{n: occ_s(n)=u} c_n D_other(n)
-      const size_t chs = (size_t)TW * Ne * nmup;
       const int conc = lu_conc;
-      for (int it = tid; it < tw * Ne; it += blockDim.x) {
+      for (int it = tid; it < tw * Ne; it += nthr) {
         const int wl = it / Ne, e = it - wl * Ne;
         const bool up = e < S.nup;
         const int n = up ? S.nup : S.ndown;
@@ -296,7 +317,7 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
           cu *= dd[up ? u : S.nuu + u];
           if (cu == 0.0) continue;
           const int item = wl * nun + (up ? u : S.nuu + u);
-          const double *inv = scr + item;   // thread `item` wrote it (single round)
+          const double *inv = scr + item;
           const int *cols = up ? T.ucu + u * S.nup : T.ucd + u * S.ndown;
           double tx = 0, ty = 0, tz = 0;
           const int ild = n <= 3 ? n : 2 * n, ioff = n <= 3 ? 0 : n;
@@ -319,23 +340,15 @@ __global__ void __launch_bounds__(512) fused_kernel(const DevSys S, const FusedA
         g[0] = ox; g[1] = oy; g[2] = oz;
       }
     }
-    __syncthreads();
+    TILE_SYNC();
   }
+#undef TILE_SYNC
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static size_t fused_smem_bytes(const DevSys &S, int mode, int tw, int lu_conc) {
-  const int nchs_ = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
-  const int nun = S.nuu + S.nud;
-  size_t d = table_doubles(S);
-  d += (size_t)tw * 3 * S.nelec + (size_t)tw * S.nelec * 8 + (size_t)nchs_ * tw * S.nelec * S.nmup;
-  d += 2 * (size_t)tw * nun + (size_t)tw * 4;
-  d += (size_t)lu_conc * lu_scratch_per_item(S, mode);
-  return d * sizeof(double);
-}
-
+#ifdef QMCB_FUSED_MAIN
 static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   const DevSys &S = p->sys;
   int mb = 1;
@@ -350,6 +363,25 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   const int nun = S.nuu + S.nud;
   const int per = lu_scratch_per_item(S, mode);
   const int budget = p->smem_optin - 1024;
+  const size_t tab = (size_t)table_doubles(S) * sizeof(double);
+  // ---- warp-owned tiles when the threads of a walker tile a warp exactly
+  if (32 % per_walker == 0) {
+    const int tw = 32 / per_walker;
+    int conc = 0;
+    if (per) {
+      conc = tw * nun;
+      if (mode != MODE_GRAD && conc > 32) conc = 32;
+    }
+    const size_t unit = tile_doubles(S, mode, tw, conc) * sizeof(double);
+    for (int warps = 8; warps >= 1; warps /= 2) {
+      const size_t sm = tab + unit * warps;
+      if ((int)sm <= budget) {
+        c.warp = 1; c.tw = tw; c.threads = warps * 32; c.smem = (int)sm; c.lu_conc = conc;
+        return 0;
+      }
+    }
+  }
+  // ---- CTA-owned tiles
   int tw = 512 / per_walker;
   if (tw > 128) tw = 128;
   for (; tw >= 1; --tw) {
@@ -360,10 +392,9 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
       conc = tw * nun;                                     // GRAD: every inverse stays resident
       if (mode != MODE_GRAD && conc > threads) conc = threads;
     }
-    size_t sm = fused_smem_bytes(S, mode, tw, conc);
-    // prefer two CTAs per SM when the tile is small
+    const size_t sm = tab + tile_doubles(S, mode, tw, conc) * sizeof(double);
     if ((int)sm <= budget) {
-      c.tw = tw; c.threads = threads; c.smem = (int)sm; c.lu_conc = conc;
+      c.warp = 0; c.tw = tw; c.threads = threads; c.smem = (int)sm; c.lu_conc = conc;
       return 0;
     }
   }
@@ -377,21 +408,31 @@ int qmcb_choose_launch(qmcb_plan *p) {
   if (!rc) rc = choose(p, MODE_GRAD, p->cfg_grad);
   return rc;
 }
+#endif  // QMCB_FUSED_MAIN
 
-template <int MODE, int MB>
-static int launch_t(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
-  auto k = fused_kernel<MODE, MB>;
+template <int MODE, int MB, int RT, bool WARP>
+static int launch_k(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
+  auto k = fused_kernel<MODE, MB, RT, WARP>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
   if (e != cudaSuccess) return (int)e;
   const int64_t ntile = (a.W + c.tw - 1) / c.tw;
+  const int64_t units_per_cta = WARP ? c.threads / 32 : 1;
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, c.threads, c.smem);
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)p->sm_count * occ;
-  if (grid > ntile) grid = ntile;
+  const int64_t need = (ntile + units_per_cta - 1) / units_per_cta;
+  if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   k<<<(unsigned)grid, c.threads, c.smem, st>>>(p->sys, a, c.tw, c.nblk, c.lu_conc);
   return (int)cudaGetLastError();
+}
+
+template <int MODE, int MB>
+static int launch_t(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
+  const bool pure = p->sys.radial_type == QMCB_GTO_PURE;
+  if (c.warp) return pure ? launch_k<MODE, MB, 0, true>(p, c, a, st) : launch_k<MODE, MB, 1, true>(p, c, a, st);
+  return pure ? launch_k<MODE, MB, 0, false>(p, c, a, st) : launch_k<MODE, MB, 1, false>(p, c, a, st);
 }
 
 template <int MODE>
@@ -404,50 +445,9 @@ static int launch(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cu
   }
 }
 
-static int check(const qmcb_plan *p, const void *pos, int64_t W) {
+
+static inline int check(const qmcb_plan *p, const void *pos, int64_t W) {
   if (!p || !p->d_dbl) { qmcb_set_error("qmcb: plan has no device tables"); return QMCB_EINVAL; }
   if (W < 0 || (W > 0 && !pos)) { qmcb_set_error("qmcb: bad walker array"); return QMCB_EINVAL; }
   return 0;
-}
-
-extern "C" int qmcb_psi(const qmcb_plan *p, const double *pos, int64_t W, double *psi, void *stream) {
-  int rc = check(p, pos, W);
-  if (rc || W == 0) return rc;
-  FusedArgs a{};
-  a.pos = pos; a.W = W; a.out0 = psi;
-  return launch<MODE_PSI>(p, p->cfg_psi, a, (cudaStream_t)stream);
-}
-
-extern "C" int qmcb_local_energy(const qmcb_plan *p, const double *pos, int64_t W, double *eloc,
-                                 double *psi, double *ekin, void *stream) {
-  int rc = check(p, pos, W);
-  if (rc || W == 0) return rc;
-  FusedArgs a{};
-  a.pos = pos; a.W = W; a.out0 = eloc; a.out1 = psi; a.out2 = ekin;
-  return launch<MODE_ELOC>(p, p->cfg_eloc, a, (cudaStream_t)stream);
-}
-
-extern "C" int qmcb_grad_psi(const qmcb_plan *p, const double *pos, int64_t W, int pdf, double *grad,
-                             void *stream) {
-  int rc = check(p, pos, W);
-  if (rc || W == 0) return rc;
-  FusedArgs a{};
-  a.pos = pos; a.W = W; a.out0 = grad; a.pdf = pdf;
-  return launch<MODE_GRAD>(p, p->cfg_grad, a, (cudaStream_t)stream);
-}
-
-extern "C" int qmcb_metropolis_step(const qmcb_plan *p, double *pos, double *fx, int64_t W,
-                                    const double *disp, const double *tau, const int32_t *elec_index,
-                                    int move_elec, int proba_normal, double scale, double eps,
-                                    uint64_t seed, uint64_t offset, uint8_t *accept,
-                                    unsigned long long *naccept, void *stream) {
-  int rc = check(p, pos, W);
-  if (rc || W == 0) return rc;
-  if (move_elec >= p->sys.nelec || move_elec < -2) { qmcb_set_error("qmcb_metropolis_step: move_elec"); return QMCB_EINVAL; }
-  FusedArgs a{};
-  a.pos = pos; a.pos_rw = pos; a.W = W; a.out0 = fx;
-  a.disp = disp; a.tau = tau; a.elec_index = elec_index; a.move_elec = move_elec;
-  a.proba_normal = proba_normal; a.scale = scale; a.eps = eps; a.seed = seed; a.offset = offset;
-  a.accept = accept; a.naccept = naccept;
-  return launch<MODE_MH>(p, p->cfg_psi, a, (cudaStream_t)stream);
 }

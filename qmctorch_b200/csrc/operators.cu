@@ -22,7 +22,7 @@ struct AoStoreSink {
 template <int NCH>
 __global__ void __launch_bounds__(256) ao_kernel(const DevSys S, const double *pos, int64_t rows, double *ao,
                                                  double *dao, double *d2ao) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   Tab T;
   stage_tables(S, smem, T);
   __syncthreads();
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) ao_kernel(const DevSys S, const double *p
     sink.ao = ao + row * S.nao;
     sink.dao = NCH > 1 ? dao + row * S.nao * 3 : nullptr;
     sink.d2ao = NCH > 1 ? d2ao + row * S.nao : nullptr;
-    eval_aos<NCH>(S, T, pos[3 * row], pos[3 * row + 1], pos[3 * row + 2], sink);
+    eval_aos<NCH, 1>(S, T, pos[3 * row], pos[3 * row + 1], pos[3 * row + 2], sink);
   }
 }
 
@@ -95,7 +95,7 @@ extern "C" int qmcb_mo(const qmcb_plan *p, const double *x, int64_t rows, double
 // ---- Jastrow factor + derivatives -------------------------------------------------------
 __global__ void __launch_bounds__(256) jastrow_kernel(DevSys S, const double *pos, int64_t W, int deriv,
                                                       double *J, double *dJ, double *d2J) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   Tab T;
   double *ws = stage_tables(S, smem, T);
   const int Ne = S.nelec, ne3 = 3 * Ne;
@@ -165,7 +165,7 @@ extern "C" int qmcb_jastrow(const qmcb_plan *p, const double *pos, int64_t W, in
 #define QMCB_SLATER_NMAX 16
 __global__ void __launch_bounds__(128) slater_kernel(DevSys S, const double *mo, const double *bop, int64_t nop,
                                                      int64_t W, double *dets, double *trace) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   Tab T;
   stage_tables(S, smem, T);
   __syncthreads();

@@ -205,12 +205,53 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   S.o_cscale = (int)hd.size();
   for (auto &sh : shells) hd.insert(hd.end(), sh.comp_scale.begin(), sh.comp_scale.end());
   S.ncomp = (int)hd.size() - S.o_cscale;
+  if (hd.size() & 1) hd.push_back(0.0);   // 16-byte aligned rows for vector loads
   S.o_mow = (int)hd.size();
   for (int a = 0; a < s->nao; ++a)
     for (int j = 0; j < S.nmup; ++j)
       hd.push_back(j < S.nmu ? s->mo[(size_t)a * s->nmo + used[j]] : 0.0);
   S.o_ci = (int)hd.size();
   for (int c = 0; c < s->nconf; ++c) hd.push_back(s->ci[c]);
+  // ---- packed shell program: per shell a header record {nprim, ngroup | -}, then nprim records
+  // {alpha, coef (, n as third field in the next record for gto/sto)}, then ngroup records
+  // {kk | type<<24, ao | scale}.  A "P" group (type 1) stands for three consecutive AOs x,y,z
+  // with a common scale; type 0 is a single component with explicit powers.
+  if (hd.size() & 1) hd.push_back(0.0);
+  S.o_stream = (int)hd.size();
+  {
+    auto push_ints = [&](int lo, int hi2, double y) {
+      union { double d; int i[2]; } u;
+      u.i[0] = lo; u.i[1] = hi2;
+      hd.push_back(u.d); hd.push_back(y);
+    };
+    const bool with_n = (s->radial_type == QMCB_GTO || s->radial_type == QMCB_STO);
+    for (auto &sh : shells) {
+      // group components
+      struct Grp { int kk, ao; double sc; };
+      std::vector<Grp> grps;
+      size_t k = 0;
+      const size_t nc = sh.comp_ao.size();
+      while (k < nc) {
+        const int kx = 1, ky = 1 << 8, kz = 1 << 16;
+        if (k + 2 < nc && sh.comp_k[k] == kx && sh.comp_k[k + 1] == ky && sh.comp_k[k + 2] == kz &&
+            sh.comp_ao[k + 1] == sh.comp_ao[k] + 1 && sh.comp_ao[k + 2] == sh.comp_ao[k] + 2 &&
+            sh.comp_scale[k + 1] == sh.comp_scale[k] && sh.comp_scale[k + 2] == sh.comp_scale[k]) {
+          grps.push_back({(1 << 24), sh.comp_ao[k], sh.comp_scale[k]});
+          k += 3;
+        } else {
+          grps.push_back({sh.comp_k[k], sh.comp_ao[k], sh.comp_scale[k]});
+          k += 1;
+        }
+      }
+      push_ints((int)sh.alpha.size(), (int)grps.size(), 0.0);
+      for (size_t q = 0; q < sh.alpha.size(); ++q) {
+        hd.push_back(sh.alpha[q]); hd.push_back(sh.coef[q]);
+        if (with_n) { hd.push_back(sh.pn[q]); hd.push_back(0.0); }
+      }
+      for (auto &g : grps) push_ints(g.kk, g.ao, g.sc);
+    }
+  }
+  S.nrec = ((int)hd.size() - S.o_stream) / 2;
   S.ndbl = (int)hd.size();
 
   S.o_ash = (int)hi.size();

@@ -42,10 +42,14 @@ struct DevSys {
   int o_cid;     // [nconf]
   int o_pflat;   // per shell: [nprim_s][ncomp_s] flat primitive index; start at o_pfo[s]
   int o_pfo;     // [nshell+1]
+  // packed "shell program" walked by the hot loops: 16-byte records (double2), see plan.cu
+  int o_stream;  // offset into dblob (doubles, even)
+  int nrec;      // number of 16-byte records
 };
 
 struct LaunchCfg {
-  int tw;        // walkers per CTA
+  int warp;      // 1: one warp owns a tile (no CTA barriers), 0: one CTA owns a tile
+  int tw;        // walkers per tile
   int nblk;      // MO column blocks per electron
   int mb;        // MO columns per block (template)
   int threads;
