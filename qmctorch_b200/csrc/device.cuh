@@ -58,26 +58,29 @@ __device__ __forceinline__ double rpow(double r, double rinv, int m) {
 // the interval, coefficients from mpmath.chebyfit); 2^k built from the exponent bits.
 // Arguments below -708 are clamped (result 3e-308 instead of a denormal/0).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double exp_neg(double x) {
-  x = x < -708.0 ? -708.0 : x;
-  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+// The constants come from the kernel-parameter struct (constant bank 0): S.expc.
+__device__ __forceinline__ double exp_core(const DevSys &S, double x) {
+  const double t = fma(x, S.expc[12], S.expc[13]);
   const int k = __double2loint(t);
-  const double kd = t - 6755399441055744.0;
-  double r = fma(kd, -0x1.62e42fee00000p-1, x);
-  r = fma(kd, -0x1.a39ef35793c76p-33, r);
-  double p = 0x1.af631d0059becp-26;
-  p = fma(p, r, 0x1.28b4057f44145p-22);
-  p = fma(p, r, 0x1.71ddf5749d126p-19);
-  p = fma(p, r, 0x1.a01991ac8730ap-16);
-  p = fma(p, r, 0x1.a01a01b14378fp-13);
-  p = fma(p, r, 0x1.6c16c187fbe02p-10);
-  p = fma(p, r, 0x1.111111110f225p-7);
-  p = fma(p, r, 0x1.555555554f0cfp-5);
-  p = fma(p, r, 0x1.555555555555ap-3);
-  p = fma(p, r, 0x1.0000000000011p-1);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  const double kd = t - S.expc[13];
+  double r = fma(kd, S.expc[14], x);
+  r = fma(kd, S.expc[15], r);
+  double p = S.expc[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) p = fma(p, r, S.expc[i]);
   return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
+__device__ __forceinline__ double exp_neg(const DevSys &S, double x) {
+  x = x < -708.0 ? -708.0 : x;
+  return exp_core(S, x);
+}
+
+// same for arguments of either sign (|x| <= 708 after clamping; NaN propagates)
+__device__ __forceinline__ double exp_clamped(const DevSys &S, double x) {
+  x = x < -708.0 ? -708.0 : x;
+  x = x > 708.0 ? 708.0 : x;
+  return exp_core(S, x);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -93,9 +96,9 @@ __device__ __forceinline__ double exp_neg(double x) {
 // RT = 0: gto_pure (compile-time fast path), RT = 1: radial type read from S at run time.
 // ---------------------------------------------------------------------------------------
 template <int NCH>
-__device__ __forceinline__ void gto_pure_prim(double a, double c, double r2, double &S0, double &S1,
+__device__ __forceinline__ void gto_pure_prim(const DevSys &S, double a, double c, double r2, double &S0, double &S1,
                                               double &S2) {
-  const double ce = c * exp_neg(-a * r2);
+  const double ce = c * exp_neg(S, -a * r2);
   S0 += ce;
   if (NCH > 1) {
     const double t = a * ce;
@@ -115,23 +118,23 @@ __device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const dou
     for (; i + 2 <= nprim; i += 2) {
       const double2 p0 = rec[0], p1 = rec[1];
       rec += 2;
-      gto_pure_prim<NCH>(p0.x, p0.y, r2, S0, S1, S2);
-      gto_pure_prim<NCH>(p1.x, p1.y, r2, T0, T1, T2);
+      gto_pure_prim<NCH>(S, p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(S, p1.x, p1.y, r2, T0, T1, T2);
     }
     if (i < nprim) {
       const double2 p0 = rec[0];
       rec += 1;
-      gto_pure_prim<NCH>(p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(S, p0.x, p0.y, r2, S0, S1, S2);
     }
     S0 += T0; S1 += T1; S2 += T2;
     return rec;
   }
   if (S.radial_type == QMCB_GTO_PURE) {
-    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(rec->x, rec->y, r2, S0, S1, S2);
+    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(S, rec->x, rec->y, r2, S0, S1, S2);
   } else if (S.radial_type == QMCB_STO_PURE) {
     for (int i = 0; i < nprim; ++i, ++rec) {
       const double a = rec->x;
-      const double ce = rec->y * exp_neg(-a * r);
+      const double ce = rec->y * exp_neg(S, -a * r);
       S0 += ce;
       if (NCH > 1) {
         const double t = a * ce;
@@ -144,7 +147,7 @@ __device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const dou
     for (int i = 0; i < nprim; ++i, rec += 2) {
       const double a = rec[0].x;
       const int n = (int)rec[1].x;
-      const double ce = rec[0].y * exp_neg(gto ? -a * r2 : -a * r);
+      const double ce = rec[0].y * exp_neg(S, gto ? -a * r2 : -a * r);
       const double rn = ipow(r, n);
       S0 += ce * rn;
       if (NCH > 1) {

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
   double *scr = wsum + TW * 4;
   const int64_t ntile = (a.W + TW - 1) / TW;
   const size_t chs = (size_t)TW * Ne * nmup;
+  const int jvs = TW * Ne;   // jv is stored [quantity][walker][electron]
   __syncthreads();
 #define TILE_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
 
@@ -149,8 +150,9 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
       const int wl = it / Ne, e = it - wl * Ne;
       ElecTerms o;
       electron_terms<(NCH > 1)>(S, T, spos + wl * ne3, e, o);
-      double *q = jv + (size_t)it * 8;
-      q[0] = o.gx; q[1] = o.gy; q[2] = o.gz; q[3] = o.lap; q[4] = o.ks; q[5] = o.ven; q[6] = o.vee;
+      double *q = jv + it;
+      if (NCH > 1) { q[0] = o.gx; q[jvs] = o.gy; q[2 * jvs] = o.gz; q[3 * jvs] = o.lap; }
+      q[4 * jvs] = o.ks; q[5 * jvs] = o.ven; q[6 * jvs] = o.vee;
     }
     if (NCH > 1) TILE_SYNC();   // P2 reads jv only when it assembles B_kin / the gradient
     // ---- P2: AO -> MO rows, thread (wl, blk, e)
@@ -163,8 +165,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
       eval_aos<NCH, RT>(S, T, sp[0], sp[1], sp[2], sink);
       double *dst = smo + ((size_t)wl * Ne + e) * nmup + blk * MB;
       if (MODE == MODE_ELOC) {
-        const double *q = jv + ((size_t)wl * Ne + e) * 8;
-        const double gx = q[0], gy = q[1], gz = q[2], lp = q[3];
+        const double *q = jv + wl * Ne + e;
+        const double gx = q[0], gy = q[jvs], gz = q[2 * jvs], lp = q[3 * jvs];
         const bool uj = S.use_jee || S.use_jen;
 #pragma unroll
         for (int j = 0; j < MB; ++j) {
@@ -250,10 +252,10 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
       }
       double ks = 0.0, ven = 0.0, vee = 0.0;
       for (int e = 0; e < Ne; ++e) {
-        const double *q = jv + ((size_t)wl * Ne + e) * 8;
-        ks += q[4]; ven += q[5]; vee += q[6];
+        const double *q = jv + wl * Ne + e;
+        ks += q[4 * jvs]; ven += q[5 * jvs]; vee += q[6 * jvs];
       }
-      const double J = (S.use_jee || S.use_jen) ? exp(ks) : 1.0;
+      const double J = (S.use_jee || S.use_jen) ? exp_clamped(S, ks) : 1.0;
       const double psi = J * sig;
       if (MODE == MODE_PSI) {
         a.out0[w0 + wl] = psi;
@@ -330,8 +332,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
           gsx += cu * tx; gsy += cu * ty; gsz += cu * tz;
         }
         const double J = wsum[wl * 4], sig = wsum[wl * 4 + 1];
-        const double *q = jv + (size_t)it * 8;
-        double ox = J * (gsx + q[0] * sig), oy = J * (gsy + q[1] * sig), oz = J * (gsz + q[2] * sig);
+        const double *q = jv + it;
+        double ox = J * (gsx + q[0] * sig), oy = J * (gsy + q[jvs] * sig), oz = J * (gsz + q[2 * jvs] * sig);
         if (a.pdf) {
           const double f = 2.0 * sig * J;
           ox *= f; oy *= f; oz *= f;

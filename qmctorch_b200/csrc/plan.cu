@@ -176,6 +176,16 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   S.radial_type = s->radial_type; S.use_jee = s->use_jee; S.use_jen = s->use_jen;
   S.gram_fma = s->gram_fma;
   S.jee_w = s->jee_w; S.jen_w = s->jen_w;
+  {
+    // degree-11 Chebyshev-economised exp on [-ln2/2, ln2/2] (mpmath.chebyfit, max error 3.2e-18),
+    // highest degree first; then log2(e), the 1.5*2^52 rounding constant, -ln2 split hi/lo
+    const double c[16] = {0x1.af631d0059becp-26, 0x1.28b4057f44145p-22, 0x1.71ddf5749d126p-19,
+                          0x1.a01991ac8730ap-16, 0x1.a01a01b14378fp-13, 0x1.6c16c187fbe02p-10,
+                          0x1.111111110f225p-7,  0x1.555555554f0cfp-5,  0x1.555555555555ap-3,
+                          0x1.0000000000011p-1,  1.0, 1.0, 1.4426950408889634, 6755399441055744.0,
+                          -0x1.62e42fee00000p-1, -0x1.a39ef35793c76p-33};
+    for (int i = 0; i < 16; ++i) S.expc[i] = c[i];
+  }
   // nuclear repulsion, wf_base.py:97-116
   double vnn = 0.0;
   for (int a = 0; a < s->natom - 1; ++a)
@@ -212,6 +222,8 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
       hd.push_back(j < S.nmu ? s->mo[(size_t)a * s->nmo + used[j]] : 0.0);
   S.o_ci = (int)hd.size();
   for (int c = 0; c < s->nconf; ++c) hd.push_back(s->ci[c]);
+  S.o_fnorm = (int)hd.size();
+  for (int i = 0; i < s->nbas; ++i) hd.push_back(s->bas_norm[i]);
   // ---- packed shell program: per shell a header record {nprim, ngroup | -}, then nprim records
   // {alpha, coef (, n as third field in the next record for gto/sto)}, then ngroup records
   // {kk | type<<24, ao | scale}.  A "P" group (type 1) stands for three consecutive AOs x,y,z
@@ -323,6 +335,13 @@ static int upload(qmcb_plan *p) {
   if ((e = cudaMemcpy(p->d_dbl, p->hd.data(), nd, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpy(p->d_int, p->hi.data(), ni, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpy(p->d_mo_full, p->mo_full.data(), nm, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  size_t nt = p->bwd_tiles.size() * sizeof(int);
+  if (nt > p->cap_bwd_tiles) {
+    if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
+    if ((e = cudaMalloc(&p->d_bwd_tiles, nt)) != cudaSuccess) return (int)e;
+    p->cap_bwd_tiles = nt;
+  }
+  if (nt && (e = cudaMemcpy(p->d_bwd_tiles, p->bwd_tiles.data(), nt, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   p->sys.dblob = p->d_dbl;
   p->sys.iblob = p->d_int;
   return 0;
@@ -348,6 +367,7 @@ extern "C" int qmcb_plan_create(const qmcb_system *sys, int device, qmcb_plan **
   }
   int rc = qmcb_build_tables(sys, p);
   if (rc == 0) rc = qmcb_choose_launch(p);
+  if (rc == 0) rc = qmcb_choose_backward(p);
   if (rc == 0 && device >= 0) {
     rc = upload(p);
     if (rc) qmcb_set_error(std::string("plan upload: ") + cudaGetErrorString((cudaError_t)rc));
@@ -362,6 +382,7 @@ extern "C" int qmcb_plan_update(qmcb_plan *p, const qmcb_system *sys) {
   if (p->device >= 0) cudaSetDevice(p->device);
   int rc = qmcb_build_tables(sys, p);
   if (rc == 0) rc = qmcb_choose_launch(p);
+  if (rc == 0) rc = qmcb_choose_backward(p);
   if (rc == 0 && p->device >= 0) {
     rc = upload(p);
     if (rc) qmcb_set_error(std::string("plan upload: ") + cudaGetErrorString((cudaError_t)rc));
@@ -375,6 +396,7 @@ extern "C" void qmcb_plan_destroy(qmcb_plan *p) {
   if (p->d_dbl) cudaFree(p->d_dbl);
   if (p->d_int) cudaFree(p->d_int);
   if (p->d_mo_full) cudaFree(p->d_mo_full);
+  if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
   delete p;
 }
 
@@ -391,6 +413,9 @@ extern "C" int qmcb_plan_info(const qmcb_plan *p, int what) {
     case 7: return p->cfg_eloc.threads;
     case 8: return p->cfg_eloc.smem;
     case 9: return p->cfg_psi.tw;
+    case 10: return p->bwd.tw;
+    case 11: return p->bwd.smem;
+    case 12: return p->bwd.ntile_mo + p->bwd.ntile_ao;
     default: return QMCB_EINVAL;
   }
 }

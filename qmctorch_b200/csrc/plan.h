@@ -42,9 +42,13 @@ struct DevSys {
   int o_cid;     // [nconf]
   int o_pflat;   // per shell: [nprim_s][ncomp_s] flat primitive index; start at o_pfo[s]
   int o_pfo;     // [nshell+1]
+  int o_fnorm;   // dblob: [nbas] norm of each flat primitive (gradient post-processing)
   // packed "shell program" walked by the hot loops: 16-byte records (double2), see plan.cu
   int o_stream;  // offset into dblob (doubles, even)
   int nrec;      // number of 16-byte records
+  // exp() polynomial + range-reduction constants.  Kernel parameters live in constant bank 0,
+  // which DFMA can take as a direct operand: no UMOV pairs / LDC to materialise 64-bit immediates.
+  double expc[16];
 };
 
 struct LaunchCfg {
@@ -68,6 +72,17 @@ struct qmcb_plan {
   int sm_count = 148;
   int smem_optin = 227 * 1024;
   LaunchCfg cfg_psi{}, cfg_eloc{}, cfg_grad{};
+  // backward (parameter gradients): contraction tiles over walker rows, see backward.cu
+  struct BwdCfg {
+    int tw = 0, rows = 0, threads = 0, smem = 0, lu_conc = 0;
+    int lda = 0, ldg = 0, ldx = 0, ppad = 0;      // leading dimensions (doubles); ppad = nprim padded to 8
+    int ntile_mo = 0, ntile_ao = 0;              // 8x8 output tiles
+    int nslot = 0;                               // doubles per CTA partial
+    int grid = 0;
+  } bwd;
+  std::vector<int> bwd_tiles;                    // [ntile][2] (row block, col block) ; MO first, then AO
+  int *d_bwd_tiles = nullptr;
+  size_t cap_bwd_tiles = 0;
   // full MO matrix for the operator-level entry point
   double *d_mo_full = nullptr;
   size_t cap_mo_full = 0;
@@ -79,3 +94,4 @@ struct qmcb_plan {
 void qmcb_set_error(const std::string &msg);
 int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p);   // host grouping -> hd/hi/sys
 int qmcb_choose_launch(qmcb_plan *p);
+int qmcb_choose_backward(qmcb_plan *p);
