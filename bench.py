@@ -48,6 +48,11 @@ def algorithmic_flops(mol, wf, info):
     return ao + mo + bkin + jast + slater + 4 * wf.nci + 10
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the dominant
+# kernel (profiles/r1_fused_ncu_raw.csv), bytes per launch, keyed by (workload, walkers)
+NCU_TRAFFIC = {("lih", 1_000_000): 96.078080e6 + 5.073408e6}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -118,12 +123,13 @@ def cpu_reference_run(key, nsample, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lih", choices=sorted(WORKLOADS))
     ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--therm", type=int, default=100, help="Metropolis thermalisation moves per ensemble")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +184,7 @@ def main():
     torch.manual_seed(1234 + rank)
     ens = []
     for b in range(NBUF):
-        s = Metropolis(nwalkers=wpg, nstep=100, step_size=step_size, nelec=wf.nelec, ndim=3,
+        s = Metropolis(nwalkers=wpg, nstep=args.therm, step_size=step_size, nelec=wf.nelec, ndim=3,
                        init=mol.domain("normal"), move={"type": "all-elec", "proba": "normal"}, cuda=True,
                        seed=1000 * rank + b, keep_on_device=True)
         ens.append(s(wf.pdf, with_tqdm=False).detach().contiguous())
@@ -306,7 +312,7 @@ def main():
         "roofline": {"bound": "fp64", "kernel": "fused_kernel<MODE_ELOC>", "achieved": achieved_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                      "peak_source": "own DFMA probe (qmcb_fp64_probe) on this GPU; MEASURED_PEAKS.json has no FP64 entry",
-                     "flops_per_eval": F, "kernel_ms": kern_ms, "traffic": None,
+                     "flops_per_eval": F, "kernel_ms": kern_ms, "traffic": NCU_TRAFFIC.get((args.workload, W)),
                      "hbm": {"achieved_gbs": W * bytes_per_eval / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "bytes_per_eval": bytes_per_eval,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

@@ -273,6 +273,7 @@ def _manual_grads(wf, pos):
     solver = Solver(wf=wf, sampler=sampler, optimizer=opt)
     solver.configure(track=["local_energy"], loss="energy", grad="manual")
     opt.zero_grad()
+    wf.ao.bas_coeffs.grad = None      # plain tensor, not reached by zero_grad (solver.py:119-120)
     solver.evaluate_grad_manual(pos)
     out = {"mo_modifier": wf.mo.mo_modifier.grad, "ci": wf.fc.weight.grad, "bas_exp": wf.ao.bas_exp.grad,
            "bas_coeffs": wf.ao.bas_coeffs.grad}
@@ -330,7 +331,8 @@ def test_solver_optimisation_lowers_energy_and_matches_oracle_step():
                      resampling={"mode": "update", "resample_every": 1, "nstep_update": 30})
     assert not wf.fc.weight.requires_grad and not wf.ao.bas_exp.requires_grad
     obs = solver.run(6, tqdm=False)
-    assert len(obs.energy) == 7 and len(obs.local_energy) == 7
+    # initial sampling stores the energy only (solver_base.py:192-201), then one entry per epoch
+    assert len(obs.energy) == 7 and len(obs.local_energy) == 6
     assert all(np.isfinite(obs.energy))
     assert wf.ao.bas_exp.grad is None and wf.mo.mo_modifier.grad is not None
     assert np.mean(obs.energy[-2:]) < obs.energy[0] + 0.02          # energy does not go up
