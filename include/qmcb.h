@@ -66,7 +66,15 @@ typedef struct {
   int32_t use_jen;  double jen_w;   /* e-n Pade Jastrow + its weight            */
   int32_t gram_fma;            /* 0: r_ij dot product unfused (ATen small-bmm path, Ne<=11),
                                   1: fma chain (MKL path); electron_electron_distance.py:177-190 */
+  /* three-body Boys-Handy e-e-n Jastrow (elec_elec_nuclei/kernels/boys_handy_jastrow_kernel.py:8-93),
+     exponents 1: K = sum_mu c_mu f_mu(r_iA) f_mu(r_jA) g_mu(r_ij), f = a r/(1+b r), g = a' r/(1+b' r) */
+  int32_t een_nterm;           /* 0: term absent; <= QMCB_EEN_MAXTERM                   */
+  const double *een_num;       /* [2,nterm] weight_num   (row 0: a, row 1: a')          */
+  const double *een_denom;     /* [2,nterm] weight_denom (row 0: b, row 1: b')          */
+  const double *een_fc;        /* [nterm]   fc.weight                                   */
 } qmcb_system;
+
+#define QMCB_EEN_MAXTERM 8
 
 int         qmcb_abi_version(void);
 const char *qmcb_last_error(void);
@@ -120,12 +128,13 @@ int qmcb_metropolis_step(const qmcb_plan *plan, double *pos, double *fx, int64_t
  * replaces the autograd backward in Solver.evaluate_grad_manual (solver/solver.py:414-429).
  * Any output pointer may be NULL.  Outputs are OVERWRITTEN (caller accumulates into .grad).
  *   g_mo [nao,nmo] (w.r.t. the effective weights mo_scf*mo_modifier), g_ci [nconf],
- *   g_bas_exp [nbas], g_bas_coeffs [nbas], g_jee_w [1], g_jen_w [1];
+ *   g_bas_exp [nbas], g_bas_coeffs [nbas], g_jee_w [1], g_jen_w [1],
+ *   g_een [5*nterm] = weight_num [2,nterm] | weight_denom [2,nterm] | fc [nterm];
  *   workspace: device scratch of qmcb_backward_workspace_bytes(plan, W) bytes. */
 int64_t qmcb_backward_workspace_bytes(const qmcb_plan *plan, int64_t W);
 int qmcb_psi_backward(const qmcb_plan *plan, const double *pos, const double *weight, int64_t W,
                       double *g_mo, double *g_ci, double *g_bas_exp, double *g_bas_coeffs,
-                      double *g_jee_w, double *g_jen_w, void *workspace, void *stream);
+                      double *g_jee_w, double *g_jen_w, double *g_een, void *workspace, void *stream);
 
 /* [sum E, sum E^2, count of finite, count of non-finite] -> out[4]; deterministic two-stage
  * reduction.  replaces torch.mean/var in SolverBase.single_point (solver/solver_base.py:371),
@@ -147,7 +156,7 @@ int qmcb_mo(const qmcb_plan *plan, const double *x, int64_t rows, double *out, v
 /* Jastrow factor and derivatives, product of the configured terms
  * (jastrow_factor_electron_electron.py:124-260, jastrow_factor_electron_nuclei.py:60-161,
  * combine_jastrow.py:33-195): J [W], dJ [W,3,nelec], d2J [W,nelec] (dJ, d2J may be NULL).
- * which: 0 product of all, 1 e-e only, 2 e-n only. */
+ * which: 0 product of all, 1 e-e only, 2 e-n only, 3 e-e-n only. */
 int qmcb_jastrow(const qmcb_plan *plan, const double *pos, int64_t W, int which,
                  double *J, double *dJ, double *d2J, void *stream);
 

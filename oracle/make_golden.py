@@ -26,6 +26,8 @@ from qmctorch.wavefunction.jastrows.elec_elec import (  # noqa: E402
     JastrowFactor as JastrowEE, PadeJastrowKernel as PadeEE)
 from qmctorch.wavefunction.jastrows.elec_nuclei import (  # noqa: E402
     JastrowFactor as JastrowEN, PadeJastrowKernel as PadeEN)
+from qmctorch.wavefunction.jastrows.elec_elec_nuclei import (  # noqa: E402
+    JastrowFactor as JastrowEEN, BoysHandyJastrowKernel as BoysHandy)
 
 import sj_oracle as orc  # noqa: E402
 from qmctorch_b200.molecules import fixture_molecule  # noqa: E402
@@ -44,6 +46,9 @@ CASES = [
     ("h2o_ground", "h2o", "ground_state", "ee", 96, 100, 0.15, "atomic"),
     ("h2o_cas44", "h2o", "cas(4,4)", "ee+en", 48, 100, 0.15, "atomic"),
     ("c4h6_ground", "c4h6", "ground_state", "ee", 16, 60, 0.05, "atomic"),
+    # three-body Boys-Handy term (BASELINE config 4: CAS + e-e-n Jastrow)
+    ("lih_sd22_een3", "lih", "single_double(2,2)", "ee+en+een", 96, 100, 0.3, "normal"),
+    ("h2o_cas44_een", "h2o", "cas(4,4)", "ee+een", 32, 100, 0.15, "atomic"),
 ]
 
 
@@ -66,8 +71,12 @@ def build(case):
         j = "default"
     elif jast is None:
         j = None
-    else:
+    elif jast == "ee+en":
         j = [JastrowEE(mol, PadeEE), JastrowEN(mol, PadeEN)]
+    elif jast == "ee+en+een":
+        j = [JastrowEE(mol, PadeEE), JastrowEN(mol, PadeEN), JastrowEEN(mol, BoysHandy)]
+    else:
+        j = [JastrowEE(mol, PadeEE), JastrowEEN(mol, BoysHandy)]
     wf = SlaterJastrow(mol, configs=configs, jastrow=j, include_all_mo=True)
     return mol, wf
 
@@ -93,22 +102,39 @@ def main(only=None):
                 wf.fc.weight.add_(0.2 * (torch.rand(wf.fc.weight.shape, generator=g) - 0.5))
             if jast == "ee":
                 wf.jastrow.jastrow_kernel.weight.fill_(0.8)
-            elif jast == "ee+en":
+            elif jast is not None:
                 wf.jastrow.jastrow_terms[0].jastrow_kernel.weight.fill_(0.8)
-                wf.jastrow.jastrow_terms[1].jastrow_kernel.weight.data.fill_(1.3)
+                if "+en" in jast:
+                    wf.jastrow.jastrow_terms[1].jastrow_kernel.weight.data.fill_(1.3)
+                if jast.endswith("een"):
+                    bh = wf.jastrow.jastrow_terms[-1].jastrow_kernel
+                    bh.weight_num.data.copy_(0.05 + 0.3 * torch.rand(1, 2, 5, generator=g))
+                    bh.weight_denom.data.copy_(0.5 + torch.rand(1, 2, 5, generator=g))
+                    bh.fc.weight.data.copy_(torch.rand(1, 5, generator=g) - 0.5)
 
+        has_en = jast is not None and "+en" in jast
+        has_een = jast is not None and jast.endswith("een")
         P = orc.make_params(mol, wf.configs,
                             jastrow_weight=None if jast is None else 0.8,
-                            en_weight=1.3 if jast == "ee+en" else None)
+                            en_weight=1.3 if has_en else None)
+        if has_een:
+            bh = wf.jastrow.jastrow_terms[-1].jastrow_kernel
+            P.een = dict(num=bh.weight_num.detach().clone(), denom=bh.weight_denom.detach().clone(),
+                         fc=bh.fc.weight.detach().clone())
         P.mo_modifier = wf.mo.mo_modifier.detach().clone()
         P.ci = wf.fc.weight.detach().clone()
 
         out = dict(pos=pos.numpy(), mo_modifier=P.mo_modifier.numpy(), ci=P.ci.numpy(),
                    cfg_up=wf.configs[0].numpy(), cfg_down=wf.configs[1].numpy(),
                    jw=np.array([0.8 if jast else np.nan]),
-                   enw=np.array([1.3 if jast == "ee+en" else np.nan]))
-        need_grad = jast == "ee+en"   # CombineJastrow flags requires_autograd
-        with torch.no_grad():
+                   enw=np.array([1.3 if has_en else np.nan]))
+        if has_een:
+            out.update(bh_num=P.een["num"].numpy(), bh_denom=P.een["denom"].numpy(), bh_fc=P.een["fc"].numpy())
+        # the reference differentiates the three-body term by autograd: positions must carry grad
+        pos_in = pos
+        if has_een:
+            pos = pos.clone().requires_grad_(True)
+        with (torch.enable_grad() if has_een else torch.no_grad()):
             ao, dao, d2ao = wf.ao(pos, derivative=[0, 1, 2])
             psi = wf(pos)
             if jast is not None:
@@ -117,6 +143,10 @@ def main(only=None):
             eloc = wf.local_energy(pos)
             gpsi = wf.gradients_jacobi(pos)
             gpdf = wf.gradients_jacobi(pos, pdf=True)
+        pos = pos_in
+        ao, dao, d2ao, psi, ekin, eloc, gpsi, gpdf = [t.detach() for t in (ao, dao, d2ao, psi, ekin, eloc, gpsi, gpdf)]
+        if jast is not None:
+            J, dJ, d2J = J.detach(), dJ.detach(), d2J.detach()
         # --- oracle vs reference
         o_ao, o_dao, o_d2ao = orc.ao_all(P, pos)
         o_psi = orc.psi(P, pos)
@@ -142,14 +172,19 @@ def main(only=None):
         solver = Solver(wf=wf, sampler=sampler, optimizer=opt)
         solver.configure(track=["local_energy"], loss="energy", grad="manual")
         opt.zero_grad()
-        solver.evaluate_grad_manual(pos.clone())
+        solver.evaluate_grad_manual(pos.clone().requires_grad_(True) if has_een else pos.clone())
         ref_g = dict(mo_modifier=wf.mo.mo_modifier.grad.clone(), ci=wf.fc.weight.grad.clone(),
                      bas_exp=wf.ao.bas_exp.grad.clone(), bas_coeffs=wf.ao.bas_coeffs.grad.clone())
         if jast == "ee":
             ref_g["jastrow_weight"] = wf.jastrow.jastrow_kernel.weight.grad.clone()
-        elif jast == "ee+en":
+        elif jast is not None:
             ref_g["jastrow_weight"] = wf.jastrow.jastrow_terms[0].jastrow_kernel.weight.grad.clone()
-        names = tuple(ref_g.keys()) + (("en_weight",) if jast == "ee+en" else ())
+        if has_een:
+            bh = wf.jastrow.jastrow_terms[-1].jastrow_kernel
+            ref_g["een_num"] = bh.weight_num.grad.clone()
+            ref_g["een_denom"] = bh.weight_denom.grad.clone()
+            ref_g["een_fc"] = bh.fc.weight.grad.clone()
+        names = tuple(ref_g.keys()) + (("en_weight",) if has_en else ())
         og, _ = orc.param_grads(P, pos, names=names)
         for k, v in ref_g.items():
             if k == "ci" and wf.nci == 1:

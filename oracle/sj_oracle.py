@@ -92,6 +92,8 @@ def make_params(mol, configs, jastrow_weight=1.0, en_weight=None):
     p.ci[0, 0] = 1.0
     p.jastrow_weight = None if jastrow_weight is None else torch.tensor([jastrow_weight], dtype=F64)
     p.en_weight = None if en_weight is None else torch.tensor([en_weight], dtype=F64)
+    # three-body Boys-Handy term: dict(num [1,2,nterm], denom [1,2,nterm], fc [1,nterm]) or None
+    p.een = None
     return p
 
 
@@ -320,6 +322,58 @@ def jastrow_en(p, pos, derivative=True):
     return J, dJ, d2J
 
 
+def _een_kernel(p, r):
+    """Boys-Handy kernel, elec_elec_nuclei/kernels/boys_handy_jastrow_kernel.py:50-93 with exponents 1:
+    r [..., 3] = (r_iA, r_jA, r_ij) -> sum_mu c_mu f_mu(r_iA) f_mu(r_jA) g_mu(r_ij)."""
+    num, den, fc = p.een["num"], p.een["denom"], p.een["fc"]
+    rep = torch.tensor([2, 1])
+    shp = list(r.shape)[:-1] + [1]
+    x = r.reshape(-1, 3, 1)
+    wn = num.repeat_interleave(rep, dim=1)
+    wd = den.repeat_interleave(rep, dim=1)
+    x = (wn * x) / (1.0 + wd * x)
+    x = x ** torch.ones(3, num.shape[-1], dtype=F64)
+    x = x.prod(1)
+    return (x @ fc.t()).reshape(*shp)
+
+
+def _een_logj(p, pos):
+    """sum_A sum_{i<j} K, distances assembled like jastrow_factor_electron_electron_nuclei.py:126-143
+    (Gram-form r_ij and r_iA)."""
+    W = pos.shape[0]
+    Ne = p.nelec
+    pos3 = pos.view(W, Ne, 3)
+    row, col = _tri_up(Ne)
+    ree = ee_distance_gram(pos3)[:, row, col]                          # [W,Np]
+    nrm = (pos3 ** 2).sum(-1).unsqueeze(-1)
+    nrm_at = (p.atom_coords ** 2).sum(-1).unsqueeze(-1).T
+    ren = torch.sqrt(nrm + nrm_at - 2.0 * pos3 @ p.atom_coords.T)      # [W,Ne,Nat]
+    nat = p.atom_coords.shape[0]
+    r = torch.stack((ren[:, row, :].transpose(1, 2), ren[:, col, :].transpose(1, 2),
+                     ree.unsqueeze(1).expand(W, nat, ree.shape[1])), dim=-1)   # [W,Nat,Np,3]
+    return _een_kernel(p, r).reshape(W, -1).sum(-1)
+
+
+def jastrow_een(p, pos, derivative=True):
+    """Three-body factor exp(sum K) with gradient / per-electron Laplacian by autograd, which is how
+    the reference obtains them (jastrow_factor_electron_electron_nuclei.py:188-251,385-439)."""
+    if not derivative:
+        return torch.exp(_een_logj(p, pos)).unsqueeze(-1)
+    W = pos.shape[0]
+    Ne = p.nelec
+    with torch.enable_grad():
+        x = pos.detach().clone().requires_grad_(True)
+        J = torch.exp(_een_logj(p, x))
+        (jac,) = torch.autograd.grad(J.sum(), x, create_graph=True)
+        hess = torch.zeros_like(jac)
+        for i in range(x.shape[1]):
+            (h,) = torch.autograd.grad(jac[:, i].sum(), x, retain_graph=True)
+            hess[:, i] = h[:, i]
+    dJ = jac.detach().view(W, Ne, 3).permute(0, 2, 1).contiguous()      # [W,3,Ne]
+    d2J = torch.nan_to_num(hess.detach().view(W, Ne, 3).sum(2), nan=0.0)
+    return J.detach().unsqueeze(-1), dJ, d2J
+
+
 def jastrow_all(p, pos):
     """Product of the active Jastrow terms, jastrows/combine_jastrow.py:33-195.
     Returns J [W,1], dJ [W,3,Ne], d2J [W,Ne]; None when no Jastrow is configured."""
@@ -328,14 +382,15 @@ def jastrow_all(p, pos):
         terms.append(jastrow_ee(p, pos))
     if p.en_weight is not None:
         terms.append(jastrow_en(p, pos))
+    if getattr(p, "een", None) is not None:
+        terms.append(jastrow_een(p, pos))
     if not terms:
         return None
-    if len(terms) == 1:
-        return terms[0]
-    (Ja, dJa, d2Ja), (Jb, dJb, d2Jb) = terms
-    J = Ja * Jb
-    dJ = dJa * Jb.unsqueeze(-1) + dJb * Ja.unsqueeze(-1)
-    d2J = d2Ja * Jb + d2Jb * Ja + 2 * (dJa * dJb).sum(1)
+    J, dJ, d2J = terms[0]
+    for (Jb, dJb, d2Jb) in terms[1:]:      # product rule, pairwise
+        d2J = d2J * Jb + d2Jb * J + 2 * (dJ * dJb).sum(1)
+        dJ = dJ * Jb.unsqueeze(-1) + dJb * J.unsqueeze(-1)
+        J = J * Jb
     return J, dJ, d2J
 
 
@@ -346,6 +401,9 @@ def jastrow_value(p, pos):
     if p.en_weight is not None:
         Jn = jastrow_en(p, pos, derivative=False)
         J = Jn if J is None else J * Jn
+    if getattr(p, "een", None) is not None:
+        Jt = jastrow_een(p, pos, derivative=False)
+        J = Jt if J is None else J * Jt
     return J
 
 
@@ -514,6 +572,13 @@ def param_grads(p, pos, eloc=None, names=("jastrow_weight", "mo_modifier", "ci",
             eloc = local_energy(p, pos)
     leaves = {}
     for nme in names:
+        if nme.startswith("een_"):
+            if p.een is None:
+                continue
+            t = p.een[nme[4:]].detach().clone().requires_grad_(True)
+            p.een[nme[4:]] = t
+            leaves[nme] = t
+            continue
         t = getattr(p, nme)
         if t is None:
             continue
@@ -527,7 +592,10 @@ def param_grads(p, pos, eloc=None, names=("jastrow_weight", "mo_modifier", "ci",
     val.backward(weight)
     out = {k: v.grad.detach().clone() for k, v in leaves.items()}
     for k, v in leaves.items():
-        setattr(p, k, v.detach())
+        if k.startswith("een_"):
+            p.een[k[4:]] = v.detach()
+        else:
+            setattr(p, k, v.detach())
     return out, eloc
 
 

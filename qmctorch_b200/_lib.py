@@ -24,6 +24,7 @@ class QmcbSystem(C.Structure):
         ("nconf", C.c_int32), ("cfg_up", C.c_void_p), ("cfg_down", C.c_void_p), ("ci", C.c_void_p),
         ("use_jee", C.c_int32), ("jee_w", C.c_double), ("use_jen", C.c_int32), ("jen_w", C.c_double),
         ("gram_fma", C.c_int32),
+        ("een_nterm", C.c_int32), ("een_num", C.c_void_p), ("een_denom", C.c_void_p), ("een_fc", C.c_void_p),
     ]
 
 
@@ -45,7 +46,7 @@ _SIGS = {
                                        C.c_double, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "qmcb_backward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
-    "qmcb_psi_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 8),
+    "qmcb_psi_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 9),
     "qmcb_stats_workspace_bytes": (C.c_int64, [C.c_int64]),
     "qmcb_energy_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qmcb_ao": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
@@ -109,6 +110,11 @@ class SystemArrays:
             setattr(s, k, int(kw[k]))
         s.jee_w = float(kw["jee_w"])
         s.jen_w = float(kw["jen_w"])
+        s.een_nterm = int(kw.get("een_nterm", 0))
+        for k in ("een_num", "een_denom", "een_fc"):
+            a = _np(kw.get(k, np.zeros(1)), np.float64)
+            self.keep[k] = a
+            setattr(s, k, a.ctypes.data)
         for k in ("atom_coords", "atomic_number", "bas_exp", "bas_coeffs", "bas_norm", "mo", "ci"):
             a = _np(kw[k], np.float64)
             self.keep[k] = a

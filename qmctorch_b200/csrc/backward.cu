@@ -51,8 +51,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Jastrow exponent of one electron (pairs j>e and all nuclei) and d/dw of it
+// een: d ln J / d(c, a, a', b, b') of every Boys-Handy term, pairs j>e: een[(5*m + k) * stride]
 __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, const double *sp, int e,
-                                                 double &ks, double &dkee, double &dken) {
+                                                 double &ks, double &dkee, double &dken, double *een,
+                                                 int stride) {
   const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
   const double ni = __dadd_rn(__dadd_rn(__dmul_rn(xi, xi), __dmul_rn(yi, yi)), __dmul_rn(zi, zi));
   ks = 0.0; dkee = 0.0; dken = 0.0;
@@ -82,6 +84,35 @@ __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, 
       const double den = 1.0 / (1.0 + wn * r);
       ks += r * den;
       dken -= r * r * den * den;
+    }
+  }
+  const int nt = S.een_nterm;
+  if (nt > 0) {
+    for (int k = 0; k < 5 * nt; ++k) een[k * stride] = 0.0;
+    for (int j = e + 1; j < S.nelec; ++j) {
+      const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
+      const double nj = gram_norm(xj, yj, zj);
+      const double rej = sqrt(gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, nj));
+      for (int A = 0; A < S.natom; ++A) {
+        const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+        const double na = gram_norm(xa, ya, za);
+        const double rE = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, na));
+        const double rJ = sqrt(gram_d2_en(xj, yj, zj, nj, xa, ya, za, na));
+        for (int m = 0; m < nt; ++m) {
+          const double a = S.een_a[m], b = S.een_b[m], a2 = S.een_a2[m], b2 = S.een_b2[m], c = S.een_c[m];
+          const double dE = 1.0 / (1.0 + b * rE), dJ = 1.0 / (1.0 + b * rJ), dG = 1.0 / (1.0 + b2 * rej);
+          const double uE = rE * dE, uJ = rJ * dJ, uG = rej * dG;
+          const double FE = a * uE, FJ = a * uJ, G = a2 * uG;
+          const double P = FE * FJ * G;
+          ks += c * P;
+          double *q = een + 5 * m * stride;
+          q[0] += P;                                        // d/dc
+          q[stride] += c * (uE * FJ + FE * uJ) * G;         // d/da
+          q[2 * stride] += c * FE * FJ * uG;                // d/da'
+          q[3 * stride] -= c * P * (uE + uJ);               // d/db   (dF/db = -F r/(1+b r))
+          q[4 * stride] -= c * P * uG;                      // d/db'
+        }
+      }
     }
   }
 }
@@ -148,16 +179,18 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
   const int conc = a.lu_conc;
   // work area
   double *spos = ws;                          // [TW][3Ne]
-  double *jv = spos + TW * ne3;               // [3][TW*Ne]  ks, dkee, dken
-  double *sao = jv + 3 * TW * Ne;             // [rows][lda]
+  const int njv = 3 + 5 * S.een_nterm;
+  double *jv = spos + TW * ne3;               // [njv][TW*Ne]  ks, dkee, dken, een derivatives
+  double *sao = jv + njv * TW * Ne;           // [rows][lda]
   double *su = sao + rows * lda;              // [rows][lda]
   double *sg = su + rows * lda;               // [rows][ldg]
   double *sx = sg + rows * ldg;               // [rows][ldx]
   double *smo = sx + rows * ldx;              // [rows][nmup]
   double *sdet = smo + rows * nmup;           // [TW][nun]
   double *wj = sdet + TW * nun;               // [TW][4]  weight*J, Sigma, weight*psi
-  double *cacc = wj + TW * 4;                 // [nconf + 2]
-  double *scr = cacc + ((S.nconf + 2 + 1) & ~1);   // inverses [inv_per][conc]
+  const int nsc = S.nconf + 2 + 5 * S.een_nterm;   // scalar-type outputs: CI, Jastrow weights, e-e-n
+  double *cacc = wj + TW * 4;                 // [nsc]
+  double *scr = cacc + ((nsc + 1) & ~1);      // inverses [inv_per][conc]
   int *stiles = reinterpret_cast<int *>(scr + (size_t)inv_per * conc);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
@@ -165,7 +198,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
   for (int i = tid; i < rows * lda; i += nthr) { sao[i] = 0.0; su[i] = 0.0; }
   for (int i = tid; i < rows * ldg; i += nthr) sg[i] = 0.0;
   for (int i = tid; i < rows * ldx; i += nthr) sx[i] = 0.0;
-  for (int i = tid; i < S.nconf + 2; i += nthr) cacc[i] = 0.0;
+  for (int i = tid; i < nsc; i += nthr) cacc[i] = 0.0;
   double c0[BWD_MAXT], c1[BWD_MAXT];
 #pragma unroll
   for (int t = 0; t < BWD_MAXT; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
@@ -183,7 +216,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       const int wl = it / Ne, e = it - wl * Ne;
       const double *sp = spos + wl * ne3;
       double ks, dkee, dken;
-      jastrow_value_dw(S, T, sp, e, ks, dkee, dken);
+      jastrow_value_dw(S, T, sp, e, ks, dkee, dken, jv + 3 * TW * Ne + it, TW * Ne);
       jv[it] = ks; jv[TW * Ne + it] = dkee; jv[2 * TW * Ne + it] = dken;
       backward_row(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda, sx + it * ldx,
                    a.ppad, a.want_ao != 0);
@@ -231,7 +264,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       for (int c = 0; c < S.nconf; ++c) sig += T.ci[c] * dd[T.ciu[c]] * dd[S.nuu + T.cid[c]];
       double ks = 0.0;
       for (int e = 0; e < Ne; ++e) ks += jv[wl * Ne + e];
-      const double J = (S.use_jee || S.use_jen) ? exp_clamped(S, ks) : 1.0;
+      const double J = (S.use_jee || S.use_jen || S.een_nterm > 0) ? exp_clamped(S, ks) : 1.0;
       const double wgt = a.weight[w0 + wl];
       wj[wl * 4] = wgt * J; wj[wl * 4 + 1] = sig; wj[wl * 4 + 2] = wgt * J * sig;
     }
@@ -269,7 +302,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       }
     }
     // ---- B5b: CI and Jastrow-weight sums (warp-striped, fixed order)
-    for (int c = warp; c < S.nconf + 2; c += nwarp) {
+    for (int c = warp; c < nsc; c += nwarp) {
       double v = 0.0;
       if (c < S.nconf) {
         const int iu = T.ciu[c], id = S.nuu + T.cid[c];
@@ -320,13 +353,13 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       out[t * 64 + row * 8 + col + 1] = v1;
     }
   }
-  for (int i = tid; i < S.nconf + 2; i += nthr) out[ntile * 64 + i] = cacc[i];
+  for (int i = tid; i < nsc; i += nthr) out[ntile * 64 + i] = cacc[i];
 }
 
 // Second stage: sum the CTA partials in index order and scatter to the caller's layouts.
 __global__ void backward_reduce(const DevSys S, const double *partial, int ngrid, int nslot, const int *tiles,
                                 int ntile_mo, int ntile_ao, int ppad, int nmo_full, double *g_mo, double *g_ci,
-                                double *g_exp, double *g_coef, double *g_jee, double *g_jen) {
+                                double *g_exp, double *g_coef, double *g_jee, double *g_jen, double *g_een) {
   const int ntile = ntile_mo + ntile_ao;
   const double *db = S.dblob;
   const int *ib = S.iblob;
@@ -365,7 +398,13 @@ __global__ void backward_reduce(const DevSys S, const double *partial, int ngrid
       const int c = i - ntile * 64;
       if (c < S.nconf) { if (g_ci) g_ci[c] = v; }
       else if (c == S.nconf) { if (g_jee) g_jee[0] = v; }
-      else if (g_jen) g_jen[0] = v;
+      else if (c == S.nconf + 1) { if (g_jen) g_jen[0] = v; }
+      else if (g_een) {
+        // slot (5*m + k), k = c, a, a', b, b'  ->  [num(2,nt) | denom(2,nt) | fc(nt)]
+        const int idx = c - S.nconf - 2, m = idx / 5, k = idx - 5 * m, nt = S.een_nterm;
+        const int dst = k == 0 ? 4 * nt + m : (k == 1 ? m : (k == 2 ? nt + m : (k == 3 ? 2 * nt + m : 3 * nt + m)));
+        g_een[dst] = v;
+      }
     }
   }
 }
@@ -406,7 +445,7 @@ int qmcb_choose_backward(qmcb_plan *p) {
   for (auto &pr : need) { tl.push_back(pr.first); tl.push_back(pr.second); }
   b.ntile_ao = (int)need.size();
   const int ntile = b.ntile_mo + b.ntile_ao;
-  b.nslot = ntile * 64 + S.nconf + 2;
+  b.nslot = ntile * 64 + S.nconf + 2 + 5 * S.een_nterm;
   const int nun = S.nuu + S.nud;
   const int nmax = S.nup > S.ndown ? S.nup : S.ndown;
   const int inv_per = nmax <= 3 ? nmax * nmax : 2 * nmax * nmax;
@@ -419,9 +458,10 @@ int qmcb_choose_backward(qmcb_plan *p) {
     if (threads < 128) threads = 128;
     if (threads > 512) continue;
     const int conc = tw * nun;
-    size_t d = (size_t)table_doubles(S) + (size_t)tw * 3 * S.nelec + 3 * (size_t)tw * S.nelec +
+    size_t d = (size_t)table_doubles(S) + (size_t)tw * 3 * S.nelec +
+               (size_t)(3 + 5 * S.een_nterm) * tw * S.nelec +
                (size_t)rows * (2 * b.lda + b.ldg + b.ldx + S.nmup) + (size_t)tw * nun + (size_t)tw * 4 +
-               (size_t)((S.nconf + 2 + 1) & ~1) + (size_t)inv_per * conc + (size_t)ntile + 2;
+               (size_t)((S.nconf + 2 + 5 * S.een_nterm + 1) & ~1) + (size_t)inv_per * conc + (size_t)ntile + 2;
     const size_t sm = d * sizeof(double);
     // keep the tile small enough for two CTAs per SM when that is possible with >= 32 rows
     if ((int)sm <= budget && ((int)sm <= 100 * 1024 || rows <= 64)) {
@@ -442,7 +482,8 @@ extern "C" int64_t qmcb_backward_workspace_bytes(const qmcb_plan *p, int64_t) {
 
 extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const double *weight, int64_t W,
                                  double *g_mo, double *g_ci, double *g_bas_exp, double *g_bas_coeffs,
-                                 double *g_jee_w, double *g_jen_w, void *workspace, void *stream) {
+                                 double *g_jee_w, double *g_jen_w, double *g_een, void *workspace,
+                                 void *stream) {
   if (!p || !p->d_dbl || !pos || !weight || !workspace || W <= 0) {
     qmcb_set_error("qmcb_psi_backward: bad arguments");
     return QMCB_EINVAL;
@@ -472,6 +513,6 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
   backward_reduce<<<(b.nslot + 127) / 128, 128, 0, st>>>(p->sys, a.partial, grid, b.nslot, p->d_bwd_tiles, b.ntile_mo,
                                                         b.ntile_ao, b.ppad, p->sys.nmo, g_mo, g_ci, g_bas_exp,
-                                                        g_bas_coeffs, g_jee_w, g_jen_w);
+                                                        g_bas_coeffs, g_jee_w, g_jen_w, g_een);
   return (int)cudaGetLastError();
 }

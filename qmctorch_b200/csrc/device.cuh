@@ -254,6 +254,74 @@ __device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double e
 //      distance/electron_nuclei_distance.py:53-162;  product rule: combine_jastrow.py:116-195;
 // potentials: wf_base.py:49-95.
 // ---------------------------------------------------------------------------------------
+// Gram-form distances exactly as the reference forms them (electron_electron_distance.py:177-190,
+// electron_nuclei_distance.py:153-162)
+__device__ __forceinline__ double gram_norm(double x, double y, double z) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+__device__ __forceinline__ double gram_d2_ee(const DevSys &S, double xi, double yi, double zi, double ni,
+                                             double xj, double yj, double zj, double nj) {
+  double dot;
+  if (S.gram_fma) dot = __fma_rn(zi, zj, __fma_rn(yi, yj, __dmul_rn(xi, xj)));
+  else dot = __dadd_rn(__dadd_rn(__dmul_rn(xi, xj), __dmul_rn(yi, yj)), __dmul_rn(zi, zj));
+  return __dsub_rn(__dadd_rn(ni, nj), __dmul_rn(2.0, dot));
+}
+__device__ __forceinline__ double gram_d2_en(double xi, double yi, double zi, double ni, double xa, double ya,
+                                             double za, double na) {
+  const double dot = __fma_rn(zi, za, __fma_rn(yi, ya, __dmul_rn(xi, xa)));
+  return __dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot));
+}
+
+// Three-body Boys-Handy term for electron e (exponents 1):
+//   ln J = sum_A sum_{i<j} sum_mu c f(r_iA) f(r_jA) g(r_ij),  f = a r/(1+b r),  g = a' r/(1+b' r)
+// adds: ks (pairs j>e), grad_e ln J, lap_e ln J.  The reference differentiates this by autograd
+// (jastrow_factor_electron_electron_nuclei.py:253-300,385-439); the closed forms use
+// |grad r| = 1, lap r = 2/r:  lap_e = F''FG + F'FG 2/r_eA + FFG'' + FFG' 2/r_ej + 2 F'FG' cos(eA,ej).
+template <bool DERIV>
+__device__ __forceinline__ void een_terms(const DevSys &S, const Tab &T, const double *sp, int e, double &gx,
+                                          double &gy, double &gz, double &h, double &ks) {
+  const int nt = S.een_nterm;
+  const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
+  const double ni = gram_norm(xi, yi, zi);
+  for (int j = DERIV ? 0 : e + 1; j < S.nelec; ++j) {
+    if (j == e) continue;
+    const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
+    const double nj = gram_norm(xj, yj, zj);
+    const double rej = sqrt(gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, nj));
+    const double irej = 1.0 / rej;
+    const double ux = (xi - xj) * irej, uy = (yi - yj) * irej, uz = (zi - zj) * irej;
+    for (int A = 0; A < S.natom; ++A) {
+      const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+      const double na = gram_norm(xa, ya, za);
+      const double rE = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, na));
+      const double rJ = sqrt(gram_d2_en(xj, yj, zj, nj, xa, ya, za, na));
+      const double irE = 1.0 / rE;
+      const double vx = (xi - xa) * irE, vy = (yi - ya) * irE, vz = (zi - za) * irE;
+      const double cosv = ux * vx + uy * vy + uz * vz;
+      double s0 = 0, s1 = 0, s3 = 0, sl = 0;   // sum c FFG ; c F'FG ; c FFG' ; laplacian terms
+      for (int m = 0; m < nt; ++m) {
+        const double a = S.een_a[m], b = S.een_b[m], a2 = S.een_a2[m], b2 = S.een_b2[m], c = S.een_c[m];
+        const double dE = 1.0 / (1.0 + b * rE), dJ = 1.0 / (1.0 + b * rJ), dG = 1.0 / (1.0 + b2 * rej);
+        const double FE = a * rE * dE, FJ = a * rJ * dJ, G = a2 * rej * dG;
+        const double cFJ = c * FJ;
+        s0 += cFJ * FE * G;
+        if (DERIV) {
+          const double FE1 = a * dE * dE, FE2 = -2.0 * b * FE1 * dE;
+          const double G1 = a2 * dG * dG, G2 = -2.0 * b2 * G1 * dG;
+          s1 += cFJ * FE1 * G;
+          s3 += cFJ * FE * G1;
+          sl += cFJ * (FE2 * G + FE * G2 + 2.0 * FE1 * G1 * cosv);
+        }
+      }
+      if (j > e) ks += s0;
+      if (DERIV) {
+        gx += s1 * vx + s3 * ux; gy += s1 * vy + s3 * uy; gz += s1 * vz + s3 * uz;
+        h += sl + 2.0 * (s1 * irE + s3 * irej);
+      }
+    }
+  }
+}
+
 struct ElecTerms {
   double gx, gy, gz, lap, ks, ven, vee;
 };
@@ -317,6 +385,7 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
     }
   }
   gx += gnx; gy += gny; gz += gnz;
+  if (S.een_nterm > 0) een_terms<DERIV>(S, T, sp, e, gx, gy, gz, h, ks);
   o.gx = gx; o.gy = gy; o.gz = gz;
   o.lap = h + gx * gx + gy * gy + gz * gz;
   o.ks = ks; o.ven = ven; o.vee = vee;

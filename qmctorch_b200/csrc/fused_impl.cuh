@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
       if (MODE == MODE_ELOC) {
         const double *q = jv + wl * Ne + e;
         const double gx = q[0], gy = q[jvs], gz = q[2 * jvs], lp = q[3 * jvs];
-        const bool uj = S.use_jee || S.use_jen;
+        const bool uj = S.use_jee || S.use_jen || S.een_nterm > 0;
 #pragma unroll
         for (int j = 0; j < MB; ++j) {
           double b = sink.acc[4][j];
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
         const double *q = jv + wl * Ne + e;
         ks += q[4 * jvs]; ven += q[5 * jvs]; vee += q[6 * jvs];
       }
-      const double J = (S.use_jee || S.use_jen) ? exp_clamped(S, ks) : 1.0;
+      const double J = (S.use_jee || S.use_jen || S.een_nterm > 0) ? exp_clamped(S, ks) : 1.0;
       const double psi = J * sig;
       if (MODE == MODE_PSI) {
         a.out0[w0 + wl] = psi;

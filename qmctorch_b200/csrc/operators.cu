@@ -137,14 +137,15 @@ __global__ void __launch_bounds__(256) jastrow_kernel(DevSys S, const double *po
 extern "C" int qmcb_jastrow(const qmcb_plan *p, const double *pos, int64_t W, int which, double *J,
                             double *dJ, double *d2J, void *stream) {
   if (!p || !p->d_dbl || !pos || !J || W < 0 || ((dJ == nullptr) != (d2J == nullptr)) || which < 0 ||
-      which > 2) {
+      which > 3) {
     qmcb_set_error("qmcb_jastrow: bad arguments");
     return QMCB_EINVAL;
   }
   if (W == 0) return 0;
   DevSys S = p->sys;
-  if (which == 1) S.use_jen = 0;
-  if (which == 2) S.use_jee = 0;
+  if (which == 1) { S.use_jen = 0; S.een_nterm = 0; }
+  if (which == 2) { S.use_jee = 0; S.een_nterm = 0; }
+  if (which == 3) { S.use_jee = 0; S.use_jen = 0; }
   const int Ne = S.nelec;
   if (Ne > 256) { qmcb_set_error("qmcb_jastrow: nelec > 256"); return QMCB_EINVAL; }
   const int tw = 256 / Ne;

@@ -176,6 +176,16 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   S.radial_type = s->radial_type; S.use_jee = s->use_jee; S.use_jen = s->use_jen;
   S.gram_fma = s->gram_fma;
   S.jee_w = s->jee_w; S.jen_w = s->jen_w;
+  S.een_nterm = s->een_nterm;
+  if (s->een_nterm < 0 || s->een_nterm > QMCB_EEN_MAXTERM) {
+    qmcb_set_error("qmcb_plan: een_nterm out of range");
+    return QMCB_EINVAL;
+  }
+  for (int m = 0; m < s->een_nterm; ++m) {
+    S.een_a[m] = s->een_num[m]; S.een_a2[m] = s->een_num[s->een_nterm + m];
+    S.een_b[m] = s->een_denom[m]; S.een_b2[m] = s->een_denom[s->een_nterm + m];
+    S.een_c[m] = s->een_fc[m];
+  }
   {
     // degree-11 Chebyshev-economised exp on [-ln2/2, ln2/2] (mpmath.chebyfit, max error 3.2e-18),
     // highest degree first; then log2(e), the 1.5*2^52 rounding constant, -ln2 split hi/lo

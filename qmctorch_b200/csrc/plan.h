@@ -49,6 +49,10 @@ struct DevSys {
   // exp() polynomial + range-reduction constants.  Kernel parameters live in constant bank 0,
   // which DFMA can take as a direct operand: no UMOV pairs / LDC to materialise 64-bit immediates.
   double expc[16];
+  // Boys-Handy three-body Jastrow parameters (constant bank): f = a r/(1+b r), g = a2 r/(1+b2 r)
+  int een_nterm;
+  double een_a[QMCB_EEN_MAXTERM], een_b[QMCB_EEN_MAXTERM], een_a2[QMCB_EEN_MAXTERM],
+      een_b2[QMCB_EEN_MAXTERM], een_c[QMCB_EEN_MAXTERM];
 };
 
 struct LaunchCfg {

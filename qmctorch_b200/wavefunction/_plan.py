@@ -19,13 +19,14 @@ def _cpu(t):
 
 class PlanHandle:
     def __init__(self, ao, mo=None, configs=None, fc=None, jastrow_ee=None, jastrow_en=None,
-                 nup=None, ndown=None, device=None):
+                 nup=None, ndown=None, device=None, jastrow_een=None):
         self.ao = ao
         self.mo = mo
         self.configs = configs
         self.fc = fc
         self.jee = jastrow_ee
         self.jen = jastrow_en
+        self.jeen = jastrow_een
         self.nup = ao.nup if nup is None else nup
         self.ndown = ao.ndown if ndown is None else ndown
         self.device = device
@@ -45,6 +46,9 @@ class PlanHandle:
             ts.append(self.jee.jastrow_kernel.weight)
         if self.jen is not None:
             ts.append(self.jen.jastrow_kernel.weight)
+        if self.jeen is not None:
+            k = self.jeen.jastrow_kernel
+            ts += [k.weight_num, k.weight_denom, k.fc.weight]
         return ts
 
     def _signature(self):
@@ -86,7 +90,14 @@ class PlanHandle:
             jee_w=float(_cpu(self.jee.jastrow_kernel.weight)[0]) if self.jee is not None else 0.0,
             use_jen=int(self.jen is not None),
             jen_w=float(_cpu(self.jen.jastrow_kernel.weight)[0]) if self.jen is not None else 0.0,
-            gram_fma=gram_fma)
+            gram_fma=gram_fma, **self._een_arrays())
+
+    def _een_arrays(self):
+        if self.jeen is None:
+            return dict(een_nterm=0)
+        k = self.jeen.jastrow_kernel
+        return dict(een_nterm=k.nterm, een_num=_cpu(k.weight_num).reshape(2, k.nterm),
+                    een_denom=_cpu(k.weight_denom).reshape(2, k.nterm), een_fc=_cpu(k.fc.weight).reshape(-1))
 
     def plan(self):
         """Returns the (up to date) ``qmcb_plan*``; rebuilds the tables if a parameter changed."""

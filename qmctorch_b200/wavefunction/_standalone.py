@@ -23,10 +23,10 @@ def _placeholder_molecule(mol):
                            atomic_number=list(getattr(mol, "atomic_number", [1] * natom)))
 
 
-def standalone_handle(mol, owner, jee=None, jen=None):
+def standalone_handle(mol, owner, jee=None, jen=None, jeen=None):
     from .orbitals.atomic_orbitals import AtomicOrbitals
     if not hasattr(mol, "basis") or not hasattr(mol.basis, "bas_exp"):
         mol = _placeholder_molecule(mol)
     ao = AtomicOrbitals(mol, cuda=True)
     owner.__dict__["_standalone_ao"] = ao      # keep alive without registering as a sub-module
-    return PlanHandle(ao, jastrow_ee=jee, jastrow_en=jen, nup=mol.nup, ndown=mol.ndown)
+    return PlanHandle(ao, jastrow_ee=jee, jastrow_en=jen, jastrow_een=jeen, nup=mol.nup, ndown=mol.ndown)

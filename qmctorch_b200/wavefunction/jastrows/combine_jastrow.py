@@ -6,6 +6,7 @@ from torch import nn
 from ._base import jastrow_forward
 from .elec_elec import JastrowFactorElectronElectron
 from .elec_nuclei import JastrowFactorElectronNuclei
+from .elec_elec_nuclei import JastrowFactorElectronElectronNuclei
 
 
 class CombineJastrow(nn.Module):
@@ -18,12 +19,13 @@ class CombineJastrow(nn.Module):
         self.nterms = len(self.jastrow_terms)
         ee = [j for j in jastrow if isinstance(j, JastrowFactorElectronElectron)]
         en = [j for j in jastrow if isinstance(j, JastrowFactorElectronNuclei)]
-        if len(ee) > 1 or len(en) > 1 or len(ee) + len(en) != len(jastrow):
+        een = [j for j in jastrow if isinstance(j, JastrowFactorElectronElectronNuclei)]
+        if len(ee) > 1 or len(en) > 1 or len(een) > 1 or len(ee) + len(en) + len(een) != len(jastrow):
             raise NotImplementedError(
-                "the CUDA path combines at most one e-e and one e-n Pade factor; the three-body "
-                "Boys-Handy term (jastrow_factor_electron_electron_nuclei.py) is a later scope row")
+                "the CUDA path combines at most one e-e Pade, one e-n Pade and one e-e-n Boys-Handy factor")
         self.__dict__["ee"] = ee[0] if ee else None      # aliases, not extra sub-modules
         self.__dict__["en"] = en[0] if en else None
+        self.__dict__["een"] = een[0] if een else None
         self.nelec = jastrow[0].nelec
         self._handle = None
 
@@ -34,7 +36,7 @@ class CombineJastrow(nn.Module):
         if self._handle is None:
             from .._standalone import standalone_handle
             first = self.jastrow_terms[0]
-            self._handle = standalone_handle(first._mol, self, jee=self.ee, jen=self.en)
+            self._handle = standalone_handle(first._mol, self, jee=self.ee, jen=self.en, jeen=self.een)
         return self._handle
 
     def forward(self, pos, derivative=0, sum_grad=True):

@@ -12,7 +12,8 @@ from torch import nn
 
 from .. import _lib
 from ._plan import PlanHandle, as_walkers
-from .jastrows import CombineJastrow, JastrowFactorElectronElectron, JastrowFactorElectronNuclei
+from .jastrows import (CombineJastrow, JastrowFactorElectronElectron, JastrowFactorElectronNuclei,
+                       JastrowFactorElectronElectronNuclei)
 from .jastrows.elec_elec import PadeJastrowKernel
 from .orbitals import AtomicOrbitals, MolecularOrbitals
 from .pooling import OrbitalConfigurations, SlaterPooling
@@ -23,7 +24,7 @@ class _PsiFunction(torch.autograd.Function):
     """psi(pos; theta) with analytic parameter gradients."""
 
     @staticmethod
-    def forward(ctx, wf, x, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w):
+    def forward(ctx, wf, x, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w, een_num, een_denom, een_fc):
         ctx.wf = wf
         ctx.save_for_backward(x)
         return wf._psi(x)
@@ -43,7 +44,10 @@ class _PsiFunction(torch.autograd.Function):
                 g["mo_modifier"] if need[4] else None,
                 g["ci"] if need[5] else None,
                 g["jee_w"] if need[6] else None,
-                g["jen_w"] if need[7] else None)
+                g["jen_w"] if need[7] else None,
+                g["een_num"] if need[8] else None,
+                g["een_denom"] if need[9] else None,
+                g["een_fc"] if need[10] else None)
 
 
 class SlaterJastrow(WaveFunction):
@@ -88,8 +92,8 @@ class SlaterJastrow(WaveFunction):
         self.kinetic_energy = self.kinetic_energy_jacobi
         # shared device tables
         self._handle = PlanHandle(self.ao, self.mo, self.configs, self.fc, self._jee, self._jen,
-                                  nup=mol.nup, ndown=mol.ndown)
-        for m in (self.ao, self.mo, self.pool, self._jee, self._jen,
+                                  nup=mol.nup, ndown=mol.ndown, jastrow_een=self._jeen)
+        for m in (self.ao, self.mo, self.pool, self._jee, self._jen, self._jeen,
                   self.jastrow if isinstance(self.jastrow, CombineJastrow) else None):
             if m is not None:
                 m._handle = self._handle
@@ -102,6 +106,7 @@ class SlaterJastrow(WaveFunction):
         # ``jastrow.`` and state_dict names must match the reference)
         self.__dict__["_jee"] = None
         self.__dict__["_jen"] = None
+        self.__dict__["_jeen"] = None
         if jastrow is None:
             self.jastrow = None
             self.use_jastrow = False
@@ -119,11 +124,15 @@ class SlaterJastrow(WaveFunction):
             self.__dict__["_jee"] = self.jastrow
         elif isinstance(self.jastrow, JastrowFactorElectronNuclei):
             self.__dict__["_jen"] = self.jastrow
+        elif isinstance(self.jastrow, JastrowFactorElectronElectronNuclei):
+            self.__dict__["_jeen"] = self.jastrow
         elif isinstance(self.jastrow, CombineJastrow):
             self.__dict__["_jee"], self.__dict__["_jen"] = self.jastrow.ee, self.jastrow.en
+            self.__dict__["_jeen"] = self.jastrow.een
         else:
             raise NotImplementedError(
-                "only the Pade e-e / e-n Jastrow factors (and their product) are fused into the CUDA path")
+                "only the Pade e-e / e-n and Boys-Handy e-e-n Jastrow factors (and their product) are "
+                "fused into the CUDA path")
         self.jastrow_type = self.jastrow.__repr__()
         if self.cuda:
             self.jastrow = self.jastrow.to(self.device)
@@ -174,6 +183,8 @@ class SlaterJastrow(WaveFunction):
         g_cf = torch.empty(nbas, dtype=torch.float64, device=dev)
         g_jee = torch.empty(1, dtype=torch.float64, device=dev)
         g_jen = torch.empty(1, dtype=torch.float64, device=dev)
+        nt = self._jeen.jastrow_kernel.nterm if self._jeen is not None else 0
+        g_een = torch.zeros(max(5 * nt, 1), dtype=torch.float64, device=dev)
         nbytes = L.qmcb_backward_workspace_bytes(plan, W)
         ws = self._ws.get("bwd")
         if ws is None or ws.numel() < nbytes or ws.device != dev:
@@ -181,9 +192,13 @@ class SlaterJastrow(WaveFunction):
             self._ws["bwd"] = ws
         _lib.check(L.qmcb_psi_backward(plan, _lib.ptr(x), _lib.ptr(weight), W, _lib.ptr(g_mo), _lib.ptr(g_ci),
                                        _lib.ptr(g_exp), _lib.ptr(g_cf), _lib.ptr(g_jee), _lib.ptr(g_jen),
-                                       _lib.ptr(ws), _lib.stream_ptr(dev)), "qmcb_psi_backward")
+                                       _lib.ptr(g_een) if nt else None, _lib.ptr(ws), _lib.stream_ptr(dev)),
+                   "qmcb_psi_backward")
         return {"mo_modifier": g_mo * self.mo.mo_scf, "ci": g_ci, "bas_exp": g_exp, "bas_coeffs": g_cf,
-                "jee_w": g_jee, "jen_w": g_jen}
+                "jee_w": g_jee, "jen_w": g_jen,
+                "een_num": g_een[: 2 * nt].view(1, 2, nt) if nt else None,
+                "een_denom": g_een[2 * nt: 4 * nt].view(1, 2, nt) if nt else None,
+                "een_fc": g_een[4 * nt: 5 * nt].view(1, nt) if nt else None}
 
     # -- public API (reference signatures) ---------------------------------------------------
     def forward(self, x, ao=None):
@@ -193,7 +208,10 @@ class SlaterJastrow(WaveFunction):
         xd = self._x(x)
         jw = self._jee.jastrow_kernel.weight if self._jee is not None else None
         nw = self._jen.jastrow_kernel.weight if self._jen is not None else None
-        leaves = [self.ao.bas_exp, self.ao.bas_coeffs, self.mo.mo_modifier, self.fc.weight, jw, nw]
+        bh = self._jeen.jastrow_kernel if self._jeen is not None else None
+        leaves = [self.ao.bas_exp, self.ao.bas_coeffs, self.mo.mo_modifier, self.fc.weight, jw, nw,
+                  bh.weight_num if bh is not None else None, bh.weight_denom if bh is not None else None,
+                  bh.fc.weight if bh is not None else None]
         track = torch.is_grad_enabled() and (
             any(t is not None and t.requires_grad for t in leaves) or x.requires_grad)
         if not track:

@@ -71,7 +71,8 @@ def test_golden_operators(name):
         assert C.scaled_err(wf.jastrow(posw, derivative=1), g["dJ"].sum(1)) < RTOL
 
 
-@pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "lih_cas24", "lih_een", "h2o_cas44", "c4h6_ground"])
+@pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "lih_cas24", "lih_een", "h2o_cas44", "c4h6_ground",
+                                  "lih_sd22_een3", "h2o_cas44_een"])
 def test_metropolis_decisions_bit_exact_teacher_forced(name):
     """Same state, same proposal and uniform draws as the reference -> identical decisions,
     identical new positions, psi^2 within tolerance (sampler/metropolis.py:134-160,279-298)."""
@@ -108,7 +109,7 @@ def _thermalised(wf, mol, nw, nstep=60, step=0.3, seed=11):
 
 
 @pytest.mark.parametrize("name,nw", [("lih_ground", 20000), ("h2_single22", 20000), ("lih_een", 4000),
-                                     ("h2o_cas44", 1500)])
+                                     ("h2o_cas44", 1500), ("lih_sd22_een3", 1500), ("h2o_cas44_een", 400)])
 def test_fresh_walkers_against_oracle(name, nw):
     """Seeded ensembles the fixtures have never seen, CUDA vs oracle, per-walker relative error."""
     g = C.load(name)
@@ -281,6 +282,9 @@ def _manual_grads(wf, pos):
         out["jastrow_weight"] = wf._jee.jastrow_kernel.weight.grad
     if wf._jen is not None:
         out["en_weight"] = wf._jen.jastrow_kernel.weight.grad
+    if wf._jeen is not None:
+        bh = wf._jeen.jastrow_kernel
+        out["een_num"], out["een_denom"], out["een_fc"] = bh.weight_num.grad, bh.weight_denom.grad, bh.fc.weight.grad
     return out
 
 

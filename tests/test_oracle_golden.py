@@ -32,7 +32,7 @@ def test_oracle_reproduces_reference(name):
     assert C.scaled_err(orc.grad_psi(P, pos, pdf=True), g["gpdf"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "lih_cas24", "lih_een", "h2o_cas44"])
+@pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "lih_cas24", "lih_een", "h2o_cas44", "lih_sd22_een3"])
 def test_oracle_parameter_gradients(name):
     g = C.load(name)
     mol, P = C.oracle_params(g)
