@@ -326,7 +326,7 @@ struct ElecTerms {
   double gx, gy, gz, lap, ks, ven, vee;
 };
 
-template <bool DERIV>
+template <bool DERIV, bool POT>
 __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, const double *sp, int e,
                                                ElecTerms &o) {
   const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
@@ -334,12 +334,12 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
   const double ni = __dadd_rn(__dadd_rn(__dmul_rn(xi, xi), __dmul_rn(yi, yi)), __dmul_rn(zi, zi));
   const bool up_i = e < S.nup;
   const double w = S.jee_w;
-  for (int j = 0; j < S.nelec; ++j) {
+  for (int j = DERIV ? 0 : e + 1; j < S.nelec; ++j) {
     if (j == e) continue;
     const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
     const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
     const double s2 = dx * dx + dy * dy + dz * dz;
-    if (j > e) vee += rsqrt(s2);
+    if (POT && j > e) vee += rsqrt(s2);
     if (S.use_jee) {
       const double nj = __dadd_rn(__dadd_rn(__dmul_rn(xj, xj), __dmul_rn(yj, yj)), __dmul_rn(zj, zj));
       double dot;
@@ -363,7 +363,7 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
     const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
     const double dx = xi - xa, dy = yi - ya, dz = zi - za;
     const double s2 = dx * dx + dy * dy + dz * dz;
-    ven -= T.atoms[4 * A + 3] * rsqrt(s2);
+    if (POT) ven -= T.atoms[4 * A + 3] * rsqrt(s2);
     if (S.use_jen) {
       const double wn = S.jen_w;
       const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));

@@ -127,32 +127,56 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
   for (int64_t tile = unit; tile < ntile; tile += nunit) {
     const int64_t w0 = tile * TW;
     const int tw = (int)((a.W - w0) < TW ? (a.W - w0) : TW);
-    // ---- P0: coordinates
-    for (int i = tid; i < tw * ne3; i += nthr) {
-      double v = a.pos[w0 * ne3 + i];
-      if (MODE == MODE_MH) {
-        const int wl = i / ne3, c = i - wl * ne3, e = c / 3;
-        int me = a.move_elec;
-        if (me == -2) {
-          if (a.elec_index) me = a.elec_index[w0 + wl];
-          else me = (int)(philox_u32(a.seed, a.offset, (uint64_t)(w0 + wl), 2u) % (unsigned)Ne);
-        }
-        if (me < 0 || me == e) {
-          double d;
-          if (a.disp) d = a.disp[w0 * ne3 + i];
-          else if (a.proba_normal) d = a.scale * philox_normal(a.seed, a.offset, (uint64_t)(w0 * ne3 + i));
-          else d = a.scale * (2.0 * philox_uniform(a.seed, a.offset, (uint64_t)(w0 * ne3 + i), 0u) - 1.0);
-          v += d;
+    // ---- P0: coordinates (+ proposal)
+    if (MODE == MODE_MH && !a.disp && a.proba_normal) {
+      // in-kernel normal proposals: one Philox call yields the two normals of a GLOBAL element
+      // pair (2p, 2p+1), so the draw of an element does not depend on the tiling
+      const int64_t g0 = w0 * ne3, g1 = g0 + (int64_t)tw * ne3;
+      for (int64_t p = (g0 >> 1) + tid; 2 * p < g1; p += nthr) {
+        double z[2];
+        philox_normal2(a.seed, a.offset, (uint64_t)p, z[0], z[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t g = 2 * p + h;
+          if (g < g0 || g >= g1) continue;
+          const int i = (int)(g - g0);
+          const int wl = i / ne3, e = (i - wl * ne3) / 3;
+          int me = a.move_elec;
+          if (me == -2) {
+            if (a.elec_index) me = a.elec_index[w0 + wl];
+            else me = (int)(philox_u32(a.seed, a.offset, (uint64_t)(w0 + wl), 2u) % (unsigned)Ne);
+          }
+          double v = a.pos[g];
+          if (me < 0 || me == e) v += a.scale * z[h];
+          spos[i] = v;
         }
       }
-      spos[i] = v;
+    } else {
+      for (int i = tid; i < tw * ne3; i += nthr) {
+        double v = a.pos[w0 * ne3 + i];
+        if (MODE == MODE_MH) {
+          const int wl = i / ne3, c = i - wl * ne3, e = c / 3;
+          int me = a.move_elec;
+          if (me == -2) {
+            if (a.elec_index) me = a.elec_index[w0 + wl];
+            else me = (int)(philox_u32(a.seed, a.offset, (uint64_t)(w0 + wl), 2u) % (unsigned)Ne);
+          }
+          if (me < 0 || me == e) {
+            double d;
+            if (a.disp) d = a.disp[w0 * ne3 + i];
+            else d = a.scale * (2.0 * philox_uniform(a.seed, a.offset, (uint64_t)(w0 * ne3 + i), 0u) - 1.0);
+            v += d;
+          }
+        }
+        spos[i] = v;
+      }
     }
     TILE_SYNC();
     // ---- P1: Jastrow + potentials, thread (wl, e)
     for (int it = tid; it < tw * Ne; it += nthr) {
       const int wl = it / Ne, e = it - wl * Ne;
       ElecTerms o;
-      electron_terms<(NCH > 1)>(S, T, spos + wl * ne3, e, o);
+      electron_terms<(NCH > 1), (MODE == MODE_ELOC)>(S, T, spos + wl * ne3, e, o);
       double *q = jv + it;
       if (NCH > 1) { q[0] = o.gx; q[jvs] = o.gy; q[2 * jvs] = o.gz; q[3 * jvs] = o.lap; }
       q[4 * jvs] = o.ks; q[5 * jvs] = o.ven; q[6 * jvs] = o.vee;

@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(256) jastrow_kernel(DevSys S, const double *po
     const int wl = it / Ne, e = it - wl * Ne;
     const bool act = it < tw * Ne;
     if (act) {
-      if (deriv) electron_terms<true>(S, T, spos + wl * ne3, e, o);
-      else electron_terms<false>(S, T, spos + wl * ne3, e, o);
+      if (deriv) electron_terms<true, false>(S, T, spos + wl * ne3, e, o);
+      else electron_terms<false, false>(S, T, spos + wl * ne3, e, o);
       sks[it] = o.ks;
     }
     __syncthreads();

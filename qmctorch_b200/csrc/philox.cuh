@@ -41,13 +41,16 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t offset,
   return u53(c[0], c[1]);
 }
 
-// standard normal (Box-Muller)
-__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t offset, uint64_t idx) {
+// two standard normals per Philox call (Box-Muller): pair index -> (z0, z1)
+__device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t offset, uint64_t pair, double &z0,
+                                               double &z1) {
   uint32_t c[4];
-  philox4(seed, offset, idx, 3u, c);
+  philox4(seed, offset, pair, 3u, c);
   const double u1 = 1.0 - u53(c[0], c[1]);   // (0,1]
   const double u2 = u53(c[2], c[3]);
   double s, co;
   sincospi(2.0 * u2, &s, &co);
-  return sqrt(-2.0 * log(u1)) * co;
+  const double r = sqrt(-2.0 * log(u1));
+  z0 = r * co;
+  z1 = r * s;
 }

@@ -7,6 +7,8 @@ sm_100a kernel per call; ``forward`` is differentiable w.r.t. the wave-function
 parameters (``psi.backward(weight)`` as used by ``Solver.evaluate_grad_manual``) through
 ``qmcb_psi_backward``.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
@@ -229,8 +231,47 @@ class SlaterJastrow(WaveFunction):
         return self.ao2mo(self.ao(x, derivative=derivative, sum_grad=sum_grad))
 
     def local_energy(self, pos):
-        """E_L [W,1]  (wf_base.py:184-215 + slater_jastrow.py:312-344)."""
+        """E_L [W,1]  (wf_base.py:184-215 + slater_jastrow.py:312-344).  A host tensor is streamed
+        to the device in chunks so that the H2D copy of chunk k+1 overlaps the kernel on chunk k."""
+        if pos.device.type == "cpu" and pos.shape[0] >= self.host_chunk_min:
+            return self._eloc_from_host(pos)
         return self._eloc(self._x(pos))[0]
+
+    host_chunk_min = 65536      # walkers; below this one copy + one launch is cheaper
+    host_chunks = 8
+
+    def _eloc_from_host(self, pos):
+        dev = self._dev()
+        if pos.dim() != 2 or pos.shape[1] != self.ndim_tot:
+            raise ValueError("positions must have shape [nwalkers, %d], got %s" % (self.ndim_tot, tuple(pos.shape)))
+        src = pos.detach()
+        if src.dtype != torch.float64 or not src.is_contiguous():
+            src = src.to(torch.float64).contiguous()
+        W = src.shape[0]
+        L = _lib.lib()
+        plan = self._handle.plan()
+        main = torch.cuda.current_stream(dev)
+        side = self._ws.get("side")
+        if side is None:
+            side = self._ws["side"] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        xbuf = self._ws.get("xbuf")
+        if xbuf is None or xbuf.shape[0] < W or xbuf.device != dev:
+            xbuf = self._ws["xbuf"] = torch.empty(W, self.ndim_tot, dtype=torch.float64, device=dev)
+        e = torch.empty(W, 1, dtype=torch.float64, device=dev)
+        step = -(-W // self.host_chunks)
+        for s_ in side:
+            s_.wait_stream(main)
+        for k, lo in enumerate(range(0, W, step)):
+            hi = min(lo + step, W)
+            st = side[k % 2]
+            with torch.cuda.stream(st):
+                xbuf[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                _lib.check(L.qmcb_local_energy(plan, _lib.ptr(xbuf[lo:hi]), hi - lo, _lib.ptr(e[lo:hi]), None, None,
+                                               C.c_void_p(st.cuda_stream)), "qmcb_local_energy")
+        for s_ in side:
+            e.record_stream(s_)
+            main.wait_stream(s_)
+        return e
 
     def kinetic_energy_jacobi(self, x, **kwargs):
         """slater_jastrow.py:312-344."""
