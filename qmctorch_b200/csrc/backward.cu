@@ -77,7 +77,7 @@ __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, 
   if (S.use_jen) {
     const double wn = S.jen_w;
     for (int A = 0; A < S.natom; ++A) {
-      const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+      const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
       const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));
       const double dot = __fma_rn(zi, za, __fma_rn(yi, ya, __dmul_rn(xi, xa)));
       const double r = sqrt(__dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot)));
@@ -94,7 +94,7 @@ __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, 
       const double nj = gram_norm(xj, yj, zj);
       const double rej = sqrt(gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, nj));
       for (int A = 0; A < S.natom; ++A) {
-        const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+        const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
         const double na = gram_norm(xa, ya, za);
         const double rE = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, na));
         const double rJ = sqrt(gram_d2_en(xj, yj, zj, nj, xa, ya, za, na));
@@ -120,15 +120,15 @@ __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, 
 // shell program, values only; fills one row of AO, Y (into U) and X = [R_q | dR_q/dalpha]
 __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, double ex, double ey, double ez,
                                              double *ao, double *u, double *xr, int ppad, bool want_ao) {
-  const double2 *rec = T.stream;
+  const double2 *rec = T.stream();
   const bool with_n = (S.radial_type == QMCB_GTO || S.radial_type == QMCB_STO);
   const bool gauss = (S.radial_type == QMCB_GTO || S.radial_type == QMCB_GTO_PURE);
   int q = 0;
   for (int A = 0; A < S.natom; ++A) {
-    const double x = ex - T.atoms[4 * A], y = ey - T.atoms[4 * A + 1], z = ez - T.atoms[4 * A + 2];
+    const double x = ex - T.atoms()[4 * A], y = ey - T.atoms()[4 * A + 1], z = ez - T.atoms()[4 * A + 2];
     const double r2 = x * x + y * y + z * z;
     const double r = gauss && !with_n ? 0.0 : sqrt(r2);
-    const int ns = T.ash[A + 1] - T.ash[A];
+    const int ns = T.ash()[A + 1] - T.ash()[A];
     for (int s = 0; s < ns; ++s) {
       const double hdr = rec->x;
       ++rec;
@@ -139,7 +139,7 @@ __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, doub
         ++rec;
         double rn = 1.0;
         if (with_n) { rn = ipow(r, (int)rec->x); ++rec; }
-        const double R = rn * exp_neg(S, gauss ? -a * r2 : -a * r);
+        const double R = rn * exp_neg(S, T.etab(), gauss ? -a * r2 : -a * r);
         S0 += c * R;
         if (want_ao) {
           xr[q] = R;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       const int row = i / nmup, m = i - row * nmup;
       const double *ar = sao + row * lda;
       double acc = 0.0;
-      for (int k = 0; k < S.nao; ++k) acc = fma(ar[k], T.mow[k * nmup + m], acc);
+      for (int k = 0; k < S.nao; ++k) acc = fma(ar[k], T.mow()[k * nmup + m], acc);
       smo[i] = acc;
     }
     __syncthreads();
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       const int wl = it / nun, u = it - wl * nun;
       const bool up = u < S.nuu;
       const int n = up ? S.nup : S.ndown;
-      const int *cols = up ? T.ucu + u * S.nup : T.ucd + (u - S.nuu) * S.ndown;
+      const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
       const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
       double *m = scr + it;
       double det = 1.0;
@@ -261,10 +261,10 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
     for (int wl = tid; wl < tw; wl += nthr) {
       const double *dd = sdet + wl * nun;
       double sig = 0.0;
-      for (int c = 0; c < S.nconf; ++c) sig += T.ci[c] * dd[T.ciu[c]] * dd[S.nuu + T.cid[c]];
+      for (int c = 0; c < S.nconf; ++c) sig += T.ci()[c] * dd[T.ciu()[c]] * dd[S.nuu + T.cid()[c]];
       double ks = 0.0;
       for (int e = 0; e < Ne; ++e) ks += jv[wl * Ne + e];
-      const double J = (S.use_jee || S.use_jen || S.een_nterm > 0) ? exp_clamped(S, ks) : 1.0;
+      const double J = (S.use_jee || S.use_jen || S.een_nterm > 0) ? exp_clamped(S, T.etab(), ks) : 1.0;
       const double wgt = a.weight[w0 + wl];
       wj[wl * 4] = wgt * J; wj[wl * 4 + 1] = sig; wj[wl * 4 + 2] = wgt * J * sig;
     }
@@ -283,20 +283,20 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       for (int u = 0; u < nu; ++u) {
         double cu = 0.0;
         for (int c = 0; c < S.nconf; ++c) {
-          if ((up ? T.ciu[c] : T.cid[c]) != u) continue;
-          cu += T.ci[c] * dd[up ? S.nuu + T.cid[c] : T.ciu[c]];
+          if ((up ? T.ciu()[c] : T.cid()[c]) != u) continue;
+          cu += T.ci()[c] * dd[up ? S.nuu + T.cid()[c] : T.ciu()[c]];
         }
         cu *= dd[up ? u : S.nuu + u] * wJ;
         if (cu == 0.0) continue;
         const double *inv = scr + (wl * nun + (up ? u : S.nuu + u));
-        const int *cols = up ? T.ucu + u * S.nup : T.ucd + u * S.ndown;
+        const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + u * S.ndown;
         for (int j = 0; j < n; ++j) g[cols[j]] += cu * inv[(j * ild + ioff + el) * conc];
       }
       if (a.want_ao) {
         double *ur = su + it * lda;
         for (int k = 0; k < S.nao; ++k) {
           double gao = 0.0;
-          for (int m = 0; m < nmup; ++m) gao = fma(g[m], T.mow[k * nmup + m], gao);
+          for (int m = 0; m < nmup; ++m) gao = fma(g[m], T.mow()[k * nmup + m], gao);
           ur[k] *= gao;
         }
       }
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
     for (int c = warp; c < nsc; c += nwarp) {
       double v = 0.0;
       if (c < S.nconf) {
-        const int iu = T.ciu[c], id = S.nuu + T.cid[c];
+        const int iu = T.ciu()[c], id = S.nuu + T.cid()[c];
         for (int wl = lane; wl < tw; wl += 32) v += wj[wl * 4] * sdet[wl * nun + iu] * sdet[wl * nun + id];
       } else {
         const double *dk = jv + (c - S.nconf + 1) * TW * Ne;

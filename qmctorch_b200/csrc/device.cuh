@@ -10,24 +10,29 @@
 
 #define QMCB_EPS 1e-16
 
+// Views into the staged tables.  Only the two base pointers are kept live; every table pointer is
+// re-derived from the offsets in the kernel-parameter struct (constant bank) where it is used, which
+// keeps ~30 registers free in the hot loop.
 struct Tab {
-  const double *atoms, *alpha, *coef, *pn, *cscale, *mow, *ci;
-  const double2 *stream;
-  const int *ash, *spo, *sco, *ck, *cao, *used, *ucu, *ucd, *ciu, *cid, *pfo, *pflat;
+  const double *sd;
+  const int *si;
+  const DevSys *S;
+#define QMCB_TAB_D(name, off) __device__ __forceinline__ const double *name() const { return sd + S->off; }
+#define QMCB_TAB_I(name, off) __device__ __forceinline__ const int *name() const { return si + S->off; }
+  QMCB_TAB_D(atoms, o_atoms) QMCB_TAB_D(mow, o_mow) QMCB_TAB_D(ci, o_ci) QMCB_TAB_D(etab, o_etab)
+  QMCB_TAB_I(ash, o_ash) QMCB_TAB_I(used, o_used) QMCB_TAB_I(ucu, o_ucu) QMCB_TAB_I(ucd, o_ucd)
+  QMCB_TAB_I(ciu, o_ciu) QMCB_TAB_I(cid, o_cid)
+  __device__ __forceinline__ const double2 *stream() const {
+    return reinterpret_cast<const double2 *>(sd + S->o_stream);
+  }
 };
-
 // Copies both blobs into shared memory (all threads), returns the first free double slot.
 __device__ __forceinline__ double *stage_tables(const DevSys &S, double *smem, Tab &T) {
   double *sd = smem;
   int *si = reinterpret_cast<int *>(smem + S.ndbl);
   for (int i = threadIdx.x; i < S.ndbl; i += blockDim.x) sd[i] = S.dblob[i];
   for (int i = threadIdx.x; i < S.nint; i += blockDim.x) si[i] = S.iblob[i];
-  T.atoms = sd + S.o_atoms; T.alpha = sd + S.o_alpha; T.coef = sd + S.o_coef; T.pn = sd + S.o_pn;
-  T.cscale = sd + S.o_cscale; T.mow = sd + S.o_mow; T.ci = sd + S.o_ci;
-  T.stream = reinterpret_cast<const double2 *>(sd + S.o_stream);
-  T.ash = si + S.o_ash; T.spo = si + S.o_spo; T.sco = si + S.o_sco; T.ck = si + S.o_ck;
-  T.cao = si + S.o_cao; T.used = si + S.o_used; T.ucu = si + S.o_ucu; T.ucd = si + S.o_ucd;
-  T.ciu = si + S.o_ciu; T.cid = si + S.o_cid; T.pfo = si + S.o_pfo; T.pflat = si + S.o_pflat;
+  T.sd = sd; T.si = si; T.S = &S;
   return smem + S.ndbl + S.nint / 2;
 }
 
@@ -46,6 +51,27 @@ __device__ __forceinline__ double ipow(double x, int k) {
   }
 }
 
+// 1/x and 1/sqrt(x) from the hardware seeds (MUFU.RCP64H / MUFU.RSQ64H, ~2^-22) plus two
+// Newton steps: ~1 ulp, no slow-path branches.  x must be a normal positive number (distances,
+// 1 + w r); NaN propagates, x = 0 gives inf/NaN like the exact operations would.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+
 // r^m for m >= -2 given r and 1/r
 __device__ __forceinline__ double rpow(double r, double rinv, int m) {
   if (m >= 0) return ipow(r, m);
@@ -53,34 +79,38 @@ __device__ __forceinline__ double rpow(double r, double rinv, int m) {
 }
 
 // ---------------------------------------------------------------------------------------
-// exp(x) for x <= 0 (any x <= 709 works), ~1 ulp, NaN propagates, no branches:
-// x = k ln2 + r, |r| <= ln2/2; degree-11 Chebyshev-economised polynomial (max error 3.2e-18 on
-// the interval, coefficients from mpmath.chebyfit); 2^k built from the exponent bits.
-// Arguments below -708 are clamped (result 3e-308 instead of a denormal/0).
-// ---------------------------------------------------------------------------------------
+// exp(x), ~1 ulp, NaN propagates, no branches:
+//   x = (64 m + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^m * T[j] * (1 + q(r)),
+//   T[j] = 2^(j/64) from a 64-entry shared-memory table, q = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)
+//   (truncation 3.5e-17); 2^m is applied by an integer add on the exponent field.
+// 10 FP64 instructions.  Arguments are clamped to [-708, 708] (3e-308 instead of a denormal).
 // The constants come from the kernel-parameter struct (constant bank 0): S.expc.
-__device__ __forceinline__ double exp_core(const DevSys &S, double x) {
-  const double t = fma(x, S.expc[12], S.expc[13]);
-  const int k = __double2loint(t);
-  const double kd = t - S.expc[13];
-  double r = fma(kd, S.expc[14], x);
-  r = fma(kd, S.expc[15], r);
-  double p = S.expc[0];
-#pragma unroll
-  for (int i = 1; i < 12; ++i) p = fma(p, r, S.expc[i]);
-  return p * __hiloint2double((k + 1023) << 20, 0);
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp_core(const DevSys &S, const double *etab, double x) {
+  const double t = fma(x, S.expc[0], S.expc[1]);
+  const int ki = __double2loint(t);
+  const double kd = t - S.expc[1];
+  double r = fma(kd, S.expc[2], x);
+  r = fma(kd, S.expc[3], r);
+  double p = fma(r, S.expc[4], S.expc[5]);
+  p = fma(p, r, S.expc[6]);
+  p = fma(p, r, 0.5);
+  const double q = fma(r * r, p, r);
+  const double tj = etab[ki & 63];
+  const double y = fma(tj, q, tj);
+  return __hiloint2double(__double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
 }
 
-__device__ __forceinline__ double exp_neg(const DevSys &S, double x) {
+__device__ __forceinline__ double exp_neg(const DevSys &S, const double *etab, double x) {
   x = x < -708.0 ? -708.0 : x;
-  return exp_core(S, x);
+  return exp_core(S, etab, x);
 }
 
-// same for arguments of either sign (|x| <= 708 after clamping; NaN propagates)
-__device__ __forceinline__ double exp_clamped(const DevSys &S, double x) {
+// arguments of either sign
+__device__ __forceinline__ double exp_clamped(const DevSys &S, const double *etab, double x) {
   x = x < -708.0 ? -708.0 : x;
   x = x > 708.0 ? 708.0 : x;
-  return exp_core(S, x);
+  return exp_core(S, etab, x);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -96,9 +126,9 @@ __device__ __forceinline__ double exp_clamped(const DevSys &S, double x) {
 // RT = 0: gto_pure (compile-time fast path), RT = 1: radial type read from S at run time.
 // ---------------------------------------------------------------------------------------
 template <int NCH>
-__device__ __forceinline__ void gto_pure_prim(const DevSys &S, double a, double c, double r2, double &S0, double &S1,
+__device__ __forceinline__ void gto_pure_prim(const DevSys &S, const double *etab, double a, double c, double r2, double &S0, double &S1,
                                               double &S2) {
-  const double ce = c * exp_neg(S, -a * r2);
+  const double ce = c * exp_neg(S, etab, -a * r2);
   S0 += ce;
   if (NCH > 1) {
     const double t = a * ce;
@@ -108,7 +138,8 @@ __device__ __forceinline__ void gto_pure_prim(const DevSys &S, double a, double 
 }
 
 template <int NCH, int RT>
-__device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const double2 *rec, int nprim, double r2,
+__device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const double *etab, const double2 *rec,
+                                                      int nprim, double r2,
                                                       double r, double rinv, double &S0, double &S1,
                                                       double &S2) {
   S0 = 0.0; S1 = 0.0; S2 = 0.0;
@@ -118,23 +149,23 @@ __device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const dou
     for (; i + 2 <= nprim; i += 2) {
       const double2 p0 = rec[0], p1 = rec[1];
       rec += 2;
-      gto_pure_prim<NCH>(S, p0.x, p0.y, r2, S0, S1, S2);
-      gto_pure_prim<NCH>(S, p1.x, p1.y, r2, T0, T1, T2);
+      gto_pure_prim<NCH>(S, etab, p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(S, etab, p1.x, p1.y, r2, T0, T1, T2);
     }
     if (i < nprim) {
       const double2 p0 = rec[0];
       rec += 1;
-      gto_pure_prim<NCH>(S, p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(S, etab, p0.x, p0.y, r2, S0, S1, S2);
     }
     S0 += T0; S1 += T1; S2 += T2;
     return rec;
   }
   if (S.radial_type == QMCB_GTO_PURE) {
-    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(S, rec->x, rec->y, r2, S0, S1, S2);
+    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(S, etab, rec->x, rec->y, r2, S0, S1, S2);
   } else if (S.radial_type == QMCB_STO_PURE) {
     for (int i = 0; i < nprim; ++i, ++rec) {
       const double a = rec->x;
-      const double ce = rec->y * exp_neg(S, -a * r);
+      const double ce = rec->y * exp_neg(S, etab, -a * r);
       S0 += ce;
       if (NCH > 1) {
         const double t = a * ce;
@@ -147,7 +178,7 @@ __device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const dou
     for (int i = 0; i < nprim; ++i, rec += 2) {
       const double a = rec[0].x;
       const int n = (int)rec[1].x;
-      const double ce = rec[0].y * exp_neg(S, gto ? -a * r2 : -a * r);
+      const double ce = rec[0].y * exp_neg(S, etab, gto ? -a * r2 : -a * r);
       const double rn = ipow(r, n);
       S0 += ce * rn;
       if (NCH > 1) {
@@ -193,19 +224,19 @@ __device__ __forceinline__ void generic_component(int kk, double sc, double x, d
 template <int NCH, int RT, class Sink>
 __device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double ex, double ey, double ez,
                                          Sink &sink) {
-  const double2 *rec = T.stream;
+  const double2 *rec = T.stream();
   for (int A = 0; A < S.natom; ++A) {
-    const double x = ex - T.atoms[4 * A], y = ey - T.atoms[4 * A + 1], z = ez - T.atoms[4 * A + 2];
+    const double x = ex - T.atoms()[4 * A], y = ey - T.atoms()[4 * A + 1], z = ez - T.atoms()[4 * A + 2];
     const double r2 = x * x + y * y + z * z;
     double r = 0.0, rinv = 0.0;
     if (RT != 0 && S.radial_type != QMCB_GTO_PURE) { r = sqrt(r2); rinv = 1.0 / r; }
-    const int ns = T.ash[A + 1] - T.ash[A];
+    const int ns = T.ash()[A + 1] - T.ash()[A];
     for (int s = 0; s < ns; ++s) {
       const double hdr = rec->x;
       ++rec;
       const int nprim = __double2loint(hdr), ngrp = __double2hiint(hdr);
       double S0, S1, S2;
-      rec = radial_sums<NCH, RT>(S, rec, nprim, r2, r, rinv, S0, S1, S2);
+      rec = radial_sums<NCH, RT>(S, T.etab(), rec, nprim, r2, r, rinv, S0, S1, S2);
       for (int g = 0; g < ngrp; ++g, ++rec) {
         const double2 gr = *rec;
         const int kk = __double2loint(gr.x), ao = __double2hiint(gr.x);
@@ -291,7 +322,7 @@ __device__ __forceinline__ void een_terms(const DevSys &S, const Tab &T, const d
     const double irej = 1.0 / rej;
     const double ux = (xi - xj) * irej, uy = (yi - yj) * irej, uz = (zi - zj) * irej;
     for (int A = 0; A < S.natom; ++A) {
-      const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+      const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
       const double na = gram_norm(xa, ya, za);
       const double rE = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, na));
       const double rJ = sqrt(gram_d2_en(xj, yj, zj, nj, xa, ya, za, na));
@@ -339,17 +370,17 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
     const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
     const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
     const double s2 = dx * dx + dy * dy + dz * dz;
-    if (POT && j > e) vee += rsqrt(s2);
+    if (POT && j > e) vee += fast_rsqrt(s2);
     if (S.use_jee) {
       const double nj = __dadd_rn(__dadd_rn(__dmul_rn(xj, xj), __dmul_rn(yj, yj)), __dmul_rn(zj, zj));
       double dot;
       if (S.gram_fma) dot = __fma_rn(zi, zj, __fma_rn(yi, yj, __dmul_rn(xi, xj)));
       else dot = __dadd_rn(__dadd_rn(__dmul_rn(xi, xj), __dmul_rn(yi, yj)), __dmul_rn(zi, zj));
       const double d2 = __dsub_rn(__dadd_rn(ni, nj), __dmul_rn(2.0, dot));
-      const double rinv = rsqrt(d2);
+      const double rinv = fast_rsqrt(d2);
       const double r = d2 * rinv;
       const double w0 = (up_i == (j < S.nup)) ? 0.25 : 0.5;
-      const double den = 1.0 / (1.0 + w * r);
+      const double den = fast_rcp(1.0 + w * r);
       if (j > e) ks += w0 * r * den;
       if (DERIV) {
         const double kp = w0 * den * den * rinv;
@@ -360,10 +391,10 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
   }
   double gnx = 0, gny = 0, gnz = 0;
   for (int A = 0; A < S.natom; ++A) {
-    const double xa = T.atoms[4 * A], ya = T.atoms[4 * A + 1], za = T.atoms[4 * A + 2];
+    const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
     const double dx = xi - xa, dy = yi - ya, dz = zi - za;
     const double s2 = dx * dx + dy * dy + dz * dz;
-    if (POT) ven -= T.atoms[4 * A + 3] * rsqrt(s2);
+    if (POT) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
     if (S.use_jen) {
       const double wn = S.jen_w;
       const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));

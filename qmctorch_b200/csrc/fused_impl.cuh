@@ -89,15 +89,20 @@ __host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw
 // CTAs (256 threads) per SM the compiler must allow for warp-owned tiles.  Measured on B200,
 // LiH E_L kernel: 1 -> 0.677 ms, 2 -> 0.466 ms (123 regs, no spills), 3 -> 0.502 ms (80 regs,
 // spills), 4 -> 0.535 ms (64 regs).
+// Later: 128-thread CTAs x 5 per SM (96 registers, no spills, 20 warps/SM) measured equal on the
+// E_L kernel and 3-7 % faster on psi / grad / H2 than 256 x 2.
 #ifndef QMCB_MINBLOCKS
-#define QMCB_MINBLOCKS 2
+#define QMCB_MINBLOCKS 5
+#endif
+#ifndef QMCB_WARP_CTA
+#define QMCB_WARP_CTA 128      // threads per CTA for warp-owned tiles
 #endif
 
 // WARP = true : a tile belongs to ONE WARP (Ne * NBLK divides 32); phases are separated by
 //               __syncwarp only, warps never wait for each other.
 // WARP = false: a tile belongs to the CTA; phases are separated by __syncthreads.
 template <int MODE, int MB, int RT, bool WARP>
-__global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
+__global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLOCKS : 1)
     fused_kernel(const DevSys S, const FusedArgs a, const int TW, const int NBLK, const int lu_conc) {
   constexpr int NCH = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? 5 : 1;
   constexpr int NCHS = nchs<MODE>();
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
       const int blk = rem / Ne, e = rem - blk * Ne;
       const double *sp = spos + wl * ne3 + 3 * e;
       MoSink<NCH, MB> sink;
-      sink.init(T.mow + blk * MB, nmup);
+      sink.init(T.mow() + blk * MB, nmup);
       eval_aos<NCH, RT>(S, T, sp[0], sp[1], sp[2], sink);
       double *dst = smo + ((size_t)wl * Ne + e) * nmup + blk * MB;
       if (MODE == MODE_ELOC) {
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
           const int wl = it / nun, u = it - wl * nun;
           const bool up = u < S.nuu;
           const int n = up ? S.nup : S.ndown;
-          const int *cols = up ? T.ucu + u * S.nup : T.ucd + (u - S.nuu) * S.ndown;
+          const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
           const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
           double det = 1.0, tr = 0.0;
           if (n == 0) {
@@ -272,8 +277,8 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
       const double *dd = sdet + wl * nun, *tt = str + wl * nun;
       double sig = 0.0, ksig = 0.0;
       for (int c = 0; c < S.nconf; ++c) {
-        const int iu = T.ciu[c], id = S.nuu + T.cid[c];
-        const double d = T.ci[c] * dd[iu] * dd[id];
+        const int iu = T.ciu()[c], id = S.nuu + T.cid()[c];
+        const double d = T.ci()[c] * dd[iu] * dd[id];
         sig += d;
         if (MODE == MODE_ELOC) ksig += d * (tt[iu] + tt[id]);
       }
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
         const double *q = jv + wl * Ne + e;
         ks += q[4 * jvs]; ven += q[5 * jvs]; vee += q[6 * jvs];
       }
-      const double J = (S.use_jee || S.use_jen || S.een_nterm > 0) ? exp_clamped(S, ks) : 1.0;
+      const double J = (S.use_jee || S.use_jen || S.een_nterm > 0) ? exp_clamped(S, T.etab(), ks) : 1.0;
       const double psi = J * sig;
       if (MODE == MODE_PSI) {
         a.out0[w0 + wl] = psi;
@@ -340,14 +345,14 @@ __global__ void __launch_bounds__(WARP ? 256 : 512, WARP ? QMCB_MINBLOCKS : 1)
         for (int u = 0; u < nu; ++u) {
           double cu = 0.0;
           for (int c = 0; c < S.nconf; ++c) {
-            if ((up ? T.ciu[c] : T.cid[c]) != u) continue;
-            cu += T.ci[c] * dd[up ? S.nuu + T.cid[c] : T.ciu[c]];
+            if ((up ? T.ciu()[c] : T.cid()[c]) != u) continue;
+            cu += T.ci()[c] * dd[up ? S.nuu + T.cid()[c] : T.ciu()[c]];
           }
           cu *= dd[up ? u : S.nuu + u];
           if (cu == 0.0) continue;
           const int item = wl * nun + (up ? u : S.nuu + u);
           const double *inv = scr + item;
-          const int *cols = up ? T.ucu + u * S.nup : T.ucd + u * S.ndown;
+          const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + u * S.ndown;
           double tx = 0, ty = 0, tz = 0;
           const int ild = n <= 3 ? n : 2 * n, ioff = n <= 3 ? 0 : n;
           for (int j = 0; j < n; ++j) {
@@ -402,7 +407,7 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
       if (mode != MODE_GRAD && conc > 32) conc = 32;
     }
     const size_t unit = tile_doubles(S, mode, tw, conc) * sizeof(double);
-    for (int warps = 8; warps >= 1; warps /= 2) {
+    for (int warps = QMCB_WARP_CTA / 32; warps >= 1; warps /= 2) {
       const size_t sm = tab + unit * warps;
       if ((int)sm <= budget) {
         c.warp = 1; c.tw = tw; c.threads = warps * 32; c.smem = (int)sm; c.lu_conc = conc;

@@ -180,14 +180,14 @@ __global__ void __launch_bounds__(128) slater_kernel(DevSys S, const double *mo,
     for (int u = 0; u < nun; ++u) {
       const bool up = u < S.nuu;
       const int n = up ? S.nup : S.ndown;
-      const int *colsu = up ? T.ucu + u * S.nup : T.ucd + (u - S.nuu) * S.ndown;
+      const int *colsu = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
       const double *A = mo + (w * Ne + (up ? 0 : S.nup)) * nmo;
       const double *B = bop ? bop + ((op * W + w) * Ne + (up ? 0 : S.nup)) * nmo : nullptr;
       double m[QMCB_SLATER_NMAX * 2 * QMCB_SLATER_NMAX];
       const int nr = B ? n : 0, ldw = n + nr;
       for (int r = 0; r < n; ++r)
         for (int c = 0; c < n; ++c) {
-          const int col = T.used[colsu[c]];
+          const int col = T.used()[colsu[c]];
           m[r * ldw + c] = A[r * nmo + col];
           if (nr) m[r * ldw + n + c] = B[r * nmo + col];
         }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) slater_kernel(DevSys S, const double *mo,
       du[u] = det; tu[u] = tr;
     }
     for (int c = 0; c < S.nconf; ++c) {
-      const int iu = T.ciu[c], id = S.nuu + T.cid[c];
+      const int iu = T.ciu()[c], id = S.nuu + T.cid()[c];
       if (op == 0 && dets) dets[w * S.nconf + c] = du[iu] * du[id];
       if (trace && bop) trace[(op * W + w) * S.nconf + c] = tu[iu] + tu[id];
     }

@@ -187,13 +187,12 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
     S.een_c[m] = s->een_fc[m];
   }
   {
-    // degree-11 Chebyshev-economised exp on [-ln2/2, ln2/2] (mpmath.chebyfit, max error 3.2e-18),
-    // highest degree first; then log2(e), the 1.5*2^52 rounding constant, -ln2 split hi/lo
-    const double c[16] = {0x1.af631d0059becp-26, 0x1.28b4057f44145p-22, 0x1.71ddf5749d126p-19,
-                          0x1.a01991ac8730ap-16, 0x1.a01a01b14378fp-13, 0x1.6c16c187fbe02p-10,
-                          0x1.111111110f225p-7,  0x1.555555554f0cfp-5,  0x1.555555555555ap-3,
-                          0x1.0000000000011p-1,  1.0, 1.0, 1.4426950408889634, 6755399441055744.0,
-                          -0x1.62e42fee00000p-1, -0x1.a39ef35793c76p-33};
+    // exp(x) = 2^m * 2^(j/64) * exp(r), x = (64 m + j) ln2/64 + r, |r| <= ln2/128:
+    // 64/ln2, the 1.5*2^52 rounding constant, -ln2/64 split hi/lo, Taylor 1/120, 1/24, 1/6
+    // (degree-5 truncation error 3.5e-17 on that interval)
+    const double c[16] = {0x1.71547652b82fep+6, 6755399441055744.0, -0x1.62e42fee00000p-7,
+                          -0x1.a39ef35793c76p-39, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,
+                          0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 16; ++i) S.expc[i] = c[i];
   }
   // nuclear repulsion, wf_base.py:97-116
@@ -234,6 +233,9 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   for (int c = 0; c < s->nconf; ++c) hd.push_back(s->ci[c]);
   S.o_fnorm = (int)hd.size();
   for (int i = 0; i < s->nbas; ++i) hd.push_back(s->bas_norm[i]);
+  if (hd.size() & 1) hd.push_back(0.0);
+  S.o_etab = (int)hd.size();
+  for (int j = 0; j < 64; ++j) hd.push_back(std::exp2((double)j / 64.0));
   // ---- packed shell program: per shell a header record {nprim, ngroup | -}, then nprim records
   // {alpha, coef (, n as third field in the next record for gto/sto)}, then ngroup records
   // {kk | type<<24, ao | scale}.  A "P" group (type 1) stands for three consecutive AOs x,y,z
