@@ -27,6 +27,7 @@
 #include "device.cuh"
 
 #define BWD_MAXT 16   // output tiles per warp
+#define BWD_WARP_LU_MIN 7   // spin blocks at least this large: one warp per block (see fused_impl.cuh)
 
 struct BwdArgs {
   const double *pos, *weight;
@@ -234,27 +235,50 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       smo[i] = acc;
     }
     __syncthreads();
-    // ---- B3: determinants and inverses, one thread per (walker, unique occupation)
-    for (int it = tid; it < tw * nun; it += nthr) {
-      const int wl = it / nun, u = it - wl * nun;
-      const bool up = u < S.nuu;
-      const int n = up ? S.nup : S.ndown;
-      const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
-      const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
-      double *m = scr + it;
-      double det = 1.0;
-      if (n == 0) det = 1.0;
-      else if (n <= 3) det = inverse_small(n, A, nmup, cols, m, conc);
-      else {
+    // ---- B3: determinants and inverses per (walker, unique occupation): one thread (closed forms,
+    // blocks <= 3x3, interleaved scratch) or one warp (warp_gauss_jordan, contiguous scratch)
+    if (nmax >= BWD_WARP_LU_MIN) {
+      for (int it = warp; it < tw * nun; it += nwarp) {
+        const int wl = it / nun, u = it - wl * nun;
+        const bool up = u < S.nuu;
+        const int n = up ? S.nup : S.ndown;
+        const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
+        const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
+        double *m = scr + (size_t)it * inv_per;
         const int ldw = 2 * n;
-        for (int i = 0; i < n; ++i)
-          for (int j = 0; j < n; ++j) {
-            m[(i * ldw + j) * conc] = A[i * nmup + cols[j]];
-            m[(i * ldw + n + j) * conc] = i == j ? 1.0 : 0.0;
+        double det = 1.0;
+        if (n > 0) {
+          for (int idx = lane; idx < n * n; idx += 32) {
+            const int i = idx / n, j = idx - i * n;
+            m[i * ldw + j] = A[i * nmup + cols[j]];
+            m[i * ldw + n + j] = i == j ? 1.0 : 0.0;
           }
-        det = gauss_jordan(n, n, m, conc);
+          __syncwarp();
+          det = warp_gauss_jordan(n, n, m, lane);
+        }
+        if (lane == 0) sdet[it] = det;
       }
-      sdet[it] = det;
+    } else {
+      for (int it = tid; it < tw * nun; it += nthr) {
+        const int wl = it / nun, u = it - wl * nun;
+        const bool up = u < S.nuu;
+        const int n = up ? S.nup : S.ndown;
+        const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
+        const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
+        double det = 1.0;
+        if (n > 0 && n <= 3) det = inverse_small(n, A, nmup, cols, scr + it, conc);
+        else if (n > 3) {
+          double *m = scr + it;
+          const int ldw = 2 * n;
+          for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+              m[(i * ldw + j) * conc] = A[i * nmup + cols[j]];
+              m[(i * ldw + n + j) * conc] = i == j ? 1.0 : 0.0;
+            }
+          det = gauss_jordan(n, n, m, conc);
+        }
+        sdet[it] = det;
+      }
     }
     __syncthreads();
     // ---- B4: per walker
@@ -279,7 +303,8 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       for (int m = 0; m < nmup; ++m) g[m] = 0.0;
       const double wJ = wj[wl * 4];
       const int nu = up ? S.nuu : S.nud;
-      const int ild = n <= 3 ? n : 2 * n, ioff = n <= 3 ? 0 : n;
+      const bool contiguous = nmax >= BWD_WARP_LU_MIN;
+      const int ild = (contiguous || n > 3) ? 2 * n : n, ioff = (contiguous || n > 3) ? n : 0, es = contiguous ? 1 : conc;
       for (int u = 0; u < nu; ++u) {
         double cu = 0.0;
         for (int c = 0; c < S.nconf; ++c) {
@@ -288,9 +313,10 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
         }
         cu *= dd[up ? u : S.nuu + u] * wJ;
         if (cu == 0.0) continue;
-        const double *inv = scr + (wl * nun + (up ? u : S.nuu + u));
+        const int item = wl * nun + (up ? u : S.nuu + u);
+        const double *inv = contiguous ? scr + (size_t)item * inv_per : scr + item;
         const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + u * S.ndown;
-        for (int j = 0; j < n; ++j) g[cols[j]] += cu * inv[(j * ild + ioff + el) * conc];
+        for (int j = 0; j < n; ++j) g[cols[j]] += cu * inv[(j * ild + ioff + el) * es];
       }
       if (a.want_ao) {
         double *ur = su + it * lda;

@@ -537,3 +537,49 @@ __device__ inline double gauss_jordan(int n, int nr, double *scr, int es) {
   }
   return det;
 }
+
+// Warp-cooperative Gauss-Jordan with partial pivoting on [A | R] (n x (n+nr), row-major, leading
+// dimension n+nr) in shared memory: lanes own columns, the pivot search is a warp arg-max
+// (smallest index wins ties, like LAPACK).  On exit the right block holds inv(A) R.  Returns det(A)
+// on every lane.  One warp per spin block: replaces the batched torch.det / torch.inverse of
+// slater_pooling.py:96-111,348-387,827-849 for blocks larger than 3 x 3.
+__device__ inline double warp_gauss_jordan(int n, int nr, double *m, int lane) {
+  const int ldw = n + nr;
+  double det = 1.0;
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0;
+    int piv = k;
+    for (int i = k + lane; i < n; i += 32) {
+      const double v = fabs(m[i * ldw + k]);
+      if (v > best) { best = v; piv = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    if (piv != k) {
+      for (int j = lane; j < ldw; j += 32) {
+        const double t = m[k * ldw + j];
+        m[k * ldw + j] = m[piv * ldw + j];
+        m[piv * ldw + j] = t;
+      }
+      det = -det;
+    }
+    __syncwarp();
+    const double pv = m[k * ldw + k];
+    det *= pv;
+    const double ip = 1.0 / pv;
+    __syncwarp();
+    for (int j = k + 1 + lane; j < ldw; j += 32) m[k * ldw + j] *= ip;
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = m[i * ldw + k];
+      for (int j = k + 1 + lane; j < ldw; j += 32) m[i * ldw + j] -= f * m[k * ldw + j];
+    }
+    __syncwarp();
+  }
+  return det;
+}

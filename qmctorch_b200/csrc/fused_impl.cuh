@@ -68,6 +68,15 @@ struct MoSink {
 template <int MODE>
 __host__ __device__ constexpr int nchs() { return MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1); }
 
+// Spin blocks larger than this are factorised by one WARP each (warp_gauss_jordan); smaller ones
+// by one THREAD each (many independent small blocks, e.g. CAS expansions).  Measured on B200:
+// H2O cas(4,4) (n=5, 12 blocks/walker) 0.96 ms thread-per-block vs 3.4 ms warp-per-block;
+// C4H6 (n=15, 2 blocks/walker) 4.4 ms vs 2.1 ms.
+#define QMCB_WARP_LU_MIN 7
+__host__ __device__ inline bool use_warp_lu(const DevSys &S) {
+  return (S.nup > S.ndown ? S.nup : S.ndown) >= QMCB_WARP_LU_MIN;
+}
+
 __host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode) {
   const int n = S.nup > S.ndown ? S.nup : S.ndown;
   if (mode == MODE_GRAD) return n <= 3 ? n * n : 2 * n * n;   // inverse kept ([A|I] for n>3)
@@ -225,8 +234,43 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
     {
       const int nitem = tw * nun;
       const int per = lu_scratch_per_item(S, MODE);
+      if (!WARP && use_warp_lu(S)) {
+        // CTA tiles with blocks larger than 3x3: ONE WARP per spin block (warp_gauss_jordan);
+        // scratch is contiguous per slot: slot = item (GRAD keeps every inverse) or the warp
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+        for (int it = warp; it < nitem; it += nwarp) {
+          const int wl = it / nun, u = it - wl * nun;
+          const bool up = u < S.nuu;
+          const int n = up ? S.nup : S.ndown;
+          const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
+          const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
+          double *m = scr + (size_t)(MODE == MODE_GRAD ? it : warp) * per;
+          const int nr = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? n : 0;
+          const int ldw = n + nr;
+          double det = 1.0, tr = 0.0;
+          if (n > 0) {
+            for (int idx = lane; idx < n * n; idx += 32) {
+              const int i = idx / n, j = idx - i * n;
+              m[i * ldw + j] = A[i * nmup + cols[j]];
+              if (MODE == MODE_ELOC) m[i * ldw + n + j] = A[chs + i * nmup + cols[j]];
+              if (MODE == MODE_GRAD) m[i * ldw + n + j] = i == j ? 1.0 : 0.0;
+            }
+            __syncwarp();
+            det = warp_gauss_jordan(n, nr, m, lane);
+            if (MODE == MODE_ELOC) {
+              double v = 0.0;
+              for (int i = lane; i < n; i += 32) v += m[i * ldw + n + i];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              tr = v;
+            }
+            __syncwarp();
+          }
+          if (lane == 0) { sdet[wl * nun + u] = det; str[wl * nun + u] = tr; }
+        }
+      } else {
       // scratch slot: GRAD keeps every inverse resident (slot = item); otherwise one slot
-      // per participating thread, reused across rounds
+      // per participating thread, reused across rounds; elements interleaved (stride conc)
       const int conc = per ? lu_conc : nthr;
       const int stride = (MODE == MODE_GRAD) ? nthr : (conc < nthr ? conc : nthr);
       if (tid < stride) {
@@ -269,6 +313,7 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
           sdet[wl * nun + u] = det;
           str[wl * nun + u] = tr;
         }
+      }
       }
     }
     TILE_SYNC();
@@ -351,12 +396,14 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
           cu *= dd[up ? u : S.nuu + u];
           if (cu == 0.0) continue;
           const int item = wl * nun + (up ? u : S.nuu + u);
-          const double *inv = scr + item;
+          const bool contiguous = !WARP && use_warp_lu(S);   // layout written by P3
+          const double *inv = contiguous ? scr + (size_t)item * lu_scratch_per_item(S, MODE) : scr + item;
+          const int es = contiguous ? 1 : conc;
           const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + u * S.ndown;
           double tx = 0, ty = 0, tz = 0;
-          const int ild = n <= 3 ? n : 2 * n, ioff = n <= 3 ? 0 : n;
+          const int ild = (n <= 3 && !contiguous) ? n : 2 * n, ioff = (n <= 3 && !contiguous) ? 0 : n;
           for (int j = 0; j < n; ++j) {
-            const double iv = inv[(j * ild + ioff + el) * conc];
+            const double iv = inv[(j * ild + ioff + el) * es];
             tx += iv * row[chs + cols[j]];
             ty += iv * row[2 * chs + cols[j]];
             tz += iv * row[3 * chs + cols[j]];
@@ -424,7 +471,9 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
     int conc = 0;
     if (per) {
       conc = tw * nun;                                     // GRAD: every inverse stays resident
-      if (mode != MODE_GRAD && conc > threads) conc = threads;
+      // otherwise one slot per warp (warp-cooperative Gauss-Jordan) or per thread
+      const int slots = use_warp_lu(S) ? threads / 32 : threads;
+      if (mode != MODE_GRAD && conc > slots) conc = slots;
     }
     const size_t sm = tab + tile_doubles(S, mode, tw, conc) * sizeof(double);
     if ((int)sm <= budget) {
