@@ -119,9 +119,27 @@ __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, 
 }
 
 // shell program, values only; fills one row of AO, Y (into U) and X = [R_q | dR_q/dalpha]
+// MOR > 0: the MO values of the (<= MOR) used columns are accumulated in registers on the fly and
+// written to mo_row; MOR = 0: the caller forms them from the AO row afterwards.
+template <int MOR>
 __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, double ex, double ey, double ez,
-                                             double *ao, double *u, double *xr, int ppad, bool want_ao) {
+                                             double *ao, double *u, double *xr, int ppad, bool want_ao,
+                                             double *mo_row) {
   const double2 *rec = T.stream();
+  const double *W = T.mow();
+  const int nmup = S.nmup;
+  double macc[MOR > 0 ? MOR : 1];
+#pragma unroll
+  for (int m = 0; m < (MOR > 0 ? MOR : 1); ++m) macc[m] = 0.0;
+#define BWD_EMIT(idx, val)                                             \
+  do {                                                                 \
+    const double v_ = (val);                                           \
+    ao[idx] = v_;                                                      \
+    if (MOR > 0) {                                                     \
+      _Pragma("unroll") for (int m = 0; m < MOR; ++m)                  \
+        if (m < nmup) macc[m] = fma(v_, W[(idx)*nmup + m], macc[m]);   \
+    }                                                                  \
+  } while (0)
   const bool with_n = (S.radial_type == QMCB_GTO || S.radial_type == QMCB_STO);
   const bool gauss = (S.radial_type == QMCB_GTO || S.radial_type == QMCB_GTO_PURE);
   int q = 0;
@@ -152,20 +170,26 @@ __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, doub
         const int kk = __double2loint(gr.x), a0 = __double2hiint(gr.x);
         const double sc = gr.y;
         if (kk == 0) {
-          ao[a0] = S0 * sc;
-          u[a0] = 1.0;
+          BWD_EMIT(a0, S0 * sc);
+          if (want_ao) u[a0] = 1.0;
         } else if (kk == (1 << 24)) {
           const double R = S0 * sc;
-          ao[a0] = R * x; ao[a0 + 1] = R * y; ao[a0 + 2] = R * z;
-          u[a0] = x; u[a0 + 1] = y; u[a0 + 2] = z;
+          BWD_EMIT(a0, R * x); BWD_EMIT(a0 + 1, R * y); BWD_EMIT(a0 + 2, R * z);
+          if (want_ao) { u[a0] = x; u[a0 + 1] = y; u[a0 + 2] = z; }
         } else {
           const double Y = ipow(x, kk & 255) * ipow(y, (kk >> 8) & 255) * ipow(z, (kk >> 16) & 255);
-          ao[a0] = S0 * sc * Y;
-          u[a0] = Y;
+          BWD_EMIT(a0, S0 * sc * Y);
+          if (want_ao) u[a0] = Y;
         }
       }
     }
   }
+  if (MOR > 0) {
+#pragma unroll
+    for (int m = 0; m < MOR; ++m)
+      if (m < nmup) mo_row[m] = macc[m];
+  }
+#undef BWD_EMIT
 }
 
 __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const BwdArgs a) {
@@ -183,10 +207,11 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
   const int njv = 3 + 5 * S.een_nterm;
   double *jv = spos + TW * ne3;               // [njv][TW*Ne]  ks, dkee, dken, een derivatives
   double *sao = jv + njv * TW * Ne;           // [rows][lda]
+  const bool wao = a.want_ao != 0;            // U and X exist only when basis gradients are wanted
   double *su = sao + rows * lda;              // [rows][lda]
-  double *sg = su + rows * lda;               // [rows][ldg]
+  double *sg = su + (wao ? rows * lda : 0);   // [rows][ldg]
   double *sx = sg + rows * ldg;               // [rows][ldx]
-  double *smo = sx + rows * ldx;              // [rows][nmup]
+  double *smo = sx + (wao ? rows * ldx : 0);  // [rows][nmup]
   double *sdet = smo + rows * nmup;           // [TW][nun]
   double *wj = sdet + TW * nun;               // [TW][4]  weight*J, Sigma, weight*psi
   const int nsc = S.nconf + 2 + 5 * S.een_nterm;   // scalar-type outputs: CI, Jastrow weights, e-e-n
@@ -196,9 +221,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
   for (int i = tid; i < 2 * ntile; i += nthr) stiles[i] = a.tiles[i];
-  for (int i = tid; i < rows * lda; i += nthr) { sao[i] = 0.0; su[i] = 0.0; }
+  for (int i = tid; i < rows * lda; i += nthr) { sao[i] = 0.0; if (wao) su[i] = 0.0; }
   for (int i = tid; i < rows * ldg; i += nthr) sg[i] = 0.0;
-  for (int i = tid; i < rows * ldx; i += nthr) sx[i] = 0.0;
+  for (int i = tid; wao && i < rows * ldx; i += nthr) sx[i] = 0.0;
   for (int i = tid; i < nsc; i += nthr) cacc[i] = 0.0;
   double c0[BWD_MAXT], c1[BWD_MAXT];
 #pragma unroll
@@ -219,15 +244,25 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       double ks, dkee, dken;
       jastrow_value_dw(S, T, sp, e, ks, dkee, dken, jv + 3 * TW * Ne + it, TW * Ne);
       jv[it] = ks; jv[TW * Ne + it] = dkee; jv[2 * TW * Ne + it] = dken;
-      backward_row(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda, sx + it * ldx,
-                   a.ppad, a.want_ao != 0);
+      if (nmup <= 2)
+        backward_row<2>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
+                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup);
+      else if (nmup <= 4)
+        backward_row<4>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
+                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup);
+      else if (nmup <= 8)
+        backward_row<8>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
+                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup);
+      else
+        backward_row<0>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
+                        sx + it * ldx, a.ppad, a.want_ao != 0, nullptr);
     }
     // rows of a ragged last tile must not contribute
     for (int i = tid + nrow * ldg; i < rows * ldg; i += nthr) sg[i] = 0.0;
-    for (int i = tid + nrow * lda; i < rows * lda; i += nthr) su[i] = 0.0;
+    for (int i = tid + nrow * lda; wao && i < rows * lda; i += nthr) su[i] = 0.0;
     __syncthreads();
-    // ---- B2b: MO values of the used columns
-    for (int i = tid; i < nrow * nmup; i += nthr) {
+    // ---- B2b: MO values of the used columns (only when they were not formed on the fly)
+    for (int i = tid; nmup > 8 && i < nrow * nmup; i += nthr) {
       const int row = i / nmup, m = i - row * nmup;
       const double *ar = sao + row * lda;
       double acc = 0.0;
@@ -476,34 +511,41 @@ int qmcb_choose_backward(qmcb_plan *p) {
   const int nmax = S.nup > S.ndown ? S.nup : S.ndown;
   const int inv_per = nmax <= 3 ? nmax * nmax : 2 * nmax * nmax;
   const int budget = p->smem_optin - 1024;
-  for (int tw = 64; tw >= 1; tw = tw > 8 ? tw / 2 : tw - 1) {
-    const int rows = ((tw * S.nelec + 3) / 4) * 4;
-    int threads = ((rows + 31) / 32) * 32;
-    const int need_warps = (ntile + BWD_MAXT - 1) / BWD_MAXT;
-    if (threads < 32 * need_warps) threads = 32 * need_warps;
-    if (threads < 128) threads = 128;
-    if (threads > 512) continue;
-    const int conc = tw * nun;
-    size_t d = (size_t)table_doubles(S) + (size_t)tw * 3 * S.nelec +
-               (size_t)(3 + 5 * S.een_nterm) * tw * S.nelec +
-               (size_t)rows * (2 * b.lda + b.ldg + b.ldx + S.nmup) + (size_t)tw * nun + (size_t)tw * 4 +
-               (size_t)((S.nconf + 2 + 5 * S.een_nterm + 1) & ~1) + (size_t)inv_per * conc + (size_t)ntile + 2;
-    const size_t sm = d * sizeof(double);
-    // keep the tile small enough for two CTAs per SM when that is possible with >= 32 rows
-    if ((int)sm <= budget && ((int)sm <= 100 * 1024 || rows <= 64)) {
-      b.tw = tw; b.rows = rows; b.threads = threads; b.smem = (int)sm; b.lu_conc = conc;
-      b.grid = 2 * p->sm_count;
-      return 0;
+  // two tilings: with the basis-parameter part (U, X resident) and without it (larger tiles)
+  for (int wao = 1; wao >= 0; --wao) {
+    auto &c = wao ? p->bwd : p->bwd0;
+    if (!wao) c = p->bwd;
+    c.tw = 0;
+    for (int tw = 128; tw >= 1; tw = tw > 8 ? tw / 2 : tw - 1) {
+      const int rows = ((tw * S.nelec + 3) / 4) * 4;
+      int threads = ((rows + 31) / 32) * 32;
+      const int ntile_act = b.ntile_mo + (wao ? b.ntile_ao : 0);
+      const int need_warps = (ntile_act + BWD_MAXT - 1) / BWD_MAXT;
+      if (threads < 32 * need_warps) threads = 32 * need_warps;
+      if (threads < 128) threads = 128;
+      if (threads > 512) continue;
+      const int conc = tw * nun;
+      size_t d = (size_t)table_doubles(S) + (size_t)tw * 3 * S.nelec +
+                 (size_t)(3 + 5 * S.een_nterm) * tw * S.nelec +
+                 (size_t)rows * ((wao ? 2 : 1) * b.lda + b.ldg + (wao ? b.ldx : 0) + S.nmup) + (size_t)tw * nun +
+                 (size_t)tw * 4 + (size_t)((S.nconf + 2 + 5 * S.een_nterm + 1) & ~1) + (size_t)inv_per * conc +
+                 (size_t)ntile + 2;
+      const size_t sm = d * sizeof(double);
+      // keep the tile small enough for two CTAs per SM when that is possible with >= 64 rows
+      if ((int)sm <= budget && ((int)sm <= 100 * 1024 || rows <= 64)) {
+        c.tw = tw; c.rows = rows; c.threads = threads; c.smem = (int)sm; c.lu_conc = conc;
+        c.grid = 2 * p->sm_count;
+        break;
+      }
     }
   }
-  // backward unavailable for this system: forward entry points still work
-  b.tw = 0;
+  // tw == 0: backward unavailable for this system; forward entry points still work
   return 0;
 }
 
 extern "C" int64_t qmcb_backward_workspace_bytes(const qmcb_plan *p, int64_t) {
-  if (!p || p->bwd.tw == 0) return 0;
-  return (int64_t)p->bwd.grid * p->bwd.nslot * (int64_t)sizeof(double);
+  if (!p || (p->bwd.tw == 0 && p->bwd0.tw == 0)) return 0;
+  return (int64_t)2 * p->sm_count * p->bwd.nslot * (int64_t)sizeof(double);
 }
 
 extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const double *weight, int64_t W,
@@ -514,7 +556,8 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
     qmcb_set_error("qmcb_psi_backward: bad arguments");
     return QMCB_EINVAL;
   }
-  const auto &b = p->bwd;
+  const int want_ao = (g_bas_exp || g_bas_coeffs) ? 1 : 0;
+  const auto &b = want_ao ? p->bwd : p->bwd0;
   if (b.tw == 0) {
     qmcb_set_error("qmcb_psi_backward: system does not fit the backward tiling");
     return QMCB_ESMEM;
@@ -522,7 +565,7 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
   cudaStream_t st = (cudaStream_t)stream;
   BwdArgs a{};
   a.pos = pos; a.weight = weight; a.W = W; a.partial = (double *)workspace; a.tiles = p->d_bwd_tiles;
-  a.want_ao = (g_bas_exp || g_bas_coeffs) ? 1 : 0;
+  a.want_ao = want_ao;
   a.tw = b.tw; a.rows = b.rows; a.lda = b.lda; a.ldg = b.ldg; a.ldx = b.ldx; a.ppad = b.ppad;
   a.ntile_mo = b.ntile_mo; a.ntile_ao = b.ntile_ao; a.nslot = b.nslot; a.lu_conc = b.lu_conc;
   cudaError_t e = cudaFuncSetAttribute(backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem);

@@ -84,7 +84,7 @@ struct qmcb_plan {
     int ntile_mo = 0, ntile_ao = 0;              // 8x8 output tiles
     int nslot = 0;                               // doubles per CTA partial
     int grid = 0;
-  } bwd;
+  } bwd, bwd0;   // with / without the basis-parameter gradients
   std::vector<int> bwd_tiles;                    // [ntile][2] (row block, col block) ; MO first, then AO
   int *d_bwd_tiles = nullptr;
   size_t cap_bwd_tiles = 0;
