@@ -46,6 +46,10 @@ CASES = [
     ("h2o_ground", "h2o", "ground_state", "ee", 96, 100, 0.15, "atomic"),
     ("h2o_cas44", "h2o", "cas(4,4)", "ee+en", 48, 100, 0.15, "atomic"),
     ("c4h6_ground", "c4h6", "ground_state", "ee", 16, 60, 0.05, "atomic"),
+    # the other radial forms (ADF-style uncontracted bases)
+    ("lih_sto", "lih_sto", "single_double(2,2)", "ee", 96, 100, 0.3, "normal"),
+    ("lih_sto_pure", "lih_sto_pure", "ground_state", "ee", 64, 100, 0.3, "normal"),
+    ("lih_gto_kr", "lih_gto_kr", "ground_state", "ee+en", 64, 100, 0.3, "normal"),
     # three-body Boys-Handy term (BASELINE config 4: CAS + e-e-n Jastrow)
     ("lih_sd22_een3", "lih", "single_double(2,2)", "ee+en+een", 96, 100, 0.3, "normal"),
     ("h2o_cas44_een", "h2o", "cas(4,4)", "ee+een", 32, 100, 0.15, "atomic"),
@@ -174,7 +178,9 @@ def main(only=None):
         opt.zero_grad()
         solver.evaluate_grad_manual(pos.clone().requires_grad_(True) if has_een else pos.clone())
         ref_g = dict(mo_modifier=wf.mo.mo_modifier.grad.clone(), ci=wf.fc.weight.grad.clone(),
-                     bas_exp=wf.ao.bas_exp.grad.clone(), bas_coeffs=wf.ao.bas_coeffs.grad.clone())
+                     bas_exp=wf.ao.bas_exp.grad.clone())
+        if wf.ao.bas_coeffs.grad is not None:      # uncontracted bases never use the coefficients in psi
+            ref_g["bas_coeffs"] = wf.ao.bas_coeffs.grad.clone()
         if jast == "ee":
             ref_g["jastrow_weight"] = wf.jastrow.jastrow_kernel.weight.grad.clone()
         elif jast is not None:

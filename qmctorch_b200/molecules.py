@@ -113,6 +113,18 @@ _BASIS = {
     },
 }
 
+# uncontracted (ADF-style, scf/calculator/adf.py:189-296) tables: element -> list of (kx, ky, kz, kr, zeta).
+# One AO per entry, bas_coeffs = 1, index_ctr = arange(nao).  Exponents are plausible double-zeta
+# Slater values typed by hand ("approximate"); they exercise the sto / sto_pure / gto radial forms.
+_P = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+_UNCONTRACTED = {
+    "sto-dz": {
+        "H": [(0, 0, 0, 0, 0.76), (0, 0, 0, 0, 1.28)] + [(a, b, c, 0, 1.25) for a, b, c in _P],
+        "Li": [(0, 0, 0, 0, 2.45), (0, 0, 0, 0, 3.90), (0, 0, 0, 1, 0.65), (0, 0, 0, 1, 1.05)]
+              + [(a, b, c, 0, 0.70) for a, b, c in _P],
+    },
+}
+
 _DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
@@ -178,6 +190,41 @@ def build_basis(atoms, atom_coords, basis_name):
     return b
 
 
+def build_basis_uncontracted(atoms, atom_coords, basis_name, radial_type):
+    """ADF-style namespace: every AO is a single Slater/Gaussian primitive x^kx y^ky z^kz r^kr."""
+    table = _UNCONTRACTED[basis_name.lower()]
+    b = SimpleNamespace()
+    b.radial_type = radial_type
+    b.harmonics_type = "cart"
+    rows, nshells = [], []
+    for el in atoms:
+        rows += table[el]
+        nshells.append(len(table[el]))
+    n = len(rows)
+    b.nao = n
+    b.nshells = nshells
+    b.nao_per_atom = nshells
+    b.index_ctr = np.arange(n)
+    b.nctr_per_ao = np.ones(n)
+    b.bas_kx = np.array([r[0] for r in rows])
+    b.bas_ky = np.array([r[1] for r in rows])
+    b.bas_kz = np.array([r[2] for r in rows])
+    b.bas_kr = np.array([0 if radial_type.endswith("pure") else r[3] for r in rows])
+    b.bas_exp = np.array([r[4] for r in rows], dtype=np.float64)
+    b.bas_coeffs = np.ones(n)
+    b.bas_n = (b.bas_kx + b.bas_ky + b.bas_kz + b.bas_kr + 1).tolist()
+    b.atom_coords_internal = [list(c) for c in atom_coords]
+    b.TotalEnergy = 0.0
+    return b
+
+
+def _seeded_mos(n, seed):
+    """Deterministic, well-conditioned, diagonally dominant orthonormal matrix (test fixtures only)."""
+    rng = np.random.RandomState(seed)
+    q, _ = np.linalg.qr(np.eye(n) + 0.35 * rng.standard_normal((n, n)))
+    return q * np.sign(np.diag(q))
+
+
 class Molecule:
     """Duck-typed stand-in for ``qmctorch.scf.Molecule`` (``scf/molecule.py:21``).
 
@@ -187,7 +234,7 @@ class Molecule:
     """
 
     def __init__(self, atom, basis="sto-3g", unit="bohr", charge=0, spin=0, name=None,
-                 calculator="builtin", mos=None):
+                 calculator="builtin", mos=None, radial_type=None):
         self.atoms_str = atom
         self.unit = unit
         self.charge = charge
@@ -209,7 +256,12 @@ class Molecule:
         self.ndown = int((self.nelec - spin) / 2)
         self.name = name or "".join(names)
         self.hdf5file = "_".join([self.name, calculator, basis]) + ".hdf5"
-        self.basis = build_basis(names, coords, basis)
+        if basis.lower() in _UNCONTRACTED:
+            self.basis = build_basis_uncontracted(names, coords, basis, radial_type or "sto")
+            if mos is None:
+                mos = _seeded_mos(self.basis.nao, 17)
+        else:
+            self.basis = build_basis(names, coords, basis)
         if mos is None:
             mos = _load_cached_mos(self.name, basis, self.basis.nao)
         mos = np.asarray(mos, dtype=np.float64)
@@ -286,6 +338,12 @@ _SPECS = {
     "h2": dict(atom="H 0 0 -0.69; H 0 0 0.69", unit="bohr", basis="sto-3g", name="H2"),
     "lih_sto3g": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="sto-3g", name="LiH"),
     "lih": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="6-31g", name="LiH"),
+    # ADF-style uncontracted Slater / Gaussian-with-r^n bases (radial_slater, radial_slater_pure,
+    # radial_gaussian of radial_functions.py); seeded orthonormal MOs
+    "lih_sto": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="sto-dz", name="LiH", radial_type="sto"),
+    "lih_sto_pure": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="sto-dz", name="LiH",
+                         radial_type="sto_pure"),
+    "lih_gto_kr": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="sto-dz", name="LiH", radial_type="gto"),
     "h2o": dict(atom="O 0 0 0; H 0.757 0.587 0; H -0.757 0.587 0", unit="angs",
                 basis="cc-pvdz", name="H2O"),
     "c4h6": dict(atom=None, unit="angs", basis="dzp", name="C4H6"),

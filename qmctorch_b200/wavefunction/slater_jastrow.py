@@ -42,7 +42,9 @@ class _PsiFunction(torch.autograd.Function):
             gx = wf._grad_psi(x, pdf=False) * grad_out.reshape(-1, 1)
         return (None, gx,
                 g["bas_exp"] if need[2] else None,
-                g["bas_coeffs"] if need[3] else None,
+                # uncontracted bases: the reference never multiplies bas_coeffs into psi
+                # (atomic_orbitals.py:236-249), so its .grad stays None
+                g["bas_coeffs"] if (need[3] and wf.ao.contract) else None,
                 g["mo_modifier"] if need[4] else None,
                 g["ci"] if need[5] else None,
                 g["jee_w"] if need[6] else None,

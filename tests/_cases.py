@@ -9,7 +9,8 @@ from qmctorch_b200.molecules import fixture_molecule
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["h2_single22", "h2_ground", "lih_ground", "lih_nojastrow", "lih_sd22", "lih_cas24", "lih_een",
-         "h2o_ground", "h2o_cas44", "c4h6_ground", "lih_sd22_een3", "h2o_cas44_een"]
+         "h2o_ground", "h2o_cas44", "c4h6_ground", "lih_sd22_een3", "h2o_cas44_een",
+         "lih_sto", "lih_sto_pure", "lih_gto_kr"]
 
 
 def load(name):
