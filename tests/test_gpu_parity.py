@@ -342,3 +342,75 @@ def test_solver_optimisation_lowers_energy_and_matches_oracle_step():
     assert wf.ao.bas_exp.grad is None and wf.mo.mo_modifier.grad is not None
     assert np.mean(obs.energy[-2:]) < obs.energy[0] + 0.02          # energy does not go up
     assert hasattr(obs.models, "best") and "mo.mo_modifier" in obs.models.best
+
+
+@pytest.mark.parametrize("move_type,proba", [("one-elec", "normal"), ("all-elec-iter", "normal"),
+                                             ("all-elec", "uniform"), ("one-elec", "uniform")])
+def test_sampler_move_types_replay_reference_draws(move_type, proba):
+    """Every move type / proposal of sampler/metropolis.py:179-277 with rng='torch': same generator
+    calls in the same order as the reference, so the trajectory equals the oracle's bit for bit."""
+    from qmctorch_b200.sampler import Metropolis
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    mol_o, P = C.oracle_params(g)
+    nw, nstep, step, ne = 200, 6, 0.4, wf.nelec
+    torch.manual_seed(77)
+    s = Metropolis(nwalkers=nw, nstep=nstep, step_size=step, nelec=ne, ndim=3, init=mol.domain("normal"),
+                   move={"type": move_type, "proba": proba}, cuda=True, rng="torch")
+    out = s(wf.pdf, with_tqdm=False).detach()
+    # oracle replay
+    torch.manual_seed(77)
+    from torch.distributions import MultivariateNormal
+    d = mol.domain("normal")
+    pos = MultivariateNormal(torch.as_tensor(d["mean"]), torch.as_tensor(d["sigma"])).sample((nw, ne))
+    pos = pos.type(torch.float64).view(nw, -1)
+    fx = (orc.psi(P, pos) ** 2).reshape(-1)
+
+    def draw(n):
+        if proba == "uniform":
+            return step * (2.0 * torch.rand((nw, n, 3), dtype=torch.float64) - 1.0)
+        return s.multiVariate.sample((nw, n)).to(torch.float64)
+
+    for _ in range(nstep):
+        for id_elec in (range(ne) if move_type == "all-elec-iter" else [None]):
+            if move_type == "all-elec":
+                disp = draw(ne).view(nw, -1)
+            else:
+                idx = torch.LongTensor(nw).random_(0, ne) if id_elec is None else torch.full((nw,), id_elec)
+                full = torch.zeros(nw, ne, 3, dtype=torch.float64)
+                full[torch.arange(nw), idx, :] = draw(1).view(nw, 3)
+                disp = full.view(nw, -1)
+            tau = torch.rand(nw, dtype=torch.float64)
+            pos, fx, acc, _ = orc.metropolis_step(P, pos, fx, disp, tau)
+    assert torch.equal(out, pos)
+    assert 0.0 < s.acceptance_rate <= 1.0
+
+
+def test_philox_sampler_is_tiling_independent_and_samples_psi2():
+    """In-kernel Philox draws are functions of (seed, step, global index): the same seed gives the
+    same ensemble whatever the number of walkers processed together; the sampled energy agrees
+    with the torch-draw sampler within statistical error."""
+    from qmctorch_b200.sampler import Metropolis
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    torch.manual_seed(3)
+    init = Metropolis(nwalkers=4096, nstep=1, nelec=wf.nelec, ndim=3, init=mol.domain("normal"), cuda=True)
+    init.walkers.initialize()
+    start = init.walkers.pos.clone()
+
+    def run(pos, seed, rng):
+        s = Metropolis(nwalkers=pos.shape[0], nstep=150, step_size=0.3, nelec=wf.nelec, ndim=3,
+                       init=mol.domain("normal"), move={"type": "all-elec", "proba": "normal"}, cuda=True, seed=seed,
+                       rng=rng, keep_on_device=True)
+        return s(wf.pdf, pos=pos.clone(), with_tqdm=False).detach()
+    a = run(start, 9, "philox")
+    b = run(start, 9, "philox")
+    assert torch.equal(a, b)
+    head = run(start[:1000], 9, "philox")
+    assert torch.equal(head, a[:1000])                      # independent of the ensemble size / tiling
+    assert not torch.equal(run(start, 10, "philox"), a)
+    e_philox = wf.local_energy(a)
+    torch.manual_seed(4)
+    e_torch = wf.local_energy(run(start, 0, "torch"))
+    err = float((e_philox.var() / len(e_philox) + e_torch.var() / len(e_torch)).sqrt())
+    assert abs(float(e_philox.mean() - e_torch.mean())) < 6 * err
