@@ -166,8 +166,8 @@ int qmcb_jastrow(const qmcb_plan *plan, const double *pos, int64_t W, int which,
 int qmcb_slater(const qmcb_plan *plan, const double *mo, const double *bop, int64_t nop,
                 int64_t W, double *dets, double *trace, void *stream);
 
-/* FP64 pipe probes for the roofline denominator: runs `iters` dependent-chain DFMA (kind 0)
- * or DMMA m8n8k4 (kind 1) per thread on the whole GPU and returns flop count through
+/* FP64 pipe probes for the roofline denominator: runs `iters` dependent-chain DFMA (kind 0),
+ * DMMA m8n8k4 (kind 1) or both interleaved (kind 2) per thread on the whole GPU and returns flop count through
  * *flops; time it with events on `stream`. */
 int qmcb_fp64_probe(int kind, int64_t iters, double *sink, double *flops, void *stream);
 

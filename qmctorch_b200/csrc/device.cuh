@@ -583,3 +583,80 @@ __device__ inline double warp_gauss_jordan(int n, int nr, double *m, int lane) {
   }
   return det;
 }
+
+// Register-resident Gauss-Jordan with partial pivoting for N = 4..6 (fully unrolled, row swaps by
+// predicated moves): det(A) and, if WITH_B, Tr(A^-1 B) without any shared-memory scratch.
+// A(i,j) = mo[row0+i][cols[j]], B likewise (ld = row stride).
+// __noinline__: its register/local-memory footprint must not leak into the callers' allocation.
+template <int N, bool WITH_B>
+__device__ __noinline__ void det_trace_reg(const double *A, const double *B, int ld, const int *cols,
+                                              double &det_out, double &tr_out) {
+  double a[N][N], b[N][WITH_B ? N : 1];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const int c = cols[j];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      a[i][j] = A[i * ld + c];
+      if (WITH_B) b[i][j] = B[i * ld + c];
+    }
+  }
+  double det = 1.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    // pivot: first row with the largest |a[i][k]|, i >= k
+    int piv = k;
+    double best = fabs(a[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(a[i][k]);
+      if (v > best) { best = v; piv = i; }
+    }
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const bool sw = piv == i;
+#pragma unroll
+      for (int j = k; j < N; ++j) {
+        const double t = a[k][j];
+        a[k][j] = sw ? a[i][j] : t;
+        a[i][j] = sw ? t : a[i][j];
+      }
+      if (WITH_B) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const double t = b[k][j];
+          b[k][j] = sw ? b[i][j] : t;
+          b[i][j] = sw ? t : b[i][j];
+        }
+      }
+    }
+    if (piv != k) det = -det;
+    const double pv = a[k][k];
+    det *= pv;
+    const double ip = 1.0 / pv;
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) a[k][j] *= ip;
+    if (WITH_B) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) b[k][j] *= ip;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+#pragma unroll
+      for (int j = k + 1; j < N; ++j) a[i][j] -= f * a[k][j];
+      if (WITH_B) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) b[i][j] -= f * b[k][j];
+      }
+    }
+  }
+  det_out = det;
+  double tr = 0.0;
+  if (WITH_B) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) tr += b[i][i];
+  }
+  tr_out = tr;
+}

@@ -77,21 +77,22 @@ __host__ __device__ inline bool use_warp_lu(const DevSys &S) {
   return (S.nup > S.ndown ? S.nup : S.ndown) >= QMCB_WARP_LU_MIN;
 }
 
-__host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode) {
+__host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode, bool warp_tiles) {
   const int n = S.nup > S.ndown ? S.nup : S.ndown;
   if (mode == MODE_GRAD) return n <= 3 ? n * n : 2 * n * n;   // inverse kept ([A|I] for n>3)
-  if (n <= 3) return 0;
+  if (n <= 3) return 0;                                      // closed forms
+  if (!warp_tiles && n <= 6) return 0;                       // register Gauss-Jordan (CTA-tile kernels)
   return mode == MODE_ELOC ? 2 * n * n : n * n;            // [A|B] or A
 }
 
 // Work area of one tile (doubles): spos [TW][3Ne] | jv [TW][Ne][8] | mo [NCHS][TW][Ne][nmup]
 // | dets [TW][nun] | trs [TW][nun] | wsum [TW][4] | LU scratch
-__host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw, int lu_conc) {
+__host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw, int lu_conc, bool warp_tiles) {
   const int nchs_ = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
   const int nun = S.nuu + S.nud;
   size_t d = (size_t)tw * 3 * S.nelec + (size_t)tw * S.nelec * 8 + (size_t)nchs_ * tw * S.nelec * S.nmup;
   d += 2 * (size_t)tw * nun + (size_t)tw * 4;
-  d += (size_t)lu_conc * lu_scratch_per_item(S, mode);
+  d += (size_t)lu_conc * lu_scratch_per_item(S, mode, warp_tiles);
   return (d + 1) & ~(size_t)1;
 }
 
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
   const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
   const int64_t unit = WARP ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
   const int64_t nunit = WARP ? (int64_t)gridDim.x * (blockDim.x >> 5) : gridDim.x;
-  if (WARP) ws += (threadIdx.x >> 5) * tile_doubles(S, MODE, TW, lu_conc);
+  if (WARP) ws += (threadIdx.x >> 5) * tile_doubles(S, MODE, TW, lu_conc, true);
   double *spos = ws;
   double *jv = spos + TW * ne3;
   double *smo = jv + TW * Ne * 8;
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
     // ---- P3: determinants (and traces / inverses) per (wl, unique occupation)
     {
       const int nitem = tw * nun;
-      const int per = lu_scratch_per_item(S, MODE);
+      const int per = lu_scratch_per_item(S, MODE, WARP);
       if (!WARP && use_warp_lu(S)) {
         // CTA tiles with blocks larger than 3x3: ONE WARP per spin block (warp_gauss_jordan);
         // scratch is contiguous per slot: slot = item (GRAD keeps every inverse) or the warp
@@ -297,6 +298,12 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
             }
           } else if (n <= 3) {
             det_trace_small(n, A, A + chs, nmup, cols, MODE == MODE_ELOC, det, tr);
+          } else if (!WARP && n == 4) {   // CTA-tile kernels only: keeps calls out of the warp-tile kernels
+            det_trace_reg<4, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
+          } else if (!WARP && n == 5) {
+            det_trace_reg<5, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
+          } else if (!WARP && n == 6) {
+            det_trace_reg<6, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
           } else {
             double *m = scr + tid;
             const int nr = MODE == MODE_ELOC ? n : 0;
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
           if (cu == 0.0) continue;
           const int item = wl * nun + (up ? u : S.nuu + u);
           const bool contiguous = !WARP && use_warp_lu(S);   // layout written by P3
-          const double *inv = contiguous ? scr + (size_t)item * lu_scratch_per_item(S, MODE) : scr + item;
+          const double *inv = contiguous ? scr + (size_t)item * lu_scratch_per_item(S, MODE, WARP) : scr + item;
           const int es = contiguous ? 1 : conc;
           const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + u * S.ndown;
           double tx = 0, ty = 0, tz = 0;
@@ -442,18 +449,18 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
     return QMCB_ESMEM;
   }
   const int nun = S.nuu + S.nud;
-  const int per = lu_scratch_per_item(S, mode);
   const int budget = p->smem_optin - 1024;
   const size_t tab = (size_t)table_doubles(S) * sizeof(double);
   // ---- warp-owned tiles when the threads of a walker tile a warp exactly
   if (32 % per_walker == 0) {
     const int tw = 32 / per_walker;
+    const int per = lu_scratch_per_item(S, mode, true);
     int conc = 0;
     if (per) {
       conc = tw * nun;
       if (mode != MODE_GRAD && conc > 32) conc = 32;
     }
-    const size_t unit = tile_doubles(S, mode, tw, conc) * sizeof(double);
+    const size_t unit = tile_doubles(S, mode, tw, conc, true) * sizeof(double);
     for (int warps = QMCB_WARP_CTA / 32; warps >= 1; warps /= 2) {
       const size_t sm = tab + unit * warps;
       if ((int)sm <= budget) {
@@ -468,6 +475,7 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   for (; tw >= 1; --tw) {
     int threads = ((tw * per_walker + 31) / 32) * 32;
     if (threads > 512) continue;
+    const int per = lu_scratch_per_item(S, mode, false);
     int conc = 0;
     if (per) {
       conc = tw * nun;                                     // GRAD: every inverse stays resident
@@ -475,7 +483,7 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
       const int slots = use_warp_lu(S) ? threads / 32 : threads;
       if (mode != MODE_GRAD && conc > slots) conc = slots;
     }
-    const size_t sm = tab + tile_doubles(S, mode, tw, conc) * sizeof(double);
+    const size_t sm = tab + tile_doubles(S, mode, tw, conc, false) * sizeof(double);
     if ((int)sm <= budget) {
       c.warp = 0; c.tw = tw; c.threads = threads; c.smem = (int)sm; c.lu_conc = conc;
       return 0;

@@ -303,6 +303,31 @@ __global__ void __launch_bounds__(256) dmma_probe(int64_t iters, double *sink) {
   if (r == 123.456) sink[0] = r;
 }
 
+// both at once: does the DMMA sub-pipe run concurrently with the FP64 vector pipe?
+__global__ void __launch_bounds__(256) mixed_probe(int64_t iters, double *sink) {
+  double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double a = 1e-3 * (threadIdx.x & 7), b = 1e-3 * (threadIdx.x >> 3), bb = 0.999999999, cc = 1e-12;
+  for (int64_t i = 0; i < iters; ++i) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0[0]), "+d"(c0[1]) : "d"(a), "d"(b));
+    a0 = fma(a0, bb, cc); a1 = fma(a1, bb, cc);
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c1[0]), "+d"(c1[1]) : "d"(a), "d"(b));
+    a2 = fma(a2, bb, cc); a3 = fma(a3, bb, cc);
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c2[0]), "+d"(c2[1]) : "d"(a), "d"(b));
+    a4 = fma(a4, bb, cc); a5 = fma(a5, bb, cc);
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c3[0]), "+d"(c3[1]) : "d"(a), "d"(b));
+    a6 = fma(a6, bb, cc); a7 = fma(a7, bb, cc);
+  }
+  const double r = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1] + a0 + a1 + a2 + a3 + a4 + a5 +
+                   a6 + a7;
+  if (r == 123.456) sink[0] = r;
+}
+
 extern "C" int qmcb_fp64_probe(int kind, int64_t iters, double *sink, double *flops, void *stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -311,10 +336,14 @@ extern "C" int qmcb_fp64_probe(int kind, int64_t iters, double *sink, double *fl
   if (kind == 0) {
     dfma_probe<<<ctas, threads, 0, (cudaStream_t)stream>>>(iters, sink);
     if (flops) *flops = 2.0 * 8.0 * (double)iters * ctas * threads;
-  } else {
+  } else if (kind == 1) {
     dmma_probe<<<ctas, threads, 0, (cudaStream_t)stream>>>(iters, sink);
     // one m8n8k4 = 8*8*4 FMA = 512 flop per warp
     if (flops) *flops = 512.0 * 4.0 * (double)iters * ctas * (threads / 32);
+  } else {
+    mixed_probe<<<ctas, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    // per iteration and warp: 4 DMMA (2048 flop) + 8 DFMA x 32 lanes (512 flop)
+    if (flops) *flops = (2048.0 + 512.0) * (double)iters * ctas * (threads / 32);
   }
   return (int)cudaGetLastError();
 }

@@ -8,7 +8,7 @@ dev = torch.device("cuda", 0)
 sink = torch.zeros(1, dtype=torch.float64, device=dev)
 fl = ctypes.c_double(0.0)
 sp = _lib.stream_ptr(dev)
-for kind, name in ((0, "DFMA"), (1, "DMMA m8n8k4")):
+for kind, name in ((0, "DFMA"), (1, "DMMA m8n8k4"), (2, "mixed 4 DMMA + 8 DFMA")):
     best = 0.0
     for rep in range(4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
