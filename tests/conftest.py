@@ -21,3 +21,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The tests call through libqmcb.so; build it in-tree if a fresh checkout has none."""
+    from qmctorch_b200 import build as b
+    if not os.path.isfile(b.LIB):
+        b.build()
+    yield
