@@ -277,6 +277,10 @@ def main():
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
+    # last collective is behind us: leave the process group together, rank 0 finishes alone
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
     # ---- FP64 pipe peak (own probe: dependent-chain-free DFMA loop over the whole GPU)
     sink = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -293,8 +297,6 @@ def main():
         peak_tf = tf if peak_tf is None else max(peak_tf, tf)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     value = world * W * args.steps / (elapsed_ms * 1e-3)
     F = algorithmic_flops(mol, wf, info)
@@ -330,8 +332,6 @@ def main():
                                 "sample": "%d walkers x 3 steps of oracle.local_energy (torch CPU FP64, "
                                           "reference algorithm)" % ncpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

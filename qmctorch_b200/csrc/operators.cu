@@ -252,12 +252,14 @@ __global__ void __launch_bounds__(256) stats_stage1(const double *e, int64_t W, 
   if (threadIdx.x < 4) part[blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// one warp per quantity: lane-strided partial sums, then a fixed-order butterfly
 __global__ void stats_stage2(const double *part, int n, double *out4) {
-  if (threadIdx.x < 4) {
-    double s = 0;
-    for (int i = 0; i < n; ++i) s += part[i * 4 + threadIdx.x];
-    out4[threadIdx.x] = s;
-  }
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0;
+  for (int i = lane; i < n; i += 32) s += part[i * 4 + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out4[q] = s;
 }
 
 extern "C" int64_t qmcb_stats_workspace_bytes(int64_t) { return (int64_t)STATS_CTAS * 4 * 8; }
@@ -269,7 +271,7 @@ extern "C" int qmcb_energy_stats(const double *eloc, int64_t W, double *out4, vo
   }
   cudaStream_t st = (cudaStream_t)stream;
   stats_stage1<<<STATS_CTAS, 256, 0, st>>>(eloc, W, (double *)workspace);
-  stats_stage2<<<1, 32, 0, st>>>((const double *)workspace, STATS_CTAS, out4);
+  stats_stage2<<<1, 128, 0, st>>>((const double *)workspace, STATS_CTAS, out4);
   return (int)cudaGetLastError();
 }
 
