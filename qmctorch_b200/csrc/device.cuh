@@ -422,6 +422,72 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
   o.ks = ks; o.ven = ven; o.vee = vee;
 }
 
+// One-walker-per-thread variant: every electron pair is visited ONCE.  jv[k*jvs + e] receives
+// gx, gy, gz, lap (k = 0..3, DERIV only); the walker totals of ln J, V_en, V_ee are returned.
+template <bool DERIV, bool POT>
+__device__ __forceinline__ void walker_terms(const DevSys &S, const Tab &T, const double *sp, double *jv,
+                                             int jvs, double &tks, double &tven, double &tvee) {
+  const int Ne = S.nelec;
+  if (DERIV)
+    for (int e = 0; e < Ne; ++e) { jv[e] = 0.0; jv[jvs + e] = 0.0; jv[2 * jvs + e] = 0.0; jv[3 * jvs + e] = 0.0; }
+  tks = 0.0; tven = 0.0; tvee = 0.0;
+  const double w = S.jee_w;
+  for (int i = 0; i < Ne; ++i) {
+    const double xi = sp[3 * i], yi = sp[3 * i + 1], zi = sp[3 * i + 2];
+    const double ni = gram_norm(xi, yi, zi);
+    const bool up_i = i < S.nup;
+    double gx = 0, gy = 0, gz = 0, h = 0, ks = 0, vee = 0, ven = 0;
+    for (int j = i + 1; j < Ne; ++j) {
+      const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
+      const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+      const double s2 = dx * dx + dy * dy + dz * dz;
+      if (POT) vee += fast_rsqrt(s2);
+      if (S.use_jee) {
+        const double d2 = gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, gram_norm(xj, yj, zj));
+        const double rinv = fast_rsqrt(d2);
+        const double r = d2 * rinv;
+        const double w0 = (up_i == (j < S.nup)) ? 0.25 : 0.5;
+        const double den = fast_rcp(1.0 + w * r);
+        ks += w0 * r * den;
+        if (DERIV) {
+          const double kp = w0 * den * den * rinv;
+          const double px = kp * dx, py = kp * dy, pz = kp * dz;
+          const double hp = 2.0 * kp * den * (s2 * rinv * rinv);
+          gx += px; gy += py; gz += pz; h += hp;
+          jv[j] -= px; jv[jvs + j] -= py; jv[2 * jvs + j] -= pz; jv[3 * jvs + j] += hp;
+        }
+      }
+    }
+    // nuclei
+    for (int A = 0; A < S.natom; ++A) {
+      const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
+      const double dx = xi - xa, dy = yi - ya, dz = zi - za;
+      const double s2 = dx * dx + dy * dy + dz * dz;
+      if (POT) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
+      if (S.use_jen) {
+        const double wn = S.jen_w;
+        const double r = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, gram_norm(xa, ya, za)));
+        const double den = 1.0 / (1.0 + wn * r);
+        ks += r * den;
+        if (DERIV) {
+          const double invr = 1.0 / (r + QMCB_EPS);
+          const double invr3 = 1.0 / (r * r * r + QMCB_EPS);
+          const double kp = den * den * invr;
+          gx += kp * dx; gy += kp * dy; gz += kp * dz;
+          const double sdr2 = s2 * invr * invr, sd2r = 2.0 * s2 * invr3, den2 = den * den;
+          h += den * sd2r - 2.0 * wn * den2 * sdr2 - wn * r * den2 * sd2r + 2.0 * wn * wn * r * den2 * den * sdr2;
+        }
+      }
+    }
+    if (DERIV) {
+      gx += jv[i]; gy += jv[jvs + i]; gz += jv[2 * jvs + i]; h += jv[3 * jvs + i];
+      jv[i] = gx; jv[jvs + i] = gy; jv[2 * jvs + i] = gz;
+      jv[3 * jvs + i] = h + gx * gx + gy * gy + gz * gz;
+    }
+    tks += ks; tven += ven; tvee += vee;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Small dense LU-type kernels on one spin block (n x n), one thread per matrix.
 // A(i,j) = mo[row0+i][cols[j]], B likewise.  Closed forms for n<=3; Gauss-Jordan with

@@ -15,6 +15,8 @@
 #include <cstdio>
 
 #pragma once
+#include <cstdlib>
+
 #include "device.cuh"
 #include "philox.cuh"
 
@@ -101,6 +103,14 @@ __host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw
 // spills), 4 -> 0.535 ms (64 regs).
 // Later: 128-thread CTAs x 5 per SM (96 registers, no spills, 20 warps/SM) measured equal on the
 // E_L kernel and 3-7 % faster on psi / grad / H2 than 256 x 2.
+// private slice of one thread in THREAD tiles: pos | g,lap [4][Ne] (E_L only) | mo (,B) rows | dets | traces | 2
+__host__ __device__ inline size_t thread_tile_doubles(const DevSys &S, int mode) {
+  const int nchs_ = mode == MODE_ELOC ? 2 : 1;
+  const size_t d = (size_t)3 * S.nelec + (mode == MODE_ELOC ? 4 * S.nelec : 0) + (size_t)nchs_ * S.nelec * S.nmup +
+                   2 * (size_t)(S.nuu + S.nud) + 2;
+  return d | 1;   // odd stride: lanes hit distinct banks
+}
+
 #ifndef QMCB_MINBLOCKS
 #define QMCB_MINBLOCKS 5
 #endif
@@ -108,12 +118,21 @@ __host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw
 #define QMCB_WARP_CTA 128      // threads per CTA for warp-owned tiles
 #endif
 
-// WARP = true : a tile belongs to ONE WARP (Ne * NBLK divides 32); phases are separated by
-//               __syncwarp only, warps never wait for each other.
-// WARP = false: a tile belongs to the CTA; phases are separated by __syncthreads.
-template <int MODE, int MB, int RT, bool WARP>
-__global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLOCKS : 1)
+// Tile ownership (template TILE):
+//   0 CTA    : a tile of TW walkers belongs to the CTA; phases are separated by __syncthreads.
+//   1 WARP   : a tile belongs to ONE WARP (Ne * NBLK divides 32); phases are separated by
+//              __syncwarp only, warps never wait for each other.
+//   2 THREAD : one walker per THREAD (small systems, closed-form determinants): no synchronisation
+//              at all, every electron pair of the Jastrow factor is visited once instead of twice,
+//              and the per-walker epilogue runs on all lanes.  Work area: a private, odd-strided
+//              slice of shared memory per thread.
+#define QMCB_THREAD_CTA 128
+template <int MODE, int MB, int RT, int TILE>
+__global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_THREAD_CTA : 512),
+                                  TILE == 1 ? QMCB_MINBLOCKS : (TILE == 2 ? 4 : 1))
     fused_kernel(const DevSys S, const FusedArgs a, const int TW, const int NBLK, const int lu_conc) {
+  constexpr bool WARP = TILE == 1;
+  constexpr bool THREAD = TILE == 2;
   constexpr int NCH = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? 5 : 1;
   constexpr int NCHS = nchs<MODE>();
   extern __shared__ __align__(16) double smem[];
@@ -121,14 +140,17 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
   double *ws = stage_tables(S, smem, T);
   const int Ne = S.nelec, ne3 = 3 * Ne, nmup = S.nmup;
   const int nun = S.nuu + S.nud;
-  const int nthr = WARP ? 32 : (int)blockDim.x;
-  const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-  const int64_t unit = WARP ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
-  const int64_t nunit = WARP ? (int64_t)gridDim.x * (blockDim.x >> 5) : gridDim.x;
+  const int nthr = THREAD ? 1 : (WARP ? 32 : (int)blockDim.x);
+  const int tid = THREAD ? 0 : (WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x);
+  const int64_t unit = THREAD ? (int64_t)blockIdx.x * blockDim.x + threadIdx.x
+                              : (WARP ? (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x);
+  const int64_t nunit = THREAD ? (int64_t)gridDim.x * blockDim.x
+                               : (WARP ? (int64_t)gridDim.x * (blockDim.x >> 5) : gridDim.x);
   if (WARP) ws += (threadIdx.x >> 5) * tile_doubles(S, MODE, TW, lu_conc, true);
+  if (THREAD) ws += threadIdx.x * thread_tile_doubles(S, MODE);
   double *spos = ws;
   double *jv = spos + TW * ne3;
-  double *smo = jv + TW * Ne * 8;
+  double *smo = jv + (THREAD ? (NCH > 1 ? 4 * Ne : 0) : TW * Ne * 8);
   double *sdet = smo + (size_t)NCHS * TW * Ne * nmup;
   double *str = sdet + TW * nun;
   double *wsum = str + TW * nun;
@@ -137,7 +159,7 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
   const size_t chs = (size_t)TW * Ne * nmup;
   const int jvs = TW * Ne;   // jv is stored [quantity][walker][electron]
   __syncthreads();
-#define TILE_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
+#define TILE_SYNC() do { if (THREAD) {} else if (WARP) __syncwarp(); else __syncthreads(); } while (0)
 
   for (int64_t tile = unit; tile < ntile; tile += nunit) {
     const int64_t w0 = tile * TW;
@@ -188,6 +210,10 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
     }
     TILE_SYNC();
     // ---- P1: Jastrow + potentials, thread (wl, e)
+    double tks = 0.0, tven = 0.0, tvee = 0.0;   // THREAD tiles: walker totals stay in registers
+    if (THREAD) {
+      walker_terms<(NCH > 1), (MODE == MODE_ELOC)>(S, T, spos, jv, jvs, tks, tven, tvee);
+    } else
     for (int it = tid; it < tw * Ne; it += nthr) {
       const int wl = it / Ne, e = it - wl * Ne;
       ElecTerms o;
@@ -234,8 +260,8 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
     // ---- P3: determinants (and traces / inverses) per (wl, unique occupation)
     {
       const int nitem = tw * nun;
-      const int per = lu_scratch_per_item(S, MODE, WARP);
-      if (!WARP && use_warp_lu(S)) {
+      const int per = lu_scratch_per_item(S, MODE, TILE != 0);
+      if (TILE == 0 && use_warp_lu(S)) {
         // CTA tiles with blocks larger than 3x3: ONE WARP per spin block (warp_gauss_jordan);
         // scratch is contiguous per slot: slot = item (GRAD keeps every inverse) or the warp
         const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
@@ -298,11 +324,11 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
             }
           } else if (n <= 3) {
             det_trace_small(n, A, A + chs, nmup, cols, MODE == MODE_ELOC, det, tr);
-          } else if (!WARP && n == 4) {   // CTA-tile kernels only: keeps calls out of the warp-tile kernels
+          } else if (TILE == 0 && n == 4) {   // CTA-tile kernels only: keeps calls out of the warp-tile kernels
             det_trace_reg<4, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
-          } else if (!WARP && n == 5) {
+          } else if (TILE == 0 && n == 5) {
             det_trace_reg<5, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
-          } else if (!WARP && n == 6) {
+          } else if (TILE == 0 && n == 6) {
             det_trace_reg<6, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
           } else {
             double *m = scr + tid;
@@ -334,8 +360,8 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
         sig += d;
         if (MODE == MODE_ELOC) ksig += d * (tt[iu] + tt[id]);
       }
-      double ks = 0.0, ven = 0.0, vee = 0.0;
-      for (int e = 0; e < Ne; ++e) {
+      double ks = tks, ven = tven, vee = tvee;
+      for (int e = 0; !THREAD && e < Ne; ++e) {
         const double *q = jv + wl * Ne + e;
         ks += q[4 * jvs]; ven += q[5 * jvs]; vee += q[6 * jvs];
       }
@@ -376,8 +402,10 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
         }
       }
       if (a.naccept) {
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(a.naccept, (unsigned long long)cnt);
+        // (THREAD tiles: lanes leave the tile loop at different times)
+        const unsigned mask = THREAD ? __activemask() : 0xffffffffu;
+        cnt = __reduce_add_sync(mask, cnt);
+        if ((int)(threadIdx.x & 31) == __ffs(mask) - 1 && cnt) atomicAdd(a.naccept, (unsigned long long)cnt);
       }
     }
     if (MODE == MODE_GRAD) {
@@ -403,8 +431,8 @@ __global__ void __launch_bounds__(WARP ? QMCB_WARP_CTA : 512, WARP ? QMCB_MINBLO
           cu *= dd[up ? u : S.nuu + u];
           if (cu == 0.0) continue;
           const int item = wl * nun + (up ? u : S.nuu + u);
-          const bool contiguous = !WARP && use_warp_lu(S);   // layout written by P3
-          const double *inv = contiguous ? scr + (size_t)item * lu_scratch_per_item(S, MODE, WARP) : scr + item;
+          const bool contiguous = TILE == 0 && use_warp_lu(S);   // layout written by P3
+          const double *inv = contiguous ? scr + (size_t)item * lu_scratch_per_item(S, MODE, TILE != 0) : scr + item;
           const int es = contiguous ? 1 : conc;
           const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + u * S.ndown;
           double tx = 0, ty = 0, tz = 0;
@@ -451,8 +479,23 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   const int nun = S.nuu + S.nud;
   const int budget = p->smem_optin - 1024;
   const size_t tab = (size_t)table_doubles(S) * sizeof(double);
+  // ---- one walker per thread: small systems with closed-form determinants (not for grad psi)
+  {
+    const int nbig = S.nup > S.ndown ? S.nup : S.ndown;
+    const char *env = getenv("QMCB_TILE");          // tuning experiments: force 0/1 (never 2 by force)
+    const bool allow = !(env && (env[0] == '0' || env[0] == '1'));
+    if (allow && mode != MODE_GRAD && c.nblk == 1 && mb <= 4 && nbig <= 3 && S.nelec <= 8 && nun <= 8 &&
+        S.een_nterm == 0) {
+      const size_t unit = thread_tile_doubles(S, mode) * sizeof(double);
+      const size_t sm = tab + unit * QMCB_THREAD_CTA;
+      if ((int)sm <= budget / 4) {
+        c.warp = 2; c.tw = 1; c.threads = QMCB_THREAD_CTA; c.smem = (int)sm; c.lu_conc = 0;
+        return 0;
+      }
+    }
+  }
   // ---- warp-owned tiles when the threads of a walker tile a warp exactly
-  if (32 % per_walker == 0) {
+  if (32 % per_walker == 0 && !(getenv("QMCB_TILE") && getenv("QMCB_TILE")[0] == '0')) {
     const int tw = 32 / per_walker;
     const int per = lu_scratch_per_item(S, mode, true);
     int conc = 0;
@@ -501,13 +544,14 @@ int qmcb_choose_launch(qmcb_plan *p) {
 }
 #endif  // QMCB_FUSED_MAIN
 
-template <int MODE, int MB, int RT, bool WARP>
+template <int MODE, int MB, int RT, int TILE>
 static int launch_k(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
-  auto k = fused_kernel<MODE, MB, RT, WARP>;
+  constexpr bool WARP = TILE == 1;
+  auto k = fused_kernel<MODE, MB, RT, TILE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
   if (e != cudaSuccess) return (int)e;
   const int64_t ntile = (a.W + c.tw - 1) / c.tw;
-  const int64_t units_per_cta = WARP ? c.threads / 32 : 1;
+  const int64_t units_per_cta = TILE == 2 ? c.threads : (WARP ? c.threads / 32 : 1);
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, c.threads, c.smem);
   if (occ < 1) occ = 1;
@@ -522,8 +566,13 @@ static int launch_k(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, 
 template <int MODE, int MB>
 static int launch_t(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cudaStream_t st) {
   const bool pure = p->sys.radial_type == QMCB_GTO_PURE;
-  if (c.warp) return pure ? launch_k<MODE, MB, 0, true>(p, c, a, st) : launch_k<MODE, MB, 1, true>(p, c, a, st);
-  return pure ? launch_k<MODE, MB, 0, false>(p, c, a, st) : launch_k<MODE, MB, 1, false>(p, c, a, st);
+  if (c.warp == 2) {
+    // one walker per thread: instantiated for psi / E_L / Metropolis and narrow column blocks only
+    if constexpr (MODE != MODE_GRAD && MB <= 4)
+      return pure ? launch_k<MODE, MB, 0, 2>(p, c, a, st) : launch_k<MODE, MB, 1, 2>(p, c, a, st);
+  }
+  if (c.warp == 1) return pure ? launch_k<MODE, MB, 0, 1>(p, c, a, st) : launch_k<MODE, MB, 1, 1>(p, c, a, st);
+  return pure ? launch_k<MODE, MB, 0, 0>(p, c, a, st) : launch_k<MODE, MB, 1, 0>(p, c, a, st);
 }
 
 template <int MODE>
