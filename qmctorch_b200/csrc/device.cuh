@@ -225,18 +225,21 @@ template <int NCH, int RT, class Sink>
 __device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double ex, double ey, double ez,
                                          Sink &sink) {
   const double2 *rec = T.stream();
+  const double *et = T.etab();          // hoisted: one live pointer instead of a re-derivation per exp
+  const double *at = T.atoms();
+  const int *ash = T.ash();
   for (int A = 0; A < S.natom; ++A) {
-    const double x = ex - T.atoms()[4 * A], y = ey - T.atoms()[4 * A + 1], z = ez - T.atoms()[4 * A + 2];
+    const double x = ex - at[4 * A], y = ey - at[4 * A + 1], z = ez - at[4 * A + 2];
     const double r2 = x * x + y * y + z * z;
     double r = 0.0, rinv = 0.0;
     if (RT != 0 && S.radial_type != QMCB_GTO_PURE) { r = sqrt(r2); rinv = 1.0 / r; }
-    const int ns = T.ash()[A + 1] - T.ash()[A];
+    const int ns = ash[A + 1] - ash[A];
     for (int s = 0; s < ns; ++s) {
       const double hdr = rec->x;
       ++rec;
       const int nprim = __double2loint(hdr), ngrp = __double2hiint(hdr);
       double S0, S1, S2;
-      rec = radial_sums<NCH, RT>(S, T.etab(), rec, nprim, r2, r, rinv, S0, S1, S2);
+      rec = radial_sums<NCH, RT>(S, et, rec, nprim, r2, r, rinv, S0, S1, S2);
       for (int g = 0; g < ngrp; ++g, ++rec) {
         const double2 gr = *rec;
         const int kk = __double2loint(gr.x), ao = __double2hiint(gr.x);

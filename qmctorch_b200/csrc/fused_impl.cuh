@@ -225,8 +225,9 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
     if (NCH > 1) TILE_SYNC();   // P2 reads jv only when it assembles B_kin / the gradient
     // ---- P2: AO -> MO rows, thread (wl, blk, e)
     for (int it = tid; it < tw * NBLK * Ne; it += nthr) {
-      const int wl = it / (NBLK * Ne), rem = it - wl * NBLK * Ne;
-      const int blk = rem / Ne, e = rem - blk * Ne;
+      // (THREAD tiles: one walker, one column block - no integer divisions in the electron loop)
+      const int wl = THREAD ? 0 : it / (NBLK * Ne), rem = it - wl * NBLK * Ne;
+      const int blk = THREAD ? 0 : rem / Ne, e = rem - blk * Ne;
       const double *sp = spos + wl * ne3 + 3 * e;
       MoSink<NCH, MB> sink;
       sink.init(T.mow() + blk * MB, nmup);
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
       const int stride = (MODE == MODE_GRAD) ? nthr : (conc < nthr ? conc : nthr);
       if (tid < stride) {
         for (int it = tid; it < nitem; it += stride) {
-          const int wl = it / nun, u = it - wl * nun;
+          const int wl = THREAD ? 0 : it / nun, u = it - wl * nun;
           const bool up = u < S.nuu;
           const int n = up ? S.nup : S.ndown;
           const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
