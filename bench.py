@@ -201,6 +201,9 @@ def main():
     W = wpg
     eloc = torch.empty(W, 1, dtype=torch.float64, device=dev)
     out4 = torch.zeros(4, dtype=torch.float64, device=dev)
+    # N > 1: the 4-double all-reduce of step i is issued asynchronously (its own buffer) and only
+    # waited for at the end of the timed region, so it overlaps the kernel of step i+1
+    ring = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(8)]
     ws = torch.empty(int(L.qmcb_stats_workspace_bytes(W)), dtype=torch.uint8, device=dev)
     plan = wf._handle.plan()
     stream = torch.cuda.current_stream(dev)
@@ -227,14 +230,22 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     ev0.record(stream)
+    pending = []
     for i in range(args.steps):
         x = ens[i % NBUF]
+        o4 = ring[i % len(ring)] if world > 1 else out4
+        if world > 1 and len(pending) >= len(ring):
+            pending.pop(0).wait()          # the buffer about to be reused must have been reduced
         kev[i][0].record(stream)
         _lib.check(L.qmcb_local_energy(plan, _lib.ptr(x), W, _lib.ptr(eloc), None, None, sp), "local_energy")
         kev[i][1].record(stream)
-        _lib.check(L.qmcb_energy_stats(_lib.ptr(eloc), W, _lib.ptr(out4), _lib.ptr(ws), sp), "stats")
+        _lib.check(L.qmcb_energy_stats(_lib.ptr(eloc), W, _lib.ptr(o4), _lib.ptr(ws), sp), "stats")
         if world > 1:
-            dist.all_reduce(out4)
+            pending.append(dist.all_reduce(o4, async_op=True))
+    for h in pending:
+        h.wait()
+    if world > 1:
+        out4.copy_(ring[(args.steps - 1) % len(ring)])
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)

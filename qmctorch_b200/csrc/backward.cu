@@ -569,19 +569,19 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
   a.tw = b.tw; a.rows = b.rows; a.lda = b.lda; a.ldg = b.ldg; a.ldx = b.ldx; a.ppad = b.ppad;
   a.ntile_mo = b.ntile_mo; a.ntile_ao = b.ntile_ao; a.nslot = b.nslot; a.lu_conc = b.lu_conc;
   cudaError_t e = cudaFuncSetAttribute(backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return qmcb_cuda_rc((int)e, "backward.cu");
   const int64_t ntile_w = (W + b.tw - 1) / b.tw;
   int grid = b.grid;
   if (grid > ntile_w) grid = (int)ntile_w;
   const size_t nmo_bytes = (size_t)p->sys.nao * p->sys.nmo * sizeof(double);
-  if (g_mo && (e = cudaMemsetAsync(g_mo, 0, nmo_bytes, st)) != cudaSuccess) return (int)e;
-  if (g_bas_exp && (e = cudaMemsetAsync(g_bas_exp, 0, p->sys.nbas * sizeof(double), st)) != cudaSuccess) return (int)e;
+  if (g_mo && (e = cudaMemsetAsync(g_mo, 0, nmo_bytes, st)) != cudaSuccess) return qmcb_cuda_rc((int)e, "backward.cu");
+  if (g_bas_exp && (e = cudaMemsetAsync(g_bas_exp, 0, p->sys.nbas * sizeof(double), st)) != cudaSuccess) return qmcb_cuda_rc((int)e, "backward.cu");
   if (g_bas_coeffs && (e = cudaMemsetAsync(g_bas_coeffs, 0, p->sys.nbas * sizeof(double), st)) != cudaSuccess)
-    return (int)e;
+    return qmcb_cuda_rc((int)e, "backward.cu");
   backward_kernel<<<grid, b.threads, b.smem, st>>>(p->sys, a);
-  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  if ((e = cudaGetLastError()) != cudaSuccess) return qmcb_cuda_rc((int)e, "backward.cu");
   backward_reduce<<<(b.nslot + 127) / 128, 128, 0, st>>>(p->sys, a.partial, grid, b.nslot, p->d_bwd_tiles, b.ntile_mo,
                                                         b.ntile_ao, b.ppad, p->sys.nmo, g_mo, g_ci, g_bas_exp,
                                                         g_bas_coeffs, g_jee_w, g_jen_w, g_een);
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "backward.cu launch");
 }

@@ -550,7 +550,7 @@ static int launch_k(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, 
   constexpr bool WARP = TILE == 1;
   auto k = fused_kernel<MODE, MB, RT, TILE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return qmcb_cuda_rc((int)e, "fused_impl.cuh");
   const int64_t ntile = (a.W + c.tw - 1) / c.tw;
   const int64_t units_per_cta = TILE == 2 ? c.threads : (WARP ? c.threads / 32 : 1);
   int occ = 1;
@@ -561,7 +561,7 @@ static int launch_k(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, 
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   k<<<(unsigned)grid, c.threads, c.smem, st>>>(p->sys, a, c.tw, c.nblk, c.lu_conc);
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "fused_impl.cuh launch");
 }
 
 template <int MODE, int MB>

@@ -55,7 +55,7 @@ extern "C" int qmcb_ao(const qmcb_plan *p, const double *pos, int64_t W, int one
     cudaFuncSetAttribute(ao_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     ao_kernel<1><<<(unsigned)grid, 256, smem, st>>>(p->sys, pos, rows, ao, nullptr, nullptr);
   }
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }
 
 // ---- MolecularOrbitals.forward: [rows,nao] x [nao,nmo] ----------------------------------
@@ -89,7 +89,7 @@ extern "C" int qmcb_mo(const qmcb_plan *p, const double *x, int64_t rows, double
   int64_t grid = (rows * nmo + 255) / 256;
   if (grid > (int64_t)p->sm_count * 8) grid = (int64_t)p->sm_count * 8;
   mo_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(x, p->d_mo_full, rows, nao, nmo, out);
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }
 
 // ---- Jastrow factor + derivatives -------------------------------------------------------
@@ -157,7 +157,7 @@ extern "C" int qmcb_jastrow(const qmcb_plan *p, const double *pos, int64_t W, in
   // blockDim must be a multiple of Ne for the (wl,e) mapping: launch tw*Ne threads rounded up,
   // the kernel derives TW from blockDim/Ne which is still tw.
   jastrow_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(S, pos, W, dJ != nullptr, J, dJ, d2J);
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }
 
 // ---- SlaterPooling.forward / .operator --------------------------------------------------
@@ -222,7 +222,7 @@ extern "C" int qmcb_slater(const qmcb_plan *p, const double *mo, const double *b
   int64_t grid = (total + 127) / 128;
   if (grid > (int64_t)p->sm_count * 8) grid = (int64_t)p->sm_count * 8;
   slater_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(S, mo, bop, nop, W, dets, trace);
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }
 
 // ---- energy statistics ------------------------------------------------------------------
@@ -272,7 +272,7 @@ extern "C" int qmcb_energy_stats(const double *eloc, int64_t W, double *out4, vo
   cudaStream_t st = (cudaStream_t)stream;
   stats_stage1<<<STATS_CTAS, 256, 0, st>>>(eloc, W, (double *)workspace);
   stats_stage2<<<1, 128, 0, st>>>((const double *)workspace, STATS_CTAS, out4);
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }
 
 // ---- FP64 pipe probes ---------------------------------------------------------------------
@@ -347,5 +347,5 @@ extern "C" int qmcb_fp64_probe(int kind, int64_t iters, double *sink, double *fl
     // per iteration and warp: 4 DMMA (2048 flop) + 8 DFMA x 32 lanes (512 flop)
     if (flops) *flops = (2048.0 + 512.0) * (double)iters * ctas * (threads / 32);
   }
-  return (int)cudaGetLastError();
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }

@@ -15,6 +15,11 @@
 
 static thread_local std::string g_err;
 void qmcb_set_error(const std::string &msg) { g_err = msg; }
+int qmcb_cuda_rc(int cuda_error, const char *where) {
+  if (cuda_error != 0)
+    g_err = std::string(where) + ": " + cudaGetErrorString((cudaError_t)cuda_error);
+  return cuda_error;
+}
 extern "C" const char *qmcb_last_error(void) { return g_err.c_str(); }
 extern "C" int qmcb_abi_version(void) { return QMCB_ABI_VERSION; }
 

@@ -97,6 +97,8 @@ struct qmcb_plan {
 };
 
 void qmcb_set_error(const std::string &msg);
+// maps a cudaError_t to the ABI return code and records its text for qmcb_last_error()
+int qmcb_cuda_rc(int cuda_error, const char *where);
 int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p);   // host grouping -> hd/hi/sys
 int qmcb_choose_launch(qmcb_plan *p);
 int qmcb_choose_backward(qmcb_plan *p);
