@@ -653,27 +653,26 @@ __device__ inline double warp_gauss_jordan(int n, int nr, double *m, int lane) {
   return det;
 }
 
-// Register-resident Gauss-Jordan with partial pivoting for N = 4..6 (fully unrolled, row swaps by
-// predicated moves): det(A) and, if WITH_B, Tr(A^-1 B) without any shared-memory scratch.
-// A(i,j) = mo[row0+i][cols[j]], B likewise (ld = row stride).
-// __noinline__: its register/local-memory footprint must not leak into the callers' allocation.
+// Register-resident LU with partial pivoting for N = 4..6 (fully unrolled): det(A) and, if
+// WITH_B, Tr(A^-1 B) = sum_j (A^-1 b_j)_j by one forward/back substitution per column of B.
+// Only A (N^2 doubles) lives in registers; B is read from shared memory through the row
+// permutation.  A(i,j) = mo[row0+i][cols[j]], B likewise (ld = row stride).
+// __noinline__: its register footprint must not leak into the callers' allocation.
 template <int N, bool WITH_B>
 __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int ld, const int *cols,
-                                              double &det_out, double &tr_out) {
-  double a[N][N], b[N][WITH_B ? N : 1];
+                                           double &det_out, double &tr_out) {
+  double a[N][N];
+  int perm[N], cj[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    const int c = cols[j];
+    cj[j] = cols[j];
+    perm[j] = j;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      a[i][j] = A[i * ld + c];
-      if (WITH_B) b[i][j] = B[i * ld + c];
-    }
+    for (int i = 0; i < N; ++i) a[i][j] = A[i * ld + cj[j]];
   }
   double det = 1.0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    // pivot: first row with the largest |a[i][k]|, i >= k
     int piv = k;
     double best = fabs(a[k][k]);
 #pragma unroll
@@ -685,47 +684,93 @@ __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int
     for (int i = k + 1; i < N; ++i) {
       const bool sw = piv == i;
 #pragma unroll
-      for (int j = k; j < N; ++j) {
+      for (int j = 0; j < N; ++j) {
         const double t = a[k][j];
         a[k][j] = sw ? a[i][j] : t;
         a[i][j] = sw ? t : a[i][j];
       }
-      if (WITH_B) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const double t = b[k][j];
-          b[k][j] = sw ? b[i][j] : t;
-          b[i][j] = sw ? t : b[i][j];
-        }
-      }
+      const int tp = perm[k];
+      perm[k] = sw ? perm[i] : tp;
+      perm[i] = sw ? tp : perm[i];
     }
     if (piv != k) det = -det;
-    const double pv = a[k][k];
-    det *= pv;
-    const double ip = 1.0 / pv;
+    det *= a[k][k];
+    const double ip = 1.0 / a[k][k];
 #pragma unroll
-    for (int j = k + 1; j < N; ++j) a[k][j] *= ip;
-    if (WITH_B) {
+    for (int i = k + 1; i < N; ++i) {
+      const double l = a[i][k] * ip;
+      a[i][k] = l;                                   // L below the diagonal
 #pragma unroll
-      for (int j = 0; j < N; ++j) b[k][j] *= ip;
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if (i == k) continue;
-      const double f = a[i][k];
-#pragma unroll
-      for (int j = k + 1; j < N; ++j) a[i][j] -= f * a[k][j];
-      if (WITH_B) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) b[i][j] -= f * b[k][j];
-      }
+      for (int j = k + 1; j < N; ++j) a[i][j] -= l * a[k][j];
     }
   }
   det_out = det;
   double tr = 0.0;
   if (WITH_B) {
+    double inv_d[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) tr += b[i][i];
+    for (int i = 0; i < N; ++i) inv_d[i] = 1.0 / a[i][i];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double x[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {                   // forward: L y = P b_j
+        double v = B[perm[i] * ld + cj[j]];
+#pragma unroll
+        for (int m = 0; m < i; ++m) v -= a[i][m] * x[m];
+        x[i] = v;
+      }
+#pragma unroll
+      for (int i = N - 1; i >= j; --i) {              // backward: U x = y, down to component j
+        double v = x[i];
+#pragma unroll
+        for (int m = i + 1; m < N; ++m) v -= a[i][m] * x[m];
+        x[i] = v * inv_d[i];
+      }
+      tr += x[j];
+    }
   }
   tr_out = tr;
+}
+
+// Register-resident warp Gauss-Jordan: lane j owns column j of [A | R] (n + nr <= 32, n <= NMAX),
+// rows are registers.  Per elimination step: lane k finds the pivot in its registers, the pivot
+// row index and the multipliers travel by warp shuffles - no shared-memory round trips.
+// On exit lanes n..n+nr-1 hold the columns of inv(A) R.  Returns det(A) on every lane.
+template <int NMAX>
+__device__ __forceinline__ double warp_gauss_jordan_reg(int n, double (&col)[NMAX], int lane) {
+  double det = 1.0;
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    if (k < n) {
+      double best = -1.0;
+      int piv = k;
+#pragma unroll
+      for (int i = k; i < NMAX; ++i) {
+        const double v = fabs(col[i]);
+        if (i < n && v > best) { best = v; piv = i; }
+      }
+      piv = __shfl_sync(0xffffffffu, piv, k);
+#pragma unroll
+      for (int i = k + 1; i < NMAX; ++i) {
+        const bool sw = piv == i;
+        const double t = col[k];
+        col[k] = sw ? col[i] : t;
+        col[i] = sw ? t : col[i];
+      }
+      if (piv != k) det = -det;
+      const double pv = __shfl_sync(0xffffffffu, col[k], k);
+      det *= pv;
+      const double pk = col[k] * (1.0 / pv);          // pivot row, scaled (meaningful for lanes > k)
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        if (i != k && i < n) {
+          const double f = __shfl_sync(0xffffffffu, col[i], k);   // element (i, k)
+          if (lane > k) col[i] = fma(-f, pk, col[i]);
+        }
+      }
+      if (lane > k) col[k] = pk;
+    }
+  }
+  return det;
 }

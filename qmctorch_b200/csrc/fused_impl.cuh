@@ -83,7 +83,7 @@ __host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode, bo
   const int n = S.nup > S.ndown ? S.nup : S.ndown;
   if (mode == MODE_GRAD) return n <= 3 ? n * n : 2 * n * n;   // inverse kept ([A|I] for n>3)
   if (n <= 3) return 0;                                      // closed forms
-  if (!warp_tiles && n <= 6) return 0;                       // register Gauss-Jordan (CTA-tile kernels)
+  if (!warp_tiles && n <= 16) return 0;                      // register LU (n <= 6) / register warp Gauss-Jordan
   return mode == MODE_ELOC ? 2 * n * n : n * n;            // [A|B] or A
 }
 
@@ -276,7 +276,40 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
           const int nr = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? n : 0;
           const int ldw = n + nr;
           double det = 1.0, tr = 0.0;
-          if (n > 0) {
+          if (n > 0 && n <= 16) {
+            // register-resident: lane j owns column j of [A | B] (or [A | I])
+            double col[16];
+            const int jc = lane < n ? cols[lane] : (lane < ldw ? cols[lane - n] : 0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              double v = 0.0;
+              if (i < n) {
+                if (lane < n) v = A[i * nmup + jc];
+                else if (lane < ldw) v = MODE == MODE_ELOC ? A[chs + i * nmup + jc] : (i == lane - n ? 1.0 : 0.0);
+              }
+              col[i] = v;
+            }
+            det = warp_gauss_jordan_reg<16>(n, col, lane);
+            if (MODE == MODE_ELOC) {
+              double v = 0.0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i == lane - n) v = col[i];          // diagonal element (i, i) of inv(A) B
+              if (lane < n || lane >= ldw) v = 0.0;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              tr = v;
+            }
+            if (MODE == MODE_GRAD) {
+              // the gradient phase reads inv(A) from the scratch: right block of [A | I]
+              if (lane >= n && lane < ldw) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < n) m[i * ldw + lane] = col[i];
+              }
+              __syncwarp();
+            }
+          } else if (n > 0) {
             for (int idx = lane; idx < n * n; idx += 32) {
               const int i = idx / n, j = idx - i * n;
               m[i * ldw + j] = A[i * nmup + cols[j]];
@@ -514,8 +547,14 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
     }
   }
   // ---- CTA-owned tiles
-  int tw = 512 / per_walker;
+  // two 256-thread CTAs per SM overlap each other's barriers (measured, C4H6: E_L 1.59 -> 1.42 ms,
+  // psi 0.92 -> 0.76 ms; H2O unchanged); grad psi keeps its inverses resident and prefers one large CTA
+  int cta_max = mode == MODE_GRAD ? 512 : 256;
+  if (const char *env = getenv("QMCB_CTA_THREADS")) cta_max = atoi(env) > 0 ? atoi(env) : cta_max;
+  if (cta_max < per_walker) cta_max = ((per_walker + 31) / 32) * 32;
+  int tw = cta_max / per_walker;
   if (tw > 128) tw = 128;
+  if (tw < 1) tw = 1;
   for (; tw >= 1; --tw) {
     int threads = ((tw * per_walker + 31) / 32) * 32;
     if (threads > 512) continue;
