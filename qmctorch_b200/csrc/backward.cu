@@ -282,7 +282,27 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
         double *m = scr + (size_t)it * inv_per;
         const int ldw = 2 * n;
         double det = 1.0;
-        if (n > 0) {
+        if (n > 0 && n <= 16) {
+          // register-resident: lane j owns column j of [A | I]; the inverse goes back to the scratch
+          double col[16];
+          const int jc = lane < n ? cols[lane] : 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            double v = 0.0;
+            if (i < n) {
+              if (lane < n) v = A[i * nmup + jc];
+              else if (lane < ldw) v = i == lane - n ? 1.0 : 0.0;
+            }
+            col[i] = v;
+          }
+          det = warp_gauss_jordan_reg<16>(n, col, lane);
+          if (lane >= n && lane < ldw) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < n) m[i * ldw + lane] = col[i];
+          }
+          __syncwarp();
+        } else if (n > 0) {
           for (int idx = lane; idx < n * n; idx += 32) {
             const int i = idx / n, j = idx - i * n;
             m[i * ldw + j] = A[i * nmup + cols[j]];
