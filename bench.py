@@ -50,7 +50,7 @@ def algorithmic_flops(mol, wf, info):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the dominant
 # kernel (profiles/r1_fused_ncu_raw.csv), bytes per launch, keyed by (workload, walkers)
-NCU_TRAFFIC = {("lih", 1_000_000): 96.078080e6 + 5.073408e6}
+NCU_TRAFFIC = {("lih", 1_000_000): 96.070912e6 + 5.570048e6}
 
 
 class ClockSampler(threading.Thread):
