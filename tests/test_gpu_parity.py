@@ -414,3 +414,59 @@ def test_philox_sampler_is_tiling_independent_and_samples_psi2():
     e_torch = wf.local_energy(run(start, 0, "torch"))
     err = float((e_philox.var() / len(e_philox) + e_torch.var() / len(e_torch)).sqrt())
     assert abs(float(e_philox.mean() - e_torch.mean())) < 6 * err
+
+
+def test_solver_api_batching_trajectory_checkpoint(tmp_path):
+    """Solver.single_point(batchsize), sampling_traj, save/load checkpoint (solver_base.py:316-471)."""
+    import os
+    from qmctorch_b200.sampler import Metropolis
+    from qmctorch_b200.solver import Solver
+    g = C.load("lih_sd22")
+    mol, wf = C.build_wf(g)
+    torch.manual_seed(2)
+    sampler = Metropolis(nwalkers=500, nstep=40, step_size=0.3, ntherm=30, ndecor=5, nelec=wf.nelec, ndim=3,
+                         init=mol.domain("normal"), move={"type": "all-elec", "proba": "normal"}, cuda=True, seed=2)
+    assert sampler.get_sampling_size() == 500 * 2
+    opt = torch.optim.Adam(wf.parameters(), lr=0.01)
+    solver = Solver(wf=wf, sampler=sampler, optimizer=opt)
+    full = solver.single_point(with_tqdm=False)
+    assert full.pos.shape == (1000, 12)
+    with torch.no_grad():
+        whole = wf.local_energy(full.pos)
+        parts = torch.cat([wf.local_energy(full.pos[i:i + 300]) for i in range(0, 1000, 300)])
+    assert torch.equal(whole, parts)                       # batching does not change a single bit
+    traj = solver.sampling_traj(pos=full.pos.detach(), with_tqdm=False)
+    assert traj.local_energy.shape == (2, 500)
+    assert np.allclose(traj.local_energy.reshape(-1), whole.cpu().numpy().reshape(-1), rtol=0, atol=0)
+    # checkpoint round trip keeps the device tables in sync
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with torch.no_grad():
+            wf.jastrow.jastrow_kernel.weight.fill_(0.9)
+        before = wf(full.pos[:64]).detach().clone()
+        solver.save_checkpoint(3, 0.5)
+        with torch.no_grad():
+            wf.jastrow.jastrow_kernel.weight.fill_(1.7)
+        assert not torch.equal(wf(full.pos[:64]).detach(), before)
+        epoch, loss = solver.load_checkpoint("checkpoint_epoch3.pth")
+        assert epoch == 3 and loss == 0.5
+        assert torch.equal(wf(full.pos[:64]).detach(), before)
+    finally:
+        os.chdir(cwd)
+
+
+def test_one_electron_ao_and_update():
+    """AtomicOrbitals.forward(one_elec=True) and .update (atomic_orbitals.py:131-218,671-695)."""
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    pos = _dev(g["pos"][:32])
+    ao = wf.ao(pos)
+    one = wf.ao(pos[:, 3:6], one_elec=True)
+    assert one.shape == (32, 1, ao.shape[-1])
+    assert torch.equal(one[:, 0], ao[:, 1])
+    moved = pos.clone()
+    moved[:, 3:6] += 0.1
+    upd = wf.ao.update(ao, moved, 1)
+    assert torch.equal(upd, wf.ao(moved))
+    assert torch.equal(upd[:, 0], ao[:, 0]) and not torch.equal(upd[:, 1], ao[:, 1])
