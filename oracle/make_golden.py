@@ -242,5 +242,25 @@ def main(only=None):
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def walker_init_fixture():
+    """Initial ensembles of the reference's ``Walkers.initialize`` (sampler/walkers.py:41-150) for
+    the four ``Molecule.domain`` methods, seeds 5/5 -> tests/golden/walkers_init.npz."""
+    from qmctorch.sampler.walkers import Walkers
+    out = {}
+    for key in ("lih", "h2o"):
+        mol = fixture_molecule(key)
+        for method in ("center", "uniform", "normal", "atomic"):
+            torch.manual_seed(5)
+            np.random.seed(5)
+            w = Walkers(nwalkers=9, nelec=mol.nelec, ndim=3, init=mol.domain(method))
+            w.initialize()
+            out["%s_%s" % (key, method)] = w.pos.double().numpy()
+    np.savez_compressed(os.path.join(OUT, "walkers_init.npz"), **out)
+    print("walkers_init  %d ensembles" % len(out))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    if not sys.argv[1:] or "walkers_init" in sys.argv[1:]:
+        walker_init_fixture()
+    if sys.argv[1:] != ["walkers_init"]:
+        main([a for a in sys.argv[1:] if a != "walkers_init"])

@@ -1,2 +1,2 @@
 from .metropolis import Metropolis, SamplerBase  # noqa: F401
-from .walkers import Walkers  # noqa: F401
+from .ensemble import Walkers  # noqa: F401

@@ -16,7 +16,7 @@ from torch.distributions import MultivariateNormal
 from tqdm import tqdm
 
 from .. import _lib
-from .walkers import Walkers
+from .ensemble import Walkers
 
 
 class SamplerBase:

@@ -75,6 +75,10 @@ class Solver:
         if self.cuda:
             self.sampler.cuda = True
             self.sampler.walkers.cuda = True
+            # the ensemble stays on the device between sampling, E_L, backward and
+            # resampling; the reference copies it to the host at every kept step (metropolis.py:164)
+            if hasattr(self.sampler, "keep_on_device"):
+                self.sampler.keep_on_device = True
         self.hdf5file = output
         if output is None:
             base = os.path.basename(getattr(wf.mol, "hdf5file", "mol.hdf5")).split(".")[0]

@@ -36,10 +36,14 @@ class _PsiFunction(torch.autograd.Function):
         wf = ctx.wf
         (x,) = ctx.saved_tensors
         need = ctx.needs_input_grad
-        g = wf._psi_backward(x, grad_out.reshape(-1).contiguous())
+        # parameter gradients only when some parameter asks for them (position-only autograd,
+        # e.g. drift / Hamiltonian samplers, just needs qmcb_grad_psi)
+        g = wf._psi_backward(x, grad_out.reshape(-1).contiguous()) if any(need[2:]) else {}
         gx = None
         if need[1]:
             gx = wf._grad_psi(x, pdf=False) * grad_out.reshape(-1, 1)
+        g = {k: g.get(k) for k in ("bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w", "jen_w", "een_num",
+                                   "een_denom", "een_fc")}
         return (None, gx,
                 g["bas_exp"] if need[2] else None,
                 # uncontracted bases: the reference never multiplies bas_coeffs into psi

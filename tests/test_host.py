@@ -117,6 +117,27 @@ def test_generic_sampler_reproduces_reference_algorithm():
     assert out.requires_grad and s.get_sampling_size() == 50
 
 
+def test_walker_initialisation_matches_reference_fixture():
+    """Walkers.initialize (sampler/walkers.py:41-150): same generator calls in the same order as the
+    reference for every Molecule.domain method -> bit-identical start ensembles."""
+    from qmctorch_b200.sampler.ensemble import Walkers
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "walkers_init.npz"))
+    for key in ("lih", "h2o"):
+        mol = fixture_molecule(key)
+        for method in ("center", "uniform", "normal", "atomic"):
+            torch.manual_seed(5)
+            np.random.seed(5)
+            w = Walkers(nwalkers=9, nelec=mol.nelec, ndim=3, init=mol.domain(method))
+            w.initialize()
+            assert w.pos.dtype == torch.float64
+            assert np.array_equal(w.pos.numpy(), gold["%s_%s" % (key, method)]), (key, method)
+    with pytest.raises(ValueError):
+        Walkers(nwalkers=2, nelec=2, init={"bogus": 1}).initialize()
+    w = Walkers(nwalkers=3, nelec=2, init=mol.domain("center"))
+    w.initialize(pos=torch.arange(30.0).reshape(5, 6))
+    assert torch.equal(w.pos, torch.arange(30.0).reshape(5, 6)[-3:])
+
+
 def test_shard_walkers_partitions_everything():
     from qmctorch_b200.solver.distributed import shard_walkers
     for n, w in ((10, 3), (1000000, 8), (7, 8), (0, 2)):
