@@ -232,7 +232,7 @@ __device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double e
     const double x = ex - at[4 * A], y = ey - at[4 * A + 1], z = ez - at[4 * A + 2];
     const double r2 = x * x + y * y + z * z;
     double r = 0.0, rinv = 0.0;
-    if (RT != 0 && S.radial_type != QMCB_GTO_PURE) { r = sqrt(r2); rinv = 1.0 / r; }
+    if (RT != 0 && S.radial_type != QMCB_GTO_PURE) { rinv = fast_rsqrt(r2); r = r2 * rinv; }
     const int ns = ash[A + 1] - ash[A];
     for (int s = 0; s < ns; ++s) {
       const double hdr = rec->x;
@@ -321,30 +321,32 @@ __device__ __forceinline__ void een_terms(const DevSys &S, const Tab &T, const d
     if (j == e) continue;
     const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
     const double nj = gram_norm(xj, yj, zj);
-    const double rej = sqrt(gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, nj));
-    const double irej = 1.0 / rej;
+    const double d2 = gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, nj);
+    const double irej = fast_rsqrt(d2), rej = d2 * irej;
     const double ux = (xi - xj) * irej, uy = (yi - yj) * irej, uz = (zi - zj) * irej;
     for (int A = 0; A < S.natom; ++A) {
       const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
       const double na = gram_norm(xa, ya, za);
-      const double rE = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, na));
-      const double rJ = sqrt(gram_d2_en(xj, yj, zj, nj, xa, ya, za, na));
-      const double irE = 1.0 / rE;
+      const double dE2 = gram_d2_en(xi, yi, zi, ni, xa, ya, za, na);
+      const double dJ2 = gram_d2_en(xj, yj, zj, nj, xa, ya, za, na);
+      const double irE = fast_rsqrt(dE2), rE = dE2 * irE;
+      const double rJ = dJ2 * fast_rsqrt(dJ2);
       const double vx = (xi - xa) * irE, vy = (yi - ya) * irE, vz = (zi - za) * irE;
-      const double cosv = ux * vx + uy * vy + uz * vz;
+      const double cos2 = 2.0 * (ux * vx + uy * vy + uz * vz);
       double s0 = 0, s1 = 0, s3 = 0, sl = 0;   // sum c FFG ; c F'FG ; c FFG' ; laplacian terms
       for (int m = 0; m < nt; ++m) {
         const double a = S.een_a[m], b = S.een_b[m], a2 = S.een_a2[m], b2 = S.een_b2[m], c = S.een_c[m];
-        const double dE = 1.0 / (1.0 + b * rE), dJ = 1.0 / (1.0 + b * rJ), dG = 1.0 / (1.0 + b2 * rej);
-        const double FE = a * rE * dE, FJ = a * rJ * dJ, G = a2 * rej * dG;
-        const double cFJ = c * FJ;
-        s0 += cFJ * FE * G;
+        const double dE = fast_rcp(fma(b, rE, 1.0)), dJ = fast_rcp(fma(b, rJ, 1.0)), dG = fast_rcp(fma(b2, rej, 1.0));
+        const double adE = a * dE, adG = a2 * dG;
+        const double FE = adE * rE, G = adG * rej;
+        const double cFJ = c * (a * rJ * dJ);
+        s0 = fma(cFJ * FE, G, s0);
         if (DERIV) {
-          const double FE1 = a * dE * dE, FE2 = -2.0 * b * FE1 * dE;
-          const double G1 = a2 * dG * dG, G2 = -2.0 * b2 * G1 * dG;
-          s1 += cFJ * FE1 * G;
-          s3 += cFJ * FE * G1;
-          sl += cFJ * (FE2 * G + FE * G2 + 2.0 * FE1 * G1 * cosv);
+          const double FE1 = adE * dE, G1 = adG * dG;
+          const double FE2 = -2.0 * b * FE1 * dE, G2 = -2.0 * b2 * G1 * dG;
+          s1 = fma(cFJ * FE1, G, s1);
+          s3 = fma(cFJ * FE, G1, s3);
+          sl = fma(cFJ, fma(FE2, G, fma(FE, G2, FE1 * G1 * cos2)), sl);
         }
       }
       if (j > e) ks += s0;
@@ -402,12 +404,13 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
       const double wn = S.jen_w;
       const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));
       const double dot = __fma_rn(zi, za, __fma_rn(yi, ya, __dmul_rn(xi, xa)));
-      const double r = sqrt(__dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot)));
-      const double den = 1.0 / (1.0 + wn * r);
+      const double d2n = __dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot));
+      const double r = d2n > 0.0 ? d2n * fast_rsqrt(d2n) : 0.0;   // electron on a nucleus: r = 0, kept finite by eps below
+      const double den = fast_rcp(1.0 + wn * r);
       ks += r * den;
       if (DERIV) {
-        const double invr = 1.0 / (r + QMCB_EPS);
-        const double invr3 = 1.0 / (r * r * r + QMCB_EPS);
+        const double invr = fast_rcp(r + QMCB_EPS);
+        const double invr3 = fast_rcp(r * r * r + QMCB_EPS);
         const double kp = den * den * invr;
         gnx += kp * dx; gny += kp * dy; gnz += kp * dz;
         const double sdr2 = s2 * invr * invr;   // sum_c dr_c^2
@@ -469,12 +472,13 @@ __device__ __forceinline__ void walker_terms(const DevSys &S, const Tab &T, cons
       if (POT) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
       if (S.use_jen) {
         const double wn = S.jen_w;
-        const double r = sqrt(gram_d2_en(xi, yi, zi, ni, xa, ya, za, gram_norm(xa, ya, za)));
-        const double den = 1.0 / (1.0 + wn * r);
+        const double d2n = gram_d2_en(xi, yi, zi, ni, xa, ya, za, gram_norm(xa, ya, za));
+        const double r = d2n > 0.0 ? d2n * fast_rsqrt(d2n) : 0.0;   // electron on a nucleus: r = 0, kept finite by eps below
+        const double den = fast_rcp(1.0 + wn * r);
         ks += r * den;
         if (DERIV) {
-          const double invr = 1.0 / (r + QMCB_EPS);
-          const double invr3 = 1.0 / (r * r * r + QMCB_EPS);
+          const double invr = fast_rcp(r + QMCB_EPS);
+          const double invr3 = fast_rcp(r * r * r + QMCB_EPS);
           const double kp = den * den * invr;
           gx += kp * dx; gy += kp * dy; gz += kp * dz;
           const double sdr2 = s2 * invr * invr, sd2r = 2.0 * s2 * invr3, den2 = den * den;
@@ -595,7 +599,7 @@ __device__ inline double gauss_jordan(int n, int nr, double *scr, int es) {
     }
     const double pv = scr[(k * ldw + k) * es];
     det *= pv;
-    const double ip = 1.0 / pv;
+    const double ip = fast_rcp(pv);
     for (int j = k + 1; j < ldw; ++j) scr[(k * ldw + j) * es] *= ip;
     for (int i = 0; i < n; ++i) {
       if (i == k) continue;
@@ -639,7 +643,7 @@ __device__ inline double warp_gauss_jordan(int n, int nr, double *m, int lane) {
     __syncwarp();
     const double pv = m[k * ldw + k];
     det *= pv;
-    const double ip = 1.0 / pv;
+    const double ip = fast_rcp(pv);
     __syncwarp();
     for (int j = k + 1 + lane; j < ldw; j += 32) m[k * ldw + j] *= ip;
     __syncwarp();
@@ -695,7 +699,7 @@ __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int
     }
     if (piv != k) det = -det;
     det *= a[k][k];
-    const double ip = 1.0 / a[k][k];
+    const double ip = fast_rcp(a[k][k]);
 #pragma unroll
     for (int i = k + 1; i < N; ++i) {
       const double l = a[i][k] * ip;
@@ -709,7 +713,7 @@ __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int
   if (WITH_B) {
     double inv_d[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) inv_d[i] = 1.0 / a[i][i];
+    for (int i = 0; i < N; ++i) inv_d[i] = fast_rcp(a[i][i]);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       double x[N];
