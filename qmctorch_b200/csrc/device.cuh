@@ -2,14 +2,23 @@
 // shared-memory table staging, shell evaluation (radial x cartesian harmonic),
 // Jastrow/potential terms per electron, small dense determinants/inverses.
 #pragma once
+// QMCB_SPEC: this header is also compiled by NVRTC as part of the structure-specialised kernel
+// (spec_kernel.cuh); every function that reads the system description is a template over the
+// description type, so that the specialised build can hand in compile-time constants.
+#ifndef QMCB_SPEC
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
 #include "plan.h"
+#define QMCB_UNROLL
+#else
+#define QMCB_UNROLL _Pragma("unroll")
+#endif
 
 #define QMCB_EPS 1e-16
 
+#ifndef QMCB_SPEC
 // Views into the staged tables.  Only the two base pointers are kept live; every table pointer is
 // re-derived from the offsets in the kernel-parameter struct (constant bank) where it is used, which
 // keeps ~30 registers free in the hot loop.
@@ -37,6 +46,8 @@ __device__ __forceinline__ double *stage_tables(const DevSys &S, double *smem, T
 }
 
 __host__ __device__ inline int table_doubles(const DevSys &S) { return S.ndbl + S.nint / 2; }
+
+#endif  // QMCB_SPEC
 
 __device__ __forceinline__ double ipow(double x, int k) {
   switch (k) {
@@ -86,7 +97,8 @@ __device__ __forceinline__ double rpow(double r, double rinv, int m) {
 // 10 FP64 instructions.  Arguments are clamped to [-708, 708] (3e-308 instead of a denormal).
 // The constants come from the kernel-parameter struct (constant bank 0): S.expc.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double exp_core(const DevSys &S, const double *etab, double x) {
+template <class SYS>
+__device__ __forceinline__ double exp_core(const SYS &S, const double *etab, double x) {
   const double t = fma(x, S.expc[0], S.expc[1]);
   const int ki = __double2loint(t);
   const double kd = t - S.expc[1];
@@ -101,13 +113,15 @@ __device__ __forceinline__ double exp_core(const DevSys &S, const double *etab, 
   return __hiloint2double(__double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
 }
 
-__device__ __forceinline__ double exp_neg(const DevSys &S, const double *etab, double x) {
+template <class SYS>
+__device__ __forceinline__ double exp_neg(const SYS &S, const double *etab, double x) {
   x = x < -708.0 ? -708.0 : x;
   return exp_core(S, etab, x);
 }
 
 // arguments of either sign
-__device__ __forceinline__ double exp_clamped(const DevSys &S, const double *etab, double x) {
+template <class SYS>
+__device__ __forceinline__ double exp_clamped(const SYS &S, const double *etab, double x) {
   x = x < -708.0 ? -708.0 : x;
   x = x > 708.0 ? 708.0 : x;
   return exp_core(S, etab, x);
@@ -125,8 +139,8 @@ __device__ __forceinline__ double exp_clamped(const DevSys &S, const double *eta
 // Sink::emit(ao_index, v[NCH]) consumes the values: v[0]=ao, v[1..3]=grad, v[4]=lap.
 // RT = 0: gto_pure (compile-time fast path), RT = 1: radial type read from S at run time.
 // ---------------------------------------------------------------------------------------
-template <int NCH>
-__device__ __forceinline__ void gto_pure_prim(const DevSys &S, const double *etab, double a, double c, double r2, double &S0, double &S1,
+template <int NCH, class SYS>
+__device__ __forceinline__ void gto_pure_prim(const SYS &S, const double *etab, double a, double c, double r2, double &S0, double &S1,
                                               double &S2) {
   const double ce = c * exp_neg(S, etab, -a * r2);
   S0 += ce;
@@ -137,8 +151,8 @@ __device__ __forceinline__ void gto_pure_prim(const DevSys &S, const double *eta
   }
 }
 
-template <int NCH, int RT>
-__device__ __forceinline__ const double2 *radial_sums(const DevSys &S, const double *etab, const double2 *rec,
+template <int NCH, int RT, class SYS>
+__device__ __forceinline__ const double2 *radial_sums(const SYS &S, const double *etab, const double2 *rec,
                                                       int nprim, double r2,
                                                       double r, double rinv, double &S0, double &S1,
                                                       double &S2) {
@@ -221,8 +235,8 @@ __device__ __forceinline__ void generic_component(int kk, double sc, double x, d
   }
 }
 
-template <int NCH, int RT, class Sink>
-__device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double ex, double ey, double ez,
+template <int NCH, int RT, class Sink, class SYS, class TAB>
+__device__ __forceinline__ void eval_aos(const SYS &S, const TAB &T, double ex, double ey, double ez,
                                          Sink &sink) {
   const double2 *rec = T.stream();
   const double *et = T.etab();          // hoisted: one live pointer instead of a re-derivation per exp
@@ -293,7 +307,8 @@ __device__ __forceinline__ void eval_aos(const DevSys &S, const Tab &T, double e
 __device__ __forceinline__ double gram_norm(double x, double y, double z) {
   return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
 }
-__device__ __forceinline__ double gram_d2_ee(const DevSys &S, double xi, double yi, double zi, double ni,
+template <class SYS>
+__device__ __forceinline__ double gram_d2_ee(const SYS &S, double xi, double yi, double zi, double ni,
                                              double xj, double yj, double zj, double nj) {
   double dot;
   if (S.gram_fma) dot = __fma_rn(zi, zj, __fma_rn(yi, yj, __dmul_rn(xi, xj)));
@@ -311,8 +326,8 @@ __device__ __forceinline__ double gram_d2_en(double xi, double yi, double zi, do
 // adds: ks (pairs j>e), grad_e ln J, lap_e ln J.  The reference differentiates this by autograd
 // (jastrow_factor_electron_electron_nuclei.py:253-300,385-439); the closed forms use
 // |grad r| = 1, lap r = 2/r:  lap_e = F''FG + F'FG 2/r_eA + FFG'' + FFG' 2/r_ej + 2 F'FG' cos(eA,ej).
-template <bool DERIV>
-__device__ __forceinline__ void een_terms(const DevSys &S, const Tab &T, const double *sp, int e, double &gx,
+template <bool DERIV, class SYS, class TAB>
+__device__ __forceinline__ void een_terms(const SYS &S, const TAB &T, const double *sp, int e, double &gx,
                                           double &gy, double &gz, double &h, double &ks) {
   const int nt = S.een_nterm;
   const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
@@ -362,8 +377,8 @@ struct ElecTerms {
   double gx, gy, gz, lap, ks, ven, vee;
 };
 
-template <bool DERIV, bool POT>
-__device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, const double *sp, int e,
+template <bool DERIV, bool POT, class SYS, class TAB>
+__device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const double *sp, int e,
                                                ElecTerms &o) {
   const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
   double gx = 0, gy = 0, gz = 0, h = 0, ks = 0, ven = 0, vee = 0;
@@ -430,19 +445,22 @@ __device__ __forceinline__ void electron_terms(const DevSys &S, const Tab &T, co
 
 // One-walker-per-thread variant: every electron pair is visited ONCE.  jv[k*jvs + e] receives
 // gx, gy, gz, lap (k = 0..3, DERIV only); the walker totals of ln J, V_en, V_ee are returned.
-template <bool DERIV, bool POT>
-__device__ __forceinline__ void walker_terms(const DevSys &S, const Tab &T, const double *sp, double *jv,
+template <bool DERIV, bool POT, class SYS, class TAB>
+__device__ __forceinline__ void walker_terms(const SYS &S, const TAB &T, const double *sp, double *jv,
                                              int jvs, double &tks, double &tven, double &tvee) {
   const int Ne = S.nelec;
   if (DERIV)
+    QMCB_UNROLL
     for (int e = 0; e < Ne; ++e) { jv[e] = 0.0; jv[jvs + e] = 0.0; jv[2 * jvs + e] = 0.0; jv[3 * jvs + e] = 0.0; }
   tks = 0.0; tven = 0.0; tvee = 0.0;
   const double w = S.jee_w;
+  QMCB_UNROLL
   for (int i = 0; i < Ne; ++i) {
     const double xi = sp[3 * i], yi = sp[3 * i + 1], zi = sp[3 * i + 2];
     const double ni = gram_norm(xi, yi, zi);
     const bool up_i = i < S.nup;
     double gx = 0, gy = 0, gz = 0, h = 0, ks = 0, vee = 0, ven = 0;
+    QMCB_UNROLL
     for (int j = i + 1; j < Ne; ++j) {
       const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
       const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
@@ -465,6 +483,7 @@ __device__ __forceinline__ void walker_terms(const DevSys &S, const Tab &T, cons
       }
     }
     // nuclei
+    QMCB_UNROLL
     for (int A = 0; A < S.natom; ++A) {
       const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
       const double dx = xi - xa, dy = yi - ya, dz = zi - za;

@@ -1,0 +1,25 @@
+// Argument block of the fused walker kernels (generic and structure-specialised).  Plain C types
+// only: this header is also compiled by NVRTC.
+#pragma once
+
+enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3 };
+
+struct FusedArgs {
+  const double *pos;   // [W,3Ne]   (MH: updated in place through pos_rw)
+  double *pos_rw;
+  int64_t W;
+  double *out0;        // psi [W]           | eloc [W]      | grad [W,3Ne] | fx [W] (in/out)
+  double *out1;        // -                 | psi or null   | -            | -
+  double *out2;        // -                 | ekin or null  | -            | -
+  int pdf;             // GRAD: return grad psi^2
+  // Metropolis
+  const double *disp;  // [W,3Ne] or null
+  const double *tau;   // [W] or null
+  const int *elec_index;
+  int move_elec, proba_normal;
+  double scale, eps;
+  uint64_t seed, offset;
+  uint8_t *accept;
+  unsigned long long *naccept;
+};
+

@@ -1,5 +1,6 @@
 // qmcb_metropolis_step: instantiates the fused kernel in MODE_MH.
 #include "fused_impl.cuh"
+#include "spec.h"
 
 extern "C" int qmcb_metropolis_step(const qmcb_plan *p, double *pos, double *fx, int64_t W,
                                     const double *disp, const double *tau, const int32_t *elec_index,
@@ -14,5 +15,7 @@ extern "C" int qmcb_metropolis_step(const qmcb_plan *p, double *pos, double *fx,
   a.disp = disp; a.tau = tau; a.elec_index = elec_index; a.move_elec = move_elec;
   a.proba_normal = proba_normal; a.scale = scale; a.eps = eps; a.seed = seed; a.offset = offset;
   a.accept = accept; a.naccept = naccept;
+  rc = qmcb_spec_launch(p, MODE_MH, a, stream);   // structure-specialised kernel, when this plan has one
+  if (rc != QMCB_SPEC_SKIP) return rc;
   return launch<MODE_MH>(p, p->cfg_psi, a, (cudaStream_t)stream);
 }

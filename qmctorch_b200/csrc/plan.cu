@@ -12,6 +12,7 @@
 #include <map>
 
 #include "plan.h"
+#include "spec.h"
 
 static thread_local std::string g_err;
 void qmcb_set_error(const std::string &msg) { g_err = msg; }
@@ -397,6 +398,8 @@ extern "C" int qmcb_plan_create(const qmcb_system *sys, int device, qmcb_plan **
 extern "C" int qmcb_plan_update(qmcb_plan *p, const qmcb_system *sys) {
   if (!p) return QMCB_EINVAL;
   if (p->device >= 0) cudaSetDevice(p->device);
+  qmcb_spec_free(p);        // the structure may have changed; compiled modules stay cached by structure
+  ++p->version;
   int rc = qmcb_build_tables(sys, p);
   if (rc == 0) rc = qmcb_choose_launch(p);
   if (rc == 0) rc = qmcb_choose_backward(p);
@@ -414,6 +417,7 @@ extern "C" void qmcb_plan_destroy(qmcb_plan *p) {
   if (p->d_int) cudaFree(p->d_int);
   if (p->d_mo_full) cudaFree(p->d_mo_full);
   if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
+  qmcb_spec_free(p);
   delete p;
 }
 
@@ -433,6 +437,13 @@ extern "C" int qmcb_plan_info(const qmcb_plan *p, int what) {
     case 10: return p->bwd.tw;
     case 11: return p->bwd.smem;
     case 12: return p->bwd.ntile_mo + p->bwd.ntile_ao;
+    case 13: {   // structure-specialised kernels: compiles (and loads) them now; 1 = in use
+      std::string why;
+      const int on = qmcb_spec_status(p, &why);
+      if (!on) qmcb_set_error("qmcb: generic kernels in use: " + why);
+      return on;
+    }
+    case 14: return qmcb_spec_eligible(p);
     default: return QMCB_EINVAL;
   }
 }

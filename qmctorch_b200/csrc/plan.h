@@ -66,8 +66,12 @@ struct LaunchCfg {
   int lu_conc;   // concurrent LU scratch slots (0: closed forms only)
 };
 
+struct qmcb_spec_state;   // spec.cu
+
 struct qmcb_plan {
   int device = 0;
+  uint64_t version = 0;                          // bumped by every table rebuild
+  mutable qmcb_spec_state *spec = nullptr;       // structure-specialised kernels (lazy)
   DevSys sys{};
   std::vector<double> hd;
   std::vector<int> hi;

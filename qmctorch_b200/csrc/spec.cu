@@ -1,0 +1,420 @@
+// Structure-specialised kernels: source generation, NVRTC compilation, module cache, launch.
+//
+// For wave functions that run one walker per thread (small systems, closed-form determinants,
+// gto_pure radial functions) the basis walk, the AO -> MO contraction, the determinants and the CI
+// sum are emitted as straight-line CUDA for that one structure and compiled with NVRTC for the
+// device's architecture; see spec_kernel.cuh for the device side and the rationale.  Parameters
+// stay run-time data (kernel-parameter block), so qmcb_plan_update() never recompiles.
+//
+// libnvrtc and libcuda are opened with dlopen at first use: libqmcb.so itself links against
+// neither, loads on machines without a driver (CPU tests), and falls back to the generic CUDA
+// kernels when NVRTC is not installed (QMCB_JIT=0 forces that; QMCB_JIT=2 makes a missing or
+// failing NVRTC an error).  There is no CPU path here either.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "fused_args.h"
+#include "plan.h"
+#include "spec.h"
+
+#include "_spec_embed.inc"   // SPEC_SRC_ARGS, SPEC_SRC_DEVICE, SPEC_SRC_PHILOX, SPEC_SRC_KERNEL (build.py)
+
+namespace {
+
+constexpr int SPEC_THREADS = 128;
+constexpr int SPEC_MINB = 4;
+constexpr int SPEC_MAX_VALUES = 448;   // doubles in the parameter block (keeps it under 4 KB)
+
+// ---------------------------------------------------------------------------------------
+// dynamic bindings
+// ---------------------------------------------------------------------------------------
+typedef struct _nvrtcProgram *nvrtcProgram;
+typedef struct CUmod_st *CUmodule;
+typedef struct CUfunc_st *CUfunction;
+typedef struct CUstream_st *CUstream;
+
+struct Dyn {
+  bool tried = false, ok = false;
+  std::string why;
+  // nvrtc
+  int (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+  int (*CompileProgram)(nvrtcProgram, int, const char *const *);
+  int (*GetProgramLogSize)(nvrtcProgram, size_t *);
+  int (*GetProgramLog)(nvrtcProgram, char *);
+  int (*GetCUBINSize)(nvrtcProgram, size_t *);
+  int (*GetCUBIN)(nvrtcProgram, char *);
+  int (*DestroyProgram)(nvrtcProgram *);
+  // driver
+  bool drv = false;
+  int (*ModuleLoadData)(CUmodule *, const void *);
+  int (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+  int (*FuncSetAttribute)(CUfunction, int, int);
+  int (*OccupancyMaxActiveBlocks)(int *, CUfunction, int, size_t);
+  int (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                      void **, void **);
+  int (*GetErrorString)(int, const char **);
+};
+
+Dyn &dyn() {
+  static Dyn d;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (d.tried) return d;
+  d.tried = true;
+  void *h = nullptr;
+  const char *names[] = {getenv("QMCB_NVRTC"), "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                         "/usr/local/cuda/lib64/libnvrtc.so"};
+  for (const char *n : names) {
+    if (!n || !*n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (h) break;
+  }
+  if (!h) { d.why = "libnvrtc not found (set QMCB_NVRTC=/path/to/libnvrtc.so)"; return d; }
+#define BIND(field, sym) *(void **)(&d.field) = dlsym(h, sym); if (!d.field) { d.why = std::string("missing ") + sym; return d; }
+  BIND(CreateProgram, "nvrtcCreateProgram") BIND(CompileProgram, "nvrtcCompileProgram")
+  BIND(GetProgramLogSize, "nvrtcGetProgramLogSize") BIND(GetProgramLog, "nvrtcGetProgramLog")
+  BIND(GetCUBINSize, "nvrtcGetCUBINSize") BIND(GetCUBIN, "nvrtcGetCUBIN") BIND(DestroyProgram, "nvrtcDestroyProgram")
+#undef BIND
+  d.ok = true;
+  void *c = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+  if (c) {
+#define BINDC(field, sym) *(void **)(&d.field) = dlsym(c, sym);
+    BINDC(ModuleLoadData, "cuModuleLoadData") BINDC(ModuleGetFunction, "cuModuleGetFunction")
+    BINDC(FuncSetAttribute, "cuFuncSetAttribute")
+    BINDC(OccupancyMaxActiveBlocks, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+    BINDC(LaunchKernel, "cuLaunchKernel") BINDC(GetErrorString, "cuGetErrorString")
+#undef BINDC
+    d.drv = d.ModuleLoadData && d.ModuleGetFunction && d.FuncSetAttribute && d.OccupancyMaxActiveBlocks &&
+            d.LaunchKernel;
+  }
+  return d;
+}
+
+int jit_level() {
+  const char *e = getenv("QMCB_JIT");
+  return e ? atoi(e) : 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// the structure walk: emits the program text and/or collects the parameter values (same order)
+// ---------------------------------------------------------------------------------------
+struct Layout { int nv = 0, off_atom = 0, off_mow = 0, off_ci = 0; };
+
+bool eligible(const qmcb_plan *p, std::string *why) {
+  const DevSys &S = p->sys;
+  const int nbig = S.nup > S.ndown ? S.nup : S.ndown;
+  const char *w = nullptr;
+  if (S.radial_type != QMCB_GTO_PURE) w = "radial type is not gto_pure";
+  else if (S.een_nterm > 0) w = "three-body Jastrow";
+  else if (S.nmup > 4) w = "more than 4 occupied MO columns";
+  else if (nbig > 3) w = "spin block larger than 3x3";
+  else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
+  else if (S.nuu + S.nud > 8 || S.nconf > 64) w = "too many determinants";
+  else if (p->cfg_eloc.warp != 2 || p->cfg_psi.warp != 2) w = "not a one-walker-per-thread system";
+  if (w) { if (why) *why = w; return false; }
+  return true;
+}
+
+bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layout &L) {
+  const DevSys &S = p->sys;
+  const std::vector<double> &hd = p->hd;
+  const std::vector<int> &hi = p->hi;
+  std::ostringstream o;
+  o.precision(17);
+  int nv = 0;
+  auto push = [&](double x) { if (vals) vals->push_back(x); return nv++; };
+  L.off_atom = nv;
+  for (int i = 0; i < 4 * S.natom; ++i) push(hd[S.o_atoms + i]);
+  const double *rec = hd.data() + S.o_stream;
+  auto ints = [](double d, int &lo, int &hi2) {
+    union { double d; int i[2]; } u;
+    u.d = d; lo = u.i[0]; hi2 = u.i[1];
+  };
+  o << "template <int NCH>\n__device__ __forceinline__ void spec_aos(const SpecParams &P, const double *et, double ex, "
+       "double ey, double ez, double (&acc)[NCH][SPEC_NMUP]) {\n";
+  for (int A = 0; A < S.natom; ++A) {
+    const int ns = hi[S.o_ash + A + 1] - hi[S.o_ash + A];
+    if (ns == 0) continue;
+    const int oa = L.off_atom + 4 * A;
+    o << "  {  // atom " << A << "\n    const double x = ex - P.v[" << oa << "], y = ey - P.v[" << oa + 1
+      << "], z = ez - P.v[" << oa + 2 << "];\n    const double r2 = x * x + y * y + z * z;\n";
+    for (int s = 0; s < ns; ++s) {
+      int nprim, ngrp;
+      ints(rec[0], nprim, ngrp);
+      rec += 2;
+      o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0;\n";
+      for (int q = 0; q < nprim; ++q, rec += 2) {
+        const int ia = push(rec[0]), ic = push(rec[1]);
+        o << "      spec_prim<NCH, " << (q == 0 ? "true" : "false") << ">(P, et, P.v[" << ia << "], P.v[" << ic
+          << "], r2, S0, S1, S2);\n";
+      }
+      for (int g = 0; g < ngrp; ++g, rec += 2) {
+        int kk, ao;
+        ints(rec[0], kk, ao);
+        const int is = push(rec[1]);
+        if (kk == 0) o << "      spec_s<NCH, " << ao << ">";
+        else if (kk == (1 << 24)) o << "      spec_p<NCH, " << ao << ">";
+        else o << "      spec_g<NCH, " << ao << ", " << kk << ">";
+        o << "(P, P.v[" << is << "], x, y, z, S0, S1, S2, acc);\n";
+      }
+      o << "    }\n";
+    }
+    o << "  }\n";
+  }
+  o << "}\n\n";
+  if ((int)(rec - (hd.data() + S.o_stream)) != 2 * S.nrec) return false;   // walked exactly the program
+  L.off_mow = nv;
+  for (int i = 0; i < S.nao * S.nmup; ++i) push(hd[S.o_mow + i]);
+  L.off_ci = nv;
+  for (int c = 0; c < S.nconf; ++c) push(hd[S.o_ci + c]);
+  L.nv = nv;
+  // determinants of the unique occupations
+  const int nun = S.nuu + S.nud;
+  o << "template <bool WB>\n__device__ __forceinline__ void spec_dets(const double *A, const double *B, double (&det)["
+    << nun << "], double (&tr)[" << nun << "]) {\n";
+  for (int u = 0; u < nun; ++u) {
+    const bool up = u < S.nuu;
+    const int n = up ? S.nup : S.ndown;
+    if (n == 0) { o << "  det[" << u << "] = 1.0; tr[" << u << "] = 0.0;\n"; continue; }
+    const int *cols = hi.data() + (up ? S.o_ucu + u * S.nup : S.o_ucd + (u - S.nuu) * S.ndown);
+    const int row0 = (up ? 0 : S.nup) * S.nmup;
+    o << "  { const int cols[" << n << "] = {";
+    for (int j = 0; j < n; ++j) o << (j ? ", " : "") << cols[j];
+    o << "}; det_trace_small(" << n << ", A + " << row0 << ", B + " << row0 << ", SPEC_NMUP, cols, WB, det[" << u
+      << "], tr[" << u << "]); }\n";
+  }
+  o << "}\n\n";
+  o << "template <bool WB>\n__device__ __forceinline__ void spec_ci(const SpecParams &P, const double (&det)[" << nun
+    << "], const double (&tr)[" << nun << "], double &sig, double &ksig) {\n  sig = 0.0; ksig = 0.0;\n";
+  for (int c = 0; c < S.nconf; ++c) {
+    const int iu = hi[S.o_ciu + c], id = S.nuu + hi[S.o_cid + c];
+    o << "  { const double d = P.v[" << L.off_ci + c << "] * det[" << iu << "] * det[" << id
+      << "]; sig += d; if (WB) ksig += d * (tr[" << iu << "] + tr[" << id << "]); }\n";
+  }
+  o << "}\n";
+  if (code) *code = o.str();
+  return true;
+}
+
+std::string prelude(const qmcb_plan *p, const Layout &L) {
+  const DevSys &S = p->sys;
+  std::ostringstream o;
+  o << "typedef signed char int8_t;\ntypedef unsigned char uint8_t;\ntypedef int int32_t;\n"
+       "typedef unsigned int uint32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n"
+       "typedef unsigned long size_t;\n"
+    << "#define QMCB_GTO_PURE 0\n#define QMCB_GTO 1\n#define QMCB_STO_PURE 2\n#define QMCB_STO 3\n"
+    << "#define SPEC_NE " << S.nelec << "\n#define SPEC_NUP " << S.nup << "\n#define SPEC_NDOWN " << S.ndown
+    << "\n#define SPEC_NATOM " << S.natom << "\n#define SPEC_NMUP " << S.nmup << "\n#define SPEC_NUU " << S.nuu
+    << "\n#define SPEC_NUD " << S.nud << "\n#define SPEC_USE_JEE " << (S.use_jee ? 1 : 0) << "\n#define SPEC_USE_JEN "
+    << (S.use_jen ? 1 : 0) << "\n#define SPEC_GRAM_FMA " << (S.gram_fma ? 1 : 0) << "\n#define SPEC_NV " << L.nv
+    << "\n#define SPEC_OFF_ATOM " << L.off_atom << "\n#define SPEC_OFF_MOW " << L.off_mow << "\n#define SPEC_OFF_CI "
+    << L.off_ci << "\n#define SPEC_THREADS " << SPEC_THREADS << "\n#define SPEC_MINB " << SPEC_MINB << "\n";
+  return o.str();
+}
+
+std::string full_source(const qmcb_plan *p, const Layout &L, const std::string &code) {
+  std::string k = SPEC_SRC_KERNEL;
+  const std::string mark = "SPEC_GENERATED_CODE\n";
+  const size_t at = k.find("\n" + mark);
+  if (at == std::string::npos) return std::string();
+  k.replace(at + 1, mark.size(), code);
+  return prelude(p, L) + SPEC_SRC_ARGS + SPEC_SRC_DEVICE + SPEC_SRC_PHILOX + k;
+}
+
+// ---------------------------------------------------------------------------------------
+// compile + module cache
+// ---------------------------------------------------------------------------------------
+struct Module {
+  std::vector<char> cubin;
+  std::string log;
+  CUmodule mod = nullptr;
+  CUfunction fn[3] = {nullptr, nullptr, nullptr};   // psi, eloc, mh
+  int occ[3] = {0, 0, 0};
+  int smem[3] = {0, 0, 0};
+  bool loaded = false;
+};
+std::map<std::string, Module> &cache() { static std::map<std::string, Module> c; return c; }
+std::mutex &cache_mu() { static std::mutex m; return m; }
+
+int compile(const std::string &src, const std::string &arch, Module &m, std::string &err) {
+  Dyn &d = dyn();
+  if (!d.ok) { err = d.why; return -1; }
+  nvrtcProgram prog = nullptr;
+  if (d.CreateProgram(&prog, src.c_str(), "qmcb_spec.cu", 0, nullptr, nullptr) != 0) { err = "nvrtcCreateProgram failed"; return -1; }
+  const std::string a = "--gpu-architecture=" + arch;
+  const char *opts[] = {a.c_str(), "--std=c++17", "-lineinfo", "-DQMCB_SPEC"};
+  const int rc = d.CompileProgram(prog, 4, opts);
+  size_t n = 0;
+  d.GetProgramLogSize(prog, &n);
+  if (n > 1) { m.log.resize(n); d.GetProgramLog(prog, &m.log[0]); }
+  if (rc != 0) {
+    err = "nvrtcCompileProgram failed: " + m.log.substr(0, 2000);
+    d.DestroyProgram(&prog);
+    return -1;
+  }
+  size_t cs = 0;
+  if (d.GetCUBINSize(prog, &cs) != 0 || cs == 0) { err = "nvrtcGetCUBIN: no cubin"; d.DestroyProgram(&prog); return -1; }
+  m.cubin.resize(cs);
+  d.GetCUBIN(prog, m.cubin.data());
+  d.DestroyProgram(&prog);
+  return 0;
+}
+
+std::string drv_err(int rc) {
+  const char *s = nullptr;
+  Dyn &d = dyn();
+  if (d.GetErrorString) d.GetErrorString(rc, &s);
+  return s ? s : ("CUresult " + std::to_string(rc));
+}
+
+int slice_doubles(const DevSys &S, int mode) {
+  const bool el = mode == MODE_ELOC;
+  return (3 * S.nelec + (el ? 4 * S.nelec : 0) + (el ? 2 : 1) * S.nelec * S.nmup) | 1;
+}
+
+}  // namespace
+
+struct qmcb_spec_state {
+  bool failed = false;
+  std::string why;
+  Module *mod = nullptr;
+  Layout lay;
+  std::vector<char> params;   // host image of SpecParams
+  uint64_t params_version = ~0ull;
+};
+
+void qmcb_spec_free(qmcb_plan *p) {
+  delete p->spec;
+  p->spec = nullptr;
+}
+
+// Builds (or fetches) the specialised module of this plan.  load = false: compile only (no driver).
+// Returns 0 when the module is ready, 1 when the generic kernels must be used (st.why says why).
+static int spec_prepare(const qmcb_plan *p, bool load) {
+  if (!p->spec) p->spec = new qmcb_spec_state();
+  qmcb_spec_state &st = *p->spec;
+  if (st.failed) return 1;
+  if (st.mod && (!load || st.mod->loaded)) return 0;
+  auto fail = [&](const std::string &why) { st.failed = true; st.why = why; return 1; };
+  if (jit_level() <= 0) return fail("disabled (QMCB_JIT=0)");
+  std::string why;
+  if (!eligible(p, &why)) return fail("not eligible: " + why);
+  std::string code;
+  Layout L;
+  if (!walk(p, &code, nullptr, L)) return fail("program walk failed");
+  if (L.nv > SPEC_MAX_VALUES) return fail("parameter block too large");
+  st.lay = L;
+  std::string arch = "sm_100a";
+  if (p->device >= 0) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, p->device) == cudaSuccess) {
+      arch = "sm_" + std::to_string(pr.major) + std::to_string(pr.minor);
+      if (pr.major >= 9) arch += "a";
+    }
+  }
+  const std::string key = std::to_string(p->device) + "|" + arch + "|" + prelude(p, L) + code;
+  std::lock_guard<std::mutex> lk(cache_mu());
+  Module &m = cache()[key];
+  if (m.cubin.empty()) {
+    const std::string src = full_source(p, L, code);
+    if (src.empty()) { cache().erase(key); return fail("embedded source has no insertion mark"); }
+    const char *dump = getenv("QMCB_JIT_DUMP");
+    if (dump) {
+      FILE *f = fopen((std::string(dump) + ".cu").c_str(), "w");
+      if (f) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+    }
+    std::string err;
+    if (compile(src, arch, m, err) != 0) { cache().erase(key); return fail(err); }
+    if (dump) {
+      FILE *f = fopen((std::string(dump) + ".cubin").c_str(), "wb");
+      if (f) { fwrite(m.cubin.data(), 1, m.cubin.size(), f); fclose(f); }
+    }
+  }
+  if (load && !m.loaded) {
+    Dyn &d = dyn();
+    if (!d.drv) return fail("libcuda.so.1 not available");
+    cudaSetDevice(p->device);
+    cudaFree(nullptr);   // primary context current on this thread
+    int rc = d.ModuleLoadData(&m.mod, m.cubin.data());
+    if (rc != 0) return fail("cuModuleLoadData: " + drv_err(rc));
+    const char *names[3] = {"spec_psi", "spec_eloc", "spec_mh"};
+    const int modes[3] = {MODE_PSI, MODE_ELOC, MODE_MH};
+    for (int i = 0; i < 3; ++i) {
+      rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
+      if (rc != 0) return fail(std::string("cuModuleGetFunction ") + names[i] + ": " + drv_err(rc));
+      m.smem[i] = (int)((64 + (size_t)SPEC_THREADS * slice_doubles(p->sys, modes[i])) * sizeof(double));
+      rc = d.FuncSetAttribute(m.fn[i], 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, m.smem[i]);
+      if (rc != 0) return fail("cuFuncSetAttribute: " + drv_err(rc));
+      int occ = 0;
+      rc = d.OccupancyMaxActiveBlocks(&occ, m.fn[i], SPEC_THREADS, (size_t)m.smem[i]);
+      m.occ[i] = (rc == 0 && occ > 0) ? occ : 1;
+    }
+    m.loaded = true;
+  }
+  st.mod = &m;
+  return 0;
+}
+
+static void refresh_params(const qmcb_plan *p, qmcb_spec_state &st) {
+  if (st.params_version == p->version && !st.params.empty()) return;
+  const DevSys &S = p->sys;
+  std::vector<double> vals;
+  Layout L;
+  walk(p, nullptr, &vals, L);
+  // SpecParams: expc[8] | jee_w jen_w vnn | etab pointer | v[NV]
+  std::vector<char> buf((8 + 3 + 1 + (size_t)L.nv) * sizeof(double));
+  double *d = reinterpret_cast<double *>(buf.data());
+  for (int i = 0; i < 8; ++i) d[i] = S.expc[i];
+  d[8] = S.jee_w; d[9] = S.jen_w; d[10] = S.vnn;
+  const double *et = p->d_dbl ? p->d_dbl + S.o_etab : nullptr;
+  memcpy(&d[11], &et, sizeof(et));
+  for (int i = 0; i < L.nv; ++i) d[12 + i] = vals[i];
+  st.params.swap(buf);
+  st.params_version = p->version;
+}
+
+int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *stream) {
+  const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : -1));
+  if (slot < 0 || p->device < 0) return QMCB_SPEC_SKIP;
+  if (spec_prepare(p, true) != 0) {
+    if (jit_level() >= 2) {
+      qmcb_set_error("qmcb: structure-specialised kernel unavailable: " + p->spec->why);
+      return QMCB_EINVAL;
+    }
+    return QMCB_SPEC_SKIP;
+  }
+  qmcb_spec_state &st = *p->spec;
+  refresh_params(p, st);
+  Module &m = *st.mod;
+  int64_t grid = (int64_t)p->sm_count * m.occ[slot];
+  const int64_t need = (a.W + SPEC_THREADS - 1) / SPEC_THREADS;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  FusedArgs args = a;
+  void *kp[2] = {st.params.data(), &args};
+  const int rc = dyn().LaunchKernel(m.fn[slot], (unsigned)grid, 1, 1, SPEC_THREADS, 1, 1, (unsigned)m.smem[slot],
+                                    (CUstream)stream, kp, nullptr);
+  if (rc != 0) {
+    qmcb_set_error("qmcb: cuLaunchKernel(spec): " + drv_err(rc));
+    return QMCB_EINVAL;
+  }
+  return 0;
+}
+
+// 1: specialised kernels compiled (and loaded when the plan has a device), 0: generic kernels
+int qmcb_spec_status(const qmcb_plan *p, std::string *why) {
+  const int rc = spec_prepare(p, p->device >= 0);
+  if (why) *why = p->spec ? p->spec->why : std::string();
+  return rc == 0 ? 1 : 0;
+}
+
+int qmcb_spec_eligible(const qmcb_plan *p) { return jit_level() > 0 && eligible(p, nullptr) ? 1 : 0; }

@@ -56,6 +56,7 @@ def mh():
 
 t_m = timeit(mh)
 info = [wf._handle.info(i) for i in range(10)]
+print("specialised kernels: %d (%s)" % (wf._handle.info(13), L.qmcb_last_error().decode()[:200] if not wf._handle.info(13) else "NVRTC"))
 print("%s lib=%s W=%d tile=%d thr=%d smem=%d | eloc %.3f ms (%.3e/s) psi %.3f ms (%.3e/s) grad %.3f ms mh %.3f ms (%.3e/s)"
       % (key, os.path.basename(_lib.LIB_PATH), W, info[6], info[7], info[8], t_e, W / t_e * 1e3, t_p, W / t_p * 1e3,
          t_g, t_m, W / t_m * 1e3), flush=True)
