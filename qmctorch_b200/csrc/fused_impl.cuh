@@ -147,15 +147,15 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
     const int tw = (int)((a.W - w0) < TW ? (a.W - w0) : TW);
     // ---- P0: coordinates (+ proposal)
     if (MODE == MODE_MH && !a.disp && a.proba_normal) {
-      // in-kernel normal proposals: one Philox call yields the two normals of a GLOBAL element
-      // pair (2p, 2p+1), so the draw of an element does not depend on the tiling
+      // in-kernel normal proposals: one Philox call yields the four normals of a GLOBAL element
+      // quad (4q .. 4q+3), so the draw of an element does not depend on the tiling
       const int64_t g0 = w0 * ne3, g1 = g0 + (int64_t)tw * ne3;
-      for (int64_t p = (g0 >> 1) + tid; 2 * p < g1; p += nthr) {
-        double z[2];
-        philox_normal2(a.seed, a.offset, (uint64_t)p, z[0], z[1]);
+      for (int64_t q = (g0 >> 2) + tid; 4 * q < g1; q += nthr) {
+        double z[4];
+        philox_normal4(a.seed, a.offset, (uint64_t)q, z);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int64_t g = 2 * p + h;
+        for (int h = 0; h < 4; ++h) {
+          const int64_t g = 4 * q + h;
           if (g < g0 || g >= g1) continue;
           const int i = (int)(g - g0);
           const int wl = i / ne3, e = (i - wl * ne3) / 3;

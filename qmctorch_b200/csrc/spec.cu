@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,8 +31,14 @@
 
 namespace {
 
-constexpr int SPEC_THREADS = 128;
-constexpr int SPEC_MINB = 4;
+// CTA shape of the specialised kernels (launch bounds -> register budget).  QMCB_SPEC_THREADS /
+// QMCB_SPEC_MINB override them for tuning experiments.
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && atoi(e) > 0) ? atoi(e) : dflt;
+}
+const int SPEC_THREADS = env_int("QMCB_SPEC_THREADS", 128);
+const int SPEC_MINB = env_int("QMCB_SPEC_MINB", 4);
 constexpr int SPEC_MAX_VALUES = 448;   // doubles in the parameter block (keeps it under 4 KB)
 
 // ---------------------------------------------------------------------------------------
@@ -53,6 +60,8 @@ struct Dyn {
   int (*GetCUBINSize)(nvrtcProgram, size_t *);
   int (*GetCUBIN)(nvrtcProgram, char *);
   int (*DestroyProgram)(nvrtcProgram *);
+  int (*GetPTXSize)(nvrtcProgram, size_t *) = nullptr;   // optional (QMCB_JIT_DUMP)
+  int (*GetPTX)(nvrtcProgram, char *) = nullptr;
   // driver
   bool drv = false;
   int (*ModuleLoadData)(CUmodule *, const void *);
@@ -84,6 +93,8 @@ Dyn &dyn() {
   BIND(GetProgramLogSize, "nvrtcGetProgramLogSize") BIND(GetProgramLog, "nvrtcGetProgramLog")
   BIND(GetCUBINSize, "nvrtcGetCUBINSize") BIND(GetCUBIN, "nvrtcGetCUBIN") BIND(DestroyProgram, "nvrtcDestroyProgram")
 #undef BIND
+  *(void **)(&d.GetPTXSize) = dlsym(h, "nvrtcGetPTXSize");
+  *(void **)(&d.GetPTX) = dlsym(h, "nvrtcGetPTX");
   d.ok = true;
   void *c = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
   if (c) {
@@ -119,7 +130,8 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
   else if (S.nuu + S.nud > 8 || S.nconf > 64) w = "too many determinants";
-  else if (p->cfg_eloc.warp != 2 || p->cfg_psi.warp != 2) w = "not a one-walker-per-thread system";
+  else if ((64 + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmup) | 1)) * sizeof(double) > 100 * 1024)
+    w = "per-thread slices exceed the shared-memory budget";
   if (w) { if (why) *why = w; return false; }
   return true;
 }
@@ -139,32 +151,35 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     union { double d; int i[2]; } u;
     u.d = d; lo = u.i[0]; hi2 = u.i[1];
   };
-  o << "template <int NCH>\n__device__ __forceinline__ void spec_aos(const SpecParams &P, const double *et, double ex, "
-       "double ey, double ez, double (&acc)[NCH][SPEC_NMUP]) {\n";
+  o << "template <int MODE, int NCH>\n__device__ __forceinline__ void spec_aos(const SpecParams &P, const double *et, "
+       "double ex, double ey, double ez, double (&acc)[NCH][SPEC_NMUP]) {\n";
   for (int A = 0; A < S.natom; ++A) {
     const int ns = hi[S.o_ash + A + 1] - hi[S.o_ash + A];
     if (ns == 0) continue;
     const int oa = L.off_atom + 4 * A;
-    o << "  {  // atom " << A << "\n    const double x = ex - P.v[" << oa << "], y = ey - P.v[" << oa + 1
-      << "], z = ez - P.v[" << oa + 2 << "];\n    const double r2 = x * x + y * y + z * z;\n";
+    o << "  {  // atom " << A << "\n    const double x = ex - spec_pv<MODE, " << oa << ">(), y = ey - spec_pv<MODE, " << oa + 1
+      << ">(), z = ez - spec_pv<MODE, " << oa + 2 << ">();\n    const double r2 = x * x + y * y + z * z;\n";
     for (int s = 0; s < ns; ++s) {
       int nprim, ngrp;
       ints(rec[0], nprim, ngrp);
       rec += 2;
-      o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0;\n";
+      o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0, T2 = 0.0;\n";
       for (int q = 0; q < nprim; ++q, rec += 2) {
-        const int ia = push(rec[0]), ic = push(rec[1]);
-        o << "      spec_prim<NCH, " << (q == 0 ? "true" : "false") << ">(P, et, P.v[" << ia << "], P.v[" << ic
-          << "], r2, S0, S1, S2);\n";
+        // derived per-primitive constants, see spec_prim (spec_kernel.cuh)
+        const double a = rec[0], c = rec[1];
+        const int i0 = push(-a);
+        push(c); push(-2.0 * a * c); push(-6.0 * a * c); push(4.0 * a * a * c);
+        o << "      spec_prim<MODE, " << (q == 0 ? "true" : "false") << ", " << i0 << ">(P, et, r2, S0, S1, S2, T2);\n";
       }
+      o << "      spec_shell_end<MODE>(r2, S2, T2);\n";
       for (int g = 0; g < ngrp; ++g, rec += 2) {
         int kk, ao;
         ints(rec[0], kk, ao);
         const int is = push(rec[1]);
-        if (kk == 0) o << "      spec_s<NCH, " << ao << ">";
-        else if (kk == (1 << 24)) o << "      spec_p<NCH, " << ao << ">";
-        else o << "      spec_g<NCH, " << ao << ", " << kk << ">";
-        o << "(P, P.v[" << is << "], x, y, z, S0, S1, S2, acc);\n";
+        if (kk == 0) o << "      spec_s<MODE, " << ao << ", " << is << ">";
+        else if (kk == (1 << 24)) o << "      spec_p<MODE, " << ao << ", " << is << ">";
+        else o << "      spec_g<MODE, " << ao << ", " << is << ", " << kk << ">";
+        o << "(x, y, z, S0, S1, S2, acc);\n";
       }
       o << "    }\n";
     }
@@ -193,11 +208,12 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
       << "], tr[" << u << "]); }\n";
   }
   o << "}\n\n";
-  o << "template <bool WB>\n__device__ __forceinline__ void spec_ci(const SpecParams &P, const double (&det)[" << nun
-    << "], const double (&tr)[" << nun << "], double &sig, double &ksig) {\n  sig = 0.0; ksig = 0.0;\n";
+  o << "template <int MODE>\n__device__ __forceinline__ void spec_ci(const double (&det)[" << nun
+    << "], const double (&tr)[" << nun << "], double &sig, double &ksig) {\n  constexpr bool WB = MODE == MODE_ELOC;\n"
+       "  sig = 0.0; ksig = 0.0;\n";
   for (int c = 0; c < S.nconf; ++c) {
     const int iu = hi[S.o_ciu + c], id = S.nuu + hi[S.o_cid + c];
-    o << "  { const double d = P.v[" << L.off_ci + c << "] * det[" << iu << "] * det[" << id
+    o << "  { const double d = spec_pv<MODE, " << L.off_ci + c << ">() * det[" << iu << "] * det[" << id
       << "]; sig += d; if (WB) ksig += d * (tr[" << iu << "] + tr[" << id << "]); }\n";
   }
   o << "}\n";
@@ -265,6 +281,15 @@ int compile(const std::string &src, const std::string &arch, Module &m, std::str
   if (d.GetCUBINSize(prog, &cs) != 0 || cs == 0) { err = "nvrtcGetCUBIN: no cubin"; d.DestroyProgram(&prog); return -1; }
   m.cubin.resize(cs);
   d.GetCUBIN(prog, m.cubin.data());
+  if (const char *dump = getenv("QMCB_JIT_DUMP")) {
+    size_t ps = 0;
+    if (d.GetPTXSize && d.GetPTX && d.GetPTXSize(prog, &ps) == 0 && ps > 1) {
+      std::vector<char> ptx(ps);
+      d.GetPTX(prog, ptx.data());
+      FILE *f = fopen((std::string(dump) + ".ptx").c_str(), "w");
+      if (f) { fwrite(ptx.data(), 1, ps - 1, f); fclose(f); }
+    }
+  }
   d.DestroyProgram(&prog);
   return 0;
 }
@@ -284,6 +309,7 @@ int slice_doubles(const DevSys &S, int mode) {
 }  // namespace
 
 struct qmcb_spec_state {
+  int level = -1;             // QMCB_JIT as read when this plan was first prepared
   bool failed = false;
   std::string why;
   Module *mod = nullptr;
@@ -302,10 +328,11 @@ void qmcb_spec_free(qmcb_plan *p) {
 static int spec_prepare(const qmcb_plan *p, bool load) {
   if (!p->spec) p->spec = new qmcb_spec_state();
   qmcb_spec_state &st = *p->spec;
+  if (st.level < 0) st.level = jit_level();
   if (st.failed) return 1;
   if (st.mod && (!load || st.mod->loaded)) return 0;
   auto fail = [&](const std::string &why) { st.failed = true; st.why = why; return 1; };
-  if (jit_level() <= 0) return fail("disabled (QMCB_JIT=0)");
+  if (st.level <= 0) return fail("disabled (QMCB_JIT=0)");
   std::string why;
   if (!eligible(p, &why)) return fail("not eligible: " + why);
   std::string code;
@@ -386,7 +413,7 @@ int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *str
   const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : -1));
   if (slot < 0 || p->device < 0) return QMCB_SPEC_SKIP;
   if (spec_prepare(p, true) != 0) {
-    if (jit_level() >= 2) {
+    if (p->spec->level >= 2) {
       qmcb_set_error("qmcb: structure-specialised kernel unavailable: " + p->spec->why);
       return QMCB_EINVAL;
     }

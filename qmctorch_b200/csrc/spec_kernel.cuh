@@ -15,7 +15,7 @@
 // to the same parity bar by the same tests.
 //
 // Compiled with -DQMCB_SPEC after a generated prelude that defines SPEC_* and the functions
-// spec_aos<NCH>, spec_dets<WB>, spec_ci<WB> (see spec.cu: emit_source).
+// spec_aos<MODE>, spec_dets<WB>, spec_ci<MODE> (see spec.cu: walk).
 #pragma once
 
 // ---- the prelude has defined: SPEC_NE SPEC_NUP SPEC_NDOWN SPEC_NATOM SPEC_NMUP SPEC_NUU SPEC_NUD
@@ -42,72 +42,117 @@ struct SpecTab {
   __device__ __forceinline__ SpecVals atoms() const { return SpecVals{P, SPEC_OFF_ATOM}; }
 };
 
+// ---- parameter reads.  NVVM hoists every load of a kernel parameter out of the walker and
+// electron loops (they are loop invariant), which leaves ptxas with > 100 long-lived doubles: it
+// spills them and feeds the FP64 pipe through LDL + R2UR instead of constant-bank operands
+// (measured: 78 R2UR + 25 LDL per electron).  Reading the parameter with a volatile inline
+// ld.param at the point of use keeps the load next to its consumer, where ptxas folds it into the
+// c[0x0][offset] operand slot of DFMA/DMUL: no instruction, no register.
+#define SPEC_V_BYTE0 96   // offsetof(SpecParams, v)
+static_assert(sizeof(SpecParams) == SPEC_V_BYTE0 + 8 * SPEC_NV, "SpecParams layout");
+template <int MODE, int I>
+__device__ __forceinline__ double spec_pv() {
+  double v;
+  if constexpr (MODE == MODE_PSI)
+    asm volatile("ld.param.f64 %0, [spec_psi_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
+  else if constexpr (MODE == MODE_ELOC)
+    asm volatile("ld.param.f64 %0, [spec_eloc_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
+  else
+    asm volatile("ld.param.f64 %0, [spec_mh_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
+  return v;
+}
+template <int MODE>
+__host__ __device__ constexpr int spec_nch() { return MODE == MODE_ELOC ? 5 : 1; }
+
 // ---- building blocks the generated program calls (literal indices everywhere)
-template <int NCH, bool FIRST>
-__device__ __forceinline__ void spec_prim(const SpecParams &P, const double *et, double a, double c, double r2,
-                                          double &S0, double &S1, double &S2) {
-  const double ce = c * exp_neg(P, et, -a * r2);
-  if (FIRST) S0 = ce; else S0 += ce;
+// One primitive c exp(-a r^2) of a shell.  Every product of parameters is formed on the HOST
+// (spec.cu: walk): v[I..I+4] = { -a, c, -2 a c, -6 a c, 4 a^2 c }, and the radial sums are kept as
+//   S0 = sum c e,  S1 = sum (-2 a c) e,  S2 = sum (-6 a c) e,  T2 = sum (4 a^2 c) e   (e = exp(-a r^2))
+// with lap R = S2 + T2 r^2 formed once per shell (spec_shell_end).  Each FP64 instruction then has
+// exactly ONE parameter operand, which DFMA/DMUL read straight from the constant bank: 15 FP64-pipe
+// instructions per primitive with derivatives (12 without) and no operand loads, instead of 20 (14).
+// The lower clamp of the exponent (-708: 3e-308 instead of a denormal) is one integer min on the
+// high word: more negative doubles have larger high words.  NaN arguments are the canonical
+// positive NaN the FP64 pipe produces and pass through.
+template <int MODE, bool FIRST, int I>
+__device__ __forceinline__ void spec_prim(const SpecParams &P, const double *et, double r2, double &S0, double &S1,
+                                          double &S2, double &T2) {
+  constexpr int NCH = spec_nch<MODE>();
+  const double x = spec_pv<MODE, I>() * r2;
+  const unsigned hi = min((unsigned)__double2hiint(x), 0xC0862000u);
+  const double e = exp_core(P, et, __hiloint2double((int)hi, __double2loint(x)));
+  if (FIRST) S0 = spec_pv<MODE, I + 1>() * e; else S0 = fma(spec_pv<MODE, I + 1>(), e, S0);
   if (NCH > 1) {
-    const double t = a * ce;
-    const double u = t * fma(4.0 * a, r2, -6.0);
-    if (FIRST) { S1 = -2.0 * t; S2 = u; } else { S1 = fma(-2.0, t, S1); S2 += u; }
+    if (FIRST) { S1 = spec_pv<MODE, I + 2>() * e; S2 = spec_pv<MODE, I + 3>() * e; T2 = spec_pv<MODE, I + 4>() * e; }
+    else {
+      S1 = fma(spec_pv<MODE, I + 2>(), e, S1); S2 = fma(spec_pv<MODE, I + 3>(), e, S2);
+      T2 = fma(spec_pv<MODE, I + 4>(), e, T2);
+    }
   }
 }
-
-template <int NCH, int AO>
-__device__ __forceinline__ void spec_emit(const SpecParams &P, const double (&v)[NCH], double (&acc)[NCH][SPEC_NMUP]) {
-#pragma unroll
-  for (int j = 0; j < SPEC_NMUP; ++j) {
-    const double wj = P.v[SPEC_OFF_MOW + AO * SPEC_NMUP + j];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) acc[c][j] = fma(v[c], wj, acc[c][j]);
-  }
+template <int MODE>
+__device__ __forceinline__ void spec_shell_end(double r2, double &S2, double T2) {
+  if (spec_nch<MODE>() > 1) S2 = fma(T2, r2, S2);
 }
 
-template <int NCH, int AO>
-__device__ __forceinline__ void spec_s(const SpecParams &P, double sc, double x, double y, double z, double S0,
-                                       double S1, double S2, double (&acc)[NCH][SPEC_NMUP]) {
+template <int MODE, int AO, int NCH>
+__device__ __forceinline__ void spec_emit(const double (&v)[NCH], double (&acc)[NCH][SPEC_NMUP]) {
+  static_assert(NCH == spec_nch<MODE>(), "channel count");
+  // (the MO weights of one AO are read once per column: SPEC_NMUP <= 4)
+  double w[SPEC_NMUP];
+  w[0] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP>();
+  if (SPEC_NMUP > 1) w[1 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 1 % SPEC_NMUP>();
+  if (SPEC_NMUP > 2) w[2 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 2 % SPEC_NMUP>();
+  if (SPEC_NMUP > 3) w[3 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 3 % SPEC_NMUP>();
+#pragma unroll
+  for (int j = 0; j < SPEC_NMUP; ++j)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[c][j] = fma(v[c], w[j], acc[c][j]);
+}
+
+template <int MODE, int AO, int ISC, int NCH>
+__device__ __forceinline__ void spec_s(double x, double y, double z, double S0, double S1, double S2,
+                                       double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
-  v[0] = S0 * sc;
+  v[0] = S0 * spec_pv<MODE, ISC>();
   if (NCH > 1) {
-    const double t = S1 * sc;
+    const double t = S1 * spec_pv<MODE, ISC>();
     v[1] = t * x; v[2] = t * y; v[3] = t * z;
-    v[4] = S2 * sc;
+    v[4] = S2 * spec_pv<MODE, ISC>();
   }
-  spec_emit<NCH, AO>(P, v, acc);
+  spec_emit<MODE, AO>(v, acc);
 }
 
-template <int NCH, int AO>
-__device__ __forceinline__ void spec_p(const SpecParams &P, double sc, double x, double y, double z, double S0,
-                                       double S1, double S2, double (&acc)[NCH][SPEC_NMUP]) {
+template <int MODE, int AO, int ISC, int NCH>
+__device__ __forceinline__ void spec_p(double x, double y, double z, double S0, double S1, double S2,
+                                       double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
-  const double R = S0 * sc;
+  const double R = S0 * spec_pv<MODE, ISC>();
   if (NCH > 1) {
-    const double t = S1 * sc, lf = fma(2.0, S1, S2) * sc;
+    const double t = S1 * spec_pv<MODE, ISC>(), lf = fma(2.0, S1, S2) * spec_pv<MODE, ISC>();
     const double tx = t * x, ty = t * y, tz = t * z;
     v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z; v[4] = lf * x;
-    spec_emit<NCH, AO>(P, v, acc);
+    spec_emit<MODE, AO>(v, acc);
     v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z; v[4] = lf * y;
-    spec_emit<NCH, AO + 1>(P, v, acc);
+    spec_emit<MODE, AO + 1>(v, acc);
     v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R); v[4] = lf * z;
-    spec_emit<NCH, AO + 2>(P, v, acc);
+    spec_emit<MODE, AO + 2>(v, acc);
   } else {
-    v[0] = R * x; spec_emit<NCH, AO>(P, v, acc);
-    v[0] = R * y; spec_emit<NCH, AO + 1>(P, v, acc);
-    v[0] = R * z; spec_emit<NCH, AO + 2>(P, v, acc);
+    v[0] = R * x; spec_emit<MODE, AO>(v, acc);
+    v[0] = R * y; spec_emit<MODE, AO + 1>(v, acc);
+    v[0] = R * z; spec_emit<MODE, AO + 2>(v, acc);
   }
 }
 
-template <int NCH, int AO, int KK>
-__device__ __forceinline__ void spec_g(const SpecParams &P, double sc, double x, double y, double z, double S0,
-                                       double S1, double S2, double (&acc)[NCH][SPEC_NMUP]) {
+template <int MODE, int AO, int ISC, int KK, int NCH>
+__device__ __forceinline__ void spec_g(double x, double y, double z, double S0, double S1, double S2,
+                                       double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
-  generic_component<NCH>(KK, sc, x, y, z, S0, S1, S2, v);   // literal powers: folds to a few products
-  spec_emit<NCH, AO>(P, v, acc);
+  generic_component<NCH>(KK, spec_pv<MODE, ISC>(), x, y, z, S0, S1, S2, v);   // literal powers: a few products
+  spec_emit<MODE, AO>(v, acc);
 }
 
-// ---- generated: spec_aos<NCH>, spec_dets<WB>, spec_ci<WB>
+// ---- generated: spec_aos<MODE>, spec_dets<WB>, spec_ci<MODE>
 SPEC_GENERATED_CODE
 
 template <int MODE>
@@ -128,20 +173,20 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.W; w += stride) {
     // ---- coordinates (+ proposal)
     if (MODE == MODE_MH && !a.disp && a.proba_normal) {
-      // one Philox call yields the two normals of a GLOBAL element pair (2p, 2p+1): the draw of an
-      // element does not depend on the tiling (same stream as the generic kernel)
+      // one Philox call yields the four normals of a GLOBAL element quad (4q .. 4q+3): the draw of
+      // an element does not depend on the tiling (same stream as the generic kernel)
       const int64_t g0 = w * ne3, g1 = g0 + ne3;
       int me = a.move_elec;
       if (me == -2) {
         if (a.elec_index) me = a.elec_index[w];
         else me = (int)(philox_u32(a.seed, a.offset, (uint64_t)w, 2u) % (unsigned)Ne);
       }
-      for (int64_t p = g0 >> 1; 2 * p < g1; ++p) {
-        double z[2];
-        philox_normal2(a.seed, a.offset, (uint64_t)p, z[0], z[1]);
+      for (int64_t q = g0 >> 2; 4 * q < g1; ++q) {
+        double z[4];
+        philox_normal4(a.seed, a.offset, (uint64_t)q, z);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int64_t g = 2 * p + h;
+        for (int h = 0; h < 4; ++h) {
+          const int64_t g = 4 * q + h;
           if (g < g0 || g >= g1) continue;
           const int i = (int)(g - g0), e = i / 3;
           double v = a.pos[g];
@@ -178,7 +223,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
       for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int j = 0; j < NM; ++j) acc[c][j] = 0.0;
-      spec_aos<NCH>(P, et, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], acc);
+      spec_aos<MODE>(P, et, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], acc);
       if (MODE == MODE_ELOC) {
         const double gx = jv[e], gy = jv[Ne + e], gz = jv[2 * Ne + e], lp = jv[3 * Ne + e];
 #pragma unroll
@@ -198,7 +243,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
     double det[NUN], tr[NUN];
     spec_dets<(MODE == MODE_ELOC)>(smo, sB, det, tr);
     double sig, ksig;
-    spec_ci<(MODE == MODE_ELOC)>(P, det, tr, sig, ksig);
+    spec_ci<MODE>(det, tr, sig, ksig);
     const double J = (SPEC_USE_JEE || SPEC_USE_JEN) ? exp_clamped(P, et, tks) : 1.0;
     const double psi = J * sig;
     if (MODE == MODE_PSI) {

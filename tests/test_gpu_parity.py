@@ -470,3 +470,96 @@ def test_one_electron_ao_and_update():
     upd = wf.ao.update(ao, moved, 1)
     assert torch.equal(upd, wf.ao(moved))
     assert torch.equal(upd[:, 0], ao[:, 0]) and not torch.equal(upd[:, 1], ao[:, 1])
+
+
+def _mh_philox(wf, x, tau, seed, offset, scale=0.3, move_elec=-1):
+    """One in-kernel-Philox Metropolis move through the C ABI; returns (new pos, accept mask)."""
+    from qmctorch_b200 import _lib
+    L = _lib.lib()
+    x = x.clone()
+    W = x.shape[0]
+    fx = (wf(x).reshape(-1) ** 2).detach().contiguous()
+    acc = torch.zeros(W, dtype=torch.uint8, device="cuda")
+    _lib.check(L.qmcb_metropolis_step(
+        wf._handle.plan(), _lib.ptr(x), _lib.ptr(fx), W, None, _lib.ptr(tau) if tau is not None else None, None,
+        move_elec, 1, scale, 1e-16, seed, offset, _lib.ptr(acc), None, _lib.stream_ptr(x.device)),
+        "qmcb_metropolis_step")
+    torch.cuda.synchronize()
+    return x, acc.bool()
+
+
+@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_nojastrow", "h2_ground"])
+def test_specialised_kernels_match_generic(name, monkeypatch):
+    """The NVRTC structure-specialised kernels (spec_kernel.cuh) against the generic interpreter
+    kernels (fused_impl.cuh, QMCB_JIT=0) on the same walkers: psi, E_L, E_kin to rounding, identical
+    Philox proposals, identical accept decisions."""
+    g = C.load(name)
+    monkeypatch.setenv("QMCB_JIT", "0")
+    mol, wf0 = C.build_wf(g)
+    pos, _ = _thermalised(wf0, mol, 5003)          # ragged: not a multiple of the CTA size
+    assert wf0._handle.info(13) == 0
+    monkeypatch.setenv("QMCB_JIT", "2")              # 2: a missing / failing NVRTC is an error, not a fallback
+    mol, wf1 = C.build_wf(g)
+    assert wf1._handle.info(14) == 1 and wf1._handle.info(13) == 1
+    for f in ("__call__", "local_energy", "kinetic_energy"):
+        a, b = getattr(wf0, f)(pos), getattr(wf1, f)(pos)
+        # psi to rounding; energies can pass through zero for a walker, which inflates the
+        # element-wise relative error of both kernels alike
+        assert C.rel_err(b, a) < (1e-12 if f == "__call__" else RTOL), f
+    x0, a0 = _mh_philox(wf0, pos, None, 17, 3)
+    x1, a1 = _mh_philox(wf1, pos, None, 17, 3)
+    assert torch.equal(a0, a1) and torch.equal(x0, x1)
+    assert 0.2 < float(a1.float().mean()) < 0.95
+    for me in (-2, 1):                              # one random electron / electron 1 only
+        x0, a0 = _mh_philox(wf0, pos, None, 5, 8, move_elec=me)
+        x1, a1 = _mh_philox(wf1, pos, None, 5, 8, move_elec=me)
+        assert torch.equal(a0, a1) and torch.equal(x0, x1)
+        moved = ((x1 - pos).reshape(len(pos), -1, 3).abs().sum(-1) > 0).sum(-1)
+        assert int(moved.max()) <= 1
+
+
+def test_specialised_kernel_follows_parameter_updates():
+    """An optimiser step rewrites the parameter block of the specialised kernel (no recompilation):
+    results track the generic oracle after in-place parameter changes."""
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    _, P = C.oracle_params(g)
+    pos = _dev(g["pos"])
+    assert wf._handle.info(13) == 1
+    with torch.no_grad():
+        wf.mo.mo_modifier.mul_(1.0 + 0.03 * torch.rand_like(wf.mo.mo_modifier))
+        wf.ao.bas_exp.mul_(1.02)
+        wf.jastrow.jastrow_kernel.weight.fill_(0.6)
+    P.mo_modifier = wf.mo.mo_modifier.detach().cpu().clone()
+    P.bas_exp = wf.ao.bas_exp.detach().cpu().clone()
+    P.jastrow_weight = torch.tensor([0.6], dtype=torch.float64)
+    assert C.rel_err(wf(pos), orc.psi(P, pos.cpu())) < RTOL
+    assert C.rel_err(wf.local_energy(pos), orc.local_energy(P, pos.cpu())) < RTOL
+    assert wf._handle.info(13) == 1
+
+
+def test_philox_normal_draws_are_standard_symmetric_and_tiling_free():
+    """In-kernel proposal draws (philox.cuh: FP32 Box-Muller on the SFU, four normals per Philox
+    call): with tau = 0 every move is accepted, so (x' - x)/scale exposes the draws.  Moments of a
+    standard normal, exact sign symmetry of the pair construction, and element g of the ensemble
+    gets the same draw whatever slice of walkers is processed."""
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    pos, _ = _thermalised(wf, mol, 200_000, nstep=5)
+    tau = torch.zeros(len(pos), dtype=torch.float64, device="cuda")
+    x, acc = _mh_philox(wf, pos, tau, 123, 7, scale=0.25)
+    assert bool(acc.all())
+    z = ((x - pos) / 0.25).reshape(-1)
+    n = z.numel()
+    assert abs(float(z.mean())) < 5 / n ** 0.5
+    assert abs(float(z.var()) - 1.0) < 5 * (2.0 / n) ** 0.5
+    assert abs(float((z ** 3).mean())) < 5 * (15.0 / n) ** 0.5
+    assert abs(float((z ** 4).mean()) - 3.0) < 5 * (96.0 / n) ** 0.5
+    assert 4.0 < float(z.abs().max()) < 5.9
+    # every coordinate of every electron is drawn independently: lag-1 correlation ~ 0
+    assert abs(float((z[:-1] * z[1:]).mean())) < 5 / n ** 0.5
+    # a slice of the ensemble starting at a walker boundary that is not a multiple of 4 elements
+    part, _ = _mh_philox(wf, pos[:777], tau[:777], 123, 7, scale=0.25)
+    assert torch.equal(part, x[:777])
+    other, _ = _mh_philox(wf, pos, tau, 123, 8, scale=0.25)
+    assert not torch.equal(other, x)

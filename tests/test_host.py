@@ -138,6 +138,29 @@ def test_walker_initialisation_matches_reference_fixture():
     assert torch.equal(w.pos, torch.arange(30.0).reshape(5, 6)[-3:])
 
 
+def test_specialised_kernel_source_compiles_without_a_gpu():
+    """spec.cu generates the straight-line program of a small wave function and NVRTC compiles it for
+    sm_100a on a host-only plan (no driver needed); larger systems stay on the generic kernels."""
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    L = _lib.lib()
+
+    def status(key, configs):
+        wf = SlaterJastrow(fixture_molecule(key), configs=configs, cuda=False)
+        arrays = wf._handle._system()
+        p = ctypes.c_void_p()
+        _lib.check(L.qmcb_plan_create(ctypes.byref(arrays.struct), -1, ctypes.byref(p)), "qmcb_plan_create")
+        out = (L.qmcb_plan_info(p, 14), L.qmcb_plan_info(p, 13), L.qmcb_last_error().decode())
+        L.qmcb_plan_destroy(p)
+        return out
+    elig, on, why = status("h2o", "ground_state")
+    assert (elig, on) == (0, 0) and "not eligible" in why
+    elig, on, why = status("lih", "single_double(2,2)")
+    assert elig == 1
+    if not on and "libnvrtc not found" in why:
+        pytest.skip("NVRTC is not installed here")
+    assert on == 1, why
+
+
 def test_shard_walkers_partitions_everything():
     from qmctorch_b200.solver.distributed import shard_walkers
     for n, w in ((10, 3), (1000000, 8), (7, 8), (0, 2)):
