@@ -49,8 +49,10 @@ def algorithmic_flops(mol, wf, info):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the dominant
-# kernel (profiles/r1_fused_ncu_raw.csv), bytes per launch, keyed by (workload, walkers)
-NCU_TRAFFIC = {("lih", 1_000_000): 96.070912e6 + 5.570048e6}
+# kernel, bytes per launch, keyed by (kernel, workload, walkers): profiles/r1_spec_ncu_raw.csv
+# (structure-specialised kernel) and profiles/r1_fused_ncu_raw.csv (generic kernel)
+NCU_TRAFFIC = {("spec_eloc", "lih", 1_000_000): 96.041984e6 + 4.954368e6,
+               ("fused_kernel<MODE_ELOC>", "lih", 1_000_000): 96.070912e6 + 5.570048e6}
 
 
 class ClockSampler(threading.Thread):
@@ -211,11 +213,12 @@ def main():
 
     def step(i):
         x = ens[i % NBUF]
-        _lib.check(L.qmcb_local_energy(plan, _lib.ptr(x), W, _lib.ptr(eloc), None, None, sp), "local_energy")
-        _lib.check(L.qmcb_energy_stats(_lib.ptr(eloc), W, _lib.ptr(out4), _lib.ptr(ws), sp), "stats")
+        _lib.check(L.qmcb_local_energy_stats(plan, _lib.ptr(x), W, _lib.ptr(eloc), None, None, _lib.ptr(out4),
+                                             _lib.ptr(ws), sp), "local_energy_stats")
         if world > 1:
             dist.all_reduce(out4)
-    launches_per_step = 3
+    # one call = E_L kernel (+ fused per-CTA statistics when structure-specialised) + final reduction
+    launches_per_step = 2 if wf._handle.info(13) == 1 else 3
 
     def barrier():
         if world > 1:
@@ -237,9 +240,9 @@ def main():
         if world > 1 and len(pending) >= len(ring):
             pending.pop(0).wait()          # the buffer about to be reused must have been reduced
         kev[i][0].record(stream)
-        _lib.check(L.qmcb_local_energy(plan, _lib.ptr(x), W, _lib.ptr(eloc), None, None, sp), "local_energy")
+        _lib.check(L.qmcb_local_energy_stats(plan, _lib.ptr(x), W, _lib.ptr(eloc), None, None, _lib.ptr(o4),
+                                             _lib.ptr(ws), sp), "local_energy_stats")
         kev[i][1].record(stream)
-        _lib.check(L.qmcb_energy_stats(_lib.ptr(eloc), W, _lib.ptr(o4), _lib.ptr(ws), sp), "stats")
         if world > 1:
             pending.append(dist.all_reduce(o4, async_op=True))
     for h in pending:
@@ -249,6 +252,8 @@ def main():
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
+    # event pairs around each qmcb_local_energy_stats call: the E_L kernel (with its fused statistics
+    # stage) plus the ~2 us final reduction kernel behind it (1 % of the pair, see profiles/ launch list)
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -311,6 +316,8 @@ def main():
         return
     value = world * W * args.steps / (elapsed_ms * 1e-3)
     F = algorithmic_flops(mol, wf, info)
+    # the local-energy call runs the NVRTC structure-specialised kernel when the plan has one
+    kernel_name = "spec_eloc" if wf._handle.info(13) == 1 else "fused_kernel<MODE_ELOC>"
     achieved_tf = W * F / (kern_ms * 1e-3) / 1e12
     peaks = {}
     try:
@@ -329,10 +336,10 @@ def main():
                 "steps": nsteps_e2e, "api": "SlaterJastrow.local_energy(pinned host tensor) + qmcb_energy_stats"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "fp64", "kernel": "fused_kernel<MODE_ELOC>", "achieved": achieved_tf,
+        "roofline": {"bound": "fp64", "kernel": kernel_name, "achieved": achieved_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                      "peak_source": "own DFMA probe (qmcb_fp64_probe) on this GPU; MEASURED_PEAKS.json has no FP64 entry",
-                     "flops_per_eval": F, "kernel_ms": kern_ms, "traffic": NCU_TRAFFIC.get((args.workload, W)),
+                     "flops_per_eval": F, "kernel_ms": kern_ms, "traffic": NCU_TRAFFIC.get((kernel_name, args.workload, W)),
                      "hbm": {"achieved_gbs": W * bytes_per_eval / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "bytes_per_eval": bytes_per_eval,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

@@ -142,6 +142,14 @@ int qmcb_psi_backward(const qmcb_plan *plan, const double *pos, const double *we
 int64_t qmcb_stats_workspace_bytes(int64_t W);
 int qmcb_energy_stats(const double *eloc, int64_t W, double *out4, void *workspace, void *stream);
 
+/* qmcb_local_energy followed by qmcb_energy_stats in ONE call: eloc [W] (required), psi / ekin
+ * optional, out4 as qmcb_energy_stats.  One VMC energy step of Solver.single_point
+ * (solver/solver_base.py:355-371: local_energy per batch, then mean / var).  Structure-specialised
+ * kernels reduce their walkers inside the E_L kernel (no second pass over eloc).
+ * workspace: qmcb_stats_workspace_bytes(W). */
+int qmcb_local_energy_stats(const qmcb_plan *plan, const double *pos, int64_t W, double *eloc,
+                            double *psi, double *ekin, double *out4, void *workspace, void *stream);
+
 /* --- operator-level entry points (sub-module parity; HBM-bound by construction) ---- */
 
 /* AtomicOrbitals.forward(pos, derivative=[0,1,2]) (orbitals/atomic_orbitals.py:578-609):

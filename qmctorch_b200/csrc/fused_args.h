@@ -21,5 +21,7 @@ struct FusedArgs {
   uint64_t seed, offset;
   uint8_t *accept;
   unsigned long long *naccept;
+  // E_L: per-CTA partial statistics [gridDim.x][4] = sum, sum sq, n finite, n non-finite (or null)
+  double *stats_part;
 };
 

@@ -12,3 +12,28 @@ extern "C" int qmcb_local_energy(const qmcb_plan *p, const double *pos, int64_t 
   if (rc != QMCB_SPEC_SKIP) return rc;
   return launch<MODE_ELOC>(p, p->cfg_eloc, a, (cudaStream_t)stream);
 }
+
+// E_L and its statistics in one pass.  With a structure-specialised kernel the first statistics
+// stage is fused into the E_L kernel (per-CTA partials, fixed order); otherwise the generic E_L
+// kernel is followed by the two statistics kernels of qmcb_energy_stats.
+extern "C" int qmcb_local_energy_stats(const qmcb_plan *p, const double *pos, int64_t W, double *eloc,
+                                       double *psi, double *ekin, double *out4, void *workspace, void *stream) {
+  int rc = check(p, pos, W);
+  if (rc) return rc;
+  if (!eloc || !out4 || !workspace) { qmcb_set_error("qmcb_local_energy_stats: bad arguments"); return QMCB_EINVAL; }
+  if (W == 0) return qmcb_energy_stats(eloc, 0, out4, workspace, stream);
+  FusedArgs a{};
+  a.pos = pos; a.W = W; a.out0 = eloc; a.out1 = psi; a.out2 = ekin;
+  a.stats_part = (double *)workspace;
+  int grid = 0;
+  rc = qmcb_spec_launch(p, MODE_ELOC, a, stream, &grid);
+  if (rc == 0) {
+    if (grid > QMCB_STATS_MAX_PARTIALS) { qmcb_set_error("qmcb_local_energy_stats: grid exceeds the workspace"); return QMCB_EINVAL; }
+    return qmcb_stats_finish((const double *)workspace, grid, out4, stream);
+  }
+  if (rc != QMCB_SPEC_SKIP) return rc;
+  a.stats_part = nullptr;
+  rc = launch<MODE_ELOC>(p, p->cfg_eloc, a, (cudaStream_t)stream);
+  if (rc) return rc;
+  return qmcb_energy_stats(eloc, W, out4, workspace, stream);
+}

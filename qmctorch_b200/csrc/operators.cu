@@ -262,7 +262,15 @@ __global__ void stats_stage2(const double *part, int n, double *out4) {
   if (lane == 0) out4[q] = s;
 }
 
-extern "C" int64_t qmcb_stats_workspace_bytes(int64_t) { return (int64_t)STATS_CTAS * 4 * 8; }
+extern "C" int64_t qmcb_stats_workspace_bytes(int64_t) {
+  static_assert(STATS_CTAS <= QMCB_STATS_MAX_PARTIALS, "workspace");
+  return (int64_t)QMCB_STATS_MAX_PARTIALS * 4 * 8;
+}
+
+int qmcb_stats_finish(const double *part, int n, double *out4, void *stream) {
+  stats_stage2<<<1, 128, 0, (cudaStream_t)stream>>>(part, n, out4);
+  return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu stats_stage2");
+}
 
 extern "C" int qmcb_energy_stats(const double *eloc, int64_t W, double *out4, void *workspace, void *stream) {
   if (!eloc || !out4 || !workspace || W < 0) {

@@ -106,3 +106,6 @@ int qmcb_cuda_rc(int cuda_error, const char *where);
 int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p);   // host grouping -> hd/hi/sys
 int qmcb_choose_launch(qmcb_plan *p);
 int qmcb_choose_backward(qmcb_plan *p);
+// second stage of the energy statistics: n per-CTA partials [n][4] -> out4 (operators.cu)
+int qmcb_stats_finish(const double *part, int n, double *out4, void *stream);
+#define QMCB_STATS_MAX_PARTIALS 4096

@@ -39,6 +39,9 @@ int env_int(const char *name, int dflt) {
 }
 const int SPEC_THREADS = env_int("QMCB_SPEC_THREADS", 128);
 const int SPEC_MINB = env_int("QMCB_SPEC_MINB", 4);
+// defaults of the kernel's tuning switches (must match the #ifndef defaults in spec_kernel.cuh)
+constexpr int SPEC_DEFAULT_PREFETCH = 0;
+constexpr int SPEC_DEFAULT_MOW_SMEM = 0;
 constexpr int SPEC_MAX_VALUES = 448;   // doubles in the parameter block (keeps it under 4 KB)
 
 // ---------------------------------------------------------------------------------------
@@ -110,6 +113,24 @@ Dyn &dyn() {
   return d;
 }
 
+// QMCB_SPEC_DEFS="-DSPEC_PREFETCH=1 -DSPEC_EUNROLL=2": tuning switches of spec_kernel.cuh
+std::vector<std::string> extra_defs() {
+  std::vector<std::string> out;
+  const char *e = getenv("QMCB_SPEC_DEFS");
+  if (!e) return out;
+  std::istringstream is(e);
+  std::string tok;
+  while (is >> tok) out.push_back(tok);
+  return out;
+}
+int def_value(const char *name, int dflt) {
+  for (auto &d : extra_defs()) {
+    const std::string key = std::string("-D") + name + "=";
+    if (d.compare(0, key.size(), key) == 0) return atoi(d.c_str() + key.size());
+  }
+  return dflt;
+}
+
 int jit_level() {
   const char *e = getenv("QMCB_JIT");
   return e ? atoi(e) : 1;
@@ -152,7 +173,7 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     u.d = d; lo = u.i[0]; hi2 = u.i[1];
   };
   o << "template <int MODE, int NCH>\n__device__ __forceinline__ void spec_aos(const SpecParams &P, const double *et, "
-       "double ex, double ey, double ez, double (&acc)[NCH][SPEC_NMUP]) {\n";
+       "const double *mw, double ex, double ey, double ez, double (&acc)[NCH][SPEC_NMUP]) {\n";
   for (int A = 0; A < S.natom; ++A) {
     const int ns = hi[S.o_ash + A + 1] - hi[S.o_ash + A];
     if (ns == 0) continue;
@@ -179,7 +200,7 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
         if (kk == 0) o << "      spec_s<MODE, " << ao << ", " << is << ">";
         else if (kk == (1 << 24)) o << "      spec_p<MODE, " << ao << ", " << is << ">";
         else o << "      spec_g<MODE, " << ao << ", " << is << ", " << kk << ">";
-        o << "(x, y, z, S0, S1, S2, acc);\n";
+        o << "(mw, x, y, z, S0, S1, S2, acc);\n";
       }
       o << "    }\n";
     }
@@ -208,12 +229,13 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
       << "], tr[" << u << "]); }\n";
   }
   o << "}\n\n";
-  o << "template <int MODE>\n__device__ __forceinline__ void spec_ci(const double (&det)[" << nun
+  o << "template <int MODE>\n__device__ __forceinline__ void spec_ci(const double *mw, const double (&det)[" << nun
     << "], const double (&tr)[" << nun << "], double &sig, double &ksig) {\n  constexpr bool WB = MODE == MODE_ELOC;\n"
        "  sig = 0.0; ksig = 0.0;\n";
   for (int c = 0; c < S.nconf; ++c) {
     const int iu = hi[S.o_ciu + c], id = S.nuu + hi[S.o_cid + c];
-    o << "  { const double d = spec_pv<MODE, " << L.off_ci + c << ">() * det[" << iu << "] * det[" << id
+    o << "  { const double d = (SPEC_MOW_SMEM ? mw[" << L.off_ci - L.off_mow + c << "] : spec_pv<MODE, " << L.off_ci + c
+      << ">()) * det[" << iu << "] * det[" << id
       << "]; sig += d; if (WB) ksig += d * (tr[" << iu << "] + tr[" << id << "]); }\n";
   }
   o << "}\n";
@@ -267,8 +289,10 @@ int compile(const std::string &src, const std::string &arch, Module &m, std::str
   nvrtcProgram prog = nullptr;
   if (d.CreateProgram(&prog, src.c_str(), "qmcb_spec.cu", 0, nullptr, nullptr) != 0) { err = "nvrtcCreateProgram failed"; return -1; }
   const std::string a = "--gpu-architecture=" + arch;
-  const char *opts[] = {a.c_str(), "--std=c++17", "-lineinfo", "-DQMCB_SPEC"};
-  const int rc = d.CompileProgram(prog, 4, opts);
+  std::vector<std::string> extra = extra_defs();
+  std::vector<const char *> opts = {a.c_str(), "--std=c++17", "-lineinfo", "-DQMCB_SPEC"};
+  for (auto &e : extra) opts.push_back(e.c_str());
+  const int rc = d.CompileProgram(prog, (int)opts.size(), opts.data());
   size_t n = 0;
   d.GetProgramLogSize(prog, &n);
   if (n > 1) { m.log.resize(n); d.GetProgramLog(prog, &m.log[0]); }
@@ -301,9 +325,14 @@ std::string drv_err(int rc) {
   return s ? s : ("CUresult " + std::to_string(rc));
 }
 
-int slice_doubles(const DevSys &S, int mode) {
+// dynamic shared memory of one CTA (doubles): etab | optional MO weights + CI | per-thread slices
+size_t smem_doubles(const DevSys &S, int mode) {
   const bool el = mode == MODE_ELOC;
-  return (3 * S.nelec + (el ? 4 * S.nelec : 0) + (el ? 2 : 1) * S.nelec * S.nmup) | 1;
+  const int ne3 = 3 * S.nelec;
+  int slice = (ne3 + (el ? 4 * S.nelec : 0) + (el ? 2 : 1) * S.nelec * S.nmup) | 1;
+  if (def_value("SPEC_PREFETCH", SPEC_DEFAULT_PREFETCH)) slice += ne3 + (ne3 & 1);
+  const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmup + S.nconf + 1) & ~1) : 0;
+  return 64 + (size_t)nmw + (size_t)SPEC_THREADS * slice;
 }
 
 }  // namespace
@@ -348,7 +377,8 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
       if (pr.major >= 9) arch += "a";
     }
   }
-  const std::string key = std::to_string(p->device) + "|" + arch + "|" + prelude(p, L) + code;
+  std::string key = std::to_string(p->device) + "|" + arch + "|" + prelude(p, L) + code;
+  for (auto &e : extra_defs()) key += "|" + e;
   std::lock_guard<std::mutex> lk(cache_mu());
   Module &m = cache()[key];
   if (m.cubin.empty()) {
@@ -378,7 +408,7 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
     for (int i = 0; i < 3; ++i) {
       rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
       if (rc != 0) return fail(std::string("cuModuleGetFunction ") + names[i] + ": " + drv_err(rc));
-      m.smem[i] = (int)((64 + (size_t)SPEC_THREADS * slice_doubles(p->sys, modes[i])) * sizeof(double));
+      m.smem[i] = (int)(smem_doubles(p->sys, modes[i]) * sizeof(double));
       rc = d.FuncSetAttribute(m.fn[i], 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, m.smem[i]);
       if (rc != 0) return fail("cuFuncSetAttribute: " + drv_err(rc));
       int occ = 0;
@@ -409,7 +439,7 @@ static void refresh_params(const qmcb_plan *p, qmcb_spec_state &st) {
   st.params_version = p->version;
 }
 
-int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *stream) {
+int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *stream, int *grid_out) {
   const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : -1));
   if (slot < 0 || p->device < 0) return QMCB_SPEC_SKIP;
   if (spec_prepare(p, true) != 0) {
@@ -426,6 +456,7 @@ int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *str
   const int64_t need = (a.W + SPEC_THREADS - 1) / SPEC_THREADS;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
+  if (grid_out) *grid_out = (int)grid;
   FusedArgs args = a;
   void *kp[2] = {st.params.data(), &args};
   const int rc = dyn().LaunchKernel(m.fn[slot], (unsigned)grid, 1, 1, SPEC_THREADS, 1, 1, (unsigned)m.smem[slot],

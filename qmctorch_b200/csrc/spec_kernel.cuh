@@ -95,15 +95,32 @@ __device__ __forceinline__ void spec_shell_end(double r2, double &S2, double T2)
   if (spec_nch<MODE>() > 1) S2 = fma(T2, r2, S2);
 }
 
+#ifndef SPEC_MOW_SMEM
+#define SPEC_MOW_SMEM 0     // 1: MO weights staged in shared memory (LDS) instead of the parameter block
+#endif
+#ifndef SPEC_EUNROLL
+#define SPEC_EUNROLL 1      // electrons per trip of the electron loop
+#endif
+#ifndef SPEC_PREFETCH
+#define SPEC_PREFETCH 0     // 1: cp.async the next walker's coordinates while this one is computed
+#endif
+#ifndef SPEC_MINB_ELOC
+#define SPEC_MINB_ELOC 3     // E_L: 168 registers keep the electron loop free of spills (measured 0.199 -> 0.194 ms)
+#endif
 template <int MODE, int AO, int NCH>
-__device__ __forceinline__ void spec_emit(const double (&v)[NCH], double (&acc)[NCH][SPEC_NMUP]) {
+__device__ __forceinline__ void spec_emit(const double *mw, const double (&v)[NCH], double (&acc)[NCH][SPEC_NMUP]) {
   static_assert(NCH == spec_nch<MODE>(), "channel count");
   // (the MO weights of one AO are read once per column: SPEC_NMUP <= 4)
   double w[SPEC_NMUP];
-  w[0] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP>();
-  if (SPEC_NMUP > 1) w[1 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 1 % SPEC_NMUP>();
-  if (SPEC_NMUP > 2) w[2 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 2 % SPEC_NMUP>();
-  if (SPEC_NMUP > 3) w[3 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 3 % SPEC_NMUP>();
+  if (SPEC_MOW_SMEM) {
+#pragma unroll
+    for (int j = 0; j < SPEC_NMUP; ++j) w[j] = mw[AO * SPEC_NMUP + j];
+  } else {
+    w[0] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP>();
+    if (SPEC_NMUP > 1) w[1 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 1 % SPEC_NMUP>();
+    if (SPEC_NMUP > 2) w[2 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 2 % SPEC_NMUP>();
+    if (SPEC_NMUP > 3) w[3 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 3 % SPEC_NMUP>();
+  }
 #pragma unroll
   for (int j = 0; j < SPEC_NMUP; ++j)
 #pragma unroll
@@ -111,7 +128,7 @@ __device__ __forceinline__ void spec_emit(const double (&v)[NCH], double (&acc)[
 }
 
 template <int MODE, int AO, int ISC, int NCH>
-__device__ __forceinline__ void spec_s(double x, double y, double z, double S0, double S1, double S2,
+__device__ __forceinline__ void spec_s(const double *mw, double x, double y, double z, double S0, double S1, double S2,
                                        double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
   v[0] = S0 * spec_pv<MODE, ISC>();
@@ -120,11 +137,11 @@ __device__ __forceinline__ void spec_s(double x, double y, double z, double S0, 
     v[1] = t * x; v[2] = t * y; v[3] = t * z;
     v[4] = S2 * spec_pv<MODE, ISC>();
   }
-  spec_emit<MODE, AO>(v, acc);
+  spec_emit<MODE, AO>(mw, v, acc);
 }
 
 template <int MODE, int AO, int ISC, int NCH>
-__device__ __forceinline__ void spec_p(double x, double y, double z, double S0, double S1, double S2,
+__device__ __forceinline__ void spec_p(const double *mw, double x, double y, double z, double S0, double S1, double S2,
                                        double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
   const double R = S0 * spec_pv<MODE, ISC>();
@@ -132,24 +149,24 @@ __device__ __forceinline__ void spec_p(double x, double y, double z, double S0, 
     const double t = S1 * spec_pv<MODE, ISC>(), lf = fma(2.0, S1, S2) * spec_pv<MODE, ISC>();
     const double tx = t * x, ty = t * y, tz = t * z;
     v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z; v[4] = lf * x;
-    spec_emit<MODE, AO>(v, acc);
+    spec_emit<MODE, AO>(mw, v, acc);
     v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z; v[4] = lf * y;
-    spec_emit<MODE, AO + 1>(v, acc);
+    spec_emit<MODE, AO + 1>(mw, v, acc);
     v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R); v[4] = lf * z;
-    spec_emit<MODE, AO + 2>(v, acc);
+    spec_emit<MODE, AO + 2>(mw, v, acc);
   } else {
-    v[0] = R * x; spec_emit<MODE, AO>(v, acc);
-    v[0] = R * y; spec_emit<MODE, AO + 1>(v, acc);
-    v[0] = R * z; spec_emit<MODE, AO + 2>(v, acc);
+    v[0] = R * x; spec_emit<MODE, AO>(mw, v, acc);
+    v[0] = R * y; spec_emit<MODE, AO + 1>(mw, v, acc);
+    v[0] = R * z; spec_emit<MODE, AO + 2>(mw, v, acc);
   }
 }
 
 template <int MODE, int AO, int ISC, int KK, int NCH>
-__device__ __forceinline__ void spec_g(double x, double y, double z, double S0, double S1, double S2,
+__device__ __forceinline__ void spec_g(const double *mw, double x, double y, double z, double S0, double S1, double S2,
                                        double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
   generic_component<NCH>(KK, spec_pv<MODE, ISC>(), x, y, z, S0, S1, S2, v);   // literal powers: a few products
-  spec_emit<MODE, AO>(v, acc);
+  spec_emit<MODE, AO>(mw, v, acc);
 }
 
 // ---- generated: spec_aos<MODE>, spec_dets<WB>, spec_ci<MODE>
@@ -163,14 +180,34 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   extern __shared__ __align__(16) double smem[];
   double *et = smem;
   for (int i = threadIdx.x; i < 64; i += blockDim.x) et[i] = P.etab_g[i];
-  double *spos = smem + 64 + (size_t)threadIdx.x * SLICE;
+  constexpr int NMW = SPEC_MOW_SMEM ? ((SPEC_NV - SPEC_OFF_MOW + 1) & ~1) : 0;   // MO weights + CI, even
+  double *mw = smem + 64;
+  for (int i = threadIdx.x; i < NMW; i += blockDim.x) mw[i] = i < SPEC_NV - SPEC_OFF_MOW ? P.v[SPEC_OFF_MOW + i] : 0.0;
+  constexpr int SL = SLICE + (SPEC_PREFETCH ? ne3 + (ne3 & 1) : 0);               // stays odd
+  double *spos = smem + 64 + NMW + (size_t)threadIdx.x * SL;
   double *jv = spos + ne3;
   double *smo = jv + (NCH > 1 ? 4 * Ne : 0);
   double *sB = smo + Ne * NM;
+  double *snext = spos + SLICE;     // SPEC_PREFETCH: landing zone of the next walker's coordinates
   const SpecTab T{P};
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.W; w += stride) {
+  const int64_t wfirst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // cp.async (LDGSTS) copies one walker row global -> this thread's slice without registers
+  auto prefetch = [&](int64_t wn) {
+    if (SPEC_PREFETCH && wn < a.W) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(snext);
+      const double *src = a.pos + wn * ne3;
+#pragma unroll
+      for (int i = 0; i < ne3; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * i), "l"(src + i) : "memory");
+    }
+  };
+  prefetch(wfirst);
+  double st_s = 0.0, st_s2 = 0.0;     // fused energy statistics of this thread's walkers (E_L only)
+  int st_nf = 0, st_nb = 0;
+  for (int64_t w = wfirst; w < a.W; w += stride) {
+    if (SPEC_PREFETCH) asm volatile("cp.async.wait_all;" ::: "memory");
     // ---- coordinates (+ proposal)
     if (MODE == MODE_MH && !a.disp && a.proba_normal) {
       // one Philox call yields the four normals of a GLOBAL element quad (4q .. 4q+3): the draw of
@@ -189,7 +226,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
           const int64_t g = 4 * q + h;
           if (g < g0 || g >= g1) continue;
           const int i = (int)(g - g0), e = i / 3;
-          double v = a.pos[g];
+          double v = SPEC_PREFETCH ? snext[i] : a.pos[g];
           if (me < 0 || me == e) v += a.scale * z[h];
           spos[i] = v;
         }
@@ -202,7 +239,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
       }
 #pragma unroll
       for (int i = 0; i < ne3; ++i) {
-        double v = a.pos[w * ne3 + i];
+        double v = SPEC_PREFETCH ? snext[i] : a.pos[w * ne3 + i];
         if (MODE == MODE_MH && (me < 0 || me == i / 3)) {
           double d;
           if (a.disp) d = a.disp[w * ne3 + i];
@@ -212,18 +249,19 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
         spos[i] = v;
       }
     }
+    prefetch(w + stride);
     // ---- Jastrow gradient / Laplacian terms and potentials, every pair once
     double tks, tven, tvee;
     walker_terms<(NCH > 1), (MODE == MODE_ELOC)>(P, T, spos, jv, Ne, tks, tven, tvee);
     // ---- AO -> MO rows, one electron at a time (rolled: instruction-cache footprint)
-#pragma unroll 1
+#pragma unroll SPEC_EUNROLL
     for (int e = 0; e < Ne; ++e) {
       double acc[NCH][NM];
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int j = 0; j < NM; ++j) acc[c][j] = 0.0;
-      spec_aos<MODE>(P, et, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], acc);
+      spec_aos<MODE>(P, et, mw, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], acc);
       if (MODE == MODE_ELOC) {
         const double gx = jv[e], gy = jv[Ne + e], gz = jv[2 * Ne + e], lp = jv[3 * Ne + e];
 #pragma unroll
@@ -243,14 +281,16 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
     double det[NUN], tr[NUN];
     spec_dets<(MODE == MODE_ELOC)>(smo, sB, det, tr);
     double sig, ksig;
-    spec_ci<MODE>(det, tr, sig, ksig);
+    spec_ci<MODE>(mw, det, tr, sig, ksig);
     const double J = (SPEC_USE_JEE || SPEC_USE_JEN) ? exp_clamped(P, et, tks) : 1.0;
     const double psi = J * sig;
     if (MODE == MODE_PSI) {
       a.out0[w] = psi;
     } else if (MODE == MODE_ELOC) {
       const double ekin = ksig / sig;
-      a.out0[w] = ekin + tven + tvee + P.vnn;
+      const double el = ekin + tven + tvee + P.vnn;
+      a.out0[w] = el;
+      if (isfinite(el)) { st_s += el; st_s2 = fma(el, el, st_s2); ++st_nf; } else ++st_nb;
       if (a.out1) a.out1[w] = psi;
       if (a.out2) a.out2[w] = ekin;
     } else {
@@ -275,11 +315,31 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
       }
     }
   }
+  // ---- fused statistics: fixed-order reduction of the CTA's walkers (warp butterflies, then the
+  // warps in order) -> one partial per CTA; qmcb_local_energy_stats finishes with stats_stage2
+  if (MODE == MODE_ELOC && a.stats_part) {
+    double q[4] = {st_s, st_s2, (double)st_nf, (double)st_nb};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    __syncthreads();                     // every thread is done with its slice: reuse it
+    double *red = smem + 64;
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[(threadIdx.x >> 5) * 4 + k] = q[k];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) t += red[wq * 4 + threadIdx.x];
+      a.stats_part[blockIdx.x * 4 + threadIdx.x] = t;
+    }
+  }
 }
 
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
     spec_psi(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_PSI>(P, a); }
-extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
+extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB_ELOC)
     spec_eloc(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_ELOC>(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
     spec_mh(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_MH>(P, a); }

@@ -243,13 +243,16 @@ class Solver:
             pos = self.sampler(self.wf.pdf, with_tqdm=with_tqdm)
             if pos.device != self.device:
                 pos = pos.to(self.device)
-            if batchsize is None:
+            out4 = None
+            if batchsize is None and D.is_distributed():
+                eloc, out4 = self.wf.local_energy_stats(pos)     # E_L and its sums in one pass
+            elif batchsize is None:
                 eloc = self.wf.local_energy(pos)
             else:
                 eloc = torch.cat([self.wf.local_energy(pos[i: i + batchsize])
                                   for i in range(0, len(pos), batchsize)])
             if D.is_distributed():
-                mean, var, err, n, nbad = self._stats(eloc)
+                mean, var, err, n, nbad = D.global_stats(out4, None, None) if out4 is not None else self._stats(eloc)
                 dt = dict(dtype=torch.float64, device=eloc.device)
                 e, s, er = torch.tensor(mean, **dt), torch.tensor(var, **dt), torch.tensor(err, **dt)
             else:

@@ -243,6 +243,24 @@ class SlaterJastrow(WaveFunction):
             return self._eloc_from_host(pos)
         return self._eloc(self._x(pos))[0]
 
+    def local_energy_stats(self, pos):
+        """(E_L [W,1], device tensor [sum E_L, sum E_L^2, n finite, n non-finite]) from ONE call of
+        qmcb_local_energy_stats: the energy step of Solver.single_point (solver_base.py:355-371)
+        without a second pass over E_L.  The four sums are what ranks all-reduce."""
+        x = self._x(pos)
+        W = x.shape[0]
+        L = _lib.lib()
+        ws = self._ws.get("stats")
+        if ws is None or ws.device != x.device:
+            ws = self._ws["stats"] = torch.empty(int(L.qmcb_stats_workspace_bytes(W)), dtype=torch.uint8,
+                                                 device=x.device)
+        e = torch.empty(W, 1, dtype=torch.float64, device=x.device)
+        out4 = torch.empty(4, dtype=torch.float64, device=x.device)
+        _lib.check(L.qmcb_local_energy_stats(self._handle.plan(), _lib.ptr(x), W, _lib.ptr(e), None, None,
+                                             _lib.ptr(out4), _lib.ptr(ws), _lib.stream_ptr(x.device)),
+                   "qmcb_local_energy_stats")
+        return e, out4
+
     host_chunk_min = 65536      # walkers; below this one copy + one launch is cheaper
     host_chunks = 8
 

@@ -563,3 +563,25 @@ def test_philox_normal_draws_are_standard_symmetric_and_tiling_free():
     assert torch.equal(part, x[:777])
     other, _ = _mh_philox(wf, pos, tau, 123, 8, scale=0.25)
     assert not torch.equal(other, x)
+
+
+@pytest.mark.parametrize("name,jit", [("lih_ground", "2"), ("lih_ground", "0"), ("h2o_ground", "1")])
+def test_local_energy_stats_one_call(name, jit, monkeypatch):
+    """qmcb_local_energy_stats (E_L + [sum, sum sq, n finite, n non-finite] in one call, fused into the
+    specialised kernel / two extra kernels behind the generic one) against qmcb_local_energy +
+    torch sums; deterministic; non-finite walkers are counted, not summed."""
+    monkeypatch.setenv("QMCB_JIT", jit)
+    g = C.load(name)
+    mol, wf = C.build_wf(g)
+    pos, _ = _thermalised(wf, mol, 30011, step=g["step"])
+    pos[17, 0] = float("nan")
+    e_ref = wf.local_energy(pos)
+    e, out4 = wf.local_energy_stats(pos)
+    e2, out4b = wf.local_energy_stats(pos)
+    assert torch.equal(out4, out4b) and torch.equal(torch.nan_to_num(e, nan=7.0), torch.nan_to_num(e2, nan=7.0))
+    ok = torch.isfinite(e_ref.reshape(-1))
+    assert torch.equal(e[ok.reshape(-1, 1)], e_ref[ok.reshape(-1, 1)])
+    assert int(out4[2]) == int(ok.sum()) and int(out4[3]) == 1
+    good = e_ref.reshape(-1)[ok]
+    assert abs(float(out4[0]) - float(good.sum())) < 1e-9 * float(good.abs().sum())
+    assert abs(float(out4[1]) - float((good * good).sum())) < 1e-9 * float((good * good).sum())
