@@ -259,8 +259,53 @@ def walker_init_fixture():
     print("walkers_init  %d ensembles" % len(out))
 
 
+def gradient_sampler_fixture():
+    """Chains of the reference's GeneralizedMetropolis and Hamiltonian samplers (autograd drift,
+    sampler/generalized_metropolis.py, sampler/hamiltonian.py) on LiH 6-31G, and the check that the
+    oracle restatements with the ANALYTIC density gradient reproduce them under the same seed
+    -> tests/golden/gradient_samplers.npz."""
+    from qmctorch.sampler import GeneralizedMetropolis, Hamiltonian
+    case = [c for c in CASES if c[0] == "lih_ground"][0]
+    torch.manual_seed(1234)
+    mol, wf = build(case)
+    with torch.no_grad():
+        wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+    P = orc.make_params(mol, (wf.configs[0], wf.configs[1]), jastrow_weight=0.8)
+    torch.manual_seed(77)
+    start = Metropolis(nwalkers=48, nstep=60, step_size=0.3, nelec=wf.nelec, ndim=3, init=mol.domain("normal"),
+                       move={"type": "all-elec", "proba": "normal"})(wf.pdf, with_tqdm=False).detach().clone()
+    out = dict(start=start.numpy(), jw=np.array([0.8]))
+    # generalized Metropolis: 12 steps, keep the last 4
+    gm = GeneralizedMetropolis(nwalkers=48, nstep=12, step_size=0.2, ntherm=8, ndecor=1, nelec=wf.nelec, ndim=3,
+                               init=mol.domain("normal"))
+    torch.manual_seed(5)
+    ref = gm(wf.pdf, pos=start.clone(), with_tqdm=False).detach()
+    torch.manual_seed(5)
+    mine = orc.generalized_metropolis(P, start.clone(), 12, 0.2, ntherm=8)
+    err = relmax(mine, ref)
+    print("generalized_metropolis  chain err %.1e  moved %.2f" % (err, float((ref[-48:] != start).any(1).float().mean())))
+    assert err < 1e-9
+    out.update(gm_pos=ref.numpy(), gm_seed=np.array([5]), gm_cfg=np.array([12, 8, 1]), gm_step=np.array([0.2]))
+    # Hamiltonian: 4 trajectories of 6 leapfrog steps, keep the last 2
+    hm = Hamiltonian(nwalkers=48, nstep=4, step_size=0.05, L=6, ntherm=2, ndecor=1, nelec=wf.nelec, ndim=3,
+                     init=mol.domain("normal"))
+    torch.manual_seed(6)
+    ref = hm(wf.pdf, pos=start.clone(), with_tqdm=False).detach()
+    torch.manual_seed(6)
+    mine = orc.hamiltonian(P, start.clone(), 4, 0.05, 6, ntherm=2)
+    err = relmax(mine, ref)
+    print("hamiltonian             chain err %.1e  moved %.2f" % (err, float((ref[-48:] != start).any(1).float().mean())))
+    assert err < 1e-9
+    out.update(hm_pos=ref.numpy(), hm_seed=np.array([6]), hm_cfg=np.array([4, 2, 1, 6]), hm_step=np.array([0.05]))
+    np.savez_compressed(os.path.join(OUT, "gradient_samplers.npz"), **out)
+
+
 if __name__ == "__main__":
-    if not sys.argv[1:] or "walkers_init" in sys.argv[1:]:
-        walker_init_fixture()
-    if sys.argv[1:] != ["walkers_init"]:
-        main([a for a in sys.argv[1:] if a != "walkers_init"])
+    special = {"walkers_init": walker_init_fixture, "gradient_samplers": gradient_sampler_fixture}
+    args = sys.argv[1:]
+    for name, fn in special.items():
+        if not args or name in args:
+            fn()
+    rest = [a for a in args if a not in special]
+    if not args or rest:
+        main(rest)

@@ -560,6 +560,94 @@ def proposal_sigma(step_size):
 
 
 # --------------------------------------------------------------------------------------
+# f2: gradient-driven samplers, restated with the analytic density gradient of a16
+# --------------------------------------------------------------------------------------
+
+def _rho_and_grad(p, x):
+    return (psi(p, x) ** 2).reshape(-1), grad_psi(p, x, pdf=True)
+
+
+def generalized_metropolis(p, pos0, nstep, step_size, ntherm=-1, ndecor=1):
+    """sampler/generalized_metropolis.py:47-219 with the torch CPU generator called in the same
+    order (LongTensor.random_, MultivariateNormal.sample, torch.rand per step).  As coded there:
+    proposals start from the INITIAL positions (:127-140), the transition uses the plain norm
+    (:185-186), the proposal covariance is sqrt(step_size) I (:165-167)."""
+    from torch.distributions import MultivariateNormal
+    W, Ne = pos0.shape[0], p.nelec
+    if ntherm < 0:
+        ntherm = nstep + ntherm
+    start = pos0.clone()
+    xi = pos0.clone()
+    rhoi, g = _rho_and_grad(p, xi)
+    drifti = 0.5 * g / rhoi.view(-1, 1)
+    rhoi[rhoi == 0] = 1e-16
+    kept, idecor = [], 0
+
+    def trans(xf, x0, drift):
+        return torch.exp(-0.5 * (xf - x0 - drift * step_size).norm(dim=1) / step_size)
+    for istep in range(nstep):
+        xf = start.clone().view(W, Ne, 3)
+        index = torch.LongTensor(W).random_(0, Ne)
+        mv = MultivariateNormal(torch.zeros(3), math.sqrt(step_size) * torch.eye(3))
+        d = drifti.view(W, Ne, 3)
+        xf[range(W), index, :] += step_size * d[range(W), index, :] + mv.sample((W, 1)).squeeze()
+        xf = xf.view(W, 3 * Ne)
+        rhof, g = _rho_and_grad(p, xf)
+        driftf = 0.5 * g / rhof.view(-1, 1)
+        rhof[rhof == 0.0] = 1e-16
+        P = (trans(xi, xf, driftf) * rhof) / (trans(xf, xi, drifti) * rhoi).double()
+        P[P > 1] = 1.0
+        tau = torch.rand(W, dtype=F64)
+        acc = (P - tau >= 0).reshape(-1)
+        xi[acc, :] = xf[acc, :]
+        rhoi[acc] = rhof[acc]
+        rhoi[rhoi == 0] = 1e-16
+        drifti[acc, :] = driftf[acc, :]
+        if istep >= ntherm:
+            if idecor % ndecor == 0:
+                kept.append(xi.clone())
+            idecor += 1
+    return torch.cat(kept)
+
+
+def hamiltonian(p, pos0, nstep, step_size, L, ntherm=-1, ndecor=1):
+    """sampler/hamiltonian.py:80-201: leapfrog on U = -log psi^2 with grad U = -grad rho / rho,
+    torch.randn momenta and torch.rand accept draws in the reference's order."""
+    if ntherm < 0:
+        ntherm = nstep + ntherm
+
+    def U(x):
+        return -torch.log((psi(p, x) ** 2).reshape(-1))
+
+    def dU(x):
+        rho, g = _rho_and_grad(p, x)
+        return -g / rho.view(-1, 1)
+    q_cur = pos0.clone()
+    kept, idecor = [], 0
+    for istep in range(nstep):
+        q = q_cur.clone()
+        mom = torch.randn(q.shape)
+        e_init = U(q) + 0.5 * (mom * mom).sum(1)
+        mom -= 0.5 * step_size * dU(q)
+        for _ in range(L - 1):
+            q += step_size * mom
+            mom -= step_size * dU(q)
+        q += step_size * mom
+        mom -= 0.5 * step_size * dU(q)
+        mom = -mom
+        e_new = U(q) + 0.5 * (mom * mom).sum(1)
+        eps = torch.rand(e_new.shape)
+        rejected = torch.exp(e_init - e_new) < eps
+        q[rejected] = q_cur[rejected]
+        q_cur = q
+        if istep >= ntherm:
+            if idecor % ndecor == 0:
+                kept.append(q_cur)
+            idecor += 1
+    return torch.cat(kept)
+
+
+# --------------------------------------------------------------------------------------
 # a18-a19: psi-weighted parameter gradients, statistics
 # --------------------------------------------------------------------------------------
 

@@ -30,3 +30,14 @@ def _built_library():
     if not os.path.isfile(b.LIB):
         b.build()
     yield
+
+
+@pytest.fixture
+def double_default():
+    """torch default dtype float64 for the duration of a test (the reference runs under
+    set_torch_double_precision(); CPU-generator draws depend on the default dtype)."""
+    import torch
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)

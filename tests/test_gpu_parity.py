@@ -585,3 +585,35 @@ def test_local_energy_stats_one_call(name, jit, monkeypatch):
     good = e_ref.reshape(-1)[ok]
     assert abs(float(out4[0]) - float(good.sum())) < 1e-9 * float(good.abs().sum())
     assert abs(float(out4[1]) - float((good * good).sum())) < 1e-9 * float((good * good).sum())
+
+
+def test_gradient_samplers_replay_reference_chains(double_default):
+    """GeneralizedMetropolis and Hamiltonian on the analytic grad psi^2 of qmcb_grad_psi
+    (instead of autograd) reproduce the reference's chains from the same torch seed: the committed
+    fixture holds the positions the unmodified reference samplers returned."""
+    import os
+    from qmctorch_b200.sampler import GeneralizedMetropolis, Hamiltonian
+    f = dict(np.load(os.path.join(C.GOLDEN, "gradient_samplers.npz")))
+    g = C.load("lih_ground")
+    g = dict(g, mo_modifier=np.ones_like(g["mo_modifier"]), jw=f["jw"])
+    mol, wf = C.build_wf(g)
+    start = _dev(f["start"])
+    nstep, ntherm, ndecor = (int(v) for v in f["gm_cfg"])
+    s = GeneralizedMetropolis(nwalkers=len(start), nstep=nstep, step_size=float(f["gm_step"][0]), ntherm=ntherm,
+                              ndecor=ndecor, nelec=wf.nelec, ndim=3, init=mol.domain("normal"), cuda=True)
+    torch.manual_seed(int(f["gm_seed"][0]))
+    out = s(wf.pdf, pos=start.clone(), with_tqdm=False)
+    assert out.requires_grad and out.shape == f["gm_pos"].shape
+    assert C.scaled_err(out.detach(), f["gm_pos"]) < 1e-9
+    assert 0.0 < s.acceptance_rate <= 1.0
+    nstep, ntherm, ndecor, L = (int(v) for v in f["hm_cfg"])
+    s = Hamiltonian(nwalkers=len(start), nstep=nstep, step_size=float(f["hm_step"][0]), L=L, ntherm=ntherm,
+                    ndecor=ndecor, nelec=wf.nelec, ndim=3, init=mol.domain("normal"), cuda=True)
+    torch.manual_seed(int(f["hm_seed"][0]))
+    out = s(wf.pdf, pos=start.clone(), with_tqdm=False)
+    assert out.shape == f["hm_pos"].shape and C.scaled_err(out.detach(), f["hm_pos"]) < 1e-9
+    # a plain callable is differentiated with autograd, like the reference does
+    s = Hamiltonian(nwalkers=64, nstep=3, step_size=0.1, L=3, nelec=1, ndim=3, init={"min": -1, "max": 1}, cuda=True)
+    torch.manual_seed(0)
+    out = s(lambda x: torch.exp(-(x * x).sum(1)), with_tqdm=False)
+    assert out.shape == (64, 3) and bool(torch.isfinite(out).all())

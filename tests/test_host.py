@@ -86,11 +86,10 @@ def test_state_dict_names_match_reference():
     assert wf.get_number_parameters() > 0
 
 
-def test_generic_sampler_reproduces_reference_algorithm():
+def test_generic_sampler_reproduces_reference_algorithm(double_default):
     """Arbitrary pdf callable -> the reference's torch loop; same generator calls, so the
     same seed gives the same trajectory as a direct restatement."""
     from qmctorch_b200.sampler import Metropolis
-    torch.set_default_dtype(torch.float64)
     mol = fixture_molecule("h2")
     pdf = lambda x: torch.exp(-(x ** 2).sum(1))   # noqa: E731
     torch.manual_seed(3)
@@ -117,7 +116,7 @@ def test_generic_sampler_reproduces_reference_algorithm():
     assert out.requires_grad and s.get_sampling_size() == 50
 
 
-def test_walker_initialisation_matches_reference_fixture():
+def test_walker_initialisation_matches_reference_fixture(double_default):
     """Walkers.initialize (sampler/walkers.py:41-150): same generator calls in the same order as the
     reference for every Molecule.domain method -> bit-identical start ensembles."""
     from qmctorch_b200.sampler.ensemble import Walkers

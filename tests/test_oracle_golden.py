@@ -88,3 +88,29 @@ def test_oracle_antisymmetry():
     swapped = pos.clone()
     swapped[:, 0:3], swapped[:, 3:6] = pos[:, 3:6], pos[:, 0:3]     # two spin-up electrons
     assert torch.allclose(orc.psi(P, pos), -orc.psi(P, swapped), rtol=1e-11, atol=0)
+
+
+def _gradient_sampler_case():
+    import os
+    from qmctorch_b200.molecules import fixture_molecule
+    f = dict(np.load(os.path.join(C.GOLDEN, "gradient_samplers.npz")))
+    g = C.load("lih_ground")
+    mol = fixture_molecule("lih")
+    P = orc.make_params(mol, (g["cfg_up"], g["cfg_down"]), jastrow_weight=float(f["jw"][0]))
+    return f, mol, P
+
+
+def test_oracle_gradient_samplers_reproduce_reference_chains(double_default):
+    """the reference's GeneralizedMetropolis / Hamiltonian chains (autograd drift,
+    fixtures from oracle/make_golden.py) are reproduced by the restatements that use the analytic
+    density gradient, from the same seed."""
+    f, mol, P = _gradient_sampler_case()
+    start = torch.tensor(f["start"])
+    nstep, ntherm, ndecor = (int(v) for v in f["gm_cfg"])
+    torch.manual_seed(int(f["gm_seed"][0]))
+    out = orc.generalized_metropolis(P, start.clone(), nstep, float(f["gm_step"][0]), ntherm=ntherm, ndecor=ndecor)
+    assert out.shape == f["gm_pos"].shape and C.scaled_err(out, f["gm_pos"]) < 1e-10
+    nstep, ntherm, ndecor, L = (int(v) for v in f["hm_cfg"])
+    torch.manual_seed(int(f["hm_seed"][0]))
+    out = orc.hamiltonian(P, start.clone(), nstep, float(f["hm_step"][0]), L, ntherm=ntherm, ndecor=ndecor)
+    assert out.shape == f["hm_pos"].shape and C.scaled_err(out, f["hm_pos"]) < 1e-10
