@@ -147,11 +147,11 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   const char *w = nullptr;
   if (S.radial_type != QMCB_GTO_PURE) w = "radial type is not gto_pure";
   else if (S.een_nterm > 0) w = "three-body Jastrow";
-  else if (S.nmup > 4) w = "more than 4 occupied MO columns";
+  else if (S.nmu > 8) w = "more than 8 occupied MO columns";
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
-  else if (S.nuu + S.nud > 8 || S.nconf > 64) w = "too many determinants";
-  else if ((64 + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmup) | 1)) * sizeof(double) > 100 * 1024)
+  else if (S.nuu + S.nud > 16 || S.nconf > 64) w = "too many determinants";
+  else if ((64 + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > 100 * 1024)
     w = "per-thread slices exceed the shared-memory budget";
   if (w) { if (why) *why = w; return false; }
   return true;
@@ -208,8 +208,11 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
   }
   o << "}\n\n";
   if ((int)(rec - (hd.data() + S.o_stream)) != 2 * S.nrec) return false;   // walked exactly the program
+  // MO weights of the occupied columns only (the generic kernels pad the column count to a power of
+  // two; a specialised kernel is compiled for the exact count)
   L.off_mow = nv;
-  for (int i = 0; i < S.nao * S.nmup; ++i) push(hd[S.o_mow + i]);
+  for (int a = 0; a < S.nao; ++a)
+    for (int j = 0; j < S.nmu; ++j) push(hd[S.o_mow + a * S.nmup + j]);
   L.off_ci = nv;
   for (int c = 0; c < S.nconf; ++c) push(hd[S.o_ci + c]);
   L.nv = nv;
@@ -222,7 +225,7 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     const int n = up ? S.nup : S.ndown;
     if (n == 0) { o << "  det[" << u << "] = 1.0; tr[" << u << "] = 0.0;\n"; continue; }
     const int *cols = hi.data() + (up ? S.o_ucu + u * S.nup : S.o_ucd + (u - S.nuu) * S.ndown);
-    const int row0 = (up ? 0 : S.nup) * S.nmup;
+    const int row0 = (up ? 0 : S.nup) * S.nmu;
     o << "  { const int cols[" << n << "] = {";
     for (int j = 0; j < n; ++j) o << (j ? ", " : "") << cols[j];
     o << "}; det_trace_small(" << n << ", A + " << row0 << ", B + " << row0 << ", SPEC_NMUP, cols, WB, det[" << u
@@ -251,7 +254,7 @@ std::string prelude(const qmcb_plan *p, const Layout &L) {
        "typedef unsigned long size_t;\n"
     << "#define QMCB_GTO_PURE 0\n#define QMCB_GTO 1\n#define QMCB_STO_PURE 2\n#define QMCB_STO 3\n"
     << "#define SPEC_NE " << S.nelec << "\n#define SPEC_NUP " << S.nup << "\n#define SPEC_NDOWN " << S.ndown
-    << "\n#define SPEC_NATOM " << S.natom << "\n#define SPEC_NMUP " << S.nmup << "\n#define SPEC_NUU " << S.nuu
+    << "\n#define SPEC_NATOM " << S.natom << "\n#define SPEC_NMUP " << S.nmu << "\n#define SPEC_NUU " << S.nuu
     << "\n#define SPEC_NUD " << S.nud << "\n#define SPEC_USE_JEE " << (S.use_jee ? 1 : 0) << "\n#define SPEC_USE_JEN "
     << (S.use_jen ? 1 : 0) << "\n#define SPEC_GRAM_FMA " << (S.gram_fma ? 1 : 0) << "\n#define SPEC_NV " << L.nv
     << "\n#define SPEC_OFF_ATOM " << L.off_atom << "\n#define SPEC_OFF_MOW " << L.off_mow << "\n#define SPEC_OFF_CI "
@@ -329,9 +332,9 @@ std::string drv_err(int rc) {
 size_t smem_doubles(const DevSys &S, int mode) {
   const bool el = mode == MODE_ELOC;
   const int ne3 = 3 * S.nelec;
-  int slice = (ne3 + (el ? 4 * S.nelec : 0) + (el ? 2 : 1) * S.nelec * S.nmup) | 1;
+  int slice = (ne3 + (el ? 4 * S.nelec : 0) + (el ? 2 : 1) * S.nelec * S.nmu) | 1;
   if (def_value("SPEC_PREFETCH", SPEC_DEFAULT_PREFETCH)) slice += ne3 + (ne3 & 1);
-  const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmup + S.nconf + 1) & ~1) : 0;
+  const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmu + S.nconf + 1) & ~1) : 0;
   return 64 + (size_t)nmw + (size_t)SPEC_THREADS * slice;
 }
 

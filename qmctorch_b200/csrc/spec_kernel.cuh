@@ -110,16 +110,15 @@ __device__ __forceinline__ void spec_shell_end(double r2, double &S2, double T2)
 template <int MODE, int AO, int NCH>
 __device__ __forceinline__ void spec_emit(const double *mw, const double (&v)[NCH], double (&acc)[NCH][SPEC_NMUP]) {
   static_assert(NCH == spec_nch<MODE>(), "channel count");
-  // (the MO weights of one AO are read once per column: SPEC_NMUP <= 4)
+  // (the MO weights of one AO are read once per column: SPEC_NMUP <= 8)
   double w[SPEC_NMUP];
   if (SPEC_MOW_SMEM) {
 #pragma unroll
     for (int j = 0; j < SPEC_NMUP; ++j) w[j] = mw[AO * SPEC_NMUP + j];
   } else {
-    w[0] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP>();
-    if (SPEC_NMUP > 1) w[1 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 1 % SPEC_NMUP>();
-    if (SPEC_NMUP > 2) w[2 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 2 % SPEC_NMUP>();
-    if (SPEC_NMUP > 3) w[3 % SPEC_NMUP] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + 3 % SPEC_NMUP>();
+#define SPEC_W(J) if constexpr (SPEC_NMUP > J) w[J] = spec_pv<MODE, SPEC_OFF_MOW + AO * SPEC_NMUP + J>();
+    SPEC_W(0) SPEC_W(1) SPEC_W(2) SPEC_W(3) SPEC_W(4) SPEC_W(5) SPEC_W(6) SPEC_W(7)
+#undef SPEC_W
   }
 #pragma unroll
   for (int j = 0; j < SPEC_NMUP; ++j)

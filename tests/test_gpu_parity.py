@@ -488,7 +488,7 @@ def _mh_philox(wf, x, tau, seed, offset, scale=0.3, move_elec=-1):
     return x, acc.bool()
 
 
-@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_nojastrow", "h2_ground"])
+@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_cas24", "lih_nojastrow", "h2_ground"])
 def test_specialised_kernels_match_generic(name, monkeypatch):
     """The NVRTC structure-specialised kernels (spec_kernel.cuh) against the generic interpreter
     kernels (fused_impl.cuh, QMCB_JIT=0) on the same walkers: psi, E_L, E_kin to rounding, identical
