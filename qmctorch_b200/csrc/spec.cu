@@ -355,6 +355,24 @@ void qmcb_spec_free(qmcb_plan *p) {
   p->spec = nullptr;
 }
 
+// "sm_100a" for a host-only plan, else the device's own architecture (queried once per device:
+// plans are re-prepared after every parameter update)
+static std::string device_arch(int device) {
+  if (device < 0) return "sm_100a";
+  static std::mutex mu;
+  static std::map<int, std::string> known;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = known.find(device);
+  if (it != known.end()) return it->second;
+  int major = 10, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  std::string arch = "sm_" + std::to_string(major) + std::to_string(minor);
+  if (major >= 9) arch += "a";
+  known[device] = arch;
+  return arch;
+}
+
 // Builds (or fetches) the specialised module of this plan.  load = false: compile only (no driver).
 // Returns 0 when the module is ready, 1 when the generic kernels must be used (st.why says why).
 static int spec_prepare(const qmcb_plan *p, bool load) {
@@ -372,14 +390,7 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
   if (!walk(p, &code, nullptr, L)) return fail("program walk failed");
   if (L.nv > SPEC_MAX_VALUES) return fail("parameter block too large");
   st.lay = L;
-  std::string arch = "sm_100a";
-  if (p->device >= 0) {
-    cudaDeviceProp pr;
-    if (cudaGetDeviceProperties(&pr, p->device) == cudaSuccess) {
-      arch = "sm_" + std::to_string(pr.major) + std::to_string(pr.minor);
-      if (pr.major >= 9) arch += "a";
-    }
-  }
+  const std::string arch = device_arch(p->device);
   std::string key = std::to_string(p->device) + "|" + arch + "|" + prelude(p, L) + code;
   for (auto &e : extra_defs()) key += "|" + e;
   std::lock_guard<std::mutex> lk(cache_mu());

@@ -38,7 +38,9 @@ class _PsiFunction(torch.autograd.Function):
         need = ctx.needs_input_grad
         # parameter gradients only when some parameter asks for them (position-only autograd,
         # e.g. drift / Hamiltonian samplers, just needs qmcb_grad_psi)
-        g = wf._psi_backward(x, grad_out.reshape(-1).contiguous()) if any(need[2:]) else {}
+        names = ("bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w", "jen_w", "een", "een", "een")
+        want = {n for n, flag in zip(names, need[2:]) if flag}
+        g = wf._psi_backward(x, grad_out.reshape(-1).contiguous(), want) if want else {}
         gx = None
         if need[1]:
             gx = wf._grad_psi(x, pdf=False) * grad_out.reshape(-1, 1)
@@ -178,7 +180,10 @@ class SlaterJastrow(WaveFunction):
                                             _lib.stream_ptr(x.device)), "qmcb_grad_psi")
         return g
 
-    def _psi_backward(self, x, weight):
+    def _psi_backward(self, x, weight, want=None):
+        """want: names of the gradients to form (None = all).  Outputs that are not wanted are passed
+        as NULL, which lets qmcb_psi_backward skip the basis-parameter contractions (4 x cheaper when
+        only Jastrow / MO / CI gradients are needed, BASELINE config 3)."""
         L = _lib.lib()
         plan = self._handle.plan()
         dev = x.device
@@ -198,9 +203,12 @@ class SlaterJastrow(WaveFunction):
         if ws is None or ws.numel() < nbytes or ws.device != dev:
             ws = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
             self._ws["bwd"] = ws
-        _lib.check(L.qmcb_psi_backward(plan, _lib.ptr(x), _lib.ptr(weight), W, _lib.ptr(g_mo), _lib.ptr(g_ci),
-                                       _lib.ptr(g_exp), _lib.ptr(g_cf), _lib.ptr(g_jee), _lib.ptr(g_jen),
-                                       _lib.ptr(g_een) if nt else None, _lib.ptr(ws), _lib.stream_ptr(dev)),
+        def out(name, t):
+            return _lib.ptr(t) if (want is None or name in want) else None
+        _lib.check(L.qmcb_psi_backward(plan, _lib.ptr(x), _lib.ptr(weight), W, out("mo_modifier", g_mo),
+                                       out("ci", g_ci), out("bas_exp", g_exp), out("bas_coeffs", g_cf),
+                                       out("jee_w", g_jee), out("jen_w", g_jen),
+                                       out("een", g_een) if nt else None, _lib.ptr(ws), _lib.stream_ptr(dev)),
                    "qmcb_psi_backward")
         return {"mo_modifier": g_mo * self.mo.mo_scf, "ci": g_ci, "bas_exp": g_exp, "bas_coeffs": g_cf,
                 "jee_w": g_jee, "jen_w": g_jen,
