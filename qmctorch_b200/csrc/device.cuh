@@ -231,7 +231,7 @@ __device__ __forceinline__ void generic_component(int kk, double sc, double x, d
     v[1] = t * x + R * dYx;
     v[2] = t * y + R * dYy;
     v[3] = t * z + R * dYz;
-    v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
+    if (NCH > 4) v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
   }
 }
 

@@ -42,6 +42,7 @@ const int SPEC_MINB = env_int("QMCB_SPEC_MINB", 4);
 // defaults of the kernel's tuning switches (must match the #ifndef defaults in spec_kernel.cuh)
 constexpr int SPEC_DEFAULT_PREFETCH = 0;
 constexpr int SPEC_DEFAULT_MOW_SMEM = 0;
+constexpr size_t SPEC_SMEM_BUDGET = 100 * 1024;   // per CTA: at least two CTAs per SM
 constexpr int SPEC_MAX_VALUES = 448;   // doubles in the parameter block (keeps it under 4 KB)
 
 // ---------------------------------------------------------------------------------------
@@ -151,7 +152,7 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
   else if (S.nuu + S.nud > 16 || S.nconf > 64) w = "too many determinants";
-  else if ((64 + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > 100 * 1024)
+  else if ((64 + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
     w = "per-thread slices exceed the shared-memory budget";
   if (w) { if (why) *why = w; return false; }
   return true;
@@ -242,6 +243,50 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
       << "]; sig += d; if (WB) ksig += d * (tr[" << iu << "] + tr[" << id << "]); }\n";
   }
   o << "}\n";
+  // gradient assembly (MODE_GRAD): inverse of every unique spin block, its CI weight, then per
+  // electron and direction the trace against the derivative rows
+  o << "\ntemplate <int MODE>\n__device__ __forceinline__ void spec_grad(const double *mw, const double *A, const double *G, "
+       "const double *jv, double J, int pdf, double *out) {\n  constexpr int NE = SPEC_NE, NM = SPEC_NMUP, NENM = SPEC_NE * SPEC_NMUP;\n"
+    << "  double det[" << nun << "];\n";
+  for (int u = 0; u < nun; ++u) {
+    const bool up = u < S.nuu;
+    const int n = up ? S.nup : S.ndown;
+    if (n == 0) { o << "  det[" << u << "] = 1.0;\n"; continue; }
+    const int *cols = hi.data() + (up ? S.o_ucu + u * S.nup : S.o_ucd + (u - S.nuu) * S.ndown);
+    o << "  double inv" << u << "[" << n * n << "];\n  { const int cols[" << n << "] = {";
+    for (int j = 0; j < n; ++j) o << (j ? ", " : "") << cols[j];
+    o << "}; det[" << u << "] = inverse_small(" << n << ", A + " << (up ? 0 : S.nup) * S.nmu << ", NM, cols, inv" << u
+      << ", 1); }\n";
+  }
+  o << "  double sig = 0.0;\n";
+  for (int u = 0; u < nun; ++u) o << "  double cw" << u << " = 0.0;\n";
+  for (int c = 0; c < S.nconf; ++c) {
+    const int iu = hi[S.o_ciu + c], id = S.nuu + hi[S.o_cid + c];
+    o << "  { const double ci = SPEC_MOW_SMEM ? mw[" << L.off_ci - L.off_mow + c << "] : spec_pv<MODE, " << L.off_ci + c
+      << ">(); sig += ci * det[" << iu << "] * det[" << id << "]; cw" << iu << " += ci * det[" << id << "]; cw" << id
+      << " += ci * det[" << iu << "]; }\n";
+  }
+  for (int u = 0; u < nun; ++u) o << "  cw" << u << " *= det[" << u << "];\n";
+  o << "  const double f = pdf ? 2.0 * sig * J : 1.0;\n";
+  for (int e = 0; e < S.nelec; ++e) {
+    const bool up = e < S.nup;
+    const int n = up ? S.nup : S.ndown, el = up ? e : e - S.nup;
+    o << "  {  // electron " << e << "\n    double gx = 0.0, gy = 0.0, gz = 0.0;\n";
+    const int u0 = up ? 0 : S.nuu, u1 = up ? S.nuu : nun;
+    for (int u = u0; u < u1; ++u) {
+      const int *cols = hi.data() + (up ? S.o_ucu + u * S.nup : S.o_ucd + (u - S.nuu) * S.ndown);
+      o << "    if (cw" << u << " != 0.0) {\n      double tx = 0.0, ty = 0.0, tz = 0.0;\n";
+      for (int j = 0; j < n; ++j) {
+        const int at = e * S.nmu + cols[j];
+        o << "      { const double iv = inv" << u << "[" << j * n + el << "]; tx = fma(iv, G[" << at << "], tx); ty = fma(iv, G[NENM + "
+          << at << "], ty); tz = fma(iv, G[2 * NENM + " << at << "], tz); }\n";
+      }
+      o << "      gx = fma(cw" << u << ", tx, gx); gy = fma(cw" << u << ", ty, gy); gz = fma(cw" << u << ", tz, gz);\n    }\n";
+    }
+    o << "    out[" << 3 * e << "] = f * J * (gx + jv[" << e << "] * sig); out[" << 3 * e + 1 << "] = f * J * (gy + jv[NE + " << e
+      << "] * sig); out[" << 3 * e + 2 << "] = f * J * (gz + jv[2 * NE + " << e << "] * sig);\n  }\n";
+  }
+  o << "}\n";
   if (code) *code = o.str();
   return true;
 }
@@ -278,9 +323,9 @@ struct Module {
   std::vector<char> cubin;
   std::string log;
   CUmodule mod = nullptr;
-  CUfunction fn[3] = {nullptr, nullptr, nullptr};   // psi, eloc, mh
-  int occ[3] = {0, 0, 0};
-  int smem[3] = {0, 0, 0};
+  CUfunction fn[4] = {nullptr, nullptr, nullptr, nullptr};   // psi, eloc, mh, grad
+  int occ[4] = {0, 0, 0, 0};
+  int smem[4] = {0, 0, 0, 0};
   bool loaded = false;
 };
 std::map<std::string, Module> &cache() { static std::map<std::string, Module> c; return c; }
@@ -330,9 +375,10 @@ std::string drv_err(int rc) {
 
 // dynamic shared memory of one CTA (doubles): etab | optional MO weights + CI | per-thread slices
 size_t smem_doubles(const DevSys &S, int mode) {
-  const bool el = mode == MODE_ELOC;
+  const bool deriv = mode == MODE_ELOC || mode == MODE_GRAD;
+  const int nrow = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
   const int ne3 = 3 * S.nelec;
-  int slice = (ne3 + (el ? 4 * S.nelec : 0) + (el ? 2 : 1) * S.nelec * S.nmu) | 1;
+  int slice = (ne3 + (deriv ? 4 * S.nelec : 0) + nrow * S.nelec * S.nmu) | 1;
   if (def_value("SPEC_PREFETCH", SPEC_DEFAULT_PREFETCH)) slice += ne3 + (ne3 & 1);
   const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmu + S.nconf + 1) & ~1) : 0;
   return 64 + (size_t)nmw + (size_t)SPEC_THREADS * slice;
@@ -417,12 +463,13 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
     cudaFree(nullptr);   // primary context current on this thread
     int rc = d.ModuleLoadData(&m.mod, m.cubin.data());
     if (rc != 0) return fail("cuModuleLoadData: " + drv_err(rc));
-    const char *names[3] = {"spec_psi", "spec_eloc", "spec_mh"};
-    const int modes[3] = {MODE_PSI, MODE_ELOC, MODE_MH};
-    for (int i = 0; i < 3; ++i) {
+    const char *names[4] = {"spec_psi", "spec_eloc", "spec_mh", "spec_grad_psi"};
+    const int modes[4] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD};
+    for (int i = 0; i < 4; ++i) {
       rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
       if (rc != 0) return fail(std::string("cuModuleGetFunction ") + names[i] + ": " + drv_err(rc));
       m.smem[i] = (int)(smem_doubles(p->sys, modes[i]) * sizeof(double));
+      if ((size_t)m.smem[i] > SPEC_SMEM_BUDGET) { m.fn[i] = nullptr; continue; }   // this mode stays generic
       rc = d.FuncSetAttribute(m.fn[i], 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, m.smem[i]);
       if (rc != 0) return fail("cuFuncSetAttribute: " + drv_err(rc));
       int occ = 0;
@@ -454,7 +501,7 @@ static void refresh_params(const qmcb_plan *p, qmcb_spec_state &st) {
 }
 
 int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *stream, int *grid_out) {
-  const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : -1));
+  const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : (mode == MODE_GRAD ? 3 : -1)));
   if (slot < 0 || p->device < 0) return QMCB_SPEC_SKIP;
   if (spec_prepare(p, true) != 0) {
     if (p->spec->level >= 2) {
@@ -464,8 +511,9 @@ int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *str
     return QMCB_SPEC_SKIP;
   }
   qmcb_spec_state &st = *p->spec;
-  refresh_params(p, st);
   Module &m = *st.mod;
+  if (!m.fn[slot]) return QMCB_SPEC_SKIP;
+  refresh_params(p, st);
   int64_t grid = (int64_t)p->sm_count * m.occ[slot];
   const int64_t need = (a.W + SPEC_THREADS - 1) / SPEC_THREADS;
   if (grid > need) grid = need;

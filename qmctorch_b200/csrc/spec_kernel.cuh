@@ -57,12 +57,14 @@ __device__ __forceinline__ double spec_pv() {
     asm volatile("ld.param.f64 %0, [spec_psi_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   else if constexpr (MODE == MODE_ELOC)
     asm volatile("ld.param.f64 %0, [spec_eloc_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
+  else if constexpr (MODE == MODE_GRAD)
+    asm volatile("ld.param.f64 %0, [spec_grad_psi_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   else
     asm volatile("ld.param.f64 %0, [spec_mh_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   return v;
 }
 template <int MODE>
-__host__ __device__ constexpr int spec_nch() { return MODE == MODE_ELOC ? 5 : 1; }
+__host__ __device__ constexpr int spec_nch() { return MODE == MODE_ELOC ? 5 : (MODE == MODE_GRAD ? 4 : 1); }   // value | + grad | + lap
 
 // ---- building blocks the generated program calls (literal indices everywhere)
 // One primitive c exp(-a r^2) of a shell.  Every product of parameters is formed on the HOST
@@ -83,16 +85,16 @@ __device__ __forceinline__ void spec_prim(const SpecParams &P, const double *et,
   const double e = exp_core(P, et, __hiloint2double((int)hi, __double2loint(x)));
   if (FIRST) S0 = spec_pv<MODE, I + 1>() * e; else S0 = fma(spec_pv<MODE, I + 1>(), e, S0);
   if (NCH > 1) {
-    if (FIRST) { S1 = spec_pv<MODE, I + 2>() * e; S2 = spec_pv<MODE, I + 3>() * e; T2 = spec_pv<MODE, I + 4>() * e; }
-    else {
-      S1 = fma(spec_pv<MODE, I + 2>(), e, S1); S2 = fma(spec_pv<MODE, I + 3>(), e, S2);
-      T2 = fma(spec_pv<MODE, I + 4>(), e, T2);
-    }
+    if (FIRST) S1 = spec_pv<MODE, I + 2>() * e; else S1 = fma(spec_pv<MODE, I + 2>(), e, S1);
+  }
+  if (NCH > 4) {
+    if (FIRST) { S2 = spec_pv<MODE, I + 3>() * e; T2 = spec_pv<MODE, I + 4>() * e; }
+    else { S2 = fma(spec_pv<MODE, I + 3>(), e, S2); T2 = fma(spec_pv<MODE, I + 4>(), e, T2); }
   }
 }
 template <int MODE>
 __device__ __forceinline__ void spec_shell_end(double r2, double &S2, double T2) {
-  if (spec_nch<MODE>() > 1) S2 = fma(T2, r2, S2);
+  if (spec_nch<MODE>() > 4) S2 = fma(T2, r2, S2);
 }
 
 #ifndef SPEC_MOW_SMEM
@@ -134,7 +136,7 @@ __device__ __forceinline__ void spec_s(const double *mw, double x, double y, dou
   if (NCH > 1) {
     const double t = S1 * spec_pv<MODE, ISC>();
     v[1] = t * x; v[2] = t * y; v[3] = t * z;
-    v[4] = S2 * spec_pv<MODE, ISC>();
+    if (NCH > 4) v[4] = S2 * spec_pv<MODE, ISC>();
   }
   spec_emit<MODE, AO>(mw, v, acc);
 }
@@ -145,13 +147,16 @@ __device__ __forceinline__ void spec_p(const double *mw, double x, double y, dou
   double v[NCH];
   const double R = S0 * spec_pv<MODE, ISC>();
   if (NCH > 1) {
-    const double t = S1 * spec_pv<MODE, ISC>(), lf = fma(2.0, S1, S2) * spec_pv<MODE, ISC>();
+    const double t = S1 * spec_pv<MODE, ISC>(), lf = NCH > 4 ? fma(2.0, S1, S2) * spec_pv<MODE, ISC>() : 0.0;
     const double tx = t * x, ty = t * y, tz = t * z;
-    v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z; v[4] = lf * x;
+    v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z;
+    if (NCH > 4) v[NCH - 1] = lf * x;
     spec_emit<MODE, AO>(mw, v, acc);
-    v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z; v[4] = lf * y;
+    v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z;
+    if (NCH > 4) v[NCH - 1] = lf * y;
     spec_emit<MODE, AO + 1>(mw, v, acc);
-    v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R); v[4] = lf * z;
+    v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R);
+    if (NCH > 4) v[NCH - 1] = lf * z;
     spec_emit<MODE, AO + 2>(mw, v, acc);
   } else {
     v[0] = R * x; spec_emit<MODE, AO>(mw, v, acc);
@@ -168,14 +173,15 @@ __device__ __forceinline__ void spec_g(const double *mw, double x, double y, dou
   spec_emit<MODE, AO>(mw, v, acc);
 }
 
-// ---- generated: spec_aos<MODE>, spec_dets<WB>, spec_ci<MODE>
+// ---- generated: spec_aos<MODE>, spec_dets<WB>, spec_ci<MODE>, spec_grad<MODE>
 SPEC_GENERATED_CODE
 
 template <int MODE>
 __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &a) {
-  constexpr int NCH = MODE == MODE_ELOC ? 5 : 1;
+  constexpr int NCH = spec_nch<MODE>();
   constexpr int Ne = SPEC_NE, ne3 = 3 * SPEC_NE, NM = SPEC_NMUP, NUN = SPEC_NUU + SPEC_NUD;
-  constexpr int SLICE = (3 * Ne + (NCH > 1 ? 4 * Ne : 0) + (NCH > 1 ? 2 : 1) * Ne * NM) | 1;
+  constexpr int NROW = MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1);   // mo | B_kin or mo | d mo/dx,dy,dz
+  constexpr int SLICE = (3 * Ne + (NCH > 1 ? 4 * Ne : 0) + NROW * Ne * NM) | 1;
   extern __shared__ __align__(16) double smem[];
   double *et = smem;
   for (int i = threadIdx.x; i < 64; i += blockDim.x) et[i] = P.etab_g[i];
@@ -271,10 +277,24 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
           smo[e * NM + j] = acc[0][j];
           sB[e * NM + j] = -0.5 * b;
         }
+      } else if (MODE == MODE_GRAD) {
+#pragma unroll
+        for (int j = 0; j < NM; ++j) {
+          smo[e * NM + j] = acc[0][j];
+#pragma unroll
+          for (int c = 1; c < NCH; ++c) sB[(c - 1) * Ne * NM + e * NM + j] = acc[c][j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < NM; ++j) smo[e * NM + j] = acc[0][j];
       }
+    }
+    if (MODE == MODE_GRAD) {
+      // d psi / d r = J [ sum_u C_u sum_j inv_u[j][e] dmo[e][cols_u[j]] + grad_e(ln J) Sigma ]
+      // (slater_jastrow.py:346-447): inverses, CI weights and the electron loop are generated
+      const double J = (SPEC_USE_JEE || SPEC_USE_JEN) ? exp_clamped(P, et, tks) : 1.0;
+      spec_grad<MODE>(mw, smo, sB, jv, J, a.pdf, a.out0 + w * ne3);
+      continue;
     }
     // ---- determinants, traces, CI sum (generated, literal occupations)
     double det[NUN], tr[NUN];
@@ -340,5 +360,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
     spec_psi(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_PSI>(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB_ELOC)
     spec_eloc(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_ELOC>(P, a); }
+extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
+    spec_grad_psi(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_GRAD>(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
     spec_mh(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_MH>(P, a); }

@@ -617,3 +617,26 @@ def test_gradient_samplers_replay_reference_chains(double_default):
     torch.manual_seed(0)
     out = s(lambda x: torch.exp(-(x * x).sum(1)), with_tqdm=False)
     assert out.shape == (64, 3) and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_nojastrow"])
+def test_specialised_gradient_kernel(name, monkeypatch):
+    """spec_grad_psi (generated inverses / CI weights / electron loop) against the generic
+    fused_kernel<MODE_GRAD> and the oracle: grad psi and grad psi^2 (slater_jastrow.py:346-447)."""
+    g = C.load(name)
+    monkeypatch.setenv("QMCB_JIT", "0")
+    mol, wf0 = C.build_wf(g)
+    pos, _ = _thermalised(wf0, mol, 3001)
+    g0, p0 = wf0.gradients_jacobi(pos), wf0.gradients_jacobi(pos, pdf=True)
+    monkeypatch.setenv("QMCB_JIT", "2")
+    mol, wf1 = C.build_wf(g)
+    assert wf1._handle.info(13) == 1
+    g1, p1 = wf1.gradients_jacobi(pos), wf1.gradients_jacobi(pos, pdf=True)
+    assert C.scaled_err(g1, g0) < 1e-12 and C.scaled_err(p1, p0) < 1e-12
+    _, P = C.oracle_params(g)
+    assert C.scaled_err(g1[:128], orc.grad_psi(P, pos[:128].cpu())) < RTOL
+    assert C.scaled_err(p1[:128], orc.grad_psi(P, pos[:128].cpu(), pdf=True)) < RTOL
+    # autograd w.r.t. positions goes through the same kernel
+    x = pos[:64].clone().requires_grad_(True)
+    wf1(x).sum().backward()
+    assert C.scaled_err(x.grad, g1[:64]) < 1e-13
