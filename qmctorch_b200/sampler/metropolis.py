@@ -135,7 +135,7 @@ class Metropolis(SamplerBase):
                     if idecor % self.ndecor == 0:
                         kept.append(x.clone() if self.keep_on_device else x.to("cpu"))
                     idecor += 1
-            self.acceptance_rate = float(naccept.item()) / (W * self._move_per_iter * max(self.nstep, 1))
+            self.acceptance_rate = float(naccept.item()) / max(W * self._move_per_iter * max(self.nstep, 1), 1)
             self.sampling_time = time() - tstart
         out = self.symmetry(torch.cat(kept))
         return out.requires_grad_()
