@@ -51,7 +51,7 @@ def algorithmic_flops(mol, wf, info):
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the dominant
 # kernel, bytes per launch, keyed by (kernel, workload, walkers): profiles/r1_spec_ncu_raw.csv
 # (structure-specialised kernel) and profiles/r1_fused_ncu_raw.csv (generic kernel)
-NCU_TRAFFIC = {("spec_eloc", "lih", 1_000_000): 96.041984e6 + 4.954368e6,
+NCU_TRAFFIC = {("spec_eloc", "lih", 1_000_000): 96.302080e6 + 7.425536e6,
                ("fused_kernel<MODE_ELOC>", "lih", 1_000_000): 96.070912e6 + 5.570048e6}
 
 

@@ -113,10 +113,12 @@ __device__ __forceinline__ double exp_core(const SYS &S, const double *etab, dou
   return __hiloint2double(__double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
 }
 
+// arguments <= 0 (plus NaN, which passes): the lower clamp is one integer min on the high word -
+// more negative doubles have larger high words - instead of DSETP + 2 FSEL
 template <class SYS>
 __device__ __forceinline__ double exp_neg(const SYS &S, const double *etab, double x) {
-  x = x < -708.0 ? -708.0 : x;
-  return exp_core(S, etab, x);
+  const unsigned hi = min((unsigned)__double2hiint(x), 0xC0862000u);
+  return exp_core(S, etab, __hiloint2double((int)hi, __double2loint(x)));
 }
 
 // arguments of either sign

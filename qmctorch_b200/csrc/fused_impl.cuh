@@ -36,11 +36,22 @@ struct MoSink {
   }
   __device__ __forceinline__ void emit(int ao, const double (&v)[NCH]) {
     const double *wr = w + ao * nmup;
+    if (MB >= 2) {
+      // two weights per LDS.128: the rows are 16-byte aligned (nmup and MB are even, o_mow is even)
+      const double2 *wr2 = reinterpret_cast<const double2 *>(wr);
 #pragma unroll
-    for (int j = 0; j < MB; ++j) {
-      const double wj = wr[j];
+      for (int j = 0; j < MB / 2; ++j) {
+        const double2 wj = wr2[j];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) acc[c][j] = fma(v[c], wj, acc[c][j]);
+        for (int c = 0; c < NCH; ++c) {
+          acc[c][2 * j] = fma(v[c], wj.x, acc[c][2 * j]);
+          acc[c][2 * j + 1] = fma(v[c], wj.y, acc[c][2 * j + 1]);
+        }
+      }
+    } else {
+      const double wj = wr[0];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc[c][0] = fma(v[c], wj, acc[c][0]);
     }
   }
 };

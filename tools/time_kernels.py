@@ -11,8 +11,8 @@ from qmctorch_b200.wavefunction import SlaterJastrow
 
 key = sys.argv[1] if len(sys.argv) > 1 else "lih"
 nw = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
-cfg = {"lih": "ground_state", "h2": "single(2,2)", "h2o": "cas(4,4)", "c4h6": "ground_state"}[key]
-step = {"lih": 0.3, "h2": 0.5, "h2o": 0.15, "c4h6": 0.05}[key]
+cfg = {"lih": "ground_state", "h2": "single(2,2)", "h2o": "cas(4,4)", "c4h6": "ground_state"}.get(key, "ground_state")
+step = {"lih": 0.3, "h2": 0.5, "h2o": 0.15, "c4h6": 0.05}.get(key, 0.3)
 mol = fixture_molecule(key)
 wf = SlaterJastrow(mol, configs=cfg, cuda=True)
 s = Metropolis(nwalkers=nw, nstep=10, step_size=step, nelec=wf.nelec, ndim=3, init=mol.domain("normal"),
