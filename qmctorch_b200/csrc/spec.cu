@@ -146,8 +146,7 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   const DevSys &S = p->sys;
   const int nbig = S.nup > S.ndown ? S.nup : S.ndown;
   const char *w = nullptr;
-  if (S.radial_type != QMCB_GTO_PURE) w = "radial type is not gto_pure";
-  else if (S.een_nterm > 0) w = "three-body Jastrow";
+  if (S.een_nterm > 0) w = "three-body Jastrow";
   else if (S.nmu > 8) w = "more than 8 occupied MO columns";
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
@@ -181,19 +180,33 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     const int oa = L.off_atom + 4 * A;
     o << "  {  // atom " << A << "\n    const double x = ex - spec_pv<MODE, " << oa << ">(), y = ey - spec_pv<MODE, " << oa + 1
       << ">(), z = ez - spec_pv<MODE, " << oa + 2 << ">();\n    const double r2 = x * x + y * y + z * z;\n";
+    const int rt = S.radial_type;
+    const bool with_n = rt == QMCB_GTO || rt == QMCB_STO;
+    if (rt != QMCB_GTO_PURE) o << "    const double rinv = fast_rsqrt(r2), r = r2 * rinv;\n";
+    else o << "    const double rinv = 0.0;\n";
     for (int s = 0; s < ns; ++s) {
       int nprim, ngrp;
       ints(rec[0], nprim, ngrp);
       rec += 2;
       o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0, T2 = 0.0;\n";
-      for (int q = 0; q < nprim; ++q, rec += 2) {
-        // derived per-primitive constants, see spec_prim (spec_kernel.cuh)
+      for (int q = 0; q < nprim; ++q, rec += with_n ? 4 : 2) {
+        // derived per-primitive constants, see spec_prim* (spec_kernel.cuh)
         const double a = rec[0], c = rec[1];
         const int i0 = push(-a);
-        push(c); push(-2.0 * a * c); push(-6.0 * a * c); push(4.0 * a * a * c);
-        o << "      spec_prim<MODE, " << (q == 0 ? "true" : "false") << ", " << i0 << ">(P, et, r2, S0, S1, S2, T2);\n";
+        push(c);
+        if (rt == QMCB_GTO_PURE) {
+          push(-2.0 * a * c); push(-6.0 * a * c); push(4.0 * a * a * c);
+          o << "      spec_prim<MODE, " << (q == 0 ? "true" : "false") << ", " << i0 << ">(P, et, r2, S0, S1, S2, T2);\n";
+        } else if (rt == QMCB_STO_PURE) {
+          push(-a * c); push(a * a * c); push(0.0);
+          o << "      spec_prim_sto_pure<MODE, " << i0 << ">(P, et, r, S0, S1, S2);\n";
+        } else {
+          push(a); push(0.0); push(0.0);
+          o << "      spec_prim_power<MODE, " << i0 << ", " << (rt == QMCB_GTO ? "true" : "false") << ", " << (int)rec[2]
+            << ">(P, et, r2, r, rinv, S0, S1, S2);\n";
+        }
       }
-      o << "      spec_shell_end<MODE>(r2, S2, T2);\n";
+      o << "      spec_shell_end<MODE, " << rt << ">(r2, rinv, S1, S2, T2);\n";
       for (int g = 0; g < ngrp; ++g, rec += 2) {
         int kk, ao;
         ints(rec[0], kk, ao);

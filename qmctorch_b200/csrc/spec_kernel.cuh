@@ -92,9 +92,47 @@ __device__ __forceinline__ void spec_prim(const SpecParams &P, const double *et,
     else { S2 = fma(spec_pv<MODE, I + 3>(), e, S2); T2 = fma(spec_pv<MODE, I + 4>(), e, T2); }
   }
 }
-template <int MODE>
-__device__ __forceinline__ void spec_shell_end(double r2, double &S2, double T2) {
-  if (spec_nch<MODE>() > 4) S2 = fma(T2, r2, S2);
+// Other radial types (ADF-style bases; radial_functions.py:6-238,323-406), same conventions
+// (grad R = S1 (x,y,z), lap R = S2); v[I..I+4] as written by spec.cu for the type:
+//   sto_pure  c e^{-a r}:        { -a, c, -a c, a^2 c, - }   S0 = sum c e, S1 = sum(-a c) e, S2 = sum(a^2 c) e,
+//                                 finished per shell: S2 += 2 S1 / r, S1 /= r
+//   gto / sto c r^N e^{-a r^2 | -a r}: { -a, c, a, -, - } with the literal radial power N
+template <int MODE, int I>
+__device__ __forceinline__ void spec_prim_sto_pure(const SpecParams &P, const double *et, double r, double &S0,
+                                                   double &S1, double &S2) {
+  const double e = exp_neg(P, et, spec_pv<MODE, I>() * r);
+  S0 = fma(spec_pv<MODE, I + 1>(), e, S0);
+  if (spec_nch<MODE>() > 1) S1 = fma(spec_pv<MODE, I + 2>(), e, S1);
+  if (spec_nch<MODE>() > 4) S2 = fma(spec_pv<MODE, I + 3>(), e, S2);
+}
+template <int MODE, int I, bool GTO, int N>
+__device__ __forceinline__ void spec_prim_power(const SpecParams &P, const double *et, double r2, double r,
+                                                double rinv, double &S0, double &S1, double &S2) {
+  constexpr int NCH = spec_nch<MODE>();
+  const double a = spec_pv<MODE, I + 2>();
+  const double ce = spec_pv<MODE, I + 1>() * exp_neg(P, et, spec_pv<MODE, I>() * (GTO ? r2 : r));
+  const double rn = ipow(r, N);
+  S0 = fma(ce, rn, S0);
+  if (NCH > 1) {
+    const double nrnm2 = N == 0 ? 0.0 : N * rpow(r, rinv, N - 2);
+    if (GTO) {
+      S1 = fma(ce, nrnm2 - 2.0 * a * rn, S1);
+      if (NCH > 4) S2 = fma(ce, nrnm2 * (N + 1) - 4.0 * a * N * rn + a * rn * (4.0 * a * r2 - 6.0), S2);
+    } else {
+      S1 = fma(ce, nrnm2 - a * rn * rinv, S1);
+      if (NCH > 4) S2 = fma(ce, nrnm2 * (N + 1) - 2.0 * a * nrnm2 * r + a * rn * (a - 2.0 * rinv), S2);
+    }
+  }
+}
+
+// RT: 0 gto_pure, 1 gto, 2 sto_pure, 3 sto (QMCB_* radial types)
+template <int MODE, int RT>
+__device__ __forceinline__ void spec_shell_end(double r2, double rinv, double &S1, double &S2, double T2) {
+  if (RT == 0 && spec_nch<MODE>() > 4) S2 = fma(T2, r2, S2);
+  if (RT == 2 && spec_nch<MODE>() > 1) {
+    if (spec_nch<MODE>() > 4) S2 = fma(2.0 * S1, rinv, S2);
+    S1 *= rinv;
+  }
 }
 
 #ifndef SPEC_MOW_SMEM

@@ -488,7 +488,8 @@ def _mh_philox(wf, x, tau, seed, offset, scale=0.3, move_elec=-1):
     return x, acc.bool()
 
 
-@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_cas24", "lih_nojastrow", "h2_ground"])
+@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_cas24", "lih_nojastrow", "h2_ground",
+                                  "lih_sto", "lih_sto_pure", "lih_gto_kr"])
 def test_specialised_kernels_match_generic(name, monkeypatch):
     """The NVRTC structure-specialised kernels (spec_kernel.cuh) against the generic interpreter
     kernels (fused_impl.cuh, QMCB_JIT=0) on the same walkers: psi, E_L, E_kin to rounding, identical
@@ -619,7 +620,8 @@ def test_gradient_samplers_replay_reference_chains(double_default):
     assert out.shape == (64, 3) and bool(torch.isfinite(out).all())
 
 
-@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_nojastrow"])
+@pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_nojastrow", "lih_sto", "lih_sto_pure",
+                                  "lih_gto_kr"])
 def test_specialised_gradient_kernel(name, monkeypatch):
     """spec_grad_psi (generated inverses / CI weights / electron loop) against the generic
     fused_kernel<MODE_GRAD> and the oracle: grad psi and grad psi^2 (slater_jastrow.py:346-447)."""
