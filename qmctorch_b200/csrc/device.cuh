@@ -10,6 +10,7 @@
 
 #include <cstdint>
 
+#include "fused_args.h"
 #include "plan.h"
 #define QMCB_UNROLL
 #else
@@ -90,27 +91,31 @@ __device__ __forceinline__ double rpow(double r, double rinv, int m) {
 }
 
 // ---------------------------------------------------------------------------------------
-// exp(x), ~1 ulp, NaN propagates, no branches:
-//   x = (64 m + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^m * T[j] * (1 + q(r)),
-//   T[j] = 2^(j/64) from a 64-entry shared-memory table, q = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)
-//   (truncation 3.5e-17); 2^m is applied by an integer add on the exponent field.
-// 10 FP64 instructions.  Arguments are clamped to [-708, 708] (3e-308 instead of a denormal).
-// The constants come from the kernel-parameter struct (constant bank 0): S.expc.
+// exp(x), a few ulp, NaN propagates, no branches:
+//   x = (128 m + j) ln2/128 + r, |r| <= ln2/256;  exp(x) = 2^m * T[j] * (1 + q(r)),
+//   T[j] = 2^(j/128) from a 128-entry shared-memory table, q = r + r^2 (1/2 + r/6 + r^2/24)
+//   (truncation r^5/120 <= 1.2e-15); the reduction uses ONE constant -ln2/128 (its rounding error,
+//   4e-19 |128 m + j|, is below 1e-15 for |x| < 14); 2^m is applied by an integer add on the
+//   exponent field.  8 FP64 instructions.  Arguments are clamped to [-708, 708] (3e-308 instead of
+//   a denormal).  The constants come from the kernel-parameter struct (constant bank 0): S.expc.
 // ---------------------------------------------------------------------------------------
 template <class SYS>
 __device__ __forceinline__ double exp_core(const SYS &S, const double *etab, double x) {
   const double t = fma(x, S.expc[0], S.expc[1]);
   const int ki = __double2loint(t);
   const double kd = t - S.expc[1];
-  double r = fma(kd, S.expc[2], x);
-  r = fma(kd, S.expc[3], r);
-  double p = fma(r, S.expc[4], S.expc[5]);
-  p = fma(p, r, S.expc[6]);
-  p = fma(p, r, 0.5);
+  const double r = fma(kd, S.expc[2], x);
+  double p;
+  if (QMCB_ETAB_LOG2 >= 10) {
+    p = fma(r, S.expc[5], 0.5);
+  } else {
+    p = fma(r, S.expc[4], S.expc[5]);
+    p = fma(p, r, 0.5);
+  }
   const double q = fma(r * r, p, r);
-  const double tj = etab[ki & 63];
+  const double tj = etab[ki & (QMCB_ETAB - 1)];
   const double y = fma(tj, q, tj);
-  return __hiloint2double(__double2hiint(y) + ((ki >> 6) << 20), __double2loint(y));
+  return __hiloint2double(__double2hiint(y) + ((ki >> QMCB_ETAB_LOG2) << 20), __double2loint(y));
 }
 
 // arguments <= 0 (plus NaN, which passes): the lower clamp is one integer min on the high word -
@@ -141,15 +146,24 @@ __device__ __forceinline__ double exp_clamped(const SYS &S, const double *etab, 
 // Sink::emit(ao_index, v[NCH]) consumes the values: v[0]=ao, v[1..3]=grad, v[4]=lap.
 // RT = 0: gto_pure (compile-time fast path), RT = 1: radial type read from S at run time.
 // ---------------------------------------------------------------------------------------
+// One primitive c exp(-a r^2):  S0 += c e,  S1 += a c e,  T2 += a^2 c e;  the shell is finished by
+// grad R = -2 S1 (x,y,z),  lap R = -6 S1 + 4 r^2 T2  (gto_pure_finish): 6 FP64 instructions + exp.
 template <int NCH, class SYS>
 __device__ __forceinline__ void gto_pure_prim(const SYS &S, const double *etab, double a, double c, double r2, double &S0, double &S1,
-                                              double &S2) {
+                                              double &T2) {
   const double ce = c * exp_neg(S, etab, -a * r2);
   S0 += ce;
   if (NCH > 1) {
     const double t = a * ce;
-    S1 = fma(-2.0, t, S1);
-    S2 = fma(t, fma(4.0 * a, r2, -6.0), S2);
+    S1 += t;
+    if (NCH > 4) T2 = fma(a, t, T2);
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void gto_pure_finish(double r2, double &S1, double &S2, double T2) {
+  if (NCH > 1) {
+    if (NCH > 4) S2 = fma(4.0 * r2, T2, -6.0 * S1);
+    S1 *= -2.0;
   }
 }
 
@@ -161,23 +175,26 @@ __device__ __forceinline__ const double2 *radial_sums(const SYS &S, const double
   S0 = 0.0; S1 = 0.0; S2 = 0.0;
   if (RT == 0) {
     int i = 0;
-    double T0 = 0.0, T1 = 0.0, T2 = 0.0;      // second accumulator set: two independent chains
+    double T0 = 0.0, T1 = 0.0, T2 = 0.0, U2 = 0.0;      // second accumulator set: two independent chains
     for (; i + 2 <= nprim; i += 2) {
       const double2 p0 = rec[0], p1 = rec[1];
       rec += 2;
-      gto_pure_prim<NCH>(S, etab, p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(S, etab, p0.x, p0.y, r2, S0, S1, U2);
       gto_pure_prim<NCH>(S, etab, p1.x, p1.y, r2, T0, T1, T2);
     }
     if (i < nprim) {
       const double2 p0 = rec[0];
       rec += 1;
-      gto_pure_prim<NCH>(S, etab, p0.x, p0.y, r2, S0, S1, S2);
+      gto_pure_prim<NCH>(S, etab, p0.x, p0.y, r2, S0, S1, U2);
     }
-    S0 += T0; S1 += T1; S2 += T2;
+    S0 += T0; S1 += T1; T2 += U2;
+    gto_pure_finish<NCH>(r2, S1, S2, T2);
     return rec;
   }
   if (S.radial_type == QMCB_GTO_PURE) {
-    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(S, etab, rec->x, rec->y, r2, S0, S1, S2);
+    double T2 = 0.0;
+    for (int i = 0; i < nprim; ++i, ++rec) gto_pure_prim<NCH>(S, etab, rec->x, rec->y, r2, S0, S1, T2);
+    gto_pure_finish<NCH>(r2, S1, S2, T2);
   } else if (S.radial_type == QMCB_STO_PURE) {
     for (int i = 0; i < nprim; ++i, ++rec) {
       const double a = rec->x;
@@ -186,7 +203,7 @@ __device__ __forceinline__ const double2 *radial_sums(const SYS &S, const double
       if (NCH > 1) {
         const double t = a * ce;
         S1 -= t * rinv;
-        S2 += t * (a - 2.0 * rinv);
+        if (NCH > 4) S2 += t * (a - 2.0 * rinv);
       }
     }
   } else {
@@ -201,10 +218,10 @@ __device__ __forceinline__ const double2 *radial_sums(const SYS &S, const double
         const double nrnm2 = n == 0 ? 0.0 : n * rpow(r, rinv, n - 2);
         if (gto) {
           S1 += ce * (nrnm2 - 2.0 * a * rn);
-          S2 += ce * (nrnm2 * (n + 1) - 4.0 * a * n * rn + a * rn * (4.0 * a * r2 - 6.0));
+          if (NCH > 4) S2 += ce * (nrnm2 * (n + 1) - 4.0 * a * n * rn + a * rn * (4.0 * a * r2 - 6.0));
         } else {
           S1 += ce * (nrnm2 - a * rn * rinv);
-          S2 += ce * (nrnm2 * (n + 1) - 2.0 * a * nrnm2 * r + a * rn * (a - 2.0 * rinv));
+          if (NCH > 4) S2 += ce * (nrnm2 * (n + 1) - 2.0 * a * nrnm2 * r + a * rn * (a - 2.0 * rinv));
         }
       }
     }
@@ -212,6 +229,7 @@ __device__ __forceinline__ const double2 *radial_sums(const SYS &S, const double
   return rec;
 }
 
+// Cartesian component x^kx y^ky z^kz (degree L) of a shell: v[0] = ao, v[1..3] = grad, v[4] = lap
 template <int NCH>
 __device__ __forceinline__ void generic_component(int kk, double sc, double x, double y, double z, double S0,
                                                   double S1, double S2, double (&v)[NCH]) {
@@ -225,21 +243,56 @@ __device__ __forceinline__ void generic_component(int kk, double sc, double x, d
     const double dYx = kx ? kx * ipow(x, kx - 1) * py * pz : 0.0;
     const double dYy = ky ? ky * px * ipow(y, ky - 1) * pz : 0.0;
     const double dYz = kz ? kz * px * py * ipow(z, kz - 1) : 0.0;
-    double lapY = 0.0;
-    if (kx > 1) lapY += kx * (kx - 1) * ipow(x, kx - 2) * py * pz;
-    if (ky > 1) lapY += ky * (ky - 1) * px * ipow(y, ky - 2) * pz;
-    if (kz > 1) lapY += kz * (kz - 1) * px * py * ipow(z, kz - 2);
     const double t = S1 * sc * Y;
     v[1] = t * x + R * dYx;
     v[2] = t * y + R * dYy;
     v[3] = t * z + R * dYz;
-    if (NCH > 4) v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
+    if (NCH > 4) {
+      double lapY = 0.0;
+      if (kx > 1) lapY += kx * (kx - 1) * ipow(x, kx - 2) * py * pz;
+      if (ky > 1) lapY += ky * (ky - 1) * px * ipow(y, ky - 2) * pz;
+      if (kz > 1) lapY += kz * (kz - 1) * px * py * ipow(z, kz - 2);
+      v[4] = (S2 + 2.0 * L * S1) * sc * Y + R * lapY;
+    }
   }
 }
 
-template <int NCH, int RT, class Sink, class SYS, class TAB>
+// ---------------------------------------------------------------------------------------
+// Folded kinetic channel (local energy only).  The Jacobi kinetic operator needs, per electron e,
+//   B_kin[e][m] = -1/2 sum_a (lap ao_a + 2 g . grad ao_a + l ao_a) W[a][m],   g = grad_e ln J, l = lap_e J / J
+// (slater_jastrow.py:449-482).  The reference projects lap ao, the three grad ao and ao separately
+// (5 contractions) and combines afterwards; the combination is linear in the AO channels, so it is
+// formed PER AO before the projection:  K_a = lap ao_a + 2 g . grad ao_a + l ao_a  - two channels
+// (ao, K) are contracted instead of five.  With ao = sc R(r) Y, Y of degree L, u = (x,y,z):
+//   K = sc Y (S2 + 2 L S1 + S1 (2 g . u) + l S0) + sc S0 (2 g . grad Y + lap Y)
+// so one value per SHELL, Wf = S2 + S1 (2 g . u) + l S0, serves all its components.
+// ---------------------------------------------------------------------------------------
+struct FoldJ { double g2x, g2y, g2z, lp; };   // 2 grad_e ln J, lap_e J / J
+
+__device__ __forceinline__ void generic_component_fold(int kk, double sc, double x, double y, double z, double S0,
+                                                       double S1, double Wf, const FoldJ &f, double (&v)[2]) {
+  const int kx = kk & 255, ky = (kk >> 8) & 255, kz = (kk >> 16) & 255;
+  const int L = kx + ky + kz;
+  const double px = ipow(x, kx), py = ipow(y, ky), pz = ipow(z, kz);
+  const double Y = px * py * pz;
+  const double R = S0 * sc;
+  v[0] = R * Y;
+  double t = 0.0;    // 2 g . grad Y + lap Y
+  if (kx) t = fma(f.g2x, kx * ipow(x, kx - 1) * py * pz, t);
+  if (ky) t = fma(f.g2y, ky * px * ipow(y, ky - 1) * pz, t);
+  if (kz) t = fma(f.g2z, kz * px * py * ipow(z, kz - 1), t);
+  if (kx > 1) t += kx * (kx - 1) * ipow(x, kx - 2) * py * pz;
+  if (ky > 1) t += ky * (ky - 1) * px * ipow(y, ky - 2) * pz;
+  if (kz > 1) t += kz * (kz - 1) * px * py * ipow(z, kz - 2);
+  v[1] = fma(fma(2.0 * L, S1, Wf) * sc, Y, R * t);
+}
+
+// NCH = 1: ao;  4: ao + gradient;  5: + Laplacian;  FOLD (NCH == 2): ao and the folded kinetic channel
+template <int NCH, int RT, bool FOLD = false, class Sink, class SYS, class TAB>
 __device__ __forceinline__ void eval_aos(const SYS &S, const TAB &T, double ex, double ey, double ez,
-                                         Sink &sink) {
+                                         Sink &sink, const FoldJ fj = FoldJ{0.0, 0.0, 0.0, 0.0}) {
+  static_assert(FOLD == (NCH == 2), "two channels <=> folded kinetic channel");
+  constexpr int RD = FOLD ? 5 : NCH;        // radial derivative level
   const double2 *rec = T.stream();
   const double *et = T.etab();          // hoisted: one live pointer instead of a re-derivation per exp
   const double *at = T.atoms();
@@ -249,13 +302,15 @@ __device__ __forceinline__ void eval_aos(const SYS &S, const TAB &T, double ex, 
     const double r2 = x * x + y * y + z * z;
     double r = 0.0, rinv = 0.0;
     if (RT != 0 && S.radial_type != QMCB_GTO_PURE) { rinv = fast_rsqrt(r2); r = r2 * rinv; }
+    const double gd = FOLD ? fma(fj.g2x, x, fma(fj.g2y, y, fj.g2z * z)) : 0.0;
     const int ns = ash[A + 1] - ash[A];
     for (int s = 0; s < ns; ++s) {
       const double hdr = rec->x;
       ++rec;
       const int nprim = __double2loint(hdr), ngrp = __double2hiint(hdr);
       double S0, S1, S2;
-      rec = radial_sums<NCH, RT>(S, et, rec, nprim, r2, r, rinv, S0, S1, S2);
+      rec = radial_sums<RD, RT>(S, et, rec, nprim, r2, r, rinv, S0, S1, S2);
+      const double Wf = FOLD ? fma(S1, gd, fma(fj.lp, S0, S2)) : 0.0;
       for (int g = 0; g < ngrp; ++g, ++rec) {
         const double2 gr = *rec;
         const int kk = __double2loint(gr.x), ao = __double2hiint(gr.x);
@@ -263,22 +318,35 @@ __device__ __forceinline__ void eval_aos(const SYS &S, const TAB &T, double ex, 
         double v[NCH];
         if (kk == 0) {                       // s
           v[0] = S0 * sc;
-          if (NCH > 1) {
+          if (FOLD) {
+            v[NCH - 1] = Wf * sc;
+          } else if (NCH > 1) {
             const double t = S1 * sc;
             v[1] = t * x; v[2] = t * y; v[3] = t * z;
-            v[4] = S2 * sc;
+            if (NCH > 4) v[NCH - 1] = S2 * sc;
           }
           sink.emit(ao, v);
         } else if (kk == (1 << 24)) {        // px, py, pz on consecutive AOs
           const double R = S0 * sc;
-          if (NCH > 1) {
-            const double t = S1 * sc, lf = fma(2.0, S1, S2) * sc;
-            const double tx = t * x, ty = t * y, tz = t * z;
-            v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z; v[4] = lf * x;
+          if (FOLD) {
+            const double Wp = fma(2.0, S1, Wf) * sc;
+            v[0] = R * x; v[NCH - 1] = fma(Wp, x, R * fj.g2x);
             sink.emit(ao, v);
-            v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z; v[4] = lf * y;
+            v[0] = R * y; v[NCH - 1] = fma(Wp, y, R * fj.g2y);
             sink.emit(ao + 1, v);
-            v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R); v[4] = lf * z;
+            v[0] = R * z; v[NCH - 1] = fma(Wp, z, R * fj.g2z);
+            sink.emit(ao + 2, v);
+          } else if (NCH > 1) {
+            const double t = S1 * sc, lf = NCH > 4 ? fma(2.0, S1, S2) * sc : 0.0;
+            const double tx = t * x, ty = t * y, tz = t * z;
+            v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z;
+            if (NCH > 4) v[NCH - 1] = lf * x;
+            sink.emit(ao, v);
+            v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z;
+            if (NCH > 4) v[NCH - 1] = lf * y;
+            sink.emit(ao + 1, v);
+            v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R);
+            if (NCH > 4) v[NCH - 1] = lf * z;
             sink.emit(ao + 2, v);
           } else {
             v[0] = R * x; sink.emit(ao, v);
@@ -286,7 +354,8 @@ __device__ __forceinline__ void eval_aos(const SYS &S, const TAB &T, double ex, 
             v[0] = R * z; sink.emit(ao + 2, v);
           }
         } else {
-          generic_component<NCH>(kk, sc, x, y, z, S0, S1, S2, v);
+          if constexpr (FOLD) generic_component_fold(kk, sc, x, y, z, S0, S1, Wf, fj, v);
+          else generic_component<NCH>(kk, sc, x, y, z, S0, S1, S2, v);
           sink.emit(ao, v);
         }
       }
@@ -447,7 +516,9 @@ __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const
 
 // One-walker-per-thread variant: every electron pair is visited ONCE.  jv[k*jvs + e] receives
 // gx, gy, gz, lap (k = 0..3, DERIV only); the walker totals of ln J, V_en, V_ee are returned.
-template <bool DERIV, bool POT, class SYS, class TAB>
+// POT_EN = false: the caller adds the electron-nucleus potential itself (the specialised E_L kernel
+// takes 1/r_eA from the basis-function loop, which forms the same distance anyway)
+template <bool DERIV, bool POT, bool POT_EN = POT, class SYS, class TAB>
 __device__ __forceinline__ void walker_terms(const SYS &S, const TAB &T, const double *sp, double *jv,
                                              int jvs, double &tks, double &tven, double &tvee) {
   const int Ne = S.nelec;
@@ -490,7 +561,7 @@ __device__ __forceinline__ void walker_terms(const SYS &S, const TAB &T, const d
       const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
       const double dx = xi - xa, dy = yi - ya, dz = zi - za;
       const double s2 = dx * dx + dy * dy + dz * dz;
-      if (POT) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
+      if (POT_EN) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
       if (S.use_jen) {
         const double wn = S.jen_w;
         const double d2n = gram_d2_en(xi, yi, zi, ni, xa, ya, za, gram_norm(xa, ya, za));

@@ -4,6 +4,12 @@
 
 enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3 };
 
+// entries of the 2^(j/N) table of the exp() range reduction (device.cuh: exp_core); power of two
+#ifndef QMCB_ETAB_LOG2
+#define QMCB_ETAB_LOG2 7
+#endif
+#define QMCB_ETAB (1 << QMCB_ETAB_LOG2)
+
 struct FusedArgs {
   const double *pos;   // [W,3Ne]   (MH: updated in place through pos_rw)
   double *pos_rw;

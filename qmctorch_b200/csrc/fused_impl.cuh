@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
     fused_kernel(const DevSys S, const FusedArgs a, const int TW, const int NBLK, const int lu_conc) {
   constexpr bool WARP = TILE == 1;
   constexpr bool THREAD = TILE == 2;
-  constexpr int NCH = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? 5 : 1;
+  // AO channels contracted against the MO columns: psi 1 (ao); grad psi 4 (ao + gradient); E_L 2 - ao
+  // and the folded kinetic channel lap ao + 2 grad ln J . grad ao + (lap J / J) ao (device.cuh: FoldJ)
+  constexpr int NCH = MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1);
   constexpr int NCHS = nchs<MODE>();
   extern __shared__ __align__(16) double smem[];
   Tab T;
@@ -223,30 +225,31 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
       const double *sp = spos + wl * ne3 + 3 * e;
       MoSink<NCH, MB> sink;
       sink.init(T.mow() + blk * MB, nmup);
-      eval_aos<NCH, RT>(S, T, sp[0], sp[1], sp[2], sink);
       double *dst = smo + ((size_t)wl * Ne + e) * nmup + blk * MB;
-      if (MODE == MODE_ELOC) {
+      if constexpr (MODE == MODE_ELOC) {
+        // B_kin = -1/2 (lap mo + 2 grad ln J . grad mo + (lap J / J) mo), folded per AO
         const double *q = jv + wl * Ne + e;
-        const double gx = q[0], gy = q[jvs], gz = q[2 * jvs], lp = q[3 * jvs];
-        const bool uj = S.use_jee || S.use_jen || S.een_nterm > 0;
-#pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          double b = sink.acc[4][j];
-          if (uj) b += 2.0 * (gx * sink.acc[1][j] + gy * sink.acc[2][j] + gz * sink.acc[3][j]) + lp * sink.acc[0][j];
-          dst[j] = sink.acc[0][j];
-          dst[chs + j] = -0.5 * b;
-        }
-      } else if (MODE == MODE_GRAD) {
+        const FoldJ fj{2.0 * q[0], 2.0 * q[jvs], 2.0 * q[2 * jvs], q[3 * jvs]};
+        eval_aos<NCH, RT, true>(S, T, sp[0], sp[1], sp[2], sink, fj);
 #pragma unroll
         for (int j = 0; j < MB; ++j) {
           dst[j] = sink.acc[0][j];
-          dst[chs + j] = sink.acc[1][j];
-          dst[2 * chs + j] = sink.acc[2][j];
-          dst[3 * chs + j] = sink.acc[3][j];
+          dst[chs + j] = -0.5 * sink.acc[1][j];
         }
       } else {
+        eval_aos<NCH, RT>(S, T, sp[0], sp[1], sp[2], sink);
+        if constexpr (MODE == MODE_GRAD) {
 #pragma unroll
-        for (int j = 0; j < MB; ++j) dst[j] = sink.acc[0][j];
+          for (int j = 0; j < MB; ++j) {
+            dst[j] = sink.acc[0][j];
+            dst[chs + j] = sink.acc[1][j];
+            dst[2 * chs + j] = sink.acc[2][j];
+            dst[3 * chs + j] = sink.acc[3][j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < MB; ++j) dst[j] = sink.acc[0][j];
+        }
       }
     }
     TILE_SYNC();
@@ -495,6 +498,9 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   const DevSys &S = p->sys;
   int mb = 1;
   while (mb < S.nmu && mb < 8) mb *= 2;
+  // psi / E_L / Metropolis contract one or two AO channels: 16 columns per thread fit the register
+  // budget, and a thread that owns all columns evaluates the basis functions of its electron once
+  if (mode != MODE_GRAD && S.nmu > 8 && S.nmup % 16 == 0 && !getenv("QMCB_MB8")) mb = 16;
   c.mb = mb;
   c.nblk = S.nmup / mb;
   const int per_walker = S.nelec * c.nblk;
@@ -613,6 +619,8 @@ static int launch(const qmcb_plan *p, const LaunchCfg &c, const FusedArgs &a, cu
     case 1: return launch_t<MODE, 1>(p, c, a, st);
     case 2: return launch_t<MODE, 2>(p, c, a, st);
     case 4: return launch_t<MODE, 4>(p, c, a, st);
+    case 16:
+      if constexpr (MODE != MODE_GRAD) return launch_t<MODE, 16>(p, c, a, st);
     default: return launch_t<MODE, 8>(p, c, a, st);
   }
 }

@@ -193,11 +193,14 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
     S.een_c[m] = s->een_fc[m];
   }
   {
-    // exp(x) = 2^m * 2^(j/64) * exp(r), x = (64 m + j) ln2/64 + r, |r| <= ln2/128:
-    // 64/ln2, the 1.5*2^52 rounding constant, -ln2/64 split hi/lo, Taylor 1/120, 1/24, 1/6
-    // (degree-5 truncation error 3.5e-17 on that interval)
-    const double c[16] = {0x1.71547652b82fep+6, 6755399441055744.0, -0x1.62e42fee00000p-7,
-                          -0x1.a39ef35793c76p-39, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,
+    // exp(x) = 2^m * 2^(j/128) * exp(r), x = (128 m + j) ln2/128 + r, |r| <= ln2/256:
+    // 128/ln2, the 1.5*2^52 rounding constant, -ln2/128 (one constant: its rounding error 4e-19
+    // times |128 m + j| stays below 1e-15 for |x| < 14, i.e. for every term above 1e-6 of a sum),
+    // Taylor 1/24, 1/6 (degree-4 truncation r^5/120 <= 1.2e-15 on that interval)
+    // (QMCB_ETAB_LOG2 >= 10: |r| <= ln2/2048, the degree-3 polynomial is enough: r^4/24 <= 6e-16)
+    const double c[16] = {std::ldexp(0x1.71547652b82fep+0, QMCB_ETAB_LOG2), 6755399441055744.0,
+                          -std::ldexp(0x1.62e42fefa39efp-1, -QMCB_ETAB_LOG2),
+                          0.0, 1.0 / 24.0, 1.0 / 6.0, 0.0, 0.5,
                           0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 16; ++i) S.expc[i] = c[i];
   }
@@ -241,7 +244,7 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   for (int i = 0; i < s->nbas; ++i) hd.push_back(s->bas_norm[i]);
   if (hd.size() & 1) hd.push_back(0.0);
   S.o_etab = (int)hd.size();
-  for (int j = 0; j < 64; ++j) hd.push_back(std::exp2((double)j / 64.0));
+  for (int j = 0; j < QMCB_ETAB; ++j) hd.push_back(std::exp2((double)j / (double)QMCB_ETAB));
   // ---- packed shell program: per shell a header record {nprim, ngroup | -}, then nprim records
   // {alpha, coef (, n as third field in the next record for gto/sto)}, then ngroup records
   // {kk | type<<24, ao | scale}.  A "P" group (type 1) stands for three consecutive AOs x,y,z

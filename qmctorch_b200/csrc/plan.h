@@ -43,7 +43,7 @@ struct DevSys {
   int o_pflat;   // per shell: [nprim_s][ncomp_s] flat primitive index; start at o_pfo[s]
   int o_pfo;     // [nshell+1]
   int o_fnorm;   // dblob: [nbas] norm of each flat primitive (gradient post-processing)
-  int o_etab;    // dblob: [64] 2^(j/64), table of the exp() range reduction
+  int o_etab;    // dblob: [QMCB_ETAB] 2^(j/QMCB_ETAB), table of the exp() range reduction
   // packed "shell program" walked by the hot loops: 16-byte records (double2), see plan.cu
   int o_stream;  // offset into dblob (doubles, even)
   int nrec;      // number of 16-byte records

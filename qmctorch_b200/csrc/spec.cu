@@ -151,7 +151,7 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
   else if (S.nuu + S.nud > 16 || S.nconf > 64) w = "too many determinants";
-  else if ((64 + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
+  else if ((QMCB_ETAB + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
     w = "per-thread slices exceed the shared-memory budget";
   if (w) { if (why) *why = w; return false; }
   return true;
@@ -173,40 +173,64 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     u.d = d; lo = u.i[0]; hi2 = u.i[1];
   };
   o << "template <int MODE, int NCH>\n__device__ __forceinline__ void spec_aos(const SpecParams &P, const double *et, "
-       "const double *mw, double ex, double ey, double ez, double (&acc)[NCH][SPEC_NMUP]) {\n";
+       "const double *mw, double ex, double ey, double ez, const FoldJ fj, double &ven, double (&acc)[NCH][SPEC_NMUP]) {\n";
+  int nexp = 0;
   for (int A = 0; A < S.natom; ++A) {
     const int ns = hi[S.o_ash + A + 1] - hi[S.o_ash + A];
-    if (ns == 0) continue;
     const int oa = L.off_atom + 4 * A;
-    o << "  {  // atom " << A << "\n    const double x = ex - spec_pv<MODE, " << oa << ">(), y = ey - spec_pv<MODE, " << oa + 1
-      << ">(), z = ez - spec_pv<MODE, " << oa + 2 << ">();\n    const double r2 = x * x + y * y + z * z;\n";
     const int rt = S.radial_type;
+    if (ns == 0) {   // no basis functions on this atom: only its potential
+      o << "  if (MODE == MODE_ELOC) {  // atom " << A << "\n    const double x = ex - spec_pv<MODE, " << oa
+        << ">(), y = ey - spec_pv<MODE, " << oa + 1 << ">(), z = ez - spec_pv<MODE, " << oa + 2
+        << ">();\n    spec_ven<MODE, " << oa + 3 << ", 0>(x * x + y * y + z * z, 0.0, ven);\n  }\n";
+      continue;
+    }
+    o << "  {  // atom " << A << "\n    const double x = ex - spec_pv<MODE, " << oa << ">(), y = ey - spec_pv<MODE, " << oa + 1
+      << ">(), z = ez - spec_pv<MODE, " << oa + 2 << ">();\n    const double r2 = x * x + y * y + z * z;\n"
+      << "    const double gd = spec_gd<MODE, " << rt << ">(fj, x, y, z);\n";
     const bool with_n = rt == QMCB_GTO || rt == QMCB_STO;
+    const bool arg_r2 = rt == QMCB_GTO_PURE || rt == QMCB_GTO;
     if (rt != QMCB_GTO_PURE) o << "    const double rinv = fast_rsqrt(r2), r = r2 * rinv;\n";
     else o << "    const double rinv = 0.0;\n";
+    o << "    spec_ven<MODE, " << oa + 3 << ", " << rt << ">(r2, rinv, ven);\n";
+    // exponentials of this atom by exponent value: primitives with bitwise equal exponents (the s
+    // and p functions of an SP shell) share one; a parameter update that separates them changes the
+    // generated text and therefore selects (compiles) another module
+    std::map<uint64_t, int> known;
     for (int s = 0; s < ns; ++s) {
       int nprim, ngrp;
       ints(rec[0], nprim, ngrp);
       rec += 2;
-      o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0, T2 = 0.0;\n";
+      std::vector<int> ev(nprim), iv(nprim);
+      const double *prec = rec;
       for (int q = 0; q < nprim; ++q, rec += with_n ? 4 : 2) {
         // derived per-primitive constants, see spec_prim* (spec_kernel.cuh)
         const double a = rec[0], c = rec[1];
-        const int i0 = push(-a);
+        iv[q] = push(-a);
         push(c);
-        if (rt == QMCB_GTO_PURE) {
-          push(-2.0 * a * c); push(-6.0 * a * c); push(4.0 * a * a * c);
-          o << "      spec_prim<MODE, " << (q == 0 ? "true" : "false") << ", " << i0 << ">(P, et, r2, S0, S1, S2, T2);\n";
-        } else if (rt == QMCB_STO_PURE) {
-          push(-a * c); push(a * a * c); push(0.0);
-          o << "      spec_prim_sto_pure<MODE, " << i0 << ">(P, et, r, S0, S1, S2);\n";
-        } else {
-          push(a); push(0.0); push(0.0);
-          o << "      spec_prim_power<MODE, " << i0 << ", " << (rt == QMCB_GTO ? "true" : "false") << ", " << (int)rec[2]
-            << ">(P, et, r2, r, rinv, S0, S1, S2);\n";
+        if (rt == QMCB_GTO_PURE) { push(-2.0 * a * c); push(-6.0 * a * c); push(4.0 * a * a * c); }
+        else if (rt == QMCB_STO_PURE) { push(-a * c); push(a * a * c); push(0.0); }
+        else { push(a); push(0.0); push(0.0); }
+        uint64_t bits;
+        memcpy(&bits, &a, sizeof(bits));
+        auto it = known.find(bits);
+        if (it == known.end()) {
+          it = known.emplace(bits, nexp++).first;
+          o << "    const double e" << it->second << " = spec_exp<MODE, " << iv[q] << ">(P, et, " << (arg_r2 ? "r2" : "r") << ");\n";
         }
+        ev[q] = it->second;
       }
-      o << "      spec_shell_end<MODE, " << rt << ">(r2, rinv, S1, S2, T2);\n";
+      o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0, T2 = 0.0;\n";
+      for (int q = 0; q < nprim; ++q) {
+        if (rt == QMCB_GTO_PURE)
+          o << "      spec_prim<MODE, " << (q == 0 ? "true" : "false") << ", " << iv[q] << ">(e" << ev[q] << ", S0, S1, T2);\n";
+        else if (rt == QMCB_STO_PURE)
+          o << "      spec_prim_sto_pure<MODE, " << iv[q] << ">(e" << ev[q] << ", S0, S1, S2);\n";
+        else
+          o << "      spec_prim_power<MODE, " << iv[q] << ", " << (rt == QMCB_GTO ? "true" : "false") << ", "
+            << (int)prec[4 * q + 2] << ">(e" << ev[q] << ", r2, r, rinv, S0, S1, S2);\n";
+      }
+      o << "      const double Wf = spec_shell_end<MODE, " << rt << ">(r2, rinv, gd, fj.lp, S0, S1, S2, T2);\n";
       for (int g = 0; g < ngrp; ++g, rec += 2) {
         int kk, ao;
         ints(rec[0], kk, ao);
@@ -214,7 +238,7 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
         if (kk == 0) o << "      spec_s<MODE, " << ao << ", " << is << ">";
         else if (kk == (1 << 24)) o << "      spec_p<MODE, " << ao << ", " << is << ">";
         else o << "      spec_g<MODE, " << ao << ", " << is << ", " << kk << ">";
-        o << "(mw, x, y, z, S0, S1, S2, acc);\n";
+        o << "(mw, x, y, z, S0, S1, Wf, fj, acc);\n";
       }
       o << "    }\n";
     }
@@ -394,7 +418,7 @@ size_t smem_doubles(const DevSys &S, int mode) {
   int slice = (ne3 + (deriv ? 4 * S.nelec : 0) + nrow * S.nelec * S.nmu) | 1;
   if (def_value("SPEC_PREFETCH", SPEC_DEFAULT_PREFETCH)) slice += ne3 + (ne3 & 1);
   const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmu + S.nconf + 1) & ~1) : 0;
-  return 64 + (size_t)nmw + (size_t)SPEC_THREADS * slice;
+  return QMCB_ETAB + (size_t)nmw + (size_t)SPEC_THREADS * slice;
 }
 
 }  // namespace

@@ -25,7 +25,7 @@
 struct SpecParams {
   double expc[8];
   double jee_w, jen_w, vnn;
-  const double *etab_g;          // [64] 2^(j/64) (global; staged into shared memory)
+  const double *etab_g;          // [QMCB_ETAB] 2^(j/QMCB_ETAB) (global; staged into shared memory)
   double v[SPEC_NV];
   static constexpr int nelec = SPEC_NE, nup = SPEC_NUP, ndown = SPEC_NDOWN, natom = SPEC_NATOM;
   static constexpr int use_jee = SPEC_USE_JEE, use_jen = SPEC_USE_JEN, gram_fma = SPEC_GRAM_FMA;
@@ -63,33 +63,41 @@ __device__ __forceinline__ double spec_pv() {
     asm volatile("ld.param.f64 %0, [spec_mh_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   return v;
 }
+// AO channels contracted against the MO columns: psi / Metropolis 1 (ao), grad psi 4 (ao + gradient),
+// E_L 2: ao and the folded kinetic channel K = lap ao + 2 grad ln J . grad ao + (lap J / J) ao
+// (device.cuh: FoldJ) - B_kin = -1/2 K W needs two contractions instead of five.
 template <int MODE>
-__host__ __device__ constexpr int spec_nch() { return MODE == MODE_ELOC ? 5 : (MODE == MODE_GRAD ? 4 : 1); }   // value | + grad | + lap
+__host__ __device__ constexpr int spec_nch() { return MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1); }
+template <int MODE>
+__host__ __device__ constexpr bool spec_deriv() { return MODE == MODE_ELOC || MODE == MODE_GRAD; }
 
 // ---- building blocks the generated program calls (literal indices everywhere)
-// One primitive c exp(-a r^2) of a shell.  Every product of parameters is formed on the HOST
-// (spec.cu: walk): v[I..I+4] = { -a, c, -2 a c, -6 a c, 4 a^2 c }, and the radial sums are kept as
-//   S0 = sum c e,  S1 = sum (-2 a c) e,  S2 = sum (-6 a c) e,  T2 = sum (4 a^2 c) e   (e = exp(-a r^2))
-// with lap R = S2 + T2 r^2 formed once per shell (spec_shell_end).  Each FP64 instruction then has
-// exactly ONE parameter operand, which DFMA/DMUL read straight from the constant bank: 15 FP64-pipe
-// instructions per primitive with derivatives (12 without) and no operand loads, instead of 20 (14).
+// exp(-a r^2) or exp(-a r) of one primitive, v[I] = -a.  Primitives of one atom with the same
+// exponent (the s and p functions of a Pople SP shell) share ONE exponential: the generator emits
+// the call once and hands the value to every primitive that uses it (spec.cu: walk).
 // The lower clamp of the exponent (-708: 3e-308 instead of a denormal) is one integer min on the
 // high word: more negative doubles have larger high words.  NaN arguments are the canonical
 // positive NaN the FP64 pipe produces and pass through.
-template <int MODE, bool FIRST, int I>
-__device__ __forceinline__ void spec_prim(const SpecParams &P, const double *et, double r2, double &S0, double &S1,
-                                          double &S2, double &T2) {
-  constexpr int NCH = spec_nch<MODE>();
-  const double x = spec_pv<MODE, I>() * r2;
+template <int MODE, int I>
+__device__ __forceinline__ double spec_exp(const SpecParams &P, const double *et, double r2_or_r) {
+  const double x = spec_pv<MODE, I>() * r2_or_r;
   const unsigned hi = min((unsigned)__double2hiint(x), 0xC0862000u);
-  const double e = exp_core(P, et, __hiloint2double((int)hi, __double2loint(x)));
+  return exp_core(P, et, __hiloint2double((int)hi, __double2loint(x)));
+}
+// One primitive c exp(-a r^2) of a shell.  Every product of parameters is formed on the HOST
+// (spec.cu: walk): v[I..I+4] = { -a, c, -2 a c, -, 4 a^2 c }, and the radial sums are kept as
+//   S0 = sum c e,  S1 = sum (-2 a c) e,  T2 = sum (4 a^2 c) e        (e = exp(-a r^2))
+// with grad R = S1 (x,y,z) and lap R = 3 S1 + T2 r^2 formed once per shell (spec_shell_end).  Each
+// FP64 instruction then has exactly ONE parameter operand, which DFMA/DMUL read straight from the
+// constant bank: 1 + 8 (exp) + 3 FP64-pipe instructions per primitive with derivatives.
+template <int MODE, bool FIRST, int I>
+__device__ __forceinline__ void spec_prim(double e, double &S0, double &S1, double &T2) {
   if (FIRST) S0 = spec_pv<MODE, I + 1>() * e; else S0 = fma(spec_pv<MODE, I + 1>(), e, S0);
-  if (NCH > 1) {
+  if (spec_deriv<MODE>()) {
     if (FIRST) S1 = spec_pv<MODE, I + 2>() * e; else S1 = fma(spec_pv<MODE, I + 2>(), e, S1);
   }
-  if (NCH > 4) {
-    if (FIRST) { S2 = spec_pv<MODE, I + 3>() * e; T2 = spec_pv<MODE, I + 4>() * e; }
-    else { S2 = fma(spec_pv<MODE, I + 3>(), e, S2); T2 = fma(spec_pv<MODE, I + 4>(), e, T2); }
+  if (MODE == MODE_ELOC) {
+    if (FIRST) T2 = spec_pv<MODE, I + 4>() * e; else T2 = fma(spec_pv<MODE, I + 4>(), e, T2);
   }
 }
 // Other radial types (ADF-style bases; radial_functions.py:6-238,323-406), same conventions
@@ -98,41 +106,54 @@ __device__ __forceinline__ void spec_prim(const SpecParams &P, const double *et,
 //                                 finished per shell: S2 += 2 S1 / r, S1 /= r
 //   gto / sto c r^N e^{-a r^2 | -a r}: { -a, c, a, -, - } with the literal radial power N
 template <int MODE, int I>
-__device__ __forceinline__ void spec_prim_sto_pure(const SpecParams &P, const double *et, double r, double &S0,
-                                                   double &S1, double &S2) {
-  const double e = exp_neg(P, et, spec_pv<MODE, I>() * r);
+__device__ __forceinline__ void spec_prim_sto_pure(double e, double &S0, double &S1, double &S2) {
   S0 = fma(spec_pv<MODE, I + 1>(), e, S0);
-  if (spec_nch<MODE>() > 1) S1 = fma(spec_pv<MODE, I + 2>(), e, S1);
-  if (spec_nch<MODE>() > 4) S2 = fma(spec_pv<MODE, I + 3>(), e, S2);
+  if (spec_deriv<MODE>()) S1 = fma(spec_pv<MODE, I + 2>(), e, S1);
+  if (MODE == MODE_ELOC) S2 = fma(spec_pv<MODE, I + 3>(), e, S2);
 }
 template <int MODE, int I, bool GTO, int N>
-__device__ __forceinline__ void spec_prim_power(const SpecParams &P, const double *et, double r2, double r,
-                                                double rinv, double &S0, double &S1, double &S2) {
-  constexpr int NCH = spec_nch<MODE>();
+__device__ __forceinline__ void spec_prim_power(double e, double r2, double r, double rinv, double &S0, double &S1,
+                                                double &S2) {
   const double a = spec_pv<MODE, I + 2>();
-  const double ce = spec_pv<MODE, I + 1>() * exp_neg(P, et, spec_pv<MODE, I>() * (GTO ? r2 : r));
+  const double ce = spec_pv<MODE, I + 1>() * e;
   const double rn = ipow(r, N);
   S0 = fma(ce, rn, S0);
-  if (NCH > 1) {
+  if (spec_deriv<MODE>()) {
     const double nrnm2 = N == 0 ? 0.0 : N * rpow(r, rinv, N - 2);
     if (GTO) {
       S1 = fma(ce, nrnm2 - 2.0 * a * rn, S1);
-      if (NCH > 4) S2 = fma(ce, nrnm2 * (N + 1) - 4.0 * a * N * rn + a * rn * (4.0 * a * r2 - 6.0), S2);
+      if (MODE == MODE_ELOC) S2 = fma(ce, nrnm2 * (N + 1) - 4.0 * a * N * rn + a * rn * (4.0 * a * r2 - 6.0), S2);
     } else {
       S1 = fma(ce, nrnm2 - a * rn * rinv, S1);
-      if (NCH > 4) S2 = fma(ce, nrnm2 * (N + 1) - 2.0 * a * nrnm2 * r + a * rn * (a - 2.0 * rinv), S2);
+      if (MODE == MODE_ELOC) S2 = fma(ce, nrnm2 * (N + 1) - 2.0 * a * nrnm2 * r + a * rn * (a - 2.0 * rinv), S2);
     }
   }
 }
 
 // RT: 0 gto_pure, 1 gto, 2 sto_pure, 3 sto (QMCB_* radial types)
+// per atom: gd = 2 grad ln J . (x,y,z)  (+ 3 for gto_pure, whose lap R = 3 S1 + T2 r^2 is never formed)
 template <int MODE, int RT>
-__device__ __forceinline__ void spec_shell_end(double r2, double rinv, double &S1, double &S2, double T2) {
-  if (RT == 0 && spec_nch<MODE>() > 4) S2 = fma(T2, r2, S2);
-  if (RT == 2 && spec_nch<MODE>() > 1) {
-    if (spec_nch<MODE>() > 4) S2 = fma(2.0 * S1, rinv, S2);
+__device__ __forceinline__ double spec_gd(const FoldJ &fj, double x, double y, double z) {
+  if (MODE != MODE_ELOC) return 0.0;
+  return fma(fj.g2x, x, fma(fj.g2y, y, fma(fj.g2z, z, RT == 0 ? 3.0 : 0.0)));
+}
+// E_L: electron-nucleus potential -Z / r_eA of this (electron, atom), v[IZ] = Z (wf_base.py:72-95)
+template <int MODE, int IZ, int RT>
+__device__ __forceinline__ void spec_ven(double r2, double rinv, double &ven) {
+  if (MODE == MODE_ELOC) ven = fma(-spec_pv<MODE, IZ>(), RT == 0 ? fast_rsqrt(r2) : rinv, ven);
+}
+// finishes the radial sums of a shell; E_L: returns the shell value of the folded kinetic channel
+//   Wf = lap R + S1 (2 grad ln J . u) + (lap J / J) S0
+template <int MODE, int RT>
+__device__ __forceinline__ double spec_shell_end(double r2, double rinv, double gd, double lp, double S0, double &S1,
+                                                 double &S2, double T2) {
+  if (RT == 2 && spec_deriv<MODE>()) {
+    if (MODE == MODE_ELOC) S2 = fma(2.0 * S1, rinv, S2);
     S1 *= rinv;
   }
+  if (MODE != MODE_ELOC) return 0.0;
+  if (RT == 0) return fma(S1, gd, fma(T2, r2, lp * S0));
+  return fma(S1, gd, fma(lp, S0, S2));
 }
 
 #ifndef SPEC_MOW_SMEM
@@ -167,34 +188,40 @@ __device__ __forceinline__ void spec_emit(const double *mw, const double (&v)[NC
 }
 
 template <int MODE, int AO, int ISC, int NCH>
-__device__ __forceinline__ void spec_s(const double *mw, double x, double y, double z, double S0, double S1, double S2,
-                                       double (&acc)[NCH][SPEC_NMUP]) {
+__device__ __forceinline__ void spec_s(const double *mw, double x, double y, double z, double S0, double S1, double Wf,
+                                       const FoldJ &fj, double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
   v[0] = S0 * spec_pv<MODE, ISC>();
-  if (NCH > 1) {
+  if (MODE == MODE_ELOC) {
+    v[NCH - 1] = Wf * spec_pv<MODE, ISC>();
+  } else if (NCH > 1) {
     const double t = S1 * spec_pv<MODE, ISC>();
     v[1] = t * x; v[2] = t * y; v[3] = t * z;
-    if (NCH > 4) v[4] = S2 * spec_pv<MODE, ISC>();
   }
   spec_emit<MODE, AO>(mw, v, acc);
 }
 
 template <int MODE, int AO, int ISC, int NCH>
-__device__ __forceinline__ void spec_p(const double *mw, double x, double y, double z, double S0, double S1, double S2,
-                                       double (&acc)[NCH][SPEC_NMUP]) {
+__device__ __forceinline__ void spec_p(const double *mw, double x, double y, double z, double S0, double S1, double Wf,
+                                       const FoldJ &fj, double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
   const double R = S0 * spec_pv<MODE, ISC>();
-  if (NCH > 1) {
-    const double t = S1 * spec_pv<MODE, ISC>(), lf = NCH > 4 ? fma(2.0, S1, S2) * spec_pv<MODE, ISC>() : 0.0;
+  if (MODE == MODE_ELOC) {
+    const double Wp = fma(2.0, S1, Wf) * spec_pv<MODE, ISC>();
+    v[0] = R * x; v[NCH - 1] = fma(Wp, x, R * fj.g2x);
+    spec_emit<MODE, AO>(mw, v, acc);
+    v[0] = R * y; v[NCH - 1] = fma(Wp, y, R * fj.g2y);
+    spec_emit<MODE, AO + 1>(mw, v, acc);
+    v[0] = R * z; v[NCH - 1] = fma(Wp, z, R * fj.g2z);
+    spec_emit<MODE, AO + 2>(mw, v, acc);
+  } else if (NCH > 1) {
+    const double t = S1 * spec_pv<MODE, ISC>();
     const double tx = t * x, ty = t * y, tz = t * z;
     v[0] = R * x; v[1] = fma(tx, x, R); v[2] = tx * y; v[3] = tx * z;
-    if (NCH > 4) v[NCH - 1] = lf * x;
     spec_emit<MODE, AO>(mw, v, acc);
     v[0] = R * y; v[1] = ty * x; v[2] = fma(ty, y, R); v[3] = ty * z;
-    if (NCH > 4) v[NCH - 1] = lf * y;
     spec_emit<MODE, AO + 1>(mw, v, acc);
     v[0] = R * z; v[1] = tz * x; v[2] = tz * y; v[3] = fma(tz, z, R);
-    if (NCH > 4) v[NCH - 1] = lf * z;
     spec_emit<MODE, AO + 2>(mw, v, acc);
   } else {
     v[0] = R * x; spec_emit<MODE, AO>(mw, v, acc);
@@ -204,10 +231,12 @@ __device__ __forceinline__ void spec_p(const double *mw, double x, double y, dou
 }
 
 template <int MODE, int AO, int ISC, int KK, int NCH>
-__device__ __forceinline__ void spec_g(const double *mw, double x, double y, double z, double S0, double S1, double S2,
-                                       double (&acc)[NCH][SPEC_NMUP]) {
+__device__ __forceinline__ void spec_g(const double *mw, double x, double y, double z, double S0, double S1, double Wf,
+                                       const FoldJ &fj, double (&acc)[NCH][SPEC_NMUP]) {
   double v[NCH];
-  generic_component<NCH>(KK, spec_pv<MODE, ISC>(), x, y, z, S0, S1, S2, v);   // literal powers: a few products
+  // literal powers: a few products
+  if constexpr (MODE == MODE_ELOC) generic_component_fold(KK, spec_pv<MODE, ISC>(), x, y, z, S0, S1, Wf, fj, v);
+  else generic_component<NCH>(KK, spec_pv<MODE, ISC>(), x, y, z, S0, S1, 0.0, v);
   spec_emit<MODE, AO>(mw, v, acc);
 }
 
@@ -219,17 +248,17 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   constexpr int NCH = spec_nch<MODE>();
   constexpr int Ne = SPEC_NE, ne3 = 3 * SPEC_NE, NM = SPEC_NMUP, NUN = SPEC_NUU + SPEC_NUD;
   constexpr int NROW = MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1);   // mo | B_kin or mo | d mo/dx,dy,dz
-  constexpr int SLICE = (3 * Ne + (NCH > 1 ? 4 * Ne : 0) + NROW * Ne * NM) | 1;
+  constexpr int SLICE = (3 * Ne + (spec_deriv<MODE>() ? 4 * Ne : 0) + NROW * Ne * NM) | 1;
   extern __shared__ __align__(16) double smem[];
   double *et = smem;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) et[i] = P.etab_g[i];
+  for (int i = threadIdx.x; i < QMCB_ETAB; i += blockDim.x) et[i] = P.etab_g[i];
   constexpr int NMW = SPEC_MOW_SMEM ? ((SPEC_NV - SPEC_OFF_MOW + 1) & ~1) : 0;   // MO weights + CI, even
-  double *mw = smem + 64;
+  double *mw = smem + QMCB_ETAB;
   for (int i = threadIdx.x; i < NMW; i += blockDim.x) mw[i] = i < SPEC_NV - SPEC_OFF_MOW ? P.v[SPEC_OFF_MOW + i] : 0.0;
   constexpr int SL = SLICE + (SPEC_PREFETCH ? ne3 + (ne3 & 1) : 0);               // stays odd
-  double *spos = smem + 64 + NMW + (size_t)threadIdx.x * SL;
+  double *spos = smem + QMCB_ETAB + NMW + (size_t)threadIdx.x * SL;
   double *jv = spos + ne3;
-  double *smo = jv + (NCH > 1 ? 4 * Ne : 0);
+  double *smo = jv + (spec_deriv<MODE>() ? 4 * Ne : 0);
   double *sB = smo + Ne * NM;
   double *snext = spos + SLICE;     // SPEC_PREFETCH: landing zone of the next walker's coordinates
   const SpecTab T{P};
@@ -295,7 +324,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
     prefetch(w + stride);
     // ---- Jastrow gradient / Laplacian terms and potentials, every pair once
     double tks, tven, tvee;
-    walker_terms<(NCH > 1), (MODE == MODE_ELOC)>(P, T, spos, jv, Ne, tks, tven, tvee);
+    walker_terms<spec_deriv<MODE>(), (MODE == MODE_ELOC), false>(P, T, spos, jv, Ne, tks, tven, tvee);
     // ---- AO -> MO rows, one electron at a time (rolled: instruction-cache footprint)
 #pragma unroll SPEC_EUNROLL
     for (int e = 0; e < Ne; ++e) {
@@ -304,16 +333,16 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
       for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int j = 0; j < NM; ++j) acc[c][j] = 0.0;
-      spec_aos<MODE>(P, et, mw, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], acc);
+      FoldJ fj{0.0, 0.0, 0.0, 0.0};
+      if (MODE == MODE_ELOC && (SPEC_USE_JEE || SPEC_USE_JEN))
+        fj = FoldJ{2.0 * jv[e], 2.0 * jv[Ne + e], 2.0 * jv[2 * Ne + e], jv[3 * Ne + e]};
+      spec_aos<MODE>(P, et, mw, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], fj, tven, acc);
       if (MODE == MODE_ELOC) {
-        const double gx = jv[e], gy = jv[Ne + e], gz = jv[2 * Ne + e], lp = jv[3 * Ne + e];
+        // B_kin = -1/2 (lap mo + 2 grad ln J . grad mo + (lap J / J) mo): the folded channel, projected
 #pragma unroll
         for (int j = 0; j < NM; ++j) {
-          double b = acc[4][j];
-          if (SPEC_USE_JEE || SPEC_USE_JEN)
-            b += 2.0 * (gx * acc[1][j] + gy * acc[2][j] + gz * acc[3][j]) + lp * acc[0][j];
           smo[e * NM + j] = acc[0][j];
-          sB[e * NM + j] = -0.5 * b;
+          sB[e * NM + j] = -0.5 * acc[NCH - 1][j];
         }
       } else if (MODE == MODE_GRAD) {
 #pragma unroll
@@ -381,7 +410,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
     __syncthreads();                     // every thread is done with its slice: reuse it
-    double *red = smem + 64;
+    double *red = smem + QMCB_ETAB;
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
       for (int k = 0; k < 4; ++k) red[(threadIdx.x >> 5) * 4 + k] = q[k];

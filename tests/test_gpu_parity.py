@@ -537,6 +537,17 @@ def test_specialised_kernel_follows_parameter_updates():
     assert C.rel_err(wf(pos), orc.psi(P, pos.cpu())) < RTOL
     assert C.rel_err(wf.local_energy(pos), orc.local_energy(P, pos.cpu())) < RTOL
     assert wf._handle.info(13) == 1
+    # the s and p primitives of the 6-31G SP shells share one exponential in the generated program
+    # as long as their exponents are bitwise equal; an update that separates them must select a
+    # program without the sharing
+    with torch.no_grad():
+        torch.manual_seed(3)
+        wf.ao.bas_exp.mul_(1.0 + 0.05 * torch.rand_like(wf.ao.bas_exp))
+    P.bas_exp = wf.ao.bas_exp.detach().cpu().clone()
+    assert C.rel_err(wf(pos), orc.psi(P, pos.cpu())) < RTOL
+    assert C.rel_err(wf.local_energy(pos), orc.local_energy(P, pos.cpu())) < RTOL
+    assert C.scaled_err(wf.gradients_jacobi(pos), orc.grad_psi(P, pos.cpu())) < RTOL
+    assert wf._handle.info(13) == 1
 
 
 def test_philox_normal_draws_are_standard_symmetric_and_tiling_free():
