@@ -48,10 +48,26 @@ def algorithmic_flops(mol, wf, info):
     return ao + mo + bkin + jast + slater + 4 * wf.nci + 10
 
 
+def executed_flops(mol, wf, info):
+    """Same conventions, for the formulas the E_L kernels execute since the kinetic channel is folded
+    per AO: two projected channels instead of five, lap R from two radial sums,
+    every electron pair visited once in one-walker-per-thread kernels."""
+    ne, nat = mol.nelec, mol.natom
+    nprim, ncomp, nmu, nshell = info["nprim"], info["ncomp"], info["nmo_used"], info["nshell"]
+    npair = ne * (ne - 1) // 2
+    ao = ne * (nat * 14 + nprim * 8 + nshell * 6 + ncomp * 4)
+    mo = ne * ncomp * nmu * 2 * 2
+    jast = npair * 60 + ne * nat * 2
+    n = max(mol.nup, mol.ndown)
+    nun = info["nuniq_up"] + info["nuniq_down"]
+    slater = nun * (12 if n <= 2 else 4 * n ** 3)
+    return ao + mo + ne * nmu + jast + slater + 4 * wf.nci + 10
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the dominant
 # kernel, bytes per launch, keyed by (kernel, workload, walkers): profiles/r1_spec_ncu_raw.csv
 # (structure-specialised kernel) and profiles/r1_fused_ncu_raw.csv (generic kernel)
-NCU_TRAFFIC = {("spec_eloc", "lih", 1_000_000): 96.302080e6 + 7.425536e6,
+NCU_TRAFFIC = {("spec_eloc", "lih", 1_000_000): 96.305920e6 + 5.745920e6,
                ("fused_kernel<MODE_ELOC>", "lih", 1_000_000): 96.070912e6 + 5.570048e6}
 
 
@@ -217,8 +233,10 @@ def main():
                                              _lib.ptr(ws), sp), "local_energy_stats")
         if world > 1:
             dist.all_reduce(out4)
-    # one call = E_L kernel (+ fused per-CTA statistics when structure-specialised) + final reduction
-    launches_per_step = 2 if wf._handle.info(13) == 1 else 3
+    # one call = ONE kernel when structure-specialised (E_L with both statistics stages fused: the last
+    # CTA adds the partials); generic kernels: E_L + two statistics kernels
+    two_stage = os.environ.get("QMCB_STATS_2STAGE", "0") not in ("", "0")
+    launches_per_step = (2 if two_stage else 1) if wf._handle.info(13) == 1 else 3
 
     def barrier():
         if world > 1:
@@ -252,8 +270,7 @@ def main():
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
-    # event pairs around each qmcb_local_energy_stats call: the E_L kernel (with its fused statistics
-    # stage) plus the ~2 us final reduction kernel behind it (1 % of the pair, see profiles/ launch list)
+    # event pairs around each qmcb_local_energy_stats call: the E_L kernel with its fused statistics
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -339,7 +356,9 @@ def main():
         "roofline": {"bound": "fp64", "kernel": kernel_name, "achieved": achieved_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                      "peak_source": "own DFMA probe (qmcb_fp64_probe) on this GPU; MEASURED_PEAKS.json has no FP64 entry",
-                     "flops_per_eval": F, "kernel_ms": kern_ms, "traffic": NCU_TRAFFIC.get((kernel_name, args.workload, W)),
+                     "flops_per_eval": F, "flops_convention": "SURVEY 8(d): reference formulation, five projected "
+                     "AO channels, occupied MO columns only", "flops_executed_per_eval": executed_flops(mol, wf, info),
+                     "kernel_ms": kern_ms, "traffic": NCU_TRAFFIC.get((kernel_name, args.workload, W)),
                      "hbm": {"achieved_gbs": W * bytes_per_eval / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "bytes_per_eval": bytes_per_eval,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

@@ -29,5 +29,8 @@ struct FusedArgs {
   unsigned long long *naccept;
   // E_L: per-CTA partial statistics [gridDim.x][4] = sum, sum sq, n finite, n non-finite (or null)
   double *stats_part;
+  // with both set, the CTA that arrives last adds the partials in index order -> stats_out[4]
+  unsigned *stats_ticket;
+  double *stats_out;
 };
 

@@ -25,14 +25,19 @@ extern "C" int qmcb_local_energy_stats(const qmcb_plan *p, const double *pos, in
   FusedArgs a{};
   a.pos = pos; a.W = W; a.out0 = eloc; a.out1 = psi; a.out2 = ekin;
   a.stats_part = (double *)workspace;
+  // the last CTA of the specialised kernel finishes the reduction (grid <= SMs x CTAs per SM, far
+  // below QMCB_STATS_MAX_PARTIALS); QMCB_STATS_2STAGE=1 keeps the separate second-stage launch
+  static const bool two_stage = getenv("QMCB_STATS_2STAGE") && atoi(getenv("QMCB_STATS_2STAGE")) > 0;
+  if (!two_stage && (int64_t)p->sm_count * 16 <= QMCB_STATS_MAX_PARTIALS) { a.stats_ticket = p->d_ticket; a.stats_out = out4; }
   int grid = 0;
   rc = qmcb_spec_launch(p, MODE_ELOC, a, stream, &grid);
   if (rc == 0) {
+    if (a.stats_ticket) return 0;
     if (grid > QMCB_STATS_MAX_PARTIALS) { qmcb_set_error("qmcb_local_energy_stats: grid exceeds the workspace"); return QMCB_EINVAL; }
     return qmcb_stats_finish((const double *)workspace, grid, out4, stream);
   }
   if (rc != QMCB_SPEC_SKIP) return rc;
-  a.stats_part = nullptr;
+  a.stats_part = nullptr; a.stats_ticket = nullptr; a.stats_out = nullptr;
   rc = launch<MODE_ELOC>(p, p->cfg_eloc, a, (cudaStream_t)stream);
   if (rc) return rc;
   return qmcb_energy_stats(eloc, W, out4, workspace, stream);

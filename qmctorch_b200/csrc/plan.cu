@@ -359,10 +359,15 @@ static int upload(qmcb_plan *p) {
   size_t nt = p->bwd_tiles.size() * sizeof(int);
   if (nt > p->cap_bwd_tiles) {
     if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
+  if (p->d_ticket) cudaFree(p->d_ticket);
     if ((e = cudaMalloc(&p->d_bwd_tiles, nt)) != cudaSuccess) return (int)e;
     p->cap_bwd_tiles = nt;
   }
   if (nt && (e = cudaMemcpy(p->d_bwd_tiles, p->bwd_tiles.data(), nt, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  if (!p->d_ticket) {
+    if ((e = cudaMalloc(&p->d_ticket, 2 * sizeof(unsigned))) != cudaSuccess) return (int)e;
+    if ((e = cudaMemset(p->d_ticket, 0, 2 * sizeof(unsigned))) != cudaSuccess) return (int)e;
+  }
   p->sys.dblob = p->d_dbl;
   p->sys.iblob = p->d_int;
   return 0;

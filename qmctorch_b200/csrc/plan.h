@@ -95,6 +95,9 @@ struct qmcb_plan {
   // full MO matrix for the operator-level entry point
   double *d_mo_full = nullptr;
   size_t cap_mo_full = 0;
+  // arrival counter of the fused energy statistics (spec_eloc: the last CTA adds the partials);
+  // zero between launches (atomicInc wraps), so calls on one plan must be stream-ordered
+  unsigned *d_ticket = nullptr;
   // host copy of flat data needed by backward post-processing
   std::vector<int> index_ctr;
   std::vector<double> mo_full;

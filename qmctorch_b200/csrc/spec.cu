@@ -41,6 +41,7 @@ const int SPEC_THREADS = env_int("QMCB_SPEC_THREADS", 128);
 const int SPEC_MINB = env_int("QMCB_SPEC_MINB", 4);
 // defaults of the kernel's tuning switches (must match the #ifndef defaults in spec_kernel.cuh)
 constexpr int SPEC_DEFAULT_PREFETCH = 0;
+constexpr int SPEC_DEFAULT_PREFETCH_ELOC = 1;
 constexpr int SPEC_DEFAULT_MOW_SMEM = 0;
 constexpr size_t SPEC_SMEM_BUDGET = 100 * 1024;   // per CTA: at least two CTAs per SM
 constexpr int SPEC_MAX_VALUES = 448;   // doubles in the parameter block (keeps it under 4 KB)
@@ -151,7 +152,7 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
   else if (S.nuu + S.nud > 16 || S.nconf > 64) w = "too many determinants";
-  else if ((QMCB_ETAB + (size_t)SPEC_THREADS * ((7 * S.nelec + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
+  else if ((QMCB_ETAB + (size_t)SPEC_THREADS * ((10 * S.nelec + 1 + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
     w = "per-thread slices exceed the shared-memory budget";
   if (w) { if (why) *why = w; return false; }
   return true;
@@ -416,7 +417,9 @@ size_t smem_doubles(const DevSys &S, int mode) {
   const int nrow = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
   const int ne3 = 3 * S.nelec;
   int slice = (ne3 + (deriv ? 4 * S.nelec : 0) + nrow * S.nelec * S.nmu) | 1;
-  if (def_value("SPEC_PREFETCH", SPEC_DEFAULT_PREFETCH)) slice += ne3 + (ne3 & 1);
+  if (def_value("SPEC_PREFETCH", SPEC_DEFAULT_PREFETCH) ||
+      (mode == MODE_ELOC && def_value("SPEC_PREFETCH_ELOC", SPEC_DEFAULT_PREFETCH_ELOC)))
+    slice += ne3 + (ne3 & 1);
   const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmu + S.nconf + 1) & ~1) : 0;
   return QMCB_ETAB + (size_t)nmw + (size_t)SPEC_THREADS * slice;
 }

@@ -163,7 +163,10 @@ __device__ __forceinline__ double spec_shell_end(double r2, double rinv, double 
 #define SPEC_EUNROLL 1      // electrons per trip of the electron loop
 #endif
 #ifndef SPEC_PREFETCH
-#define SPEC_PREFETCH 0     // 1: cp.async the next walker's coordinates while this one is computed
+#define SPEC_PREFETCH 0     // 1: every kernel cp.asyncs the next walker's coordinates while this one is computed
+#endif
+#ifndef SPEC_PREFETCH_ELOC
+#define SPEC_PREFETCH_ELOC 1   // E_L kernel only (measured, LiH 1e6 walkers: 0.143 -> 0.137 ms; psi / Metropolis do not gain)
 #endif
 #ifndef SPEC_MINB_ELOC
 #define SPEC_MINB_ELOC 3     // E_L: 168 registers keep the electron loop free of spills (measured 0.199 -> 0.194 ms)
@@ -255,19 +258,20 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   constexpr int NMW = SPEC_MOW_SMEM ? ((SPEC_NV - SPEC_OFF_MOW + 1) & ~1) : 0;   // MO weights + CI, even
   double *mw = smem + QMCB_ETAB;
   for (int i = threadIdx.x; i < NMW; i += blockDim.x) mw[i] = i < SPEC_NV - SPEC_OFF_MOW ? P.v[SPEC_OFF_MOW + i] : 0.0;
-  constexpr int SL = SLICE + (SPEC_PREFETCH ? ne3 + (ne3 & 1) : 0);               // stays odd
+  constexpr bool PF = SPEC_PREFETCH || (MODE == MODE_ELOC && SPEC_PREFETCH_ELOC);
+  constexpr int SL = SLICE + (PF ? ne3 + (ne3 & 1) : 0);               // stays odd
   double *spos = smem + QMCB_ETAB + NMW + (size_t)threadIdx.x * SL;
   double *jv = spos + ne3;
   double *smo = jv + (spec_deriv<MODE>() ? 4 * Ne : 0);
   double *sB = smo + Ne * NM;
-  double *snext = spos + SLICE;     // SPEC_PREFETCH: landing zone of the next walker's coordinates
+  double *snext = spos + SLICE;     // PF: landing zone of the next walker's coordinates
   const SpecTab T{P};
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t wfirst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // cp.async (LDGSTS) copies one walker row global -> this thread's slice without registers
   auto prefetch = [&](int64_t wn) {
-    if (SPEC_PREFETCH && wn < a.W) {
+    if (PF && wn < a.W) {
       const unsigned dst = (unsigned)__cvta_generic_to_shared(snext);
       const double *src = a.pos + wn * ne3;
 #pragma unroll
@@ -279,7 +283,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   double st_s = 0.0, st_s2 = 0.0;     // fused energy statistics of this thread's walkers (E_L only)
   int st_nf = 0, st_nb = 0;
   for (int64_t w = wfirst; w < a.W; w += stride) {
-    if (SPEC_PREFETCH) asm volatile("cp.async.wait_all;" ::: "memory");
+    if (PF) asm volatile("cp.async.wait_all;" ::: "memory");
     // ---- coordinates (+ proposal)
     if (MODE == MODE_MH && !a.disp && a.proba_normal) {
       // one Philox call yields the four normals of a GLOBAL element quad (4q .. 4q+3): the draw of
@@ -298,7 +302,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
           const int64_t g = 4 * q + h;
           if (g < g0 || g >= g1) continue;
           const int i = (int)(g - g0), e = i / 3;
-          double v = SPEC_PREFETCH ? snext[i] : a.pos[g];
+          double v = PF ? snext[i] : a.pos[g];
           if (me < 0 || me == e) v += a.scale * z[h];
           spos[i] = v;
         }
@@ -311,7 +315,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
       }
 #pragma unroll
       for (int i = 0; i < ne3; ++i) {
-        double v = SPEC_PREFETCH ? snext[i] : a.pos[w * ne3 + i];
+        double v = PF ? snext[i] : a.pos[w * ne3 + i];
         if (MODE == MODE_MH && (me < 0 || me == i / 3)) {
           double d;
           if (a.disp) d = a.disp[w * ne3 + i];
@@ -419,6 +423,28 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
       double t = 0.0;
       for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) t += red[wq * 4 + threadIdx.x];
       a.stats_part[blockIdx.x * 4 + threadIdx.x] = t;
+    }
+    if (a.stats_ticket && a.stats_out) {
+      // second stage without a second launch: the CTA that arrives last adds the per-CTA partials
+      // in index order (one warp per quantity, lane-strided sums, fixed butterfly: the arithmetic
+      // of stats_stage2, bitwise the same result whichever CTA is last).  atomicInc wraps the
+      // counter back to zero for the next launch.
+      __shared__ int last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) last = atomicInc(a.stats_ticket, gridDim.x - 1) == gridDim.x - 1;
+      __syncthreads();
+      if (last) {
+        __threadfence();
+        const int lane = threadIdx.x & 31;
+        for (int q = threadIdx.x >> 5; q < 4; q += (int)(blockDim.x >> 5)) {
+          double s = 0.0;
+          for (int i = lane; i < (int)gridDim.x; i += 32) s += __ldcg(a.stats_part + i * 4 + q);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) a.stats_out[q] = s;
+        }
+      }
     }
   }
 }
