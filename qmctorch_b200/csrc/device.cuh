@@ -828,6 +828,72 @@ __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int
   tr_out = tr;
 }
 
+// Row-owner Gauss-Jordan for spin blocks of order n <= 16: TWO blocks per warp, one per half-warp.
+// Lane hl of a half owns ROW hl of [A | R]: A in a[0..15], R in r[0..15].  The pivot COLUMN k is a
+// compile-time loop index and the pivot ROW is a lane id, so no register is ever indexed dynamically
+// (the column-owner variant below pays a select chain per row access: a third of the C4H6 E_L
+// kernel, profiles/README.md).  Step k: arg-max |a[k]| over the rows not pivoted yet (four
+// xor-shuffle rounds, ties to the lower row); the pivot lane broadcasts its row UNSCALED and every
+// other row subtracts (a[k] / pivot) times it: two SHFL and one DFMA per element, no select.  Rows
+// are neither swapped nor normalised: lane p remembers the column it pivoted (kc) and its pivot
+// (pv); det = sign(kc) * prod pivots, and the lane with kc = k ends with pv * (row k of inv(A) R)
+// in r[] - the caller divides.  All shuffles use the full mask (width 16): both halves run the same
+// nmax = max order of the two blocks steps; a half whose block is smaller (or absent: n = 0) idles
+// through the extra steps with zero multipliers.
+template <bool WITH_R>
+__device__ __forceinline__ double half_warp_gauss_jordan(int n, int nmax, double (&a)[16], double (&r)[16], int hl,
+                                                         int &kc, double &ipiv) {
+  const unsigned full = 0xffffffffu;
+  double det = 1.0;
+  bool done = hl >= n;
+  kc = 16 + hl;                      // rows beyond n: distinct, above every real column
+  ipiv = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (k < nmax) {
+      const bool on = k < n;
+      double v = (done || !on) ? -1.0 : fabs(a[k]);
+      int l = hl;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(full, v, o, 16);
+        const int ol = __shfl_xor_sync(full, l, o, 16);
+        const bool take = ov > v || (ov == v && ol < l);
+        v = take ? ov : v;
+        l = take ? ol : l;
+      }
+      const int p = l;
+      const double pv = __shfl_sync(full, a[k], p, 16);
+      double ipv;                      // 1 / pivot (either sign; pv = 0: inf, as the exact division)
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ipv) : "d"(pv));
+      { const double e = fma(-pv, ipv, 1.0); ipv = fma(ipv, fma(e, e, e), ipv); }
+      { const double e = fma(-pv, ipv, 1.0); ipv = fma(ipv, e, ipv); }
+      const bool me = on && hl == p;
+      if (on) det *= pv;
+      const double f = (me || !on) ? 0.0 : a[k] * ipv;      // multiplier of this row
+#pragma unroll
+      for (int j = k + 1; j < 16; ++j)
+        if (j < nmax) a[j] = fma(-f, __shfl_sync(full, a[j], p, 16), a[j]);
+      if (WITH_R) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nmax) r[j] = fma(-f, __shfl_sync(full, r[j], p, 16), r[j]);
+      }
+      if (me) { done = true; kc = k; ipiv = ipv; }
+    }
+  }
+  // sign of the permutation row -> pivoted column: parity of the number of inversions
+  int inv = 0;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    const int oc = __shfl_sync(full, kc, o, 16);
+    inv += (o < hl && oc > kc) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) inv += __shfl_xor_sync(full, inv, o, 16);
+  return (inv & 1) ? -det : det;
+}
+
 // Register-resident warp Gauss-Jordan: lane j owns column j of [A | R] (n + nr <= 32, n <= NMAX),
 // rows are registers.  Per elimination step: lane k finds the pivot in its registers, the pivot
 // row index and the multipliers travel by warp shuffles - no shared-memory round trips.

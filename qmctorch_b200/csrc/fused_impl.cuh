@@ -71,6 +71,8 @@ __host__ __device__ inline bool use_warp_lu(const DevSys &S) {
   return (S.nup > S.ndown ? S.nup : S.ndown) >= QMCB_WARP_LU_MIN;
 }
 
+__host__ __device__ inline int mo_row_stride(const DevSys &S) { return S.nmup | 1; }
+
 __host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode, bool warp_tiles) {
   const int n = S.nup > S.ndown ? S.nup : S.ndown;
   if (mode == MODE_GRAD) return n <= 3 ? n * n : 2 * n * n;   // inverse kept ([A|I] for n>3)
@@ -84,7 +86,7 @@ __host__ __device__ inline int lu_scratch_per_item(const DevSys &S, int mode, bo
 __host__ __device__ inline size_t tile_doubles(const DevSys &S, int mode, int tw, int lu_conc, bool warp_tiles) {
   const int nchs_ = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
   const int nun = S.nuu + S.nud;
-  size_t d = (size_t)tw * 3 * S.nelec + (size_t)tw * S.nelec * 8 + (size_t)nchs_ * tw * S.nelec * S.nmup;
+  size_t d = (size_t)tw * 3 * S.nelec + (size_t)tw * S.nelec * 8 + (size_t)nchs_ * tw * S.nelec * mo_row_stride(S);
   d += 2 * (size_t)tw * nun + (size_t)tw * 4;
   d += (size_t)lu_conc * lu_scratch_per_item(S, mode, warp_tiles);
   return (d + 1) & ~(size_t)1;
@@ -133,6 +135,9 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
   Tab T;
   double *ws = stage_tables(S, smem, T);
   const int Ne = S.nelec, ne3 = 3 * Ne, nmup = S.nmup;
+  // row stride of the mo / B_kin rows in the work area: odd for shared tiles (threads of a warp own
+  // consecutive rows: conflict-free row writes and column reads); private slices keep nmup
+  const int ldm = THREAD ? nmup : mo_row_stride(S);
   const int nun = S.nuu + S.nud;
   const int nthr = THREAD ? 1 : (WARP ? 32 : (int)blockDim.x);
   const int tid = THREAD ? 0 : (WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x);
@@ -145,12 +150,12 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
   double *spos = ws;
   double *jv = spos + TW * ne3;
   double *smo = jv + (THREAD ? (NCH > 1 ? 4 * Ne : 0) : TW * Ne * 8);
-  double *sdet = smo + (size_t)NCHS * TW * Ne * nmup;
+  double *sdet = smo + (size_t)NCHS * TW * Ne * ldm;
   double *str = sdet + TW * nun;
   double *wsum = str + TW * nun;
   double *scr = wsum + TW * 4;
   const int64_t ntile = (a.W + TW - 1) / TW;
-  const size_t chs = (size_t)TW * Ne * nmup;
+  const size_t chs = (size_t)TW * Ne * ldm;
   const int jvs = TW * Ne;   // jv is stored [quantity][walker][electron]
   __syncthreads();
 #define TILE_SYNC() do { if (THREAD) {} else if (WARP) __syncwarp(); else __syncthreads(); } while (0)
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
       const double *sp = spos + wl * ne3 + 3 * e;
       MoSink<NCH, MB> sink;
       sink.init(T.mow() + blk * MB, nmup);
-      double *dst = smo + ((size_t)wl * Ne + e) * nmup + blk * MB;
+      double *dst = smo + ((size_t)wl * Ne + e) * ldm + blk * MB;
       if constexpr (MODE == MODE_ELOC) {
         // B_kin = -1/2 (lap mo + 2 grad ln J . grad mo + (lap J / J) mo), folded per AO
         const double *q = jv + wl * Ne + e;
@@ -261,54 +266,66 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
         // CTA tiles with blocks larger than 3x3: ONE WARP per spin block (warp_gauss_jordan);
         // scratch is contiguous per slot: slot = item (GRAD keeps every inverse) or the warp
         const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+        if ((S.nup > S.ndown ? S.nup : S.ndown) <= 16) {
+          // register-resident, TWO blocks per warp: lane hl of a half-warp owns row hl of [A | B]
+          // (or [A | I]); see half_warp_gauss_jordan
+          const int half = lane >> 4, hl = lane & 15;
+          const int nmax = S.nup > S.ndown ? S.nup : S.ndown;
+          for (int it0 = 2 * warp; it0 < nitem; it0 += 2 * nwarp) {
+            const int it = it0 + half;
+            const bool act = it < nitem;
+            const int wl = act ? it / nun : 0, u = act ? it - wl * nun : 0;
+            const bool up = u < S.nuu;
+            const int n = act ? (up ? S.nup : S.ndown) : 0;
+            const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
+            const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup) + hl) * ldm;
+            double a[16], r[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool in = hl < n && j < n;
+              const int c = in ? cols[j] : 0;
+              a[j] = in ? A[c] : 0.0;
+              r[j] = MODE == MODE_ELOC ? (in ? A[chs + c] : 0.0) : (j == hl ? 1.0 : 0.0);
+            }
+            int kc;
+            double ipiv;
+            const double det = half_warp_gauss_jordan<(MODE == MODE_ELOC || MODE == MODE_GRAD)>(n, nmax, a, r, hl, kc, ipiv);
+            double tr = 0.0;
+            if (MODE == MODE_ELOC) {
+              // Tr(inv(A) B): the row that pivoted column k holds pivot * element (k, k) in r[k]
+#pragma unroll
+              for (int j = 0; j < 16; ++j) tr = (j == kc) ? r[j] : tr;
+              tr *= ipiv;
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o, 16);
+            }
+            if (MODE == MODE_GRAD && kc < n) {
+              // the gradient phase reads inv(A) from the scratch: right block of [A | I], row kc
+              double *m = scr + (size_t)it * per + (size_t)kc * 2 * n + n;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < n) m[j] = r[j] * ipiv;
+            }
+            if (act && hl == 0) { sdet[wl * nun + u] = n > 0 ? det : 1.0; str[wl * nun + u] = tr; }
+          }
+          if (MODE == MODE_GRAD) __syncwarp();
+        } else
         for (int it = warp; it < nitem; it += nwarp) {
+          // blocks larger than 16x16: one warp per block on a shared-memory copy
           const int wl = it / nun, u = it - wl * nun;
           const bool up = u < S.nuu;
           const int n = up ? S.nup : S.ndown;
           const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
-          const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
+          const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * ldm;
           double *m = scr + (size_t)(MODE == MODE_GRAD ? it : warp) * per;
           const int nr = (MODE == MODE_ELOC || MODE == MODE_GRAD) ? n : 0;
           const int ldw = n + nr;
           double det = 1.0, tr = 0.0;
-          if (n > 0 && n <= 16) {
-            // register-resident: lane j owns column j of [A | B] (or [A | I])
-            double col[16];
-            const int jc = lane < n ? cols[lane] : (lane < ldw ? cols[lane - n] : 0);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              double v = 0.0;
-              if (i < n) {
-                if (lane < n) v = A[i * nmup + jc];
-                else if (lane < ldw) v = MODE == MODE_ELOC ? A[chs + i * nmup + jc] : (i == lane - n ? 1.0 : 0.0);
-              }
-              col[i] = v;
-            }
-            det = warp_gauss_jordan_reg<16>(n, col, lane);
-            if (MODE == MODE_ELOC) {
-              double v = 0.0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i == lane - n) v = col[i];          // diagonal element (i, i) of inv(A) B
-              if (lane < n || lane >= ldw) v = 0.0;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              tr = v;
-            }
-            if (MODE == MODE_GRAD) {
-              // the gradient phase reads inv(A) from the scratch: right block of [A | I]
-              if (lane >= n && lane < ldw) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i < n) m[i * ldw + lane] = col[i];
-              }
-              __syncwarp();
-            }
-          } else if (n > 0) {
+          if (n > 0) {
             for (int idx = lane; idx < n * n; idx += 32) {
               const int i = idx / n, j = idx - i * n;
-              m[i * ldw + j] = A[i * nmup + cols[j]];
-              if (MODE == MODE_ELOC) m[i * ldw + n + j] = A[chs + i * nmup + cols[j]];
+              m[i * ldw + j] = A[i * ldm + cols[j]];
+              if (MODE == MODE_ELOC) m[i * ldw + n + j] = A[chs + i * ldm + cols[j]];
               if (MODE == MODE_GRAD) m[i * ldw + n + j] = i == j ? 1.0 : 0.0;
             }
             __syncwarp();
@@ -335,38 +352,38 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
           const bool up = u < S.nuu;
           const int n = up ? S.nup : S.ndown;
           const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
-          const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
+          const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * ldm;
           double det = 1.0, tr = 0.0;
           if (n == 0) {
             det = 1.0; tr = 0.0;
           } else if (MODE == MODE_GRAD) {
             double *m = scr + it;   // element stride = conc
-            if (n <= 3) det = inverse_small(n, A, nmup, cols, m, conc);
+            if (n <= 3) det = inverse_small(n, A, ldm, cols, m, conc);
             else {
               const int ldw = 2 * n;
               for (int i = 0; i < n; ++i)
                 for (int j = 0; j < n; ++j) {
-                  m[(i * ldw + j) * conc] = A[i * nmup + cols[j]];
+                  m[(i * ldw + j) * conc] = A[i * ldm + cols[j]];
                   m[(i * ldw + n + j) * conc] = i == j ? 1.0 : 0.0;
                 }
               det = gauss_jordan(n, n, m, conc);
             }
           } else if (n <= 3) {
-            det_trace_small(n, A, A + chs, nmup, cols, MODE == MODE_ELOC, det, tr);
+            det_trace_small(n, A, A + chs, ldm, cols, MODE == MODE_ELOC, det, tr);
           } else if (TILE == 0 && n == 4) {   // CTA-tile kernels only: keeps calls out of the warp-tile kernels
-            det_trace_reg<4, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
+            det_trace_reg<4, MODE == MODE_ELOC>(A, A + chs, ldm, cols, det, tr);
           } else if (TILE == 0 && n == 5) {
-            det_trace_reg<5, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
+            det_trace_reg<5, MODE == MODE_ELOC>(A, A + chs, ldm, cols, det, tr);
           } else if (TILE == 0 && n == 6) {
-            det_trace_reg<6, MODE == MODE_ELOC>(A, A + chs, nmup, cols, det, tr);
+            det_trace_reg<6, MODE == MODE_ELOC>(A, A + chs, ldm, cols, det, tr);
           } else {
             double *m = scr + tid;
             const int nr = MODE == MODE_ELOC ? n : 0;
             const int ldw = n + nr;
             for (int i = 0; i < n; ++i)
               for (int j = 0; j < n; ++j) {
-                m[(i * ldw + j) * conc] = A[i * nmup + cols[j]];
-                if (nr) m[(i * ldw + n + j) * conc] = A[chs + i * nmup + cols[j]];
+                m[(i * ldw + j) * conc] = A[i * ldm + cols[j]];
+                if (nr) m[(i * ldw + n + j) * conc] = A[chs + i * ldm + cols[j]];
               }
             det = gauss_jordan(n, nr, m, conc);
             if (nr)
@@ -448,7 +465,7 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
         const int n = up ? S.nup : S.ndown;
         const int el = up ? e : e - S.nup;
         const double *dd = sdet + wl * nun;
-        const double *row = smo + ((size_t)wl * Ne + e) * nmup;
+        const double *row = smo + ((size_t)wl * Ne + e) * ldm;
         double gsx = 0, gsy = 0, gsz = 0;
         const int nu = up ? S.nuu : S.nud;
         for (int u = 0; u < nu; ++u) {

@@ -1,0 +1,5 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s7_gpu_tests.log
+( for w in "c4h6 20000" "h2o 100000" "lih 1000000"; do timeout 300 python tools/time_kernels.py $w 2>&1 | tail -1; done
+timeout 300 python tools/gpu_config4.py 2>&1 | tail -4 ) > gpurun_out/s7_time.log 2>&1
+timeout 300 python tools/gpu_check.py > gpurun_out/s7_check.log 2>&1
+tail -3 gpurun_out/s7_gpu_tests.log; cat gpurun_out/s7_time.log; tail -20 gpurun_out/s7_check.log
