@@ -397,9 +397,37 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
     }
     TILE_SYNC();
     // ---- P4: per-walker epilogue
+    // long CI expansions: the sum over configurations is split over `parts` threads per walker
+    // (strided configurations, partial sums added in part order: deterministic); the partials go
+    // to the rows of jv that P2 has consumed (grad psi still needs them: it keeps the serial sum)
+    int parts = 1;
+    if (!THREAD && MODE != MODE_GRAD && S.nconf >= 8) {
+      parts = nthr / TW;
+      if (parts > 2 * Ne) parts = 2 * Ne;
+      if (parts > 16) parts = 16;
+      if (parts < 1) parts = 1;
+    }
+    if (parts > 1) {
+      for (int it = tid; it < tw * parts; it += nthr) {
+        const int wl = it / parts, pt = it - wl * parts;
+        const double *dd = sdet + wl * nun, *tt = str + wl * nun;
+        double sig = 0.0, ksig = 0.0;
+        for (int c = pt; c < S.nconf; c += parts) {
+          const int iu = T.ciu()[c], id = S.nuu + T.cid()[c];
+          const double d = T.ci()[c] * dd[iu] * dd[id];
+          sig += d;
+          if (MODE == MODE_ELOC) ksig += d * (tt[iu] + tt[id]);
+        }
+        jv[2 * it] = sig; jv[2 * it + 1] = ksig;
+      }
+      TILE_SYNC();
+    }
     for (int wl = tid; wl < tw; wl += nthr) {
       const double *dd = sdet + wl * nun, *tt = str + wl * nun;
       double sig = 0.0, ksig = 0.0;
+      if (parts > 1) {
+        for (int pt = 0; pt < parts; ++pt) { sig += jv[2 * (wl * parts + pt)]; ksig += jv[2 * (wl * parts + pt) + 1]; }
+      } else
       for (int c = 0; c < S.nconf; ++c) {
         const int iu = T.ciu()[c], id = S.nuu + T.cid()[c];
         const double d = T.ci()[c] * dd[iu] * dd[id];
