@@ -840,16 +840,19 @@ __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int
 // in r[] - the caller divides.  All shuffles use the full mask (width 16): both halves run the same
 // nmax = max order of the two blocks steps; a half whose block is smaller (or absent: n = 0) idles
 // through the extra steps with zero multipliers.
-template <bool WITH_R>
-__device__ __forceinline__ double half_warp_gauss_jordan(int n, int nmax, double (&a)[16], double (&r)[16], int hl,
+template <bool WITH_R, int NP>
+__device__ __forceinline__ double half_warp_gauss_jordan(int n, int nmax, double (&a)[NP], double (&r)[NP], int hl,
                                                          int &kc, double &ipiv) {
+  // NP >= nmax: padded order (8, 12 or 16).  Padding columns hold zeros and are eliminated along with
+  // the real ones: the inner loops carry no bounds test, so the NP independent shuffle + FMA chains
+  // of a step overlap instead of running one basic block at a time.
   const unsigned full = 0xffffffffu;
   double det = 1.0;
   bool done = hl >= n;
   kc = 16 + hl;                      // rows beyond n: distinct, above every real column
   ipiv = 0.0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
+  for (int k = 0; k < NP; ++k) {
     if (k < nmax) {
       const bool on = k < n;
       double v = (done || !on) ? -1.0 : fabs(a[k]);
@@ -872,12 +875,10 @@ __device__ __forceinline__ double half_warp_gauss_jordan(int n, int nmax, double
       if (on) det *= pv;
       const double f = (me || !on) ? 0.0 : a[k] * ipv;      // multiplier of this row
 #pragma unroll
-      for (int j = k + 1; j < 16; ++j)
-        if (j < nmax) a[j] = fma(-f, __shfl_sync(full, a[j], p, 16), a[j]);
+      for (int j = k + 1; j < NP; ++j) a[j] = fma(-f, __shfl_sync(full, a[j], p, 16), a[j]);
       if (WITH_R) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nmax) r[j] = fma(-f, __shfl_sync(full, r[j], p, 16), r[j]);
+        for (int j = 0; j < NP; ++j) r[j] = fma(-f, __shfl_sync(full, r[j], p, 16), r[j]);
       }
       if (me) { done = true; kc = k; ipiv = ipv; }
     }

@@ -22,6 +22,9 @@
 
 #include "fused_args.h"
 
+template <int V>
+struct IntTag { static constexpr int value = V; };
+
 template <int NCH, int MB>
 struct MoSink {
   double acc[NCH][MB];
@@ -121,9 +124,15 @@ __host__ __device__ inline size_t thread_tile_doubles(const DevSys &S, int mode)
 //              and the per-walker epilogue runs on all lanes.  Work area: a private, odd-strided
 //              slice of shared memory per thread.
 #define QMCB_THREAD_CTA 128
+// CTA tiles with 16 MO columns per thread (psi / E_L of large systems): 32 accumulators + the shell
+// state do not fit the 128 registers that 512 threads allow (ncu: LDL in the projection loop,
+// long-scoreboard stalls 1.8 per issue); these run as two CTAs of at most QMCB_MB16_THREADS threads
+#ifndef QMCB_MB16_THREADS
+#define QMCB_MB16_THREADS 192
+#endif
 template <int MODE, int MB, int RT, int TILE>
-__global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_THREAD_CTA : 512),
-                                  TILE == 1 ? QMCB_MINBLOCKS : (TILE == 2 ? 4 : 1))
+__global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_THREAD_CTA : (MB == 16 ? QMCB_MB16_THREADS : 512)),
+                                  TILE == 1 ? QMCB_MINBLOCKS : (TILE == 2 ? 4 : (MB == 16 ? 2 : 1)))
     fused_kernel(const DevSys S, const FusedArgs a, const int TW, const int NBLK, const int lu_conc) {
   constexpr bool WARP = TILE == 1;
   constexpr bool THREAD = TILE == 2;
@@ -269,45 +278,52 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
         if ((S.nup > S.ndown ? S.nup : S.ndown) <= 16) {
           // register-resident, TWO blocks per warp: lane hl of a half-warp owns row hl of [A | B]
           // (or [A | I]); see half_warp_gauss_jordan
-          const int half = lane >> 4, hl = lane & 15;
           const int nmax = S.nup > S.ndown ? S.nup : S.ndown;
-          for (int it0 = 2 * warp; it0 < nitem; it0 += 2 * nwarp) {
-            const int it = it0 + half;
-            const bool act = it < nitem;
-            const int wl = act ? it / nun : 0, u = act ? it - wl * nun : 0;
-            const bool up = u < S.nuu;
-            const int n = act ? (up ? S.nup : S.ndown) : 0;
-            const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
-            const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup) + hl) * ldm;
-            double a[16], r[16];
+          auto run = [&](auto np_tag) {
+            constexpr int NP = decltype(np_tag)::value;
+            const int half = lane >> 4, hl = lane & 15;
+            for (int it0 = 2 * warp; it0 < nitem; it0 += 2 * nwarp) {
+              const int it = it0 + half;
+              const bool act = it < nitem;
+              const int wl = act ? it / nun : 0, u = act ? it - wl * nun : 0;
+              const bool up = u < S.nuu;
+              const int n = act ? (up ? S.nup : S.ndown) : 0;
+              const int *cols = up ? T.ucu() + u * S.nup : T.ucd() + (u - S.nuu) * S.ndown;
+              const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup) + hl) * ldm;
+              double a[NP], r[NP];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool in = hl < n && j < n;
-              const int c = in ? cols[j] : 0;
-              a[j] = in ? A[c] : 0.0;
-              r[j] = MODE == MODE_ELOC ? (in ? A[chs + c] : 0.0) : (j == hl ? 1.0 : 0.0);
+              for (int j = 0; j < NP; ++j) {
+                const bool in = hl < n && j < n;
+                const int c = in ? cols[j] : 0;
+                a[j] = in ? A[c] : 0.0;
+                r[j] = MODE == MODE_ELOC ? (in ? A[chs + c] : 0.0) : (j == hl ? 1.0 : 0.0);
+              }
+              int kc;
+              double ipiv;
+              const double det =
+                  half_warp_gauss_jordan<(MODE == MODE_ELOC || MODE == MODE_GRAD), NP>(n, nmax, a, r, hl, kc, ipiv);
+              double tr = 0.0;
+              if (MODE == MODE_ELOC) {
+                // Tr(inv(A) B): the row that pivoted column k holds pivot * element (k, k) in r[k]
+#pragma unroll
+                for (int j = 0; j < NP; ++j) tr = (j == kc) ? r[j] : tr;
+                tr *= ipiv;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o, 16);
+              }
+              if (MODE == MODE_GRAD && kc < n) {
+                // the gradient phase reads inv(A) from the scratch: right block of [A | I], row kc
+                double *m = scr + (size_t)it * per + (size_t)kc * 2 * n + n;
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                  if (j < n) m[j] = r[j] * ipiv;
+              }
+              if (act && hl == 0) { sdet[wl * nun + u] = n > 0 ? det : 1.0; str[wl * nun + u] = tr; }
             }
-            int kc;
-            double ipiv;
-            const double det = half_warp_gauss_jordan<(MODE == MODE_ELOC || MODE == MODE_GRAD)>(n, nmax, a, r, hl, kc, ipiv);
-            double tr = 0.0;
-            if (MODE == MODE_ELOC) {
-              // Tr(inv(A) B): the row that pivoted column k holds pivot * element (k, k) in r[k]
-#pragma unroll
-              for (int j = 0; j < 16; ++j) tr = (j == kc) ? r[j] : tr;
-              tr *= ipiv;
-#pragma unroll
-              for (int o = 8; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o, 16);
-            }
-            if (MODE == MODE_GRAD && kc < n) {
-              // the gradient phase reads inv(A) from the scratch: right block of [A | I], row kc
-              double *m = scr + (size_t)it * per + (size_t)kc * 2 * n + n;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < n) m[j] = r[j] * ipiv;
-            }
-            if (act && hl == 0) { sdet[wl * nun + u] = n > 0 ? det : 1.0; str[wl * nun + u] = tr; }
-          }
+          };
+          if (nmax <= 8) run(IntTag<8>{});
+          else if (nmax <= 12) run(IntTag<12>{});
+          else run(IntTag<16>{});
           if (MODE == MODE_GRAD) __syncwarp();
         } else
         for (int it = warp; it < nitem; it += nwarp) {
@@ -545,7 +561,9 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   while (mb < S.nmu && mb < 8) mb *= 2;
   // psi / E_L / Metropolis contract one or two AO channels: 16 columns per thread fit the register
   // budget, and a thread that owns all columns evaluates the basis functions of its electron once
-  if (mode != MODE_GRAD && S.nmu > 8 && S.nmup % 16 == 0 && !getenv("QMCB_MB8")) mb = 16;
+  if (mode != MODE_GRAD && S.nmu > 8 && S.nmup % 16 == 0 && S.nelec * (S.nmup / 16) <= QMCB_MB16_THREADS &&
+      !getenv("QMCB_MB8"))
+    mb = 16;
   c.mb = mb;
   c.nblk = S.nmup / mb;
   const int per_walker = S.nelec * c.nblk;
@@ -594,13 +612,15 @@ static int choose(const qmcb_plan *p, int mode, LaunchCfg &c) {
   // psi 0.92 -> 0.76 ms; H2O unchanged); grad psi keeps its inverses resident and prefers one large CTA
   int cta_max = mode == MODE_GRAD ? 512 : 256;
   if (const char *env = getenv("QMCB_CTA_THREADS")) cta_max = atoi(env) > 0 ? atoi(env) : cta_max;
+  const int hard_max = mb == 16 ? QMCB_MB16_THREADS : 512;       // launch bounds of the instantiation
+  if (cta_max > hard_max) cta_max = hard_max;
   if (cta_max < per_walker) cta_max = ((per_walker + 31) / 32) * 32;
   int tw = cta_max / per_walker;
   if (tw > 128) tw = 128;
   if (tw < 1) tw = 1;
   for (; tw >= 1; --tw) {
     int threads = ((tw * per_walker + 31) / 32) * 32;
-    if (threads > 512) continue;
+    if (threads > hard_max) continue;
     const int per = lu_scratch_per_item(S, mode, false);
     int conc = 0;
     if (per) {

@@ -1,7 +1,7 @@
 """Selects the metrics that profiles/*_ncu_raw.csv keep from `ncu -i X.ncu-rep --page raw --csv`
 exports (one column per captured kernel).
 
-    python tools/ncu_select.py out.csv name1=raw1.csv [name2=raw2.csv ...]
+    python tools/ncu_select.py out.csv name1=raw1.csv[:k] [name2=raw2.csv ...]      (k: k-th captured kernel, default 0)
 """
 import csv
 import re
@@ -24,8 +24,11 @@ KEEP = re.compile(
 
 
 def load(path):
+    k = 0
+    if ":" in path and path.rsplit(":", 1)[1].isdigit():
+        path, k = path.rsplit(":", 1)[0], int(path.rsplit(":", 1)[1])
     rows = list(csv.reader(open(path)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + k]
     return {h: (u, v) for h, u, v in zip(hdr, units, vals)}, (vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "")
 
 
