@@ -196,6 +196,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout
+        # with NCCL_DEBUG=VERSION, which some images export) goes to stderr instead
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     mol = fixture_molecule(fixture)
     wf = SlaterJastrow(mol, configs=configs, cuda=True)
