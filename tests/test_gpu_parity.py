@@ -126,6 +126,61 @@ def test_fresh_walkers_against_oracle(name, nw):
     assert C.scaled_err(wf.gradients_jacobi(pos[:512]), orc.grad_psi(P, cpu[:512])) < RTOL
 
 
+_GJ_SYSTEMS = {
+    # key: (atoms [angstrom], spin) - DZP carbon / hydrogen tables, seeded orthonormal MOs
+    # C2H4: 16 electrons, 8x8 blocks (padded order 8); triplet: 9x9 / 7x7 (padded order 12, the smaller
+    # block idles through two steps); C2H6: 18 electrons, 9x9 blocks (padded order 12)
+    "c2h4": ("C 0 0 0.667; C 0 0 -0.667; H 0 0.923 1.238; H 0 -0.923 1.238; H 0 0.923 -1.238; H 0 -0.923 -1.238", 0),
+    "c2h4_triplet": ("C 0 0 0.667; C 0 0 -0.667; H 0 0.923 1.238; H 0 -0.923 1.238; H 0 0.923 -1.238; H 0 -0.923 -1.238", 2),
+    "c2h6": ("C 0 0 0.765; C 0 0 -0.765; H 1.019 0 1.158; H -0.510 0.883 1.158; H -0.510 -0.883 1.158; "
+             "H -1.019 0 -1.158; H 0.510 0.883 -1.158; H 0.510 -0.883 -1.158", 0),
+}
+
+
+@pytest.mark.parametrize("key", sorted(_GJ_SYSTEMS))
+def test_half_warp_gauss_jordan_orders(key):
+    """Spin blocks of order 7..9 (the row-owner half-warp Gauss-Jordan with padded orders 8 and 12,
+    unequal blocks in one warp; C4H6 covers 15 -> 16): psi, E_L, grad psi and one Metropolis
+    decision against the oracle on thermalised walkers."""
+    from qmctorch_b200.molecules import Molecule, _seeded_mos, build_basis, _parse_atoms
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    from qmctorch_b200.wavefunction.pooling import OrbitalConfigurations
+    atoms, spin = _GJ_SYSTEMS[key]
+    names, coords = _parse_atoms(atoms, "angs")
+    nao = build_basis(names, coords, "dzp").nao
+    mol = Molecule(atoms, basis="dzp", unit="angs", spin=spin, name=key, mos=_seeded_mos(nao, 5))
+    wf = SlaterJastrow(mol, configs="ground_state", cuda=True)
+    assert max(mol.nup, mol.ndown) in (8, 9) and wf._handle.info(13) == 0
+    P = orc.make_params(mol, OrbitalConfigurations(mol).get_configs("ground_state"), jastrow_weight=1.0)
+    pos, _ = _thermalised(wf, mol, 777, nstep=40, step=0.1)
+    cpu = pos.cpu()
+    psi_o, el_o = orc.psi(P, cpu), orc.local_energy(P, cpu)
+    assert C.rel_err(wf(pos), psi_o) < RTOL
+    e = wf.local_energy(pos).cpu()
+    assert float(((e - el_o).abs() / el_o.abs().clamp(min=1.0)).max()) < RTOL
+    assert C.scaled_err(wf.gradients_jacobi(pos[:128]), orc.grad_psi(P, cpu[:128])) < RTOL
+    # one teacher-forced Metropolis step: identical decisions
+    gen = torch.Generator().manual_seed(3)
+    disp = 0.05 * torch.randn(pos.shape, generator=gen, dtype=torch.float64)
+    tau = torch.rand(pos.shape[0], generator=gen, dtype=torch.float64)
+    fx = (psi_o ** 2).reshape(-1)
+    x_o, fx_o, acc_o, fxn_o = orc.metropolis_step(P, cpu, fx, disp, tau)
+    from qmctorch_b200 import _lib
+    x1, fx1, d_disp, d_tau = pos.clone(), fx.cuda().contiguous(), disp.cuda(), tau.cuda()
+    acc1 = torch.zeros(pos.shape[0], dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().qmcb_metropolis_step(
+        wf._handle.plan(), _lib.ptr(x1), _lib.ptr(fx1), pos.shape[0], _lib.ptr(d_disp), _lib.ptr(d_tau), None, -1, 1,
+        1.0, 1e-16, 0, 0, _lib.ptr(acc1), None, _lib.stream_ptr(x1.device)), "qmcb_metropolis_step")
+    torch.cuda.synchronize()
+    # (a decision whose margin is below the 1e-10 tolerance of psi^2 itself is not determined)
+    margin = ((fxn_o / fx).clamp(max=1.0) - tau).abs()
+    sure = margin > 1e-8
+    assert int(sure.sum()) >= pos.shape[0] - 2
+    assert torch.equal(acc1.cpu().bool()[sure], acc_o.bool().reshape(-1)[sure])
+    assert torch.equal(x1.cpu()[sure], x_o[sure])
+    assert 0.05 < float(acc_o.float().mean()) < 0.95
+
+
 def test_sampler_replays_reference_draw_sequence():
     """rng='torch' makes the same generator calls in the same order as the reference
     (Appendix C): the whole trajectory equals the oracle's step by step, bit for bit."""
