@@ -171,6 +171,18 @@ __device__ __forceinline__ const double2 *radial_sums(const SYS &S, const double
                                                       int nprim, double r2,
                                                       double r, double rinv, double &S0, double &S1,
                                                       double &S2) {
+  if (RT == 0 && nprim == 1) {
+    // single-primitive shell (most polarisation / diffuse shells): no accumulators, no finish
+    const double2 p0 = rec[0];
+    const double ce = p0.y * exp_neg(S, etab, -p0.x * r2);
+    S0 = ce; S1 = 0.0; S2 = 0.0;
+    if (NCH > 1) {
+      const double t = p0.x * ce;
+      S1 = -2.0 * t;
+      if (NCH > 4) S2 = t * fma(4.0 * p0.x, r2, -6.0);
+    }
+    return rec + 1;
+  }
   S0 = 0.0; S1 = 0.0; S2 = 0.0;
   if (RT == 0) {
     int i = 0;
