@@ -290,8 +290,9 @@ def main():
     res_host = torch.empty(4, dtype=torch.float64).pin_memory()
 
     def e2e_step(i):
-        x = host[i % 2].to(dev, non_blocking=True)
-        e = wf.local_energy(x)
+        # the public call with a HOST tensor: SlaterJastrow.local_energy streams it to the device in
+        # chunks on two side streams, the copy of chunk k+1 overlapping the kernel on chunk k
+        e = wf.local_energy(host[i % 2])
         _lib.check(L.qmcb_energy_stats(_lib.ptr(e), W, _lib.ptr(out4), _lib.ptr(ws), sp), "stats")
         if world > 1:
             dist.all_reduce(out4)

@@ -459,6 +459,40 @@ struct ElecTerms {
   double gx, gy, gz, lap, ks, ven, vee;
 };
 
+// electron-nucleus part of electron_terms: V_en and the e-n Pade Jastrow terms of one electron
+template <bool DERIV, bool POT, class SYS, class TAB>
+__device__ __forceinline__ void nuclei_terms(const SYS &S, const TAB &T, double xi, double yi, double zi, double ni,
+                                             double &gx, double &gy, double &gz, double &h, double &ks, double &ven) {
+  double gnx = 0, gny = 0, gnz = 0;
+  for (int A = 0; A < S.natom; ++A) {
+    const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
+    const double dx = xi - xa, dy = yi - ya, dz = zi - za;
+    const double s2 = dx * dx + dy * dy + dz * dz;
+    if (POT) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
+    if (S.use_jen) {
+      const double wn = S.jen_w;
+      const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));
+      const double dot = __fma_rn(zi, za, __fma_rn(yi, ya, __dmul_rn(xi, xa)));
+      const double d2n = __dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot));
+      const double r = d2n > 0.0 ? d2n * fast_rsqrt(d2n) : 0.0;   // electron on a nucleus: r = 0, kept finite by eps below
+      const double den = fast_rcp(1.0 + wn * r);
+      ks += r * den;
+      if (DERIV) {
+        const double invr = fast_rcp(r + QMCB_EPS);
+        const double invr3 = fast_rcp(r * r * r + QMCB_EPS);
+        const double kp = den * den * invr;
+        gnx += kp * dx; gny += kp * dy; gnz += kp * dz;
+        const double sdr2 = s2 * invr * invr;   // sum_c dr_c^2
+        const double sd2r = 2.0 * s2 * invr3;   // sum_c d2r_c
+        const double den2 = den * den;
+        h += den * sd2r - 2.0 * wn * den2 * sdr2 - wn * r * den2 * sd2r +
+             2.0 * wn * wn * r * den2 * den * sdr2;
+      }
+    }
+  }
+  gx += gnx; gy += gny; gz += gnz;
+}
+
 template <bool DERIV, bool POT, class SYS, class TAB>
 __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const double *sp, int e,
                                                ElecTerms &o) {
@@ -491,35 +525,56 @@ __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const
       }
     }
   }
-  double gnx = 0, gny = 0, gnz = 0;
-  for (int A = 0; A < S.natom; ++A) {
-    const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
-    const double dx = xi - xa, dy = yi - ya, dz = zi - za;
-    const double s2 = dx * dx + dy * dy + dz * dz;
-    if (POT) ven -= T.atoms()[4 * A + 3] * fast_rsqrt(s2);
-    if (S.use_jen) {
-      const double wn = S.jen_w;
-      const double na = __dadd_rn(__dadd_rn(__dmul_rn(xa, xa), __dmul_rn(ya, ya)), __dmul_rn(za, za));
-      const double dot = __fma_rn(zi, za, __fma_rn(yi, ya, __dmul_rn(xi, xa)));
-      const double d2n = __dsub_rn(__dadd_rn(ni, na), __dmul_rn(2.0, dot));
-      const double r = d2n > 0.0 ? d2n * fast_rsqrt(d2n) : 0.0;   // electron on a nucleus: r = 0, kept finite by eps below
-      const double den = fast_rcp(1.0 + wn * r);
-      ks += r * den;
-      if (DERIV) {
-        const double invr = fast_rcp(r + QMCB_EPS);
-        const double invr3 = fast_rcp(r * r * r + QMCB_EPS);
-        const double kp = den * den * invr;
-        gnx += kp * dx; gny += kp * dy; gnz += kp * dz;
-        const double sdr2 = s2 * invr * invr;   // sum_c dr_c^2
-        const double sd2r = 2.0 * s2 * invr3;   // sum_c d2r_c
-        const double den2 = den * den;
-        h += den * sd2r - 2.0 * wn * den2 * sdr2 - wn * r * den2 * sd2r +
-             2.0 * wn * wn * r * den2 * den * sdr2;
-      }
-    }
-  }
-  gx += gnx; gy += gny; gz += gnz;
+  nuclei_terms<DERIV, POT>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
   if (S.een_nterm > 0) een_terms<DERIV>(S, T, sp, e, gx, gy, gz, h, ks);
+  o.gx = gx; o.gy = gy; o.gz = gz;
+  o.lap = h + gx * gx + gy * gy + gz * gz;
+  o.ks = ks; o.ven = ven; o.vee = vee;
+}
+
+// Pair-once variant for shared tiles (derivative modes, no three-body term): the Ne electrons of a
+// walker sit on Ne consecutive lanes of one warp (first lane: base).  In round k = 1..Ne/2 lane e
+// evaluates the pair (e, e+k mod Ne) and receives the contribution of the pair (e-k mod Ne, e) from
+// the lane that evaluated it (four double shuffles), so every pair is evaluated ONCE instead of once
+// per electron; for even Ne the last round is shared out between the two halves.  Fixed order:
+// deterministic.  All 32 lanes must call this (inactive lanes pass act = false).
+template <bool POT, class SYS, class TAB>
+__device__ __forceinline__ void electron_terms_paired(const SYS &S, const TAB &T, const double *sp, int e, int base,
+                                                      bool act, ElecTerms &o) {
+  const int Ne = S.nelec;
+  const double xi = act ? sp[3 * e] : 0.0, yi = act ? sp[3 * e + 1] : 0.0, zi = act ? sp[3 * e + 2] : 0.0;
+  double gx = 0, gy = 0, gz = 0, h = 0, ks = 0, ven = 0, vee = 0;
+  const double ni = gram_norm(xi, yi, zi);
+  const bool up_i = e < S.nup;
+  const double w = S.jee_w;
+  const int half = Ne >> 1;
+  for (int k = 1; k <= half; ++k) {
+    const bool halfround = 2 * k == Ne;
+    int j = e + k; if (j >= Ne) j -= Ne;
+    int src = e - k; if (src < 0) src += Ne;
+    double px = 0, py = 0, pz = 0, hp = 0;
+    if (act && (!halfround || e < half)) {
+      const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
+      const double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+      const double s2 = dx * dx + dy * dy + dz * dz;
+      if (POT) vee += fast_rsqrt(s2);
+      const double d2 = gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, gram_norm(xj, yj, zj));
+      const double rinv = fast_rsqrt(d2);
+      const double r = d2 * rinv;
+      const double w0 = (up_i == (j < S.nup)) ? 0.25 : 0.5;
+      const double den = fast_rcp(1.0 + w * r);
+      ks += w0 * r * den;
+      const double kp = w0 * den * den * rinv;
+      px = kp * dx; py = kp * dy; pz = kp * dz;
+      hp = 2.0 * kp * den * (s2 * rinv * rinv);
+      gx += px; gy += py; gz += pz; h += hp;
+    }
+    const int sl = (base + src) & 31;
+    const double qx = __shfl_sync(0xffffffffu, px, sl), qy = __shfl_sync(0xffffffffu, py, sl);
+    const double qz = __shfl_sync(0xffffffffu, pz, sl), qh = __shfl_sync(0xffffffffu, hp, sl);
+    if (act && (!halfround || e >= half)) { gx -= qx; gy -= qy; gz -= qz; h += qh; }
+  }
+  if (act) nuclei_terms<true, POT>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
   o.gx = gx; o.gy = gy; o.gz = gz;
   o.lap = h + gx * gx + gy * gy + gz * gz;
   o.ks = ks; o.ven = ven; o.vee = vee;

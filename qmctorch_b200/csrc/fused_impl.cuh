@@ -221,6 +221,22 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
     double tks = 0.0, tven = 0.0, tvee = 0.0;   // THREAD tiles: walker totals stay in registers
     if (THREAD) {
       walker_terms<(NCH > 1), (MODE == MODE_ELOC)>(S, T, spos, jv, jvs, tks, tven, tvee);
+    } else if (NCH > 1 && S.use_jee && S.een_nterm == 0 && Ne >= 6 && Ne <= 32 && TW <= (nthr >> 5) * (32 / Ne)) {
+      // every e-e pair once: the electrons of a walker on consecutive lanes of one warp
+      // (electron_terms_paired); one round covers the tile
+      const int lane = tid & 31, per = 32 / Ne;
+      const int sub = lane / Ne, e = lane - sub * Ne;
+      const int wl = (tid >> 5) * per + sub;
+      const bool act = sub < per && wl < tw;
+      if ((tid >> 5) * per < tw) {           // warp-uniform: this warp owns at least one walker
+        ElecTerms o;
+        electron_terms_paired<(MODE == MODE_ELOC)>(S, T, spos + (act ? wl : 0) * ne3, act ? e : 0, sub * Ne, act, o);
+        if (act) {
+          double *q = jv + wl * Ne + e;
+          q[0] = o.gx; q[jvs] = o.gy; q[2 * jvs] = o.gz; q[3 * jvs] = o.lap;
+          q[4 * jvs] = o.ks; q[5 * jvs] = o.ven; q[6 * jvs] = o.vee;
+        }
+      }
     } else
     for (int it = tid; it < tw * Ne; it += nthr) {
       const int wl = it / Ne, e = it - wl * Ne;
