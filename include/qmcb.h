@@ -145,8 +145,10 @@ int qmcb_energy_stats(const double *eloc, int64_t W, double *out4, void *workspa
 /* qmcb_local_energy followed by qmcb_energy_stats in ONE call: eloc [W] (required), psi / ekin
  * optional, out4 as qmcb_energy_stats.  One VMC energy step of Solver.single_point
  * (solver/solver_base.py:355-371: local_energy per batch, then mean / var).  Structure-specialised
- * kernels reduce their walkers inside the E_L kernel (no second pass over eloc).
- * workspace: qmcb_stats_workspace_bytes(W). */
+ * kernels reduce their walkers inside the E_L kernel (no second pass over eloc, no second launch:
+ * the CTA that arrives last adds the per-CTA partials in index order; the arrival counter belongs
+ * to the plan, so concurrent calls on ONE plan must be ordered on a stream - use one plan per
+ * concurrent stream).  workspace: qmcb_stats_workspace_bytes(W). */
 int qmcb_local_energy_stats(const qmcb_plan *plan, const double *pos, int64_t W, double *eloc,
                             double *psi, double *ekin, double *out4, void *workspace, void *stream);
 
