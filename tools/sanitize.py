@@ -1,0 +1,49 @@
+"""Small driver for compute-sanitizer (memcheck / racecheck / synccheck): a few hundred walkers
+through every fused entry point of the tile shapes in use (THREAD / specialised: LiH; CTA tiles with
+thread-per-block determinants: H2O cas(4,4); half-warp Gauss-Jordan + pair-once Jastrow + 16-column
+blocks: C4H6, triplet C2H4).
+
+    compute-sanitizer --tool racecheck python tools/sanitize.py
+"""
+import os
+import sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from qmctorch_b200 import _lib
+from qmctorch_b200.molecules import Molecule, _parse_atoms, _seeded_mos, build_basis, fixture_molecule
+from qmctorch_b200.wavefunction import SlaterJastrow
+
+C2H4 = "C 0 0 0.667; C 0 0 -0.667; H 0 0.923 1.238; H 0 -0.923 1.238; H 0 0.923 -1.238; H 0 -0.923 -1.238"
+
+
+def systems():
+    yield "lih", fixture_molecule("lih"), "ground_state", 700
+    yield "h2o", fixture_molecule("h2o"), "cas(4,4)", 130
+    yield "c4h6", fixture_molecule("c4h6"), "ground_state", 50
+    names, coords = _parse_atoms(C2H4, "angs")
+    nao = build_basis(names, coords, "dzp").nao
+    yield "c2h4_triplet", Molecule(C2H4, basis="dzp", unit="angs", spin=2, name="c2h4t", mos=_seeded_mos(nao, 5)), \
+        "ground_state", 70
+
+
+for name, mol, cfg, W in systems():
+    wf = SlaterJastrow(mol, configs=cfg, cuda=True)
+    g = torch.Generator().manual_seed(1)
+    mean = torch.as_tensor(mol.domain("normal")["mean"])
+    sig = torch.as_tensor(mol.domain("normal")["sigma"]).diagonal()
+    pos = (mean + sig * torch.randn(W, mol.nelec, 3, generator=g, dtype=torch.float64)).view(W, -1).cuda()
+    L = _lib.lib()
+    plan = wf._handle.plan()
+    sp = _lib.stream_ptr(pos.device)
+    psi = wf(pos)
+    e, s4 = wf.local_energy_stats(pos)
+    gr = wf.gradients_jacobi(pos)
+    fx = (psi.reshape(-1) ** 2).contiguous()
+    acc = torch.zeros(W, dtype=torch.uint8, device="cuda")
+    x = pos.clone()
+    _lib.check(L.qmcb_metropolis_step(plan, _lib.ptr(x), _lib.ptr(fx), W, None, None, None, -1, 1, 0.2, 1e-16, 3, 0,
+                                      _lib.ptr(acc), None, sp), "mh")
+    torch.cuda.synchronize()
+    print(name, "psi", float(psi.abs().mean()), "E", float(s4[0] / s4[2]), "grad", float(gr.abs().mean()),
+          "acc", float(acc.float().mean()), "spec", wf._handle.info(13), flush=True)
