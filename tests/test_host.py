@@ -160,6 +160,41 @@ def test_specialised_kernel_source_compiles_without_a_gpu():
     assert on == 1, why
 
 
+def test_generated_program_shares_sp_exponentials_and_launch_shapes(tmp_path, monkeypatch):
+    """Host logic of the second half of round 1: (1) the generated LiH 6-31G program evaluates ONE
+    exponential per distinct exponent of an atom (the s and p functions of the SP shells share theirs:
+    14 for 17 grouped primitives) and as many as there are primitives once an update has separated the
+    exponents; (2) the 16-column kernels of large systems run as 192-thread CTAs (C4H6: 6 walkers)."""
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    L = _lib.lib()
+
+    def generated(wf, tag):
+        monkeypatch.setenv("QMCB_JIT_DUMP", str(tmp_path / tag))
+        arrays = wf._handle._system()
+        p = ctypes.c_void_p()
+        _lib.check(L.qmcb_plan_create(ctypes.byref(arrays.struct), -1, ctypes.byref(p)), "qmcb_plan_create")
+        on, why = L.qmcb_plan_info(p, 13), L.qmcb_last_error().decode()
+        nprim = L.qmcb_plan_info(p, 1)
+        L.qmcb_plan_destroy(p)
+        if not on and "libnvrtc not found" in why:
+            pytest.skip("NVRTC is not installed here")
+        assert on == 1, why
+        src = open(str(tmp_path / tag) + ".cu").read()
+        body = src[src.index("void spec_aos("):src.index("void spec_dets(")]
+        return len(re.findall(r"= spec_exp<MODE, \d+>", body)), nprim
+
+    wf = SlaterJastrow(fixture_molecule("lih"), configs="ground_state", cuda=False)
+    nexp, nprim = generated(wf, "shared")
+    assert (nexp, nprim) == (14, 17)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        wf.ao.bas_exp.mul_(1.0 + 0.05 * torch.rand_like(wf.ao.bas_exp))
+    nexp, nprim = generated(wf, "separate")
+    assert nexp == nprim == 26          # every flat primitive is its own shell now
+    info = SlaterJastrow(fixture_molecule("c4h6"))._handle.host_plan_info()
+    assert info["threads_eloc"] == 192 and info["tw_eloc"] == 6 and info["tw_psi"] == 6
+
+
 def test_shard_walkers_partitions_everything():
     from qmctorch_b200.solver.distributed import shard_walkers
     for n, w in ((10, 3), (1000000, 8), (7, 8), (0, 2)):
