@@ -519,22 +519,31 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
       // d psi / d r_{e,c} = J [ sum_u C_u sum_j inv_u[j][e] dmo_c[e][cols_u[j]] + g_{e,c} Sigma ]
       // (slater_jastrow.py:346-447), C_u = D_u * sum_{n: occ_s(n)=u} c_n D_other(n)
       const int conc = lu_conc;
+      // C_u once per (walker, unique occupation) - not once per electron - into the trace slots,
+      // which grad psi does not use
+      for (int it = tid; it < tw * nun; it += nthr) {
+        const int wl = it / nun, u = it - wl * nun;
+        const bool up = u < S.nuu;
+        const int us = up ? u : u - S.nuu;
+        const double *dd = sdet + wl * nun;
+        double cu = 0.0;
+        for (int c = 0; c < S.nconf; ++c) {
+          if ((up ? T.ciu()[c] : T.cid()[c]) != us) continue;
+          cu += T.ci()[c] * dd[up ? S.nuu + T.cid()[c] : T.ciu()[c]];
+        }
+        str[it] = cu * dd[u];
+      }
+      TILE_SYNC();
       for (int it = tid; it < tw * Ne; it += nthr) {
         const int wl = it / Ne, e = it - wl * Ne;
         const bool up = e < S.nup;
         const int n = up ? S.nup : S.ndown;
         const int el = up ? e : e - S.nup;
-        const double *dd = sdet + wl * nun;
         const double *row = smo + ((size_t)wl * Ne + e) * ldm;
         double gsx = 0, gsy = 0, gsz = 0;
         const int nu = up ? S.nuu : S.nud;
         for (int u = 0; u < nu; ++u) {
-          double cu = 0.0;
-          for (int c = 0; c < S.nconf; ++c) {
-            if ((up ? T.ciu()[c] : T.cid()[c]) != u) continue;
-            cu += T.ci()[c] * dd[up ? S.nuu + T.cid()[c] : T.ciu()[c]];
-          }
-          cu *= dd[up ? u : S.nuu + u];
+          const double cu = str[wl * nun + (up ? u : S.nuu + u)];
           if (cu == 0.0) continue;
           const int item = wl * nun + (up ? u : S.nuu + u);
           const bool contiguous = TILE == 0 && use_warp_lu(S);   // layout written by P3
