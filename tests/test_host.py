@@ -195,6 +195,31 @@ def test_generated_program_shares_sp_exponentials_and_launch_shapes(tmp_path, mo
     assert info["threads_eloc"] == 192 and info["tw_eloc"] == 6 and info["tw_psi"] == 6
 
 
+def test_bench_flop_counts_and_reference_arm_line():
+    """bench.py host logic: the SURVEY 8(d) unit of work for LiH 6-31G is 2994 flop/eval, the
+    kernels' executed count is smaller (folded kinetic channel), and the reference arm prints one
+    JSON line with the contract's keys."""
+    import json
+    import bench
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    mol = fixture_molecule("lih")
+    wf = SlaterJastrow(mol, configs="ground_state", cuda=False)
+    info = wf._handle.host_plan_info()
+    assert bench.algorithmic_flops(mol, wf, info) == 2994
+    assert 0.4 * 2994 < bench.executed_flops(mol, wf, info) < 2994
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "local_energy_evals_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "LiH 6-31G" in line["config"]["workload"]
+
+
 def test_shard_walkers_partitions_everything():
     from qmctorch_b200.solver.distributed import shard_walkers
     for n, w in ((10, 3), (1000000, 8), (7, 8), (0, 2)):
