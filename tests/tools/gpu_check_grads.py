@@ -1,7 +1,7 @@
 """Diagnostic: parameter gradients of every golden case, CUDA path vs reference golden."""
 import os, sys, traceback
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import _cases as C  # noqa

@@ -4,7 +4,7 @@ import os
 import sys
 import time
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from qmctorch_b200 import _lib
 from qmctorch_b200.molecules import fixture_molecule

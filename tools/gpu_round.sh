@@ -12,7 +12,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1
 ( for w in "lih 1000000" "h2 1000000" "lih_sto 1000000" "h2o 100000" "c4h6 20000"; do
     timeout 300 python tools/time_kernels.py $w 2>&1 | tail -1
   done
-  timeout 300 python tools/gpu_config4.py 2>&1 | tail -3 ) > $out/${tag}_time.log 2>&1
+  timeout 300 python tests/tools/gpu_config4.py 2>&1 | tail -3 ) > $out/${tag}_time.log 2>&1
 timeout 300 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2>> $out/${tag}_bench_n1.err
 if [ "${NCU:-0}" = "1" ]; then
