@@ -50,6 +50,9 @@ CASES = [
     ("lih_sto", "lih_sto", "single_double(2,2)", "ee", 96, 100, 0.3, "normal"),
     ("lih_sto_pure", "lih_sto_pure", "ground_state", "ee", 64, 100, 0.3, "normal"),
     ("lih_gto_kr", "lih_gto_kr", "ground_state", "ee+en", 64, 100, 0.3, "normal"),
+    # real ADF results read from the reference's tests/hdf5/*.hdf5 (tools/hdf5_to_fixture.py)
+    ("lih_adf_sd22", "lih_adf", "single_double(2,2)", "ee", 96, 100, 0.3, "normal"),
+    ("co2_adf_ground", "co2_adf", "ground_state", "ee", 16, 60, 0.05, "atomic"),
     # three-body Boys-Handy term (BASELINE config 4: CAS + e-e-n Jastrow)
     ("lih_sd22_een3", "lih", "single_double(2,2)", "ee+en+een", 96, 100, 0.3, "normal"),
     ("h2o_cas44_een", "h2o", "cas(4,4)", "ee+een", 32, 100, 0.15, "atomic"),

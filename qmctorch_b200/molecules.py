@@ -233,8 +233,12 @@ class Molecule:
     contract (``scf/molecule.py:176-213``).
     """
 
-    def __init__(self, atom, basis="sto-3g", unit="bohr", charge=0, spin=0, name=None,
-                 calculator="builtin", mos=None, radial_type=None):
+    def __init__(self, atom=None, basis="sto-3g", unit="bohr", charge=0, spin=0, name=None,
+                 calculator="builtin", mos=None, radial_type=None, load=None):
+        if load is not None:      # scf/molecule.py:96-100: everything comes from the file
+            self.charge, self.spin = charge, spin
+            self._load(load)
+            return
         self.atoms_str = atom
         self.unit = unit
         self.charge = charge
@@ -268,6 +272,45 @@ class Molecule:
         self.basis.mos = mos / np.sqrt((mos ** 2).sum(0))
         self.basis.nmo = self.basis.mos.shape[1]
 
+    def _load(self, path):
+        """``Molecule(load=...)`` (``scf/molecule.py:394-402`` + ``utils/hdf5_utils.py:27-98``): every
+        dataset of the ``molecule`` group becomes an attribute, sub-groups become namespaces.
+        ``path`` is an HDF5 file written by QMCTorch (read by ``utils/hdf5_min.py``) or the JSON
+        dump of one (``tools/hdf5_to_fixture.py``).  MOs are taken verbatim (no renormalisation)."""
+        if path.endswith(".json"):
+            with open(path) as f:
+                tree = _tree_from_json(json.load(f))
+        else:
+            from .utils.hdf5_min import read_hdf5
+            tree = read_hdf5(path)
+            if "molecule" not in tree:
+                raise KeyError("no 'molecule' group in %s" % path)
+            tree = tree["molecule"]
+
+        def fill(obj, d):
+            for k, v in d.items():
+                if isinstance(v, dict):
+                    ns = SimpleNamespace()
+                    fill(ns, v)
+                    setattr(obj, k, ns)
+                else:
+                    setattr(obj, k, v.item() if isinstance(v, np.generic) else v)
+        fill(self, tree)
+        self.hdf5file = path
+        self.atoms = np.array([str(a) for a in self.atoms])
+        self.atom_coords = [list(map(float, c)) for c in np.asarray(self.atom_coords)]
+        self.atomic_number = [int(z) for z in self.atomic_number]
+        self.atomic_nelec = [int(z) for z in self.atomic_nelec]
+        b = self.basis
+        if b.harmonics_type != "cart":
+            raise ValueError("Harmonics type should be cart here (spherical harmonics are not "
+                             "supported) but %s was found in %s" % (b.harmonics_type, path))
+        b.nshells = [int(x) for x in b.nshells]
+        b.nao_per_atom = [int(x) for x in b.nao_per_atom]
+        b.bas_n = (np.asarray(b.bas_kx) + b.bas_ky + b.bas_kz + b.bas_kr + 1).tolist()
+        b.atom_coords_internal = [list(map(float, c)) for c in np.asarray(b.atom_coords_internal)]
+        b.mos = np.asarray(b.mos, dtype=np.float64)
+
     def domain(self, method):
         d = dict(method=method)
         ac = np.asarray(self.atom_coords)
@@ -289,6 +332,34 @@ class Molecule:
 
     def get_total_energy(self):
         return self.basis.TotalEnergy
+
+
+def _tree_to_json(tree):
+    """Nested dict of numpy arrays / scalars / str -> JSON-serialisable (floats round-trip exactly)."""
+    out = {}
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            out[k] = _tree_to_json(v)
+        elif isinstance(v, str):
+            out[k] = v
+        else:
+            a = np.asarray(v)
+            out[k] = {"dtype": "str" if a.dtype.kind == "U" else str(a.dtype), "shape": list(a.shape),
+                      "data": a.ravel().tolist()}
+    return out
+
+
+def _tree_from_json(js):
+    out = {}
+    for k, v in js.items():
+        if isinstance(v, str):
+            out[k] = v
+        elif "dtype" in v and "data" in v:
+            a = np.array(v["data"], dtype=None if v["dtype"] == "str" else v["dtype"]).reshape(v["shape"])
+            out[k] = a if a.ndim else a[()]
+        else:
+            out[k] = _tree_from_json(v)
+    return out
 
 
 def _load_cached_mos(name, basis, nao):
@@ -347,6 +418,11 @@ _SPECS = {
     "h2o": dict(atom="O 0 0 0; H 0.757 0.587 0; H -0.757 0.587 0", unit="angs",
                 basis="cc-pvdz", name="H2O"),
     "c4h6": dict(atom=None, unit="angs", basis="dzp", name="C4H6"),
+    # real ADF SCF results (Slater basis, cartesian, MOs from the SCF): JSON dumps of the reference's
+    # tests/hdf5/*_adf_*.hdf5 made by tools/hdf5_to_fixture.py
+    "lih_adf": dict(load=os.path.join(_DATA_DIR, "LiH_adf_dz.json")),
+    "h2_adf": dict(load=os.path.join(_DATA_DIR, "H2_adf_dzp.json")),
+    "co2_adf": dict(load=os.path.join(_DATA_DIR, "CO2_adf_dzp.json")),
 }
 
 

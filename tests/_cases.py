@@ -10,7 +10,9 @@ from qmctorch_b200.molecules import fixture_molecule
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["h2_single22", "h2_ground", "lih_ground", "lih_nojastrow", "lih_sd22", "lih_cas24", "lih_een",
          "h2o_ground", "h2o_cas44", "c4h6_ground", "lih_sd22_een3", "h2o_cas44_een",
-         "lih_sto", "lih_sto_pure", "lih_gto_kr"]
+         "lih_sto", "lih_sto_pure", "lih_gto_kr",
+         # real ADF SCF results (Slater basis, MOs of the SCF) read from the reference's HDF5 files
+         "lih_adf_sd22", "co2_adf_ground"]
 
 
 def load(name):

@@ -72,7 +72,7 @@ def test_golden_operators(name):
 
 
 @pytest.mark.parametrize("name", ["h2_single22", "lih_ground", "lih_cas24", "lih_een", "h2o_cas44", "c4h6_ground",
-                                  "lih_sd22_een3", "h2o_cas44_een"])
+                                  "lih_sd22_een3", "h2o_cas44_een", "lih_adf_sd22", "co2_adf_ground"])
 def test_metropolis_decisions_bit_exact_teacher_forced(name):
     """Same state, same proposal and uniform draws as the reference -> identical decisions,
     identical new positions, psi^2 within tolerance (sampler/metropolis.py:134-160,279-298)."""
@@ -544,7 +544,7 @@ def _mh_philox(wf, x, tau, seed, offset, scale=0.3, move_elec=-1):
 
 
 @pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_cas24", "lih_nojastrow", "h2_ground",
-                                  "lih_sto", "lih_sto_pure", "lih_gto_kr"])
+                                  "lih_sto", "lih_sto_pure", "lih_gto_kr", "lih_adf_sd22"])
 def test_specialised_kernels_match_generic(name, monkeypatch):
     """The NVRTC structure-specialised kernels (spec_kernel.cuh) against the generic interpreter
     kernels (fused_impl.cuh, QMCB_JIT=0) on the same walkers: psi, E_L, E_kin to rounding, identical
@@ -687,7 +687,7 @@ def test_gradient_samplers_replay_reference_chains(double_default):
 
 
 @pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_nojastrow", "lih_sto", "lih_sto_pure",
-                                  "lih_gto_kr"])
+                                  "lih_gto_kr", "lih_adf_sd22"])
 def test_specialised_gradient_kernel(name, monkeypatch):
     """spec_grad_psi (generated inverses / CI weights / electron loop) against the generic
     fused_kernel<MODE_GRAD> and the oracle: grad psi and grad psi^2 (slater_jastrow.py:346-447)."""

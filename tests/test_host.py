@@ -220,6 +220,50 @@ def test_bench_flop_counts_and_reference_arm_line():
     assert "LiH 6-31G" in line["config"]["workload"]
 
 
+def test_molecule_load_json_dump_of_adf_hdf5():
+    """Molecule(load=...) (scf/molecule.py:96-100,394-402): the committed JSON dumps of the reference's
+    tests/hdf5/*_adf_*.hdf5 carry the ADF basis verbatim; MOs are not renormalised."""
+    mol = fixture_molecule("lih_adf")
+    b = mol.basis
+    assert (mol.nelec, mol.nup, mol.ndown, mol.natom, mol.name) == (4, 2, 2, 2, "LiH")
+    assert (b.nao, b.nmo, b.radial_type, b.harmonics_type) == (9, 9, "sto", "cart")
+    assert list(mol.atoms) == ["Li", "H"] and mol.atom_coords[1] == [0.0, 0.0, 3.015]
+    assert b.TotalEnergy == -7.976594691003629 and b.bas_exp[0] == 4.24 and int(b.bas_kr[2]) == 1
+    assert b.mos.shape == (9, 9) and abs(b.mos[0, 0] + 0.211348386) < 1e-9
+    assert abs(float((b.mos[:, 0] ** 2).sum()) - 1.0) > 1e-3      # non-orthogonal AO basis: taken verbatim
+    assert mol.hdf5file.endswith("LiH_adf_dz.json")
+    co2 = fixture_molecule("co2_adf")
+    assert (co2.nelec, co2.basis.nao, co2.basis.nmo) == (22, 48, 45)
+    assert mol.domain("atomic")["atom_num"] == [3, 1]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests/hdf5"), reason="reference HDF5 files not on this box")
+@pytest.mark.parametrize("stem", ["LiH_adf_dz", "H2_adf_dzp", "CO2_adf_dzp"])
+def test_hdf5_reader_against_reference_files(stem):
+    """utils/hdf5_min.py (pure-Python HDF5 subset) reads the reference's own molecule files and gives
+    exactly what the committed JSON dump holds (tools/hdf5_to_fixture.py)."""
+    from qmctorch_b200.molecules import Molecule
+    from qmctorch_b200.utils.hdf5_min import read_hdf5
+    path = "/root/reference/tests/hdf5/%s.hdf5" % stem
+    tree = read_hdf5(path)["molecule"]
+    assert tree["basis"]["harmonics_type"] == "cart" and tree["basis"]["radial_type"] == "sto"
+    a = Molecule(load=path)
+    b = Molecule(load=os.path.join(os.path.dirname(_lib.__file__), "data", stem + ".json"))
+    for n in ["bas_exp", "bas_coeffs", "mos", "bas_kx", "bas_ky", "bas_kz", "bas_kr", "index_ctr", "nctr_per_ao",
+              "nshells", "nao_per_atom", "atom_coords_internal", "bas_n"]:
+        assert np.array_equal(np.asarray(getattr(a.basis, n)), np.asarray(getattr(b.basis, n))), n
+    assert a.atom_coords == b.atom_coords and list(a.atoms) == list(b.atoms)
+    assert (a.nelec, a.nup, a.ndown, a.atomic_number) == (b.nelec, b.nup, b.ndown, b.atomic_number)
+
+
+def test_hdf5_reader_rejects_other_files(tmp_path):
+    from qmctorch_b200.utils.hdf5_min import read_hdf5
+    p = tmp_path / "x.hdf5"
+    p.write_bytes(b"not an hdf5 file at all, just bytes" * 4)
+    with pytest.raises(ValueError):
+        read_hdf5(str(p))
+
+
 def test_shard_walkers_partitions_everything():
     from qmctorch_b200.solver.distributed import shard_walkers
     for n, w in ((10, 3), (1000000, 8), (7, 8), (0, 2)):
