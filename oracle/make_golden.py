@@ -303,8 +303,41 @@ def gradient_sampler_fixture():
     np.savez_compressed(os.path.join(OUT, "gradient_samplers.npz"), **out)
 
 
+def gto2sto_fixture():
+    """`SlaterJastrow.gto2sto()` of the reference (slater_jastrow.py:649-733) on LiH 6-31G and H2 STO-3G:
+    the fitted single-zeta Slater basis, and psi / E_L / grad psi of the returned wave function on
+    walkers sampled from it -> tests/golden/gto2sto.npz.  The oracle is asserted on the new basis."""
+    out = {}
+    for key in ("lih", "h2"):
+        torch.manual_seed(4321)
+        mol = fixture_molecule(key)
+        wf = SlaterJastrow(mol, configs="ground_state", include_all_mo=True).gto2sto()
+        with torch.no_grad():
+            wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+        b = wf.mol.basis
+        assert b.radial_type == "sto_pure"
+        pos = Metropolis(nwalkers=64, nstep=100, step_size=0.3, nelec=wf.nelec, ndim=3, init=mol.domain("normal"),
+                         move={"type": "all-elec", "proba": "normal"})(wf.pdf, with_tqdm=False).detach().clone()
+        psi = wf(pos).detach()
+        eloc = wf.local_energy(pos).detach()
+        gpsi = wf.gradients_jacobi(pos, sum_grad=False).detach().reshape(len(pos), -1)
+        P = orc.make_params(wf.mol, wf.configs, jastrow_weight=0.8)
+        e_psi, e_el = rel(orc.psi(P, pos), psi), rel(orc.local_energy(P, pos), eloc)
+        print("gto2sto %-4s exps %s  oracle psi=%.1e eloc=%.1e" % (key, np.round(b.bas_exp, 4), e_psi, e_el))
+        assert e_psi < 1e-12 and e_el < 1e-11
+        out.update({key + "_bas_exp": np.asarray(b.bas_exp, dtype=np.float64),
+                    key + "_bas_norm": np.asarray(b.bas_norm, dtype=np.float64),
+                    key + "_bas_k": np.stack([b.bas_kx, b.bas_ky, b.bas_kz, b.bas_kr]).astype(np.int64),
+                    key + "_nshells": np.asarray(b.nshells, dtype=np.int64),
+                    key + "_norm_cst": wf.ao.norm_cst.detach().numpy(),
+                    key + "_pos": pos.numpy(), key + "_psi": psi.numpy(), key + "_eloc": eloc.numpy(),
+                    key + "_gpsi": gpsi.numpy()})
+    np.savez_compressed(os.path.join(OUT, "gto2sto.npz"), **out)
+
+
 if __name__ == "__main__":
-    special = {"walkers_init": walker_init_fixture, "gradient_samplers": gradient_sampler_fixture}
+    special = {"walkers_init": walker_init_fixture, "gradient_samplers": gradient_sampler_fixture,
+               "gto2sto": gto2sto_fixture}
     args = sys.argv[1:]
     for name, fn in special.items():
         if not args or name in args:

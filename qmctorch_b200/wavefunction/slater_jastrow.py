@@ -346,5 +346,61 @@ class SlaterJastrow(WaveFunction):
             d.append(xyz)
         return d
 
+    def gto2sto(self, plot=False):
+        """Fit every contracted Gaussian AO with ONE Slater function ``norm * exp(-alpha |x|)`` and
+        return the wave function on that single-zeta ``sto_pure`` basis (slater_jastrow.py:649-733).
+
+        Host-side set-up code like the reference's: the radial profiles ``sum_p c_p N_p exp(-a_p x^2)``
+        are tabulated on ``torch.linspace(-5, 5, 501)`` (default dtype, as there) and fitted
+        with ``scipy.optimize.curve_fit``; norms of the new basis are recomputed by ``AtomicOrbitals``
+        (``bas_norm`` is ignored, atomic_orbitals.py:90).  The returned object evaluates on the CUDA
+        path like any other."""
+        from copy import deepcopy
+        import numpy as np
+        from scipy.optimize import curve_fit
+        assert self.ao.radial_type.startswith("gto")
+        assert self.ao.harmonics_type == "cart"
+        if plot:
+            raise NotImplementedError("plot=True needs matplotlib, which is not a dependency here")
+
+        def sto(x, norm, alpha):
+            return norm * np.exp(-alpha * np.abs(x))
+
+        nao = self.mol.basis.nao
+        new_mol = deepcopy(self.mol)
+        basis = deepcopy(self.mol.basis)
+        basis.radial_type = "sto_pure"
+        basis.nshells = self.ao.nao_per_atom.detach().cpu().numpy()
+        basis.index_ctr = np.arange(nao)
+        basis.bas_coeffs = np.ones(nao)
+        basis.bas_exp = np.zeros(nao)
+        basis.bas_norm = np.zeros(nao)
+        basis.bas_kr = np.zeros(nao)
+        basis.bas_kx = np.zeros(nao)
+        basis.bas_ky = np.zeros(nao)
+        basis.bas_kz = np.zeros(nao)
+
+        x = torch.linspace(-5, 5, 501)
+        pos = x.reshape(-1, 1).repeat(1, self.ao.nbas)
+        norm = self.ao.norm_cst.detach().cpu()
+        gto = norm * torch.exp(-self.ao.bas_exp.detach().cpu() * pos ** 2)
+        idx = self.ao.index_ctr.cpu().long()
+        ao = torch.zeros(len(x), nao, dtype=gto.dtype)
+        ao.index_add_(1, idx, gto * self.ao.bas_coeffs.detach().cpu())      # atomic_orbitals.py:654-669
+        ao = ao.numpy()
+        xdata = x.numpy()
+        for iorb in range(nao):
+            popt, _ = curve_fit(sto, xdata, ao[:, iorb])
+            basis.bas_norm[iorb], basis.bas_exp[iorb] = popt[0], popt[1]
+            sel = (idx == iorb).numpy()
+            for name, k in (("bas_kx", self.ao.bas_kx_np), ("bas_ky", self.ao.bas_ky_np), ("bas_kz", self.ao.bas_kz_np)):
+                ks = np.unique(k[sel])
+                if len(ks) != 1:
+                    raise ValueError("primitives of one AO with different powers")
+                getattr(basis, name)[iorb] = ks[0]
+        new_mol.basis = basis
+        return self.__class__(new_mol, self.jastrow, backflow=None, configs=self.configs_method,
+                              kinetic=self.kinetic_method, cuda=self.cuda, include_all_mo=self.include_all_mo)
+
     def log_data(self):
         pass

@@ -2,12 +2,15 @@
 
 Tolerances (BASELINE.json north_star): psi, E_L, gradients within 1e-10 relative in FP64;
 Metropolis accept/reject decisions bit-exact under teacher forcing."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import _cases as C
 import sj_oracle as orc
+from qmctorch_b200.molecules import fixture_molecule
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
@@ -708,3 +711,21 @@ def test_specialised_gradient_kernel(name, monkeypatch):
     x = pos[:64].clone().requires_grad_(True)
     wf1(x).sum().backward()
     assert C.scaled_err(x.grad, g1[:64]) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["lih", "h2"])
+def test_gto2sto_wave_function_on_the_cuda_path(key, double_default):
+    """The wave function returned by gto2sto() (slater_jastrow.py:649-733: single-zeta sto_pure basis fitted
+    to the Gaussian AOs) evaluates on the CUDA kernels and matches the reference's own gto2sto() object
+    on the same walkers (tests/golden/gto2sto.npz)."""
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    g = np.load(os.path.join(C.GOLDEN, "gto2sto.npz"))
+    wf = SlaterJastrow(fixture_molecule(key), configs="ground_state", cuda=True).gto2sto()
+    assert wf.cuda and wf.ao.radial_type == "sto_pure"
+    with torch.no_grad():
+        wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+    pos = torch.tensor(g[key + "_pos"]).cuda()
+    assert C.rel_err(wf(pos), g[key + "_psi"]) < RTOL
+    assert C.rel_err(wf.local_energy(pos), g[key + "_eloc"]) < RTOL
+    assert C.scaled_err(wf.gradients_jacobi(pos, sum_grad=False).reshape(len(pos), -1), g[key + "_gpsi"]) < RTOL

@@ -256,6 +256,25 @@ def test_hdf5_reader_against_reference_files(stem):
     assert (a.nelec, a.nup, a.ndown, a.atomic_number) == (b.nelec, b.nup, b.ndown, b.atomic_number)
 
 
+@pytest.mark.parametrize("key", ["lih", "h2"])
+def test_gto2sto_reproduces_reference_fit(key, double_default):
+    """SlaterJastrow.gto2sto (slater_jastrow.py:649-733) is host set-up code: the fitted single-zeta Slater
+    basis equals the reference's (golden made by oracle/make_golden.py gto2sto)."""
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    g = np.load(os.path.join(C.GOLDEN, "gto2sto.npz"))
+    wf = SlaterJastrow(fixture_molecule(key), configs="ground_state", cuda=False).gto2sto()
+    b = wf.mol.basis
+    assert b.radial_type == "sto_pure" and wf.ao.radial_type == "sto_pure"
+    np.testing.assert_allclose(b.bas_exp, g[key + "_bas_exp"], rtol=1e-12)
+    np.testing.assert_allclose(b.bas_norm, g[key + "_bas_norm"], rtol=1e-10)
+    assert np.array_equal(np.stack([b.bas_kx, b.bas_ky, b.bas_kz, b.bas_kr]).astype(np.int64), g[key + "_bas_k"])
+    assert np.array_equal(np.asarray(b.nshells), g[key + "_nshells"])
+    np.testing.assert_allclose(wf.ao.norm_cst.numpy(), g[key + "_norm_cst"], rtol=1e-12)
+    assert wf.ao.nbas == b.nao and not wf.ao.contract
+    with pytest.raises(AssertionError):
+        wf.gto2sto()                                   # already a Slater basis
+
+
 def test_hdf5_reader_rejects_other_files(tmp_path):
     from qmctorch_b200.utils.hdf5_min import read_hdf5
     p = tmp_path / "x.hdf5"
