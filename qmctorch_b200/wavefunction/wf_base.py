@@ -49,6 +49,9 @@ class WaveFunction(torch.nn.Module):
         return sum(p.data.numel() for p in self.parameters() if p.requires_grad)
 
     def load(self, filename, group="wf_opt", model="best"):
-        raise NotImplementedError(
-            "HDF5 checkpoints (wf_base.py:257-277) need h5py, which is outside the hot path; "
-            "use load_state_dict with the same parameter names")
+        """Load trained parameters from ``<group>/models/<model>`` of a QMCTorch HDF5 file
+        (wf_base.py:257-277); read with the pure-Python reader ``utils/hdf5_min.py`` (no h5py).
+        As in the reference, the stored names must be the ``state_dict`` names of this object."""
+        from ..utils.hdf5_min import read_hdf5
+        grp = read_hdf5(filename)[group]["models"][model]
+        self.load_state_dict({name: torch.as_tensor(val) for name, val in grp.items()})

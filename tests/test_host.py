@@ -275,6 +275,22 @@ def test_gto2sto_reproduces_reference_fit(key, double_default):
         wf.gto2sto()                                   # already a Slater basis
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests/hdf5"), reason="reference HDF5 files not on this box")
+def test_wf_load_reads_reference_checkpoint_group():
+    """WaveFunction.load (wf_base.py:257-277) reads <group>/models/<model> through the pure-Python reader and
+    hands it to load_state_dict.  The reference's own tests/hdf5/LiH_adf_dz_QMCTorch.hdf5 predates the current
+    parameter names (mo.weight, jastrow.weight), so - exactly like the reference - strict loading reports them."""
+    from qmctorch_b200.utils.hdf5_min import read_hdf5
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    path = "/root/reference/tests/hdf5/LiH_adf_dz_QMCTorch.hdf5"
+    best = read_hdf5(path)["wf_opt"]["models"]["best"]
+    assert best["ao.bas_exp"].shape == (9,) and best["fc.weight"].shape == (1, 4)
+    wf = SlaterJastrow(fixture_molecule("lih_adf"), configs="single_double(2,2)")
+    assert np.array_equal(best["ao.atom_coords"], wf.ao.atom_coords.detach().numpy())
+    with pytest.raises(RuntimeError, match="mo.mo_modifier"):
+        wf.load(path)
+
+
 def test_hdf5_reader_rejects_other_files(tmp_path):
     from qmctorch_b200.utils.hdf5_min import read_hdf5
     p = tmp_path / "x.hdf5"
