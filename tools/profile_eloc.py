@@ -10,7 +10,8 @@ from qmctorch_b200.wavefunction import SlaterJastrow
 
 key = sys.argv[1] if len(sys.argv) > 1 else "lih"
 nw = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
-cfg = {"lih": "ground_state", "h2": "single(2,2)", "h2o": "cas(4,4)", "c4h6": "ground_state"}[key]
+cfg = {"lih": "ground_state", "h2": "single(2,2)", "h2o": "cas(4,4)", "c4h6": "ground_state",
+       "lih_adf": "single_double(2,2)"}.get(key, "ground_state")
 mol = fixture_molecule(key)
 wf = SlaterJastrow(mol, configs=cfg, cuda=True)
 s = Metropolis(nwalkers=nw, nstep=5, step_size=0.3, nelec=wf.nelec, ndim=3, init=mol.domain("normal"),
