@@ -3,7 +3,7 @@
 statistical error.  Molecules: the ADF results read from the reference's HDF5 files (lih_adf, h2_adf,
 co2_adf; `Molecule(load=...)`).
 
-    python tools/vmc_hf_check.py lih_adf 1000000 1000
+    python tools/vmc_hf_check.py lih_adf 1000000 1000 [step_size] [all-elec|one-elec]
 """
 import os
 import sys
@@ -21,11 +21,12 @@ key = sys.argv[1] if len(sys.argv) > 1 else "lih_adf"
 nw = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 nstep = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 step = float(sys.argv[4]) if len(sys.argv) > 4 else 0.3
+move = sys.argv[5] if len(sys.argv) > 5 else "all-elec"
 set_torch_double_precision()
 mol = fixture_molecule(key)
 wf = SlaterJastrow(mol, configs="ground_state", jastrow=None, cuda=True)
 sampler = Metropolis(nwalkers=nw, nstep=nstep, step_size=step, ntherm=-1, ndecor=1, nelec=wf.nelec, ndim=3,
-                     init=mol.domain("atomic"), move={"type": "all-elec", "proba": "normal"}, cuda=True, seed=3)
+                     init=mol.domain("atomic"), move={"type": move, "proba": "normal"}, cuda=True, seed=3)
 solver = Solver(wf=wf, sampler=sampler, optimizer=torch.optim.Adam(wf.parameters(), lr=0.01))
 t0 = time.time()
 obs = solver.single_point(with_tqdm=False)
