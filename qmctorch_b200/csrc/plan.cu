@@ -359,7 +359,7 @@ static int upload(qmcb_plan *p) {
   size_t nt = p->bwd_tiles.size() * sizeof(int);
   if (nt > p->cap_bwd_tiles) {
     if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
-  if (p->d_ticket) cudaFree(p->d_ticket);
+    p->d_bwd_tiles = nullptr;
     if ((e = cudaMalloc(&p->d_bwd_tiles, nt)) != cudaSuccess) return (int)e;
     p->cap_bwd_tiles = nt;
   }
@@ -379,12 +379,15 @@ extern "C" int qmcb_plan_create(const qmcb_system *sys, int device, qmcb_plan **
   // device < 0: host-only plan (tables + tiling, no upload) for CPU-side tests of the
   // grouping logic; every compute call on it fails with QMCB_EINVAL.
   if (device >= 0) {
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) {
-      qmcb_set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-      return (int)e;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device >= ndev) {
+      qmcb_set_error(std::string("qmcb_plan_create: no such CUDA device: ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : std::to_string(device).c_str()));
+      return e != cudaSuccess ? (int)e : QMCB_EINVAL;
     }
   }
+  DeviceGuard guard(device);
   qmcb_plan *p = new qmcb_plan();
   p->device = device;
   if (device >= 0) {
@@ -405,7 +408,7 @@ extern "C" int qmcb_plan_create(const qmcb_system *sys, int device, qmcb_plan **
 
 extern "C" int qmcb_plan_update(qmcb_plan *p, const qmcb_system *sys) {
   if (!p) return QMCB_EINVAL;
-  if (p->device >= 0) cudaSetDevice(p->device);
+  DeviceGuard guard(p->device);
   qmcb_spec_free(p);        // the structure may have changed; compiled modules stay cached by structure
   ++p->version;
   int rc = qmcb_build_tables(sys, p);
@@ -420,11 +423,12 @@ extern "C" int qmcb_plan_update(qmcb_plan *p, const qmcb_system *sys) {
 
 extern "C" void qmcb_plan_destroy(qmcb_plan *p) {
   if (!p) return;
-  if (p->device >= 0) cudaSetDevice(p->device);
+  DeviceGuard guard(p->device);
   if (p->d_dbl) cudaFree(p->d_dbl);
   if (p->d_int) cudaFree(p->d_int);
   if (p->d_mo_full) cudaFree(p->d_mo_full);
   if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
+  if (p->d_ticket) cudaFree(p->d_ticket);
   qmcb_spec_free(p);
   delete p;
 }

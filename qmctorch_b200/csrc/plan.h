@@ -1,5 +1,7 @@
 // Host-side plan and the device table layout shared by all kernels.
 #pragma once
+#include <cuda_runtime.h>
+
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -101,6 +103,20 @@ struct qmcb_plan {
   // host copy of flat data needed by backward post-processing
   std::vector<int> index_ctr;
   std::vector<double> mo_full;
+};
+
+// Switches to the plan's device for the scope of a host entry point and restores the caller's
+// current device on exit (a finalizer may call qmcb_plan_destroy at any time: it must not change
+// the device the caller - e.g. torch - believes to be current).
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  explicit DeviceGuard(int device) {
+    if (device < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != device) { active = cudaSetDevice(device) == cudaSuccess; }
+  }
+  ~DeviceGuard() { if (active && prev >= 0) cudaSetDevice(prev); }
 };
 
 void qmcb_set_error(const std::string &msg);

@@ -499,7 +499,7 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
   if (load && !m.loaded) {
     Dyn &d = dyn();
     if (!d.drv) return fail("libcuda.so.1 not available");
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     cudaFree(nullptr);   // primary context current on this thread
     int rc = d.ModuleLoadData(&m.mod, m.cubin.data());
     if (rc != 0) return fail("cuModuleLoadData: " + drv_err(rc));

@@ -20,7 +20,7 @@ from .ensemble import Walkers
 
 
 class SamplerBase:
-    def __init__(self, nwalkers, nstep, step_size, ntherm, ndecor, nelec, ndim, init, cuda):
+    def __init__(self, nwalkers, nstep, step_size, ntherm, ndecor, nelec, ndim, init, cuda, init_rng="torch"):
         self.nelec = nelec
         self.ndim = ndim
         self.nstep = nstep
@@ -29,7 +29,7 @@ class SamplerBase:
         self.ndecor = ndecor
         self.cuda = cuda
         self.device = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
-        self.walkers = Walkers(nwalkers=nwalkers, nelec=nelec, ndim=ndim, init=init, cuda=cuda)
+        self.walkers = Walkers(nwalkers=nwalkers, nelec=nelec, ndim=ndim, init=init, cuda=cuda, init_rng=init_rng)
 
     def __call__(self, pdf, *args, **kwargs):
         raise NotImplementedError("Sampler must have a __call__ method")
@@ -47,8 +47,8 @@ class SamplerBase:
 class Metropolis(SamplerBase):
     def __init__(self, nwalkers=100, nstep=1000, step_size=0.2, ntherm=-1, ndecor=1, nelec=1, ndim=3,
                  init={"min": -5, "max": 5}, move={"type": "all-elec", "proba": "normal"}, logspace=False,
-                 symmetry=None, cuda=False, rng="philox", seed=None, keep_on_device=False):
-        SamplerBase.__init__(self, nwalkers, nstep, step_size, ntherm, ndecor, nelec, ndim, init, cuda)
+                 symmetry=None, cuda=False, rng="philox", seed=None, keep_on_device=False, init_rng="torch"):
+        SamplerBase.__init__(self, nwalkers, nstep, step_size, ntherm, ndecor, nelec, ndim, init, cuda, init_rng)
         self.logspace = logspace
         self.configure_move(move)
         self.symmetry = (lambda x: x) if symmetry is None else symmetry
@@ -112,7 +112,10 @@ class Metropolis(SamplerBase):
             plan = wf._handle.plan()
             normal = self.movedict["proba"] == "normal"
             scale = math.sqrt(self._sigma) if normal else self.step_size
-            seed = self.seed if self.seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+            # the kernel indexes its Philox draws by the rank-LOCAL walker index: fold the rank into the
+            # seed so that shards are independent even when every rank called the same manual_seed
+            from ..solver.distributed import rank_seed
+            seed = rank_seed(self.seed if self.seed is not None else int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF))
             kept, idecor = [], 0
             tstart = time()
             for istep in tqdm(range(self.nstep), desc="INFO:QMCTorch|  Sampling", disable=not with_tqdm):

@@ -33,6 +33,20 @@ def allreduce_sum_(t):
     return t
 
 
+def allreduce_max_(t):
+    """In-place MAX all-reduce (no-op on one rank)."""
+    if is_distributed():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+def rank_seed(seed):
+    """Folds the rank into a 63-bit seed so that shards draw independent streams even when every rank
+    called the same torch.manual_seed (usual DDP practice); rank 0 / single process: unchanged."""
+    rank, _ = world()
+    return (int(seed) + rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+
+
 def global_stats(sum_e, sum_e2, n, nbad=0.0, device=None):
     """(mean, unbiased variance, standard error, n, nbad) from per-rank partial sums; one
     all-reduce of four doubles."""

@@ -260,20 +260,26 @@ class Solver:
             if pos.device != self.device:
                 pos = pos.to(self.device)
             out4 = None
-            if batchsize is None and D.is_distributed():
+            if batchsize is None:
                 eloc, out4 = self.wf.local_energy_stats(pos)     # E_L and its sums in one pass
-            elif batchsize is None:
-                eloc = self.wf.local_energy(pos)
             else:
                 eloc = torch.cat([self.wf.local_energy(pos[i: i + batchsize])
                                   for i in range(0, len(pos), batchsize)])
-            if D.is_distributed():
-                mean, var, err, n, nbad = D.global_stats(out4, None, None) if out4 is not None else self._stats(eloc)
-                dt = dict(dtype=torch.float64, device=eloc.device)
-                e, s, er = torch.tensor(mean, **dt), torch.tensor(var, **dt), torch.tensor(err, **dt)
-            else:
-                e, s, er = torch.mean(eloc), torch.var(eloc), self.wf.sampling_error(eloc)
-        return SimpleNamespace(pos=pos, local_energy=eloc, energy=e, variance=s, error=er)
+            # mean / unbiased variance / standard error from the four device sums (one all-reduce of
+            # four doubles under torch.distributed); solver_base.py:371, wf_base.py:217-229
+            mean, var, err, n, nbad = D.global_stats(out4, None, None) if out4 is not None else self._stats(eloc)
+            dt = dict(dtype=torch.float64, device=eloc.device)
+            e, s, er = torch.tensor(mean, **dt), torch.tensor(var, **dt), torch.tensor(err, **dt)
+            res = SimpleNamespace(pos=pos, local_energy=eloc, energy=e, variance=s, error=er)
+        self._dump("single_point", hdf5_group, res)
+        return res
+
+    def _dump(self, kind, group, obj):
+        """HDF5 dump of a result (solver_base.py:381-385, solver.py:260,330); see utils/hdf5_write.py."""
+        if not getattr(self, "write_hdf5", False):
+            return
+        from ..utils.hdf5_write import dump_to_hdf5
+        dump_to_hdf5(obj, self.hdf5file, group)
 
     # -- optimisation (solver.py:186-431) --------------------------------------------------------
     def save_sampling_parameters(self):
@@ -301,6 +307,16 @@ class Solver:
             batchsize = len(pos)
         self.save_sampling_parameters()
         self.dataloader = _Loader(pos, batchsize)
+        if D.is_distributed():
+            # every rank must run the same number of batches: each batch carries one all-reduce of
+            # (sum E_L, n) for the global mean, and ranks with different counts would hang
+            nb = torch.tensor([float(ceil(len(pos) / batchsize)), -float(ceil(len(pos) / batchsize))],
+                              dtype=torch.float64, device=self.device)
+            D.allreduce_max_(nb)
+            if nb[0] != -nb[1]:
+                raise ValueError("torch.distributed: ranks would run different numbers of batches "
+                                 "(%d..%d); choose nwalkers / batchsize so that every rank has the same "
+                                 "count" % (int(-nb[1]), int(nb[0])))
         with torch.no_grad():
             for ibatch, data in enumerate(self.dataloader):
                 self.store_observable(data, ibatch=ibatch)
@@ -316,11 +332,13 @@ class Solver:
             self.wf.zero_grad()
             for ibatch, data in enumerate(self.dataloader):
                 lpos = data.to(self.device)
-                loss, eloc = self.evaluate_gradient(lpos)
+                # gradients of the batches accumulate locally in .grad; ONE all-reduce per epoch below
+                loss, eloc = self.evaluate_gradient(lpos, allreduce=False)
                 cumulative_loss += float(loss)
                 if torch.isnan(eloc).any():
                     return cumulative_loss
                 self.store_observable(lpos, local_energy=eloc, ibatch=ibatch)
+            D.allreduce_gradients(self._trainable())
             self.optimization_step(lpos)
             if n == 0 or cumulative_loss < min_loss:
                 min_loss = cumulative_loss
@@ -333,14 +351,15 @@ class Solver:
             self.epoch_time = time() - tstart
         return cumulative_loss
 
-    def evaluate_grad_manual(self, lpos):
+    def evaluate_grad_manual(self, lpos, allreduce=True):
         """dE/dk = < (dpsi/dk)/psi (E_L - <E_L>) > * 2   (solver.py:372-431); the mean and the
-        normalisation are GLOBAL over all ranks, gradients are summed over ranks."""
+        normalisation are GLOBAL over all ranks.  ``allreduce=True`` (a direct call) sums the
+        accumulated ``.grad`` over the ranks before returning - call it once per zero_grad();
+        ``run_epochs`` passes False and all-reduces once per epoch after the batch loop."""
         if self.loss.method not in ["energy", "weighted-energy"]:
             raise ValueError("Manual gradient only for energy minimization")
-        with torch.no_grad():
-            eloc = self.wf.local_energy(lpos)
-        psi = self.wf(lpos)
+        # ONE E_L launch yields E_L and psi; psi enters the autograd graph without a second launch
+        eloc, psi = self.wf.local_energy_and_psi(lpos)
         if D.is_distributed():
             buf = torch.stack([eloc.sum(), torch.tensor(float(len(psi)), dtype=torch.float64, device=eloc.device)])
             D.allreduce_sum_(buf)
@@ -357,7 +376,8 @@ class Solver:
         if not bool(mask.all()):
             weight = weight * mask
         psi.backward(weight)
-        D.allreduce_gradients([p for p in self._trainable()])
+        if allreduce:
+            D.allreduce_gradients(self._trainable())
         return mean, eloc
 
     def _trainable(self):

@@ -32,8 +32,15 @@ class PlanHandle:
         self.device = device
         self._plan = C.c_void_p()
         self._sig = None
+        self._content = None
         self._arrays = None
         self._finalizer = None
+        # "content": every plan() call compares the parameter VALUES with the ones the device tables
+        # were built from (a few small device ops + one 1-byte read-back, ~50 us), so in-place edits
+        # through ``.data`` - which change neither data_ptr nor Tensor._version - are seen.
+        # "version": (data_ptr, _version) only - no read-back, for callers that never edit ``.data``
+        # (or call invalidate() after doing so) and want fully asynchronous launches.
+        self.param_check = "content"
 
     # -- parameters that feed the device tables
     def _tracked(self):
@@ -53,6 +60,14 @@ class PlanHandle:
 
     def _signature(self):
         return tuple((t.data_ptr(), t._version) for t in self._tracked())
+
+    def _flat(self):
+        return torch.cat([t.detach().reshape(-1).to(torch.float64) for t in self._tracked()])
+
+    def invalidate(self):
+        """Forces the next plan() call to rebuild the device tables from the current parameters."""
+        self._sig = None
+        self._content = None
 
     def _system(self):
         ao = self.ao
@@ -107,8 +122,14 @@ class PlanHandle:
                 "qmctorch_b200 runs on CUDA devices only (construct the wave function with "
                 "cuda=True); there is no CPU path")
         sig = self._signature()
+        flat = None
         if sig == self._sig:
-            return self._plan
+            if self.param_check != "content":
+                return self._plan
+            flat = self._flat()
+            if self._content is not None and self._content.shape == flat.shape and \
+                    self._content.device == flat.device and torch.equal(self._content, flat):
+                return self._plan
         L = _lib.lib()
         arrays = self._system()
         index = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -124,6 +145,8 @@ class PlanHandle:
             _lib.check(L.qmcb_plan_update(self._plan, C.byref(arrays.struct)), "qmcb_plan_update")
         self._arrays = arrays
         self._sig = sig
+        if self.param_check == "content":
+            self._content = (self._flat() if flat is None else flat).clone()
         return self._plan
 
     def host_plan_info(self):

@@ -26,10 +26,12 @@ class _PsiFunction(torch.autograd.Function):
     """psi(pos; theta) with analytic parameter gradients."""
 
     @staticmethod
-    def forward(ctx, wf, x, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w, een_num, een_denom, een_fc):
+    def forward(ctx, wf, x, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w, een_num, een_denom, een_fc,
+                psi_value=None):
         ctx.wf = wf
         ctx.save_for_backward(x)
-        return wf._psi(x)
+        # psi_value: psi of exactly these walkers, already produced by the E_L launch (out1)
+        return wf._psi(x) if psi_value is None else psi_value.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -57,7 +59,8 @@ class _PsiFunction(torch.autograd.Function):
                 g["jen_w"] if need[7] else None,
                 g["een_num"] if need[8] else None,
                 g["een_denom"] if need[9] else None,
-                g["een_fc"] if need[10] else None)
+                g["een_fc"] if need[10] else None,
+                None)
 
 
 class SlaterJastrow(WaveFunction):
@@ -217,7 +220,7 @@ class SlaterJastrow(WaveFunction):
                 "een_fc": g_een[4 * nt: 5 * nt].view(1, nt) if nt else None}
 
     # -- public API (reference signatures) ---------------------------------------------------
-    def forward(self, x, ao=None):
+    def forward(self, x, ao=None, _psi_value=None):
         """psi(R) [W,1]  (slater_jastrow.py:243-286)."""
         if ao is not None:
             raise NotImplementedError("forward(x, ao=...) only serves the one-electron update sampler path")
@@ -231,11 +234,21 @@ class SlaterJastrow(WaveFunction):
         track = torch.is_grad_enabled() and (
             any(t is not None and t.requires_grad for t in leaves) or x.requires_grad)
         if not track:
-            return self._psi(xd)
+            return self._psi(xd) if _psi_value is None else _psi_value
         if x.requires_grad:
             xd = x if (x.device == xd.device and x.dtype == torch.float64 and x.is_contiguous()) else \
                 x.to(device=xd.device, dtype=torch.float64).contiguous()
-        return _PsiFunction.apply(self, xd, *leaves)
+        return _PsiFunction.apply(self, xd, *leaves, _psi_value)
+
+    def local_energy_and_psi(self, pos):
+        """(E_L [W,1] without graph, psi [W,1] in the autograd graph of the parameters) from ONE
+        qmcb_local_energy launch: the kernel returns psi alongside E_L (out1), and the autograd node
+        of psi is built around that value instead of a second forward launch.  This is the pair
+        Solver.evaluate_grad_manual needs (solver.py:410-414)."""
+        x = self._x(pos)
+        with torch.no_grad():
+            eloc, psi, _ = self._eloc(x, want_psi=True)
+        return eloc, self.forward(pos if pos.requires_grad else x, _psi_value=psi)
 
     def ao2mo(self, ao):
         return self.mo(ao)
