@@ -6,15 +6,19 @@ and none of them carries hot-path arithmetic.  This shim
 registers inert stubs for exactly those names, puts the reference root on
 ``sys.path`` and returns the ``qmctorch`` package.  It is used in the build
 container (where ``/root/reference`` is mounted) by ``oracle/make_golden.py`` to
-pin ``oracle/sj_oracle.py`` and to write ``tests/golden/*.npz``.  It does not
-exist on the GPU box and nothing under ``qmctorch_b200/`` imports it.
+pin ``oracle/sj_oracle.py`` and to write ``tests/golden/*.npz``.  Nothing under
+``qmctorch_b200/`` imports it; ``bench.py`` uses it only for the CPU legs (the reference arm and
+``cpu_baseline``), from ``baseline/_ref`` on the GPU box.
 """
 
 import os
 import sys
 import types
 
-REF_ROOTS = ["/root/reference"]
+# /root/reference: the build container.  baseline/_ref: `pip install --no-deps --target baseline/_ref` of the
+# unmodified reference (DESIGN.md section 5) - git-ignored, but it travels to the GPU box with the snapshot,
+# so bench.py's CPU legs can time the REAL reference there (cpu_baseline.kind = "reference").
+REF_ROOTS = ["/root/reference", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
 
 
 class _AnyMeta(type):
@@ -68,7 +72,7 @@ def load_reference():
     """Returns the reference ``qmctorch`` package (FP64 default dtype set)."""
     root = next((r for r in REF_ROOTS if os.path.isdir(os.path.join(r, "qmctorch"))), None)
     if root is None:
-        raise RuntimeError("reference tree not mounted (expected /root/reference)")
+        raise RuntimeError("reference tree not found (expected /root/reference or baseline/_ref)")
     for name in _STUBS:
         if name not in sys.modules:
             mod = _StubModule(name)

@@ -91,6 +91,25 @@ _BASIS = {
             (2, [1.185], [1.0]),
         ],
     },
+    # DZP without its polarisation shells (second point of the C4H6 basis-size sweep, BASELINE config 5)
+    "dz": {
+        "H": [
+            (0, [19.2406, 2.8992, 0.6534], [0.032828, 0.231208, 0.817238]),
+            (0, [0.1776], [1.0]),
+        ],
+        "C": [
+            (
+                0,
+                [4232.61, 634.882, 146.097, 42.4974, 14.1892, 1.9666],
+                [0.002029, 0.015535, 0.075411, 0.257121, 0.596555, 0.242517],
+            ),
+            (0, [5.1477], [1.0]),
+            (0, [0.4962], [1.0]),
+            (0, [0.1533], [1.0]),
+            (1, [18.1557, 3.9864, 1.1429, 0.3594], [0.018534, 0.115442, 0.386206, 0.640089]),
+            (1, [0.1146], [1.0]),
+        ],
+    },
     "dzp": {
         "H": [
             (0, [19.2406, 2.8992, 0.6534], [0.032828, 0.231208, 0.817238]),
@@ -418,17 +437,21 @@ _SPECS = {
     "h2o": dict(atom="O 0 0 0; H 0.757 0.587 0; H -0.757 0.587 0", unit="angs",
                 basis="cc-pvdz", name="H2O"),
     "c4h6": dict(atom=None, unit="angs", basis="dzp", name="C4H6"),
-    # real ADF SCF results (Slater basis, cartesian, MOs from the SCF): JSON dumps of the reference's
-    # tests/hdf5/*_adf_*.hdf5 made by tools/hdf5_to_fixture.py
-    "lih_adf": dict(load=os.path.join(_DATA_DIR, "LiH_adf_dz.json")),
-    "h2_adf": dict(load=os.path.join(_DATA_DIR, "H2_adf_dzp.json")),
-    "co2_adf": dict(load=os.path.join(_DATA_DIR, "CO2_adf_dzp.json")),
+    "c4h6_dz": dict(atom=None, unit="angs", basis="dz", name="C4H6"),
 }
+
+# Test inputs that are dumps of the reference's own files (tests/data/*_adf_*.json, made by
+# tools/hdf5_to_fixture.py from the reference's tests/hdf5/*.hdf5) live with the tests, not in the
+# package: keys lih_adf | h2_adf | co2_adf resolve there when that directory exists (a source checkout).
+_TEST_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "data")
+for _k, _f in (("lih_adf", "LiH_adf_dz.json"), ("h2_adf", "H2_adf_dzp.json"), ("co2_adf", "CO2_adf_dzp.json")):
+    if os.path.isfile(os.path.join(_TEST_DATA, _f)):
+        _SPECS[_k] = dict(load=os.path.join(_TEST_DATA, _f))
 
 
 def fixture_spec(key):
     spec = dict(_SPECS[key])
-    if key == "c4h6":
+    if key.startswith("c4h6"):
         spec["atom"] = _butadiene_atoms()
     return spec
 

@@ -3,7 +3,7 @@ tests/hdf5/LiH_adf_dz.hdf5, written by `Molecule(calculator='adf')`) into the JS
 `qmctorch_b200.molecules.Molecule(load=...)` also accepts.  h5py is not needed: the file is read by
 qmctorch_b200/utils/hdf5_min.py.
 
-    python tools/hdf5_to_fixture.py /root/reference/tests/hdf5/LiH_adf_dz.hdf5 qmctorch_b200/data/LiH_adf_dz.json
+    python tools/hdf5_to_fixture.py /root/reference/tests/hdf5/LiH_adf_dz.hdf5 tests/data/LiH_adf_dz.json
 """
 import json
 import os
