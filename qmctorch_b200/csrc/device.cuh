@@ -493,7 +493,9 @@ __device__ __forceinline__ void nuclei_terms(const SYS &S, const TAB &T, double 
   gx += gnx; gy += gny; gz += gnz;
 }
 
-template <bool DERIV, bool POT, class SYS, class TAB>
+// POT_EN = false: the caller adds the electron-nucleus potential itself (specialised kernels take
+// 1/r_eA from the basis-function loop, which forms the same distance anyway)
+template <bool DERIV, bool POT, bool POT_EN = POT, class SYS, class TAB>
 __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const double *sp, int e,
                                                ElecTerms &o) {
   const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
@@ -525,7 +527,7 @@ __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const
       }
     }
   }
-  nuclei_terms<DERIV, POT>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
+  nuclei_terms<DERIV, POT_EN>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
   if (S.een_nterm > 0) een_terms<DERIV>(S, T, sp, e, gx, gy, gz, h, ks);
   o.gx = gx; o.gy = gy; o.gz = gz;
   o.lap = h + gx * gx + gy * gy + gz * gz;
@@ -538,7 +540,7 @@ __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const
 // the lane that evaluated it (four double shuffles), so every pair is evaluated ONCE instead of once
 // per electron; for even Ne the last round is shared out between the two halves.  Fixed order:
 // deterministic.  All 32 lanes must call this (inactive lanes pass act = false).
-template <bool POT, class SYS, class TAB>
+template <bool POT, bool POT_EN = POT, class SYS, class TAB>
 __device__ __forceinline__ void electron_terms_paired(const SYS &S, const TAB &T, const double *sp, int e, int base,
                                                       bool act, ElecTerms &o) {
   const int Ne = S.nelec;
@@ -574,7 +576,7 @@ __device__ __forceinline__ void electron_terms_paired(const SYS &S, const TAB &T
     const double qz = __shfl_sync(0xffffffffu, pz, sl), qh = __shfl_sync(0xffffffffu, hp, sl);
     if (act && (!halfround || e >= half)) { gx -= qx; gy -= qy; gz -= qz; h += qh; }
   }
-  if (act) nuclei_terms<true, POT>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
+  if (act) nuclei_terms<true, POT_EN>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
   o.gx = gx; o.gy = gy; o.gz = gz;
   o.lap = h + gx * gx + gy * gy + gz * gz;
   o.ks = ks; o.ven = ven; o.vee = vee;

@@ -455,7 +455,11 @@ extern "C" int qmcb_plan_info(const qmcb_plan *p, int what) {
       if (!on) qmcb_set_error("qmcb: generic kernels in use: " + why);
       return on;
     }
-    case 14: return qmcb_spec_eligible(p);
+    case 14: return qmcb_spec_eligible(p);     // 0: none, 1: one walker per thread, 2: warp tiles
+    case 15: {                                   // kind of the specialised kernels in use (compiles them now)
+      std::string why;
+      return qmcb_spec_status(p, &why) ? qmcb_spec_kind(p) : 0;
+    }
     default: return QMCB_EINVAL;
   }
 }

@@ -12,6 +12,8 @@
 // failing NVRTC an error).  There is no CPU path here either.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
@@ -39,6 +41,12 @@ int env_int(const char *name, int dflt) {
 }
 const int SPEC_THREADS = env_int("QMCB_SPEC_THREADS", 128);
 const int SPEC_MINB = env_int("QMCB_SPEC_MINB", 4);
+// warp-tile kernels (spec_tile.cuh): CTA shape and where the MO weights live
+const int TILE_THREADS = env_int("QMCB_TILE_THREADS", 128);
+const int TILE_MINB = env_int("QMCB_TILE_MINB", 0);          // 0: chosen from the accumulator count
+const int TILE_MOW = env_int("QMCB_TILE_MOW", 0);            // 0: auto, 1: constant bank, 2: shared memory
+constexpr int TILE_MAX_VALUES = 3800;  // doubles in the parameter block (32 KB of kernel parameters on sm_70+)
+constexpr size_t TILE_SMEM_BUDGET = 110 * 1024;
 // defaults of the kernel's tuning switches (must match the #ifndef defaults in spec_kernel.cuh)
 constexpr int SPEC_DEFAULT_PREFETCH = 0;
 constexpr int SPEC_DEFAULT_PREFETCH_ELOC = 1;
@@ -143,6 +151,23 @@ int jit_level() {
 // ---------------------------------------------------------------------------------------
 struct Layout { int nv = 0, off_atom = 0, off_mow = 0, off_ci = 0; };
 
+// kind of specialised kernel a plan gets: one walker per thread (small systems, spec_kernel.cuh) or
+// warp-owned walker tiles (mid-size / large systems, spec_tile.cuh)
+enum Kind { KIND_NONE = 0, KIND_THREAD = 1, KIND_TILE = 2 };
+
+bool tile_mow_smem(const DevSys &S) {
+  if (TILE_MOW == 1) return false;
+  if (TILE_MOW == 2) return true;
+  // constant-bank operands cost no instruction and no register; measured on C4H6 (94 x 15 weights, 12 KB):
+  // E_L 0.374 ms per 2e4 walkers against 0.421 ms with LDS.128 broadcasts.  Shared memory only when the
+  // weights would not fit the 32 KB kernel-parameter space next to the primitive constants.
+  return S.nao * S.nmu + 6 * S.nprim + S.ncomp + 4 * S.natom > TILE_MAX_VALUES;
+}
+int tile_minb(const DevSys &S) {
+  if (TILE_MINB > 0) return TILE_MINB;
+  return S.nmu > 8 ? 3 : 4;          // 2 x nmu accumulators per thread: 168 / 128 registers
+}
+
 bool eligible(const qmcb_plan *p, std::string *why) {
   const DevSys &S = p->sys;
   const int nbig = S.nup > S.ndown ? S.nup : S.ndown;
@@ -158,7 +183,34 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   return true;
 }
 
-bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layout &L) {
+size_t tile_smem_doubles(const DevSys &S, int mode);
+
+bool eligible_tile(const qmcb_plan *p, std::string *why) {
+  const DevSys &S = p->sys;
+  const int nbig = S.nup > S.ndown ? S.nup : S.ndown;
+  const char *w = nullptr;
+  if (S.nelec > 32 || S.nelec < 1) w = "more than 32 electrons (a walker must fit one warp)";
+  else if (S.nmu > 16) w = "more than 16 occupied MO columns";
+  else if (nbig > 16) w = "spin block larger than 16x16";
+  else if (S.nconf > 4096 || S.nuu + S.nud > 256) w = "too many determinants";
+  else if (tile_smem_doubles(S, MODE_ELOC) * sizeof(double) > TILE_SMEM_BUDGET) w = "tables exceed the shared-memory budget";
+  if (w) { if (why) *why = w; return false; }
+  return true;
+}
+
+Kind choose_kind(const qmcb_plan *p, std::string *why) {
+  const char *force = getenv("QMCB_SPEC_KIND");     // tuning / tests: "thread" | "tile"
+  std::string w1, w2;
+  const bool t1 = eligible(p, &w1), t2 = eligible_tile(p, &w2);
+  if (force && !strcmp(force, "tile")) { if (!t2 && why) *why = w2; return t2 ? KIND_TILE : KIND_NONE; }
+  if (force && !strcmp(force, "thread")) { if (!t1 && why) *why = w1; return t1 ? KIND_THREAD : KIND_NONE; }
+  if (t1) return KIND_THREAD;
+  if (t2) return KIND_TILE;
+  if (why) *why = w1 + "; " + w2;
+  return KIND_NONE;
+}
+
+bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layout &L, Kind kind = KIND_THREAD) {
   const DevSys &S = p->sys;
   const std::vector<double> &hd = p->hd;
   const std::vector<int> &hi = p->hi;
@@ -250,6 +302,18 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
   // MO weights of the occupied columns only (the generic kernels pad the column count to a power of
   // two; a specialised kernel is compiled for the exact count)
   L.off_mow = nv;
+  if (kind == KIND_TILE) {
+    // warp-tile kernels: weights in the parameter block only when they are read as constant-bank
+    // operands; CI coefficients and the index tables are staged from the plan's device tables
+    if (!tile_mow_smem(S))
+      for (int a = 0; a < S.nao; ++a)
+        for (int j = 0; j < S.nmu; ++j) push(hd[S.o_mow + a * S.nmup + j]);
+    L.off_ci = nv;
+    if (nv == 0) push(0.0);
+    L.nv = nv;
+    if (code) *code = o.str();
+    return true;
+  }
   for (int a = 0; a < S.nao; ++a)
     for (int j = 0; j < S.nmu; ++j) push(hd[S.o_mow + a * S.nmup + j]);
   L.off_ci = nv;
@@ -329,9 +393,16 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
   return true;
 }
 
-std::string prelude(const qmcb_plan *p, const Layout &L) {
+std::string prelude(const qmcb_plan *p, const Layout &L, Kind kind = KIND_THREAD) {
   const DevSys &S = p->sys;
   std::ostringstream o;
+  if (kind == KIND_TILE) {
+    o << "#define SPEC_TILE 1\n#define SPEC_KPFX \"spect_\"\n#define SPEC_EEN_NTERM " << S.een_nterm
+      << "\n#define SPEC_NAO " << S.nao << "\n#define SPEC_NCONF " << S.nconf << "\n#define SPEC_MOW_SMEM "
+      << (tile_mow_smem(S) ? 1 : 0) << "\n#define SPEC_MWLD " << S.nmup << "\n#define SPEC_O_MOW " << S.o_mow
+      << "\n#define SPEC_O_CI " << S.o_ci << "\n#define SPEC_O_UCU " << S.o_ucu << "\n#define SPEC_O_UCD " << S.o_ucd
+      << "\n#define SPEC_O_CIU " << S.o_ciu << "\n#define SPEC_O_CID " << S.o_cid << "\n";
+  }
   o << "typedef signed char int8_t;\ntypedef unsigned char uint8_t;\ntypedef int int32_t;\n"
        "typedef unsigned int uint32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n"
        "typedef unsigned long size_t;\n"
@@ -341,17 +412,18 @@ std::string prelude(const qmcb_plan *p, const Layout &L) {
     << "\n#define SPEC_NUD " << S.nud << "\n#define SPEC_USE_JEE " << (S.use_jee ? 1 : 0) << "\n#define SPEC_USE_JEN "
     << (S.use_jen ? 1 : 0) << "\n#define SPEC_GRAM_FMA " << (S.gram_fma ? 1 : 0) << "\n#define SPEC_NV " << L.nv
     << "\n#define SPEC_OFF_ATOM " << L.off_atom << "\n#define SPEC_OFF_MOW " << L.off_mow << "\n#define SPEC_OFF_CI "
-    << L.off_ci << "\n#define SPEC_THREADS " << SPEC_THREADS << "\n#define SPEC_MINB " << SPEC_MINB << "\n";
+    << L.off_ci << "\n#define SPEC_THREADS " << (kind == KIND_TILE ? TILE_THREADS : SPEC_THREADS) << "\n#define SPEC_MINB "
+    << (kind == KIND_TILE ? tile_minb(S) : SPEC_MINB) << "\n";
   return o.str();
 }
 
-std::string full_source(const qmcb_plan *p, const Layout &L, const std::string &code) {
-  std::string k = SPEC_SRC_KERNEL;
+std::string full_source(const qmcb_plan *p, const Layout &L, const std::string &code, Kind kind) {
+  std::string k = kind == KIND_TILE ? SPEC_SRC_TILE : SPEC_SRC_KERNEL;
   const std::string mark = "SPEC_GENERATED_CODE\n";
   const size_t at = k.find("\n" + mark);
   if (at == std::string::npos) return std::string();
   k.replace(at + 1, mark.size(), code);
-  return prelude(p, L) + SPEC_SRC_ARGS + SPEC_SRC_DEVICE + SPEC_SRC_PHILOX + k;
+  return prelude(p, L, kind) + SPEC_SRC_ARGS + SPEC_SRC_DEVICE + SPEC_SRC_PHILOX + SPEC_SRC_COMMON + k;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -365,7 +437,60 @@ struct Module {
   int occ[4] = {0, 0, 0, 0};
   int smem[4] = {0, 0, 0, 0};
   bool loaded = false;
+  bool from_disk = false;
 };
+
+// ---- on-disk cache of compiled modules: <dir of libqmcb.so>/jitcache/<hash of source + options>.cubin
+// (QMCB_JIT_CACHE=<dir> overrides, QMCB_JIT_CACHE=0 disables).  The straight-line program of a large
+// molecule takes ptxas tens of seconds; the cache makes that a one-off per structure and lets modules
+// built ahead of time (python -m qmctorch_b200.build --prebuild) travel with the library.
+std::string cache_dir() {
+  const char *e = getenv("QMCB_JIT_CACHE");
+  if (e && !strcmp(e, "0")) return std::string();
+  if (e && *e) return e;
+  Dl_info info;
+  if (dladdr((void *)&cache_dir, &info) && info.dli_fname) {
+    std::string path = info.dli_fname;
+    const size_t at = path.rfind('/');
+    if (at != std::string::npos) return path.substr(0, at) + "/jitcache";
+  }
+  return std::string();
+}
+std::string hash_hex(const std::string &text) {
+  uint64_t h1 = 1469598103934665603ull, h2 = 0x9E3779B97F4A7C15ull;
+  for (unsigned char c : text) {
+    h1 = (h1 ^ c) * 1099511628211ull;
+    h2 = (h2 + c) * 0xD6E8FEB86659FD93ull; h2 ^= h2 >> 32;
+  }
+  char buf[40];
+  snprintf(buf, sizeof(buf), "%016llx%016llx", (unsigned long long)h1, (unsigned long long)h2);
+  return buf;
+}
+bool disk_load(const std::string &key, std::vector<char> &cubin) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return false;
+  FILE *f = fopen((dir + "/" + key + ".cubin").c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 0;
+  if (ok) { cubin.resize((size_t)n); ok = fread(cubin.data(), 1, (size_t)n, f) == (size_t)n; }
+  fclose(f);
+  if (!ok) cubin.clear();
+  return ok;
+}
+void disk_store(const std::string &key, const std::vector<char> &cubin) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return;
+  mkdir(dir.c_str(), 0755);
+  const std::string tmp = dir + "/" + key + ".tmp" + std::to_string((long)getpid());
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (ok) rename(tmp.c_str(), (dir + "/" + key + ".cubin").c_str()); else remove(tmp.c_str());
+}
 std::map<std::string, Module> &cache() { static std::map<std::string, Module> c; return c; }
 std::mutex &cache_mu() { static std::mutex m; return m; }
 
@@ -424,6 +549,20 @@ size_t smem_doubles(const DevSys &S, int mode) {
   return QMCB_ETAB + (size_t)nmw + (size_t)SPEC_THREADS * slice;
 }
 
+// warp-tile kernels (spec_tile.cuh): exp table | MO weights | CI | int tables | per-warp work areas
+size_t tile_smem_doubles(const DevSys &S, int mode) {
+  const int ne = S.nelec, per = 32 / ne, nm = S.nmu, ldm = nm | 1, nun = S.nuu + S.nud;
+  const int nrow = mode == MODE_ELOC ? 2 : 1;
+  const size_t nmw = tile_mow_smem(S) ? (size_t)S.nao * S.nmup : 0;
+  const size_t nci = (S.nconf + 1) & ~1;
+  const size_t nit = ((size_t)S.nuu * S.nup + (size_t)S.nud * S.ndown + 2 * (size_t)S.nconf + 1) & ~(size_t)1;
+  const size_t npos = ((size_t)per * 3 * ne + 1) & ~(size_t)1;
+  // psi / E_L double-buffer the coordinates (cp.async prefetch of the next tile)
+  const size_t o_jv = npos * ((mode != MODE_MH && def_value("SPEC_TILE_PREFETCH", 1)) ? 2 : 1);
+  const size_t ws = (o_jv + 96 + (size_t)nrow * per * ne * ldm + 2 * (size_t)per * nun + 1) & ~(size_t)1;
+  return QMCB_ETAB + nmw + nci + nit / 2 + (size_t)(TILE_THREADS / 32) * ws;
+}
+
 }  // namespace
 
 struct qmcb_spec_state {
@@ -432,6 +571,7 @@ struct qmcb_spec_state {
   std::string why;
   Module *mod = nullptr;
   Layout lay;
+  Kind kind = KIND_NONE;
   std::vector<char> params;   // host image of SpecParams
   uint64_t params_version = ~0ull;
 };
@@ -470,27 +610,36 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
   auto fail = [&](const std::string &why) { st.failed = true; st.why = why; return 1; };
   if (st.level <= 0) return fail("disabled (QMCB_JIT=0)");
   std::string why;
-  if (!eligible(p, &why)) return fail("not eligible: " + why);
+  const Kind kind = choose_kind(p, &why);
+  if (kind == KIND_NONE) return fail("not eligible: " + why);
+  st.kind = kind;
   std::string code;
   Layout L;
-  if (!walk(p, &code, nullptr, L)) return fail("program walk failed");
-  if (L.nv > SPEC_MAX_VALUES) return fail("parameter block too large");
+  if (!walk(p, &code, nullptr, L, kind)) return fail("program walk failed");
+  if (L.nv > (kind == KIND_TILE ? TILE_MAX_VALUES : SPEC_MAX_VALUES)) return fail("parameter block too large");
   st.lay = L;
   const std::string arch = device_arch(p->device);
-  std::string key = std::to_string(p->device) + "|" + arch + "|" + prelude(p, L) + code;
+  std::string key = std::to_string(p->device) + "|" + arch + "|" + prelude(p, L, kind) + code;
   for (auto &e : extra_defs()) key += "|" + e;
   std::lock_guard<std::mutex> lk(cache_mu());
   Module &m = cache()[key];
   if (m.cubin.empty()) {
-    const std::string src = full_source(p, L, code);
+    const std::string src = full_source(p, L, code, kind);
     if (src.empty()) { cache().erase(key); return fail("embedded source has no insertion mark"); }
+    std::string opts = arch;
+    for (auto &e : extra_defs()) opts += "|" + e;
+    const std::string dkey = hash_hex(opts + "\n" + src);
+    if (!getenv("QMCB_JIT_DUMP") && disk_load(dkey, m.cubin)) m.from_disk = true;
     const char *dump = getenv("QMCB_JIT_DUMP");
     if (dump) {
       FILE *f = fopen((std::string(dump) + ".cu").c_str(), "w");
       if (f) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
     }
     std::string err;
-    if (compile(src, arch, m, err) != 0) { cache().erase(key); return fail(err); }
+    if (m.cubin.empty()) {
+      if (compile(src, arch, m, err) != 0) { cache().erase(key); return fail(err); }
+      disk_store(dkey, m.cubin);
+    }
     if (dump) {
       FILE *f = fopen((std::string(dump) + ".cubin").c_str(), "wb");
       if (f) { fwrite(m.cubin.data(), 1, m.cubin.size(), f); fclose(f); }
@@ -503,17 +652,21 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
     cudaFree(nullptr);   // primary context current on this thread
     int rc = d.ModuleLoadData(&m.mod, m.cubin.data());
     if (rc != 0) return fail("cuModuleLoadData: " + drv_err(rc));
-    const char *names[4] = {"spec_psi", "spec_eloc", "spec_mh", "spec_grad_psi"};
+    const bool tile = kind == KIND_TILE;
+    const char *names[4] = {tile ? "spect_psi" : "spec_psi", tile ? "spect_eloc" : "spec_eloc",
+                            tile ? "spect_mh" : "spec_mh", tile ? nullptr : "spec_grad_psi"};
     const int modes[4] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD};
+    const int threads = tile ? TILE_THREADS : SPEC_THREADS;
     for (int i = 0; i < 4; ++i) {
+      if (!names[i]) { m.fn[i] = nullptr; continue; }     // grad psi of tile structures: generic kernel
       rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
       if (rc != 0) return fail(std::string("cuModuleGetFunction ") + names[i] + ": " + drv_err(rc));
-      m.smem[i] = (int)(smem_doubles(p->sys, modes[i]) * sizeof(double));
-      if ((size_t)m.smem[i] > SPEC_SMEM_BUDGET) { m.fn[i] = nullptr; continue; }   // this mode stays generic
+      m.smem[i] = (int)((tile ? tile_smem_doubles(p->sys, modes[i]) : smem_doubles(p->sys, modes[i])) * sizeof(double));
+      if ((size_t)m.smem[i] > (tile ? TILE_SMEM_BUDGET : SPEC_SMEM_BUDGET)) { m.fn[i] = nullptr; continue; }   // this mode stays generic
       rc = d.FuncSetAttribute(m.fn[i], 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, m.smem[i]);
       if (rc != 0) return fail("cuFuncSetAttribute: " + drv_err(rc));
       int occ = 0;
-      rc = d.OccupancyMaxActiveBlocks(&occ, m.fn[i], SPEC_THREADS, (size_t)m.smem[i]);
+      rc = d.OccupancyMaxActiveBlocks(&occ, m.fn[i], threads, (size_t)m.smem[i]);
       m.occ[i] = (rc == 0 && occ > 0) ? occ : 1;
     }
     m.loaded = true;
@@ -527,15 +680,24 @@ static void refresh_params(const qmcb_plan *p, qmcb_spec_state &st) {
   const DevSys &S = p->sys;
   std::vector<double> vals;
   Layout L;
-  walk(p, nullptr, &vals, L);
-  // SpecParams: expc[8] | jee_w jen_w vnn | etab pointer | v[NV]
-  std::vector<char> buf((8 + 3 + 1 + (size_t)L.nv) * sizeof(double));
+  walk(p, nullptr, &vals, L, st.kind);
+  // SpecParams (spec_common.cuh): expc[8] | jee_w jen_w vnn | etab, dtab, itab pointers | een a b a2 b2 c [8] | v[NV]
+  constexpr int HDR = 8 + 3 + 3 + 5 * 8;      // = SPEC_V_BYTE0 / 8
+  static_assert(HDR * 8 == 432, "SpecParams header layout (SPEC_V_BYTE0)");
+  static_assert(QMCB_EEN_MAXTERM == 8, "SPEC_EEN_MAX");
+  std::vector<char> buf((HDR + (size_t)L.nv) * sizeof(double));
   double *d = reinterpret_cast<double *>(buf.data());
   for (int i = 0; i < 8; ++i) d[i] = S.expc[i];
   d[8] = S.jee_w; d[9] = S.jen_w; d[10] = S.vnn;
   const double *et = p->d_dbl ? p->d_dbl + S.o_etab : nullptr;
   memcpy(&d[11], &et, sizeof(et));
-  for (int i = 0; i < L.nv; ++i) d[12 + i] = vals[i];
+  memcpy(&d[12], &p->d_dbl, sizeof(p->d_dbl));
+  memcpy(&d[13], &p->d_int, sizeof(p->d_int));
+  for (int m = 0; m < QMCB_EEN_MAXTERM; ++m) {
+    d[14 + m] = S.een_a[m]; d[22 + m] = S.een_b[m]; d[30 + m] = S.een_a2[m]; d[38 + m] = S.een_b2[m];
+    d[46 + m] = S.een_c[m];
+  }
+  for (int i = 0; i < L.nv; ++i) d[HDR + i] = vals[i];
   st.params.swap(buf);
   st.params_version = p->version;
 }
@@ -554,14 +716,18 @@ int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *str
   Module &m = *st.mod;
   if (!m.fn[slot]) return QMCB_SPEC_SKIP;
   refresh_params(p, st);
+  const bool tile = st.kind == KIND_TILE;
+  const int threads = tile ? TILE_THREADS : SPEC_THREADS;
   int64_t grid = (int64_t)p->sm_count * m.occ[slot];
-  const int64_t need = (a.W + SPEC_THREADS - 1) / SPEC_THREADS;
+  // work units per CTA: walkers (one per thread) or warp tiles of 32 / Ne walkers
+  const int64_t per_cta = tile ? (int64_t)(threads / 32) * (32 / p->sys.nelec) : threads;
+  const int64_t need = (a.W + per_cta - 1) / per_cta;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   if (grid_out) *grid_out = (int)grid;
   FusedArgs args = a;
   void *kp[2] = {st.params.data(), &args};
-  const int rc = dyn().LaunchKernel(m.fn[slot], (unsigned)grid, 1, 1, SPEC_THREADS, 1, 1, (unsigned)m.smem[slot],
+  const int rc = dyn().LaunchKernel(m.fn[slot], (unsigned)grid, 1, 1, threads, 1, 1, (unsigned)m.smem[slot],
                                     (CUstream)stream, kp, nullptr);
   if (rc != 0) {
     qmcb_set_error("qmcb: cuLaunchKernel(spec): " + drv_err(rc));
@@ -577,4 +743,7 @@ int qmcb_spec_status(const qmcb_plan *p, std::string *why) {
   return rc == 0 ? 1 : 0;
 }
 
-int qmcb_spec_eligible(const qmcb_plan *p) { return jit_level() > 0 && eligible(p, nullptr) ? 1 : 0; }
+int qmcb_spec_eligible(const qmcb_plan *p) { return jit_level() > 0 ? (int)choose_kind(p, nullptr) : 0; }
+
+// 0: generic kernels, 1: one walker per thread, 2: warp tiles (after qmcb_spec_status)
+int qmcb_spec_kind(const qmcb_plan *p) { return p->spec && !p->spec->failed ? (int)p->spec->kind : 0; }

@@ -13,4 +13,5 @@ int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *str
 // 1 when the specialised kernels are compiled (and loaded on the plan's device); `why` = reason if not
 int qmcb_spec_status(const qmcb_plan *p, std::string *why);
 int qmcb_spec_eligible(const qmcb_plan *p);
+int qmcb_spec_kind(const qmcb_plan *p);
 void qmcb_spec_free(qmcb_plan *p);

@@ -140,11 +140,14 @@ _GJ_SYSTEMS = {
 }
 
 
+@pytest.mark.parametrize("jit", ["0", "2"])
 @pytest.mark.parametrize("key", sorted(_GJ_SYSTEMS))
-def test_half_warp_gauss_jordan_orders(key):
+def test_half_warp_gauss_jordan_orders(key, jit, monkeypatch):
     """Spin blocks of order 7..9 (the row-owner half-warp Gauss-Jordan with padded orders 8 and 12,
     unequal blocks in one warp; C4H6 covers 15 -> 16): psi, E_L, grad psi and one Metropolis
-    decision against the oracle on thermalised walkers."""
+    decision against the oracle on thermalised walkers - on the generic CTA-tile kernels (QMCB_JIT=0)
+    and on the structure-specialised warp-tile kernels (spec_tile.cuh)."""
+    monkeypatch.setenv("QMCB_JIT", jit)
     from qmctorch_b200.molecules import Molecule, _seeded_mos, build_basis, _parse_atoms
     from qmctorch_b200.wavefunction import SlaterJastrow
     from qmctorch_b200.wavefunction.pooling import OrbitalConfigurations
@@ -153,7 +156,7 @@ def test_half_warp_gauss_jordan_orders(key):
     nao = build_basis(names, coords, "dzp").nao
     mol = Molecule(atoms, basis="dzp", unit="angs", spin=spin, name=key, mos=_seeded_mos(nao, 5))
     wf = SlaterJastrow(mol, configs="ground_state", cuda=True)
-    assert max(mol.nup, mol.ndown) in (8, 9) and wf._handle.info(13) == 0
+    assert max(mol.nup, mol.ndown) in (8, 9) and wf._handle.info(15) == (0 if jit == "0" else 2)
     P = orc.make_params(mol, OrbitalConfigurations(mol).get_configs("ground_state"), jastrow_weight=1.0)
     pos, _ = _thermalised(wf, mol, 777, nstep=40, step=0.1)
     cpu = pos.cpu()
@@ -546,35 +549,64 @@ def _mh_philox(wf, x, tau, seed, offset, scale=0.3, move_elec=-1):
     return x, acc.bool()
 
 
+# structures of the warp-tile kernels (spec_tile.cuh): CI expansions over 5 x 5 blocks, 11 x 11 and
+# 15 x 15 blocks, Slater radial functions with d shells, e-n and three-body Jastrow factors
+_TILE_CASES = ["h2o_ground", "h2o_cas44", "c4h6_ground", "co2_adf_ground", "lih_een", "lih_sd22_een3", "h2o_cas44_een"]
+
+
 @pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_cas24", "lih_nojastrow", "h2_ground",
-                                  "lih_sto", "lih_sto_pure", "lih_gto_kr", "lih_adf_sd22"])
+                                  "lih_sto", "lih_sto_pure", "lih_gto_kr", "lih_adf_sd22"] + _TILE_CASES)
 def test_specialised_kernels_match_generic(name, monkeypatch):
-    """The NVRTC structure-specialised kernels (spec_kernel.cuh) against the generic interpreter
-    kernels (fused_impl.cuh, QMCB_JIT=0) on the same walkers: psi, E_L, E_kin to rounding, identical
-    Philox proposals, identical accept decisions."""
+    """The NVRTC structure-specialised kernels (spec_kernel.cuh: one walker per thread; spec_tile.cuh:
+    warp tiles) against the generic interpreter kernels (fused_impl.cuh, QMCB_JIT=0) on the same
+    walkers: psi, E_L, E_kin to rounding, identical Philox proposals, identical accept decisions."""
     g = C.load(name)
+    tile = name in _TILE_CASES
     monkeypatch.setenv("QMCB_JIT", "0")
     mol, wf0 = C.build_wf(g)
-    pos, _ = _thermalised(wf0, mol, 5003)          # ragged: not a multiple of the CTA size
+    step = float(g["step"])
+    scale = (step / (2.0 * np.sqrt(2.0 * np.log(2.0)))) ** 0.5     # proposal std of the reference (metropolis.py:207-212)
+    pos, _ = _thermalised(wf0, mol, 1003 if mol.nelec > 20 else 5003, step=step)   # ragged: not a multiple of the tile size
     assert wf0._handle.info(13) == 0
     monkeypatch.setenv("QMCB_JIT", "2")              # 2: a missing / failing NVRTC is an error, not a fallback
     mol, wf1 = C.build_wf(g)
-    assert wf1._handle.info(14) == 1 and wf1._handle.info(13) == 1
+    assert wf1._handle.info(14) == (2 if tile else 1) and wf1._handle.info(13) == 1
+    assert wf1._handle.info(15) == (2 if tile else 1)
     for f in ("__call__", "local_energy", "kinetic_energy"):
         a, b = getattr(wf0, f)(pos), getattr(wf1, f)(pos)
         # psi to rounding; energies can pass through zero for a walker, which inflates the
         # element-wise relative error of both kernels alike
         assert C.rel_err(b, a) < (1e-12 if f == "__call__" else RTOL), f
-    x0, a0 = _mh_philox(wf0, pos, None, 17, 3)
-    x1, a1 = _mh_philox(wf1, pos, None, 17, 3)
+    x0, a0 = _mh_philox(wf0, pos, None, 17, 3, scale=scale)
+    x1, a1 = _mh_philox(wf1, pos, None, 17, 3, scale=scale)
     assert torch.equal(a0, a1) and torch.equal(x0, x1)
-    assert 0.2 < float(a1.float().mean()) < 0.95
+    assert 0.02 < float(a1.float().mean()) < 0.95
     for me in (-2, 1):                              # one random electron / electron 1 only
-        x0, a0 = _mh_philox(wf0, pos, None, 5, 8, move_elec=me)
-        x1, a1 = _mh_philox(wf1, pos, None, 5, 8, move_elec=me)
+        x0, a0 = _mh_philox(wf0, pos, None, 5, 8, scale=scale, move_elec=me)
+        x1, a1 = _mh_philox(wf1, pos, None, 5, 8, scale=scale, move_elec=me)
         assert torch.equal(a0, a1) and torch.equal(x0, x1)
         moved = ((x1 - pos).reshape(len(pos), -1, 3).abs().sum(-1) > 0).sum(-1)
         assert int(moved.max()) <= 1
+    # uniform proposals and injected displacements / acceptance draws take the other coordinate path
+    gen = torch.Generator().manual_seed(9)
+    disp = (scale * torch.randn(pos.shape, generator=gen, dtype=torch.float64)).cuda()
+    tau = torch.rand(pos.shape[0], generator=gen, dtype=torch.float64).cuda()
+    outs = []
+    for wf in (wf0, wf1):
+        x, fx = pos.clone(), (wf(pos).reshape(-1) ** 2).detach().contiguous()
+        acc = torch.zeros(pos.shape[0], dtype=torch.uint8, device="cuda")
+        from qmctorch_b200 import _lib
+        _lib.check(_lib.lib().qmcb_metropolis_step(
+            wf._handle.plan(), _lib.ptr(x), _lib.ptr(fx), pos.shape[0], _lib.ptr(disp), _lib.ptr(tau), None, -1, 1,
+            1.0, 1e-16, 0, 0, _lib.ptr(acc), None, _lib.stream_ptr(x.device)), "qmcb_metropolis_step")
+        x2 = pos.clone()
+        _lib.check(_lib.lib().qmcb_metropolis_step(
+            wf._handle.plan(), _lib.ptr(x2), _lib.ptr(fx.clone()), pos.shape[0], None, None, None, -1, 0,
+            step, 1e-16, 3, 1, None, None, _lib.stream_ptr(x.device)), "qmcb_metropolis_step")
+        torch.cuda.synchronize()
+        outs.append((x, acc.clone(), x2))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][2], outs[1][2])
 
 
 def test_specialised_kernel_follows_parameter_updates():

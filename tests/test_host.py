@@ -138,8 +138,10 @@ def test_walker_initialisation_matches_reference_fixture(double_default):
 
 
 def test_specialised_kernel_source_compiles_without_a_gpu():
-    """spec.cu generates the straight-line program of a small wave function and NVRTC compiles it for
-    sm_100a on a host-only plan (no driver needed); larger systems stay on the generic kernels."""
+    """spec.cu generates the straight-line program of a wave function and NVRTC compiles it for sm_100a
+    on a host-only plan (no driver needed): one walker per thread for small systems (kind 1), warp
+    tiles for mid-size / large ones (kind 2: H2O CAS with the three-body Jastrow); structures that
+    fit neither (more than 32 electrons) stay on the generic kernels."""
     from qmctorch_b200.wavefunction import SlaterJastrow
     L = _lib.lib()
 
@@ -151,13 +153,26 @@ def test_specialised_kernel_source_compiles_without_a_gpu():
         out = (L.qmcb_plan_info(p, 14), L.qmcb_plan_info(p, 13), L.qmcb_last_error().decode())
         L.qmcb_plan_destroy(p)
         return out
-    elig, on, why = status("h2o", "ground_state")
-    assert (elig, on) == (0, 0) and "not eligible" in why
     elig, on, why = status("lih", "single_double(2,2)")
     assert elig == 1
     if not on and "libnvrtc not found" in why:
         pytest.skip("NVRTC is not installed here")
     assert on == 1, why
+    elig, on, why = status("h2o", "cas(4,4)")
+    assert (elig, on) == (2, 1), why
+    # 34 electrons: a walker does not fit one warp
+    from qmctorch_b200.molecules import Molecule, _seeded_mos, build_basis, _parse_atoms
+    atoms = "C 0 0 0; C 0 0 1.4; C 0 1.3 2.1; C 0 2.5 1.4; C 0 2.5 0; H 0 -0.9 -0.5; H 0 -0.9 1.9; H 0 3.4 1.9; H 0 3.4 -0.5"
+    names, coords = _parse_atoms(atoms, "angs")
+    mol = Molecule(atoms, basis="dz", unit="angs", name="C5H4", mos=_seeded_mos(build_basis(names, coords, "dz").nao, 3))
+    wf = SlaterJastrow(mol, configs="ground_state", cuda=False)
+    assert mol.nelec == 34
+    arrays = wf._handle._system()
+    p = ctypes.c_void_p()
+    _lib.check(L.qmcb_plan_create(ctypes.byref(arrays.struct), -1, ctypes.byref(p)), "qmcb_plan_create")
+    assert (L.qmcb_plan_info(p, 14), L.qmcb_plan_info(p, 13)) == (0, 0)
+    assert "not eligible" in L.qmcb_last_error().decode()
+    L.qmcb_plan_destroy(p)
 
 
 def test_generated_program_shares_sp_exponentials_and_launch_shapes(tmp_path, monkeypatch):
