@@ -495,7 +495,9 @@ __device__ __forceinline__ void nuclei_terms(const SYS &S, const TAB &T, double 
 
 // POT_EN = false: the caller adds the electron-nucleus potential itself (specialised kernels take
 // 1/r_eA from the basis-function loop, which forms the same distance anyway)
-template <bool DERIV, bool POT, bool POT_EN = POT, class SYS, class TAB>
+// EEN = false: the three-body term is left to the caller (warp tiles: een_table_*);  FINAL = false: o.lap
+// returns the sum of the second-derivative terms WITHOUT |grad ln J|^2 (the caller adds further terms first)
+template <bool DERIV, bool POT, bool POT_EN = POT, bool EEN = true, bool FINAL = true, class SYS, class TAB>
 __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const double *sp, int e,
                                                ElecTerms &o) {
   const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
@@ -528,9 +530,9 @@ __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const
     }
   }
   nuclei_terms<DERIV, POT_EN>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
-  if (S.een_nterm > 0) een_terms<DERIV>(S, T, sp, e, gx, gy, gz, h, ks);
+  if (EEN && S.een_nterm > 0) een_terms<DERIV>(S, T, sp, e, gx, gy, gz, h, ks);
   o.gx = gx; o.gy = gy; o.gz = gz;
-  o.lap = h + gx * gx + gy * gy + gz * gz;
+  o.lap = FINAL ? h + gx * gx + gy * gy + gz * gz : h;
   o.ks = ks; o.ven = ven; o.vee = vee;
 }
 
@@ -540,7 +542,7 @@ __device__ __forceinline__ void electron_terms(const SYS &S, const TAB &T, const
 // the lane that evaluated it (four double shuffles), so every pair is evaluated ONCE instead of once
 // per electron; for even Ne the last round is shared out between the two halves.  Fixed order:
 // deterministic.  All 32 lanes must call this (inactive lanes pass act = false).
-template <bool POT, bool POT_EN = POT, class SYS, class TAB>
+template <bool POT, bool POT_EN = POT, bool FINAL = true, class SYS, class TAB>
 __device__ __forceinline__ void electron_terms_paired(const SYS &S, const TAB &T, const double *sp, int e, int base,
                                                       bool act, ElecTerms &o) {
   const int Ne = S.nelec;
@@ -578,8 +580,102 @@ __device__ __forceinline__ void electron_terms_paired(const SYS &S, const TAB &T
   }
   if (act) nuclei_terms<true, POT_EN>(S, T, xi, yi, zi, ni, gx, gy, gz, h, ks, ven);
   o.gx = gx; o.gy = gy; o.gz = gz;
-  o.lap = h + gx * gx + gy * gy + gz * gz;
+  o.lap = FINAL ? h + gx * gx + gy * gy + gz * gz : h;
   o.ks = ks; o.ven = ven; o.vee = vee;
+}
+
+// ---------------------------------------------------------------------------------------
+// Three-body Boys-Handy term through per-(electron, atom, term) factor tables (warp tiles, spec_tile.cuh).
+// een_terms above recomputes f, f', f'' of BOTH electrons for every (partner, atom, term) - three
+// reciprocals and two reciprocal square roots per innermost iteration, 85 % of the time of BASELINE
+// config 4.  Here every lane first tabulates its own electron (een_table_fill):
+//     tab[A * (1 + 3 NT)]            = 1 / r_eA
+//     tab[A * (1 + 3 NT) + 1 + 3 m ..] = F, F', F''  with F = a r d, F' = a d^2, F'' = -2 a b d^3, d = 1 / (1 + b r)
+// and the pair loop (een_table_terms) takes its own factors and the partner's F from the tables (shared
+// memory, lane-major with an odd stride): one reciprocal per (pair, term) and none per atom.
+// Same formulas and summation order as een_terms.
+// ---------------------------------------------------------------------------------------
+template <class SYS>
+__host__ __device__ constexpr int een_table_doubles() { return (SYS::natom * (1 + 3 * SYS::een_nterm)) | 1; }
+
+template <class SYS, class TAB>
+__device__ __forceinline__ void een_table_fill(const SYS &S, const TAB &T, const double *sp, int e, double *tab) {
+  constexpr int NT = SYS::een_nterm, NA = SYS::natom;
+  const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
+  const double ni = gram_norm(xi, yi, zi);
+  QMCB_UNROLL
+  for (int A = 0; A < NA; ++A) {
+    const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
+    const double d2 = gram_d2_en(xi, yi, zi, ni, xa, ya, za, gram_norm(xa, ya, za));
+    const double ir = fast_rsqrt(d2), r = d2 * ir;
+    double *q = tab + A * (1 + 3 * NT);
+    q[0] = ir;
+    QMCB_UNROLL
+    for (int m = 0; m < NT; ++m) {
+      const double b = S.een_b[m];
+      const double d = fast_rcp(fma(b, r, 1.0));
+      const double ad = S.een_a[m] * d;
+      const double F1 = ad * d;
+      q[1 + 3 * m] = ad * r;
+      q[2 + 3 * m] = F1;
+      q[3 + 3 * m] = -2.0 * b * F1 * d;
+    }
+  }
+}
+
+// tabs: the walker's tables (lane of electron 0), stride = doubles between consecutive electrons
+template <bool DERIV, class SYS, class TAB>
+__device__ __forceinline__ void een_table_terms(const SYS &S, const TAB &T, const double *sp, int e,
+                                                const double *tabs, int stride, double &gx, double &gy,
+                                                double &gz, double &h, double &ks) {
+  constexpr int NT = SYS::een_nterm, NA = SYS::natom, Ne = SYS::nelec;
+  const double xi = sp[3 * e], yi = sp[3 * e + 1], zi = sp[3 * e + 2];
+  const double ni = gram_norm(xi, yi, zi);
+  const double *own = tabs + e * stride;
+  for (int j = DERIV ? 0 : e + 1; j < Ne; ++j) {
+    if (j == e) continue;
+    const double xj = sp[3 * j], yj = sp[3 * j + 1], zj = sp[3 * j + 2];
+    const double d2 = gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, gram_norm(xj, yj, zj));
+    const double irej = fast_rsqrt(d2), rej = d2 * irej;
+    const double ux = (xi - xj) * irej, uy = (yi - yj) * irej, uz = (zi - zj) * irej;
+    double G[NT], G1[NT], G2[NT];
+    QMCB_UNROLL
+    for (int m = 0; m < NT; ++m) {
+      const double b2 = S.een_b2[m];
+      const double dG = fast_rcp(fma(b2, rej, 1.0));
+      const double adG = S.een_a2[m] * dG;
+      G[m] = adG * rej;
+      G1[m] = adG * dG;
+      G2[m] = -2.0 * b2 * G1[m] * dG;
+    }
+    const double *par = tabs + j * stride;
+    QMCB_UNROLL
+    for (int A = 0; A < NA; ++A) {
+      const double *qo = own + A * (1 + 3 * NT), *qp = par + A * (1 + 3 * NT);
+      const double irE = qo[0];
+      const double vx = (xi - T.atoms()[4 * A]) * irE, vy = (yi - T.atoms()[4 * A + 1]) * irE,
+                   vz = (zi - T.atoms()[4 * A + 2]) * irE;
+      const double cos2 = 2.0 * (ux * vx + uy * vy + uz * vz);
+      double s0 = 0, s1 = 0, s3 = 0, sl = 0;
+      QMCB_UNROLL
+      for (int m = 0; m < NT; ++m) {
+        const double FE = qo[1 + 3 * m];
+        const double cFJ = S.een_c[m] * qp[1 + 3 * m];
+        s0 = fma(cFJ * FE, G[m], s0);
+        if (DERIV) {
+          const double FE1 = qo[2 + 3 * m], FE2 = qo[3 + 3 * m];
+          s1 = fma(cFJ * FE1, G[m], s1);
+          s3 = fma(cFJ * FE, G1[m], s3);
+          sl = fma(cFJ, fma(FE2, G[m], fma(FE, G2[m], FE1 * G1[m] * cos2)), sl);
+        }
+      }
+      if (j > e) ks += s0;
+      if (DERIV) {
+        gx += s1 * vx + s3 * ux; gy += s1 * vy + s3 * uy; gz += s1 * vz + s3 * uz;
+        h += sl + 2.0 * (s1 * irE + s3 * irej);
+      }
+    }
+  }
 }
 
 // One-walker-per-thread variant: every electron pair is visited ONCE.  jv[k*jvs + e] receives
@@ -924,16 +1020,17 @@ __device__ __forceinline__ double half_warp_gauss_jordan(int n, int nmax, double
   for (int k = 0; k < NP; ++k) {
     if (k < nmax) {
       const bool on = k < n;
-      double v = (done || !on) ? -1.0 : fabs(a[k]);
-      int l = hl;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(full, v, o, 16);
-        const int ol = __shfl_xor_sync(full, l, o, 16);
-        const bool take = ov > v || (ov == v && ol < l);
-        v = take ? ov : v;
-        l = take ? ol : l;
-      }
+      // arg-max of |a[k]| over the rows not pivoted yet: ONE integer warp reduction per half-warp.  The
+      // key is the high word of |a[k]| (for non-negative doubles the high word orders like the value:
+      // sign 0 | exponent | top 20 mantissa bits) with 16 - row in its low 5 bits (ties -> lower row; never
+      // 0 for a candidate), so a row within 2^-15 of the largest magnitude may be chosen instead of the
+      // largest itself - an equally valid partial pivot (growth bound unchanged to 1 + 2^-15); NaN rows
+      // compare as large and propagate.  Replaces four rounds of three shuffles + compare/select chains.
+      unsigned key = 0u;
+      if (!done && on) key = ((unsigned)__double2hiint(fabs(a[k])) & 0xffffffe0u) | (unsigned)(16 - hl);
+      const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+      const unsigned kmax = __reduce_max_sync(hmask, key);
+      const int l = kmax ? 16 - (int)(kmax & 31u) : 0;   // (0: this half has no active row left)
       const int p = l;
       const double pv = __shfl_sync(full, a[k], p, 16);
       double ipv;                      // 1 / pivot (either sign; pv = 0: inf, as the exact division)

@@ -42,7 +42,7 @@ int env_int(const char *name, int dflt) {
 const int SPEC_THREADS = env_int("QMCB_SPEC_THREADS", 128);
 const int SPEC_MINB = env_int("QMCB_SPEC_MINB", 4);
 // warp-tile kernels (spec_tile.cuh): CTA shape and where the MO weights live
-const int TILE_THREADS = env_int("QMCB_TILE_THREADS", 128);
+const int TILE_THREADS = env_int("QMCB_TILE_THREADS", 256);
 const int TILE_MINB = env_int("QMCB_TILE_MINB", 0);          // 0: chosen from the accumulator count
 const int TILE_MOW = env_int("QMCB_TILE_MOW", 0);            // 0: auto, 1: constant bank, 2: shared memory
 constexpr int TILE_MAX_VALUES = 3800;  // doubles in the parameter block (32 KB of kernel parameters on sm_70+)
@@ -163,9 +163,16 @@ bool tile_mow_smem(const DevSys &S) {
   // weights would not fit the 32 KB kernel-parameter space next to the primitive constants.
   return S.nao * S.nmu + 6 * S.nprim + S.ncomp + 4 * S.natom > TILE_MAX_VALUES;
 }
+int tile_threads(const DevSys &S) {
+  // the three-body factor tables need ~12 KB per warp: smaller CTAs keep 12 warps per SM resident
+  if (!getenv("QMCB_TILE_THREADS") && S.een_nterm > 0) return 128;
+  return TILE_THREADS;
+}
 int tile_minb(const DevSys &S) {
   if (TILE_MINB > 0) return TILE_MINB;
-  return S.nmu > 8 ? 3 : 4;          // 2 x nmu accumulators per thread: 168 / 128 registers
+  // 256 threads x 2 = 16 warps per SM at 128 registers.  Measured (E_L, ms): C4H6 2e4 walkers 0.400 against
+  // 0.442 for 128 x 3 (168 registers, 12 warps) and 0.479 for 128 x 5; H2O cas(4,4) 1e5 walkers 0.173 / 0.177
+  return S.een_nterm > 0 ? 3 : 2;
 }
 
 bool eligible(const qmcb_plan *p, std::string *why) {
@@ -412,7 +419,7 @@ std::string prelude(const qmcb_plan *p, const Layout &L, Kind kind = KIND_THREAD
     << "\n#define SPEC_NUD " << S.nud << "\n#define SPEC_USE_JEE " << (S.use_jee ? 1 : 0) << "\n#define SPEC_USE_JEN "
     << (S.use_jen ? 1 : 0) << "\n#define SPEC_GRAM_FMA " << (S.gram_fma ? 1 : 0) << "\n#define SPEC_NV " << L.nv
     << "\n#define SPEC_OFF_ATOM " << L.off_atom << "\n#define SPEC_OFF_MOW " << L.off_mow << "\n#define SPEC_OFF_CI "
-    << L.off_ci << "\n#define SPEC_THREADS " << (kind == KIND_TILE ? TILE_THREADS : SPEC_THREADS) << "\n#define SPEC_MINB "
+    << L.off_ci << "\n#define SPEC_THREADS " << (kind == KIND_TILE ? tile_threads(S) : SPEC_THREADS) << "\n#define SPEC_MINB "
     << (kind == KIND_TILE ? tile_minb(S) : SPEC_MINB) << "\n";
   return o.str();
 }
@@ -559,8 +566,10 @@ size_t tile_smem_doubles(const DevSys &S, int mode) {
   const size_t npos = ((size_t)per * 3 * ne + 1) & ~(size_t)1;
   // psi / E_L double-buffer the coordinates (cp.async prefetch of the next tile)
   const size_t o_jv = npos * ((mode != MODE_MH && def_value("SPEC_TILE_PREFETCH", 1)) ? 2 : 1);
-  const size_t ws = (o_jv + 96 + (size_t)nrow * per * ne * ldm + 2 * (size_t)per * nun + 1) & ~(size_t)1;
-  return QMCB_ETAB + nmw + nci + nit / 2 + (size_t)(TILE_THREADS / 32) * ws;
+  const size_t rows = (size_t)nrow * per * ne * ldm;
+  const size_t tls = S.een_nterm > 0 ? (size_t)((S.natom * (1 + 3 * S.een_nterm)) | 1) : 0;   // een_table_doubles
+  const size_t ws = (o_jv + 96 + (rows > 32 * tls ? rows : 32 * tls) + 2 * (size_t)per * nun + 1) & ~(size_t)1;
+  return QMCB_ETAB + nmw + nci + nit / 2 + (size_t)(tile_threads(S) / 32) * ws;
 }
 
 }  // namespace
@@ -656,7 +665,7 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
     const char *names[4] = {tile ? "spect_psi" : "spec_psi", tile ? "spect_eloc" : "spec_eloc",
                             tile ? "spect_mh" : "spec_mh", tile ? nullptr : "spec_grad_psi"};
     const int modes[4] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD};
-    const int threads = tile ? TILE_THREADS : SPEC_THREADS;
+    const int threads = tile ? tile_threads(p->sys) : SPEC_THREADS;
     for (int i = 0; i < 4; ++i) {
       if (!names[i]) { m.fn[i] = nullptr; continue; }     // grad psi of tile structures: generic kernel
       rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
@@ -717,7 +726,7 @@ int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *str
   if (!m.fn[slot]) return QMCB_SPEC_SKIP;
   refresh_params(p, st);
   const bool tile = st.kind == KIND_TILE;
-  const int threads = tile ? TILE_THREADS : SPEC_THREADS;
+  const int threads = tile ? tile_threads(p->sys) : SPEC_THREADS;
   int64_t grid = (int64_t)p->sm_count * m.occ[slot];
   // work units per CTA: walkers (one per thread) or warp tiles of 32 / Ne walkers
   const int64_t per_cta = tile ? (int64_t)(threads / 32) * (32 / p->sys.nelec) : threads;

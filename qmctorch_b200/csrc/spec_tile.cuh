@@ -61,7 +61,10 @@ __device__ __forceinline__ void spect_body(const SpecParams &P, const FusedArgs 
   constexpr int O_JV = NPOS * (PF ? 2 : 1);
   constexpr int O_MO = O_JV + 3 * 32;                // jv [3][32]: per-lane ks / ven / vee (later CI partials)
   constexpr int ROWS = PER * Ne * LDM;
-  constexpr int O_DET = O_MO + NROW * ROWS;
+  // the three-body factor tables (device.cuh: een_table_*) live where the mo / B_kin rows are written later
+  constexpr int TLS = SPEC_EEN_NTERM > 0 ? een_table_doubles<SpecParams>() : 0;
+  constexpr int NMO = NROW * ROWS > 32 * TLS ? NROW * ROWS : 32 * TLS;
+  constexpr int O_DET = O_MO + NMO;
   constexpr int O_TR = O_DET + PER * NUN;
   constexpr int WS = (O_TR + PER * NUN + 1) & ~1;
   extern __shared__ __align__(16) double smem[];
@@ -164,11 +167,22 @@ __device__ __forceinline__ void spect_body(const SpecParams &P, const FusedArgs 
     ElecTerms o;
     o.gx = o.gy = o.gz = o.lap = o.ks = o.ven = o.vee = 0.0;
     if (HASJ || WB) {
-      if (spec_deriv<MODE>() && SPEC_EEN_NTERM == 0 && Ne >= 2) {
+      if (spec_deriv<MODE>() && Ne >= 2) {
         // every e-e pair once; partners exchange their contributions by shuffles (all lanes take part)
-        electron_terms_paired<WB, false>(P, T, sp, act ? e : 0, sub * Ne, act, o);
+        electron_terms_paired<WB, false, SPEC_EEN_NTERM == 0>(P, T, sp, act ? e : 0, sub * Ne, act, o);
       } else if (act) {
-        electron_terms<spec_deriv<MODE>(), WB, false>(P, T, sp, e, o);
+        electron_terms<spec_deriv<MODE>(), WB, false, false, SPEC_EEN_NTERM == 0>(P, T, sp, e, o);
+      }
+      if constexpr (SPEC_EEN_NTERM > 0) {
+        // three-body term: tabulate this lane's electron, then the pair loop on the tables
+        double *tab = smo + lane * TLS;
+        if (act) een_table_fill(P, T, sp, e, tab);
+        __syncwarp();
+        if (act) {
+          een_table_terms<spec_deriv<MODE>()>(P, T, sp, e, smo + sub * Ne * TLS, TLS, o.gx, o.gy, o.gz, o.lap, o.ks);
+          if (spec_deriv<MODE>()) o.lap += o.gx * o.gx + o.gy * o.gy + o.gz * o.gz;
+        }
+        __syncwarp();       // the tables are dead: the rows of mo / B_kin reuse the space
       }
     }
     // ---- P2: generated shell walk + projection; rows of mo (and B_kin) -> shared memory

@@ -551,17 +551,24 @@ def _mh_philox(wf, x, tau, seed, offset, scale=0.3, move_elec=-1):
 
 # structures of the warp-tile kernels (spec_tile.cuh): CI expansions over 5 x 5 blocks, 11 x 11 and
 # 15 x 15 blocks, Slater radial functions with d shells, e-n and three-body Jastrow factors
-_TILE_CASES = ["h2o_ground", "h2o_cas44", "c4h6_ground", "co2_adf_ground", "lih_een", "lih_sd22_een3", "h2o_cas44_een"]
+_TILE_CASES = ["h2o_ground", "h2o_cas44", "c4h6_ground", "co2_adf_ground", "lih_sd22_een3", "h2o_cas44_een"]
+# small structures FORCED onto the warp-tile kernels (QMCB_SPEC_KIND=tile): 8 and 16 walkers per warp,
+# closed-form determinants, e-n Jastrow, Slater radial functions
+_FORCED_TILE = ["lih_een@tile", "lih_cas24@tile", "h2_single22@tile", "lih_sto@tile", "lih_nojastrow@tile"]
 
 
 @pytest.mark.parametrize("name", ["lih_ground", "h2_single22", "lih_sd22", "lih_cas24", "lih_nojastrow", "h2_ground",
-                                  "lih_sto", "lih_sto_pure", "lih_gto_kr", "lih_adf_sd22"] + _TILE_CASES)
+                                  "lih_sto", "lih_sto_pure", "lih_gto_kr", "lih_adf_sd22", "lih_een"] + _TILE_CASES
+                         + _FORCED_TILE)
 def test_specialised_kernels_match_generic(name, monkeypatch):
     """The NVRTC structure-specialised kernels (spec_kernel.cuh: one walker per thread; spec_tile.cuh:
     warp tiles) against the generic interpreter kernels (fused_impl.cuh, QMCB_JIT=0) on the same
     walkers: psi, E_L, E_kin to rounding, identical Philox proposals, identical accept decisions."""
+    tile = name in _TILE_CASES or name.endswith("@tile")
+    if name.endswith("@tile"):
+        name = name[:-5]
+        monkeypatch.setenv("QMCB_SPEC_KIND", "tile")
     g = C.load(name)
-    tile = name in _TILE_CASES
     monkeypatch.setenv("QMCB_JIT", "0")
     mol, wf0 = C.build_wf(g)
     step = float(g["step"])
