@@ -86,7 +86,11 @@ int  qmcb_plan_update(qmcb_plan *plan, const qmcb_system *sys);
 void qmcb_plan_destroy(qmcb_plan *plan);
 /* introspection for tests: 0 nshell, 1 nprim(grouped), 2 ncomp, 3 nmo_used, 4 nuniq_up,
  * 5 nuniq_down, 6 walkers per CTA (local energy), 7 threads per CTA, 8 dynamic smem bytes,
- * 9 walkers per CTA (psi) */
+ * 9 walkers per CTA (psi) [6-9: tiling of the generic kernels], 10-12 backward tiling,
+ * 13: 1 when this plan runs structure-specialised (NVRTC) kernels - compiles / loads them now;
+ *     0: generic kernels, qmcb_last_error() says why,
+ * 14: kind of specialised kernel the structure is eligible for (0 none, 1 one walker per thread,
+ *     2 warp tiles), 15: kind in use (compiles / loads now) */
 int  qmcb_plan_info(const qmcb_plan *plan, int what);
 
 /* --- fused hot path --------------------------------------------------------------- */

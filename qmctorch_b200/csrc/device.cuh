@@ -1028,8 +1028,12 @@ __device__ __forceinline__ double half_warp_gauss_jordan(int n, int nmax, double
       // compare as large and propagate.  Replaces four rounds of three shuffles + compare/select chains.
       unsigned key = 0u;
       if (!done && on) key = ((unsigned)__double2hiint(fabs(a[k])) & 0xffffffe0u) | (unsigned)(16 - hl);
-      const unsigned hmask = 0xffffu << (threadIdx.x & 16);
-      const unsigned kmax = __reduce_max_sync(hmask, key);
+      // (two full-mask reductions, one per half-warp: a half-mask reduction makes the compiler treat the
+      // warp as diverged and wrap every later shuffle in WARPSYNC / ENDCOLLECTIVE)
+      const bool upper = (threadIdx.x & 16) != 0;
+      const unsigned k_lo = __reduce_max_sync(full, upper ? 0u : key);
+      const unsigned k_hi = __reduce_max_sync(full, upper ? key : 0u);
+      const unsigned kmax = upper ? k_hi : k_lo;
       const int l = kmax ? 16 - (int)(kmax & 31u) : 0;   // (0: this half has no active row left)
       const int p = l;
       const double pv = __shfl_sync(full, a[k], p, 16);

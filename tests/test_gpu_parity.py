@@ -768,3 +768,13 @@ def test_gto2sto_wave_function_on_the_cuda_path(key, double_default):
     assert C.rel_err(wf(pos), g[key + "_psi"]) < RTOL
     assert C.rel_err(wf.local_energy(pos), g[key + "_eloc"]) < RTOL
     assert C.scaled_err(wf.gradients_jacobi(pos, sum_grad=False).reshape(len(pos), -1), g[key + "_gpsi"]) < RTOL
+
+
+def test_c_program_evaluates_psi_on_the_device(tmp_path):
+    """The pure-C client of include/qmcb.h (tests/c/abi_smoke.c) on a device: H2 STO-3G psi against the
+    closed form evaluated in the C program itself, E_L finite."""
+    import subprocess
+    from test_host import _build_abi_smoke
+    r = subprocess.run([_build_abi_smoke(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "ABI_OK device" in r.stdout
