@@ -22,9 +22,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <set>
 
 #include "device.cuh"
+#include "spec.h"
 
 #define BWD_MAXT 16   // output tiles per warp
 #define BWD_WARP_LU_MIN 7   // spin blocks at least this large: one warp per block (see fused_impl.cuh)
@@ -490,6 +492,27 @@ __global__ void backward_reduce(const DevSys S, const double *partial, int ngrid
   }
 }
 
+// Second stage of the structure-specialised backward (spec_kernel.cuh: spec_bwd_body): per-CTA partials
+// [ngrid][nacc], nacc = nao * nmu + nconf + 2, summed in index order and scattered to the caller's layouts.
+__global__ void bwd_spec_reduce(const DevSys S, const double *partial, int ngrid, int nacc, int nmo_full, double *g_mo,
+                                double *g_ci, double *g_jee, double *g_jen) {
+  const int *ib = S.iblob;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nacc; i += gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int g = 0; g < ngrid; ++g) v += partial[(size_t)g * nacc + i];
+    const int nw = S.nao * S.nmu;
+    if (i < nw) {
+      const int a = i / S.nmu, j = i - a * S.nmu;
+      if (g_mo) g_mo[(size_t)a * nmo_full + ib[S.o_used + j]] = v;
+    } else {
+      const int c = i - nw;
+      if (c < S.nconf) { if (g_ci) g_ci[c] = v; }
+      else if (c == S.nconf) { if (g_jee) g_jee[0] = v; }
+      else if (g_jen) g_jen[0] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------
@@ -564,8 +587,11 @@ int qmcb_choose_backward(qmcb_plan *p) {
 }
 
 extern "C" int64_t qmcb_backward_workspace_bytes(const qmcb_plan *p, int64_t) {
-  if (!p || (p->bwd.tw == 0 && p->bwd0.tw == 0)) return 0;
-  return (int64_t)2 * p->sm_count * p->bwd.nslot * (int64_t)sizeof(double);
+  if (!p) return 0;
+  // tile kernel: 2 CTAs per SM x nslot;  specialised kernel: up to 8 CTAs per SM x (nao nmu + nconf + 2)
+  const int64_t spec = (int64_t)8 * p->sm_count * ((int64_t)p->sys.nao * p->sys.nmu + p->sys.nconf + 2);
+  const int64_t tile = (p->bwd.tw == 0 && p->bwd0.tw == 0) ? 0 : (int64_t)2 * p->sm_count * p->bwd.nslot;
+  return (spec > tile ? spec : tile) * (int64_t)sizeof(double);
 }
 
 extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const double *weight, int64_t W,
@@ -577,12 +603,31 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
     return QMCB_EINVAL;
   }
   const int want_ao = (g_bas_exp || g_bas_coeffs) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // Jastrow / MO / CI gradients of a one-walker-per-thread structure (BASELINE config 3): the
+  // structure-specialised backward, register accumulators, no tile staging (QMCB_BWD_SPEC=0 disables)
+  static const bool spec_off = getenv("QMCB_BWD_SPEC") && atoi(getenv("QMCB_BWD_SPEC")) == 0;
+  if (!want_ao && !g_een && !spec_off) {
+    cudaError_t e0;
+    const size_t nmo_b = (size_t)p->sys.nao * p->sys.nmo * sizeof(double);
+    if (g_mo && (e0 = cudaMemsetAsync(g_mo, 0, nmo_b, st)) != cudaSuccess) return qmcb_cuda_rc((int)e0, "backward.cu");
+    FusedArgs fa{};
+    fa.pos = pos; fa.W = W; fa.weight = weight; fa.bwd_part = (double *)workspace;
+    int grid = 0;
+    const int rc = qmcb_spec_launch(p, MODE_BWD, fa, stream, &grid);
+    if (rc == 0) {
+      const int nacc = p->sys.nao * p->sys.nmu + p->sys.nconf + 2;
+      bwd_spec_reduce<<<(nacc + 127) / 128, 128, 0, st>>>(p->sys, (const double *)workspace, grid, nacc, p->sys.nmo, g_mo,
+                                                          g_ci, g_jee_w, g_jen_w);
+      return qmcb_cuda_rc((int)cudaGetLastError(), "backward.cu spec reduce");
+    }
+    if (rc != QMCB_SPEC_SKIP) return rc;
+  }
   const auto &b = want_ao ? p->bwd : p->bwd0;
   if (b.tw == 0) {
     qmcb_set_error("qmcb_psi_backward: system does not fit the backward tiling");
     return QMCB_ESMEM;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   BwdArgs a{};
   a.pos = pos; a.weight = weight; a.W = W; a.partial = (double *)workspace; a.tiles = p->d_bwd_tiles;
   a.want_ao = want_ao;

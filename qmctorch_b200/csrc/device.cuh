@@ -18,6 +18,9 @@
 #endif
 
 #define QMCB_EPS 1e-16
+#ifndef QMCB_ETAB_REP
+#define QMCB_ETAB_REP 1
+#endif
 
 #ifndef QMCB_SPEC
 // Views into the staged tables.  Only the two base pointers are kept live; every table pointer is
@@ -112,7 +115,10 @@ __device__ __forceinline__ double exp_core(const SYS &S, const double *etab, dou
     p = fma(p, r, 0.5);
   }
   const double q = fma(r * r, p, r);
-  const double tj = etab[ki & (QMCB_ETAB - 1)];
+  // QMCB_ETAB_REP > 1: the table is replicated REP times, entry j of replica c at [j * REP + c], and the
+  // caller passes etab + (lane % REP): lanes of a half-warp that look up different entries then hit
+  // different bank pairs (the random-index lookup of the unreplicated table costs ~5 wavefronts)
+  const double tj = etab[(ki & (QMCB_ETAB - 1)) * QMCB_ETAB_REP];
   const double y = fma(tj, q, tj);
   return __hiloint2double(__double2hiint(y) + ((ki >> QMCB_ETAB_LOG2) << 20), __double2loint(y));
 }
@@ -704,6 +710,10 @@ __device__ __forceinline__ void walker_terms(const SYS &S, const TAB &T, const d
       const double s2 = dx * dx + dy * dy + dz * dz;
       if (POT) vee += fast_rsqrt(s2);
       if (S.use_jee) {
+        // (the reference forms r_ij twice - Gram-form here, directly for the potential - and so do we: taking
+        // 1/r_ij of the potential from the Gram value as well saves one reciprocal square root per pair, 2 % of
+        // the LiH kernel, but carries the Gram form's cancellation error, up to 5e-12 Hartree per close pair,
+        // into E_L: measured and not kept)
         const double d2 = gram_d2_ee(S, xi, yi, zi, ni, xj, yj, zj, gram_norm(xj, yj, zj));
         const double rinv = fast_rsqrt(d2);
         const double r = d2 * rinv;

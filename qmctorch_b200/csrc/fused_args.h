@@ -2,7 +2,7 @@
 // only: this header is also compiled by NVRTC.
 #pragma once
 
-enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3 };
+enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3, MODE_BWD = 4 };
 
 // entries of the 2^(j/N) table of the exp() range reduction (device.cuh: exp_core); power of two
 #ifndef QMCB_ETAB_LOG2
@@ -32,5 +32,9 @@ struct FusedArgs {
   // with both set, the CTA that arrives last adds the partials in index order -> stats_out[4]
   unsigned *stats_ticket;
   double *stats_out;
+  // parameter-gradient backward of the one-walker-per-thread kernels (MODE_BWD): weight [W] of
+  // psi.backward(weight), per-CTA partial sums [gridDim.x][SPEC_NAO * SPEC_NMUP + nconf + 2]
+  const double *weight;
+  double *bwd_part;
 };
 

@@ -141,6 +141,14 @@ int def_value(const char *name, int dflt) {
   return dflt;
 }
 
+// replicas of the exp table in the one-walker-per-thread kernels (power of two <= 16; device.cuh: exp_core)
+int spec_etab_rep() {
+  int r = env_int("QMCB_SPEC_ETAB_REP", 1);   // measured (LiH E_L, ms): 1 -> 0.136, 4 / 8 -> 0.141, 16 -> 0.142: the conflicts of the unreplicated table are not the limiter
+  int p2 = 1;
+  while (p2 * 2 <= r && p2 < 16) p2 *= 2;
+  return p2;
+}
+
 int jit_level() {
   const char *e = getenv("QMCB_JIT");
   return e ? atoi(e) : 1;
@@ -184,7 +192,7 @@ bool eligible(const qmcb_plan *p, std::string *why) {
   else if (nbig > 3) w = "spin block larger than 3x3";
   else if (S.nelec > 8 || S.nelec < 1) w = "more than 8 electrons";
   else if (S.nuu + S.nud > 16 || S.nconf > 64) w = "too many determinants";
-  else if ((QMCB_ETAB + (size_t)SPEC_THREADS * ((10 * S.nelec + 1 + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
+  else if (((size_t)QMCB_ETAB * spec_etab_rep() + (size_t)SPEC_THREADS * ((10 * S.nelec + 1 + 2 * S.nelec * S.nmu) | 1)) * sizeof(double) > SPEC_SMEM_BUDGET)
     w = "per-thread slices exceed the shared-memory budget";
   if (w) { if (why) *why = w; return false; }
   return true;
@@ -396,6 +404,45 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
       << "] * sig); out[" << 3 * e + 2 << "] = f * J * (gz + jv[2 * NE + " << e << "] * sig);\n  }\n";
   }
   o << "}\n";
+  // parameter-gradient backward (MODE_BWD, spec_kernel.cuh: spec_bwd_body): inverses and CI weights as in
+  // spec_grad, then G[e][m] = w J sum_u C_u inv_u[j(m)][e] and dW[a][m] += AO[e][a] G[e][m]
+  o << "\ntemplate <int MODE>\n__device__ __forceinline__ void spec_bwd(const double *A, const double *sao, double wJ, "
+       "double (&dW)[SPEC_NAO][SPEC_NMUP], double (&dci)[SPEC_NCONF], double &sig_out) {\n"
+       "  constexpr int NM = SPEC_NMUP, NAO = SPEC_NAO;\n"
+    << "  double det[" << nun << "];\n";
+  for (int u = 0; u < nun; ++u) {
+    const bool up = u < S.nuu;
+    const int n = up ? S.nup : S.ndown;
+    if (n == 0) { o << "  det[" << u << "] = 1.0;\n"; continue; }
+    const int *cols = hi.data() + (up ? S.o_ucu + u * S.nup : S.o_ucd + (u - S.nuu) * S.ndown);
+    o << "  double inv" << u << "[" << n * n << "];\n  { const int cols[" << n << "] = {";
+    for (int j = 0; j < n; ++j) o << (j ? ", " : "") << cols[j];
+    o << "}; det[" << u << "] = inverse_small(" << n << ", A + " << (up ? 0 : S.nup) * S.nmu << ", NM, cols, inv" << u
+      << ", 1); }\n";
+  }
+  o << "  double sig = 0.0;\n";
+  for (int u = 0; u < nun; ++u) o << "  double cw" << u << " = 0.0;\n";
+  for (int c = 0; c < S.nconf; ++c) {
+    const int iu = hi[S.o_ciu + c], id = S.nuu + hi[S.o_cid + c];
+    o << "  { const double ci = spec_pv<MODE, " << L.off_ci + c << ">(), dd = det[" << iu << "] * det[" << id
+      << "]; sig = fma(ci, dd, sig); cw" << iu << " = fma(ci, det[" << id << "], cw" << iu << "); cw" << id
+      << " = fma(ci, det[" << iu << "], cw" << id << "); dci[" << c << "] = fma(wJ, dd, dci[" << c << "]); }\n";
+  }
+  for (int u = 0; u < nun; ++u) o << "  cw" << u << " *= det[" << u << "] * wJ;\n";
+  for (int e = 0; e < S.nelec; ++e) {
+    const bool up = e < S.nup;
+    const int n = up ? S.nup : S.ndown, el = up ? e : e - S.nup;
+    o << "  {  // electron " << e << "\n    double g[NM];\n#pragma unroll\n    for (int m = 0; m < NM; ++m) g[m] = 0.0;\n";
+    const int u0 = up ? 0 : S.nuu, u1 = up ? S.nuu : nun;
+    for (int u = u0; u < u1; ++u) {
+      const int *cols = hi.data() + (up ? S.o_ucu + u * S.nup : S.o_ucd + (u - S.nuu) * S.ndown);
+      for (int j = 0; j < n; ++j)
+        o << "    g[" << cols[j] << "] = fma(cw" << u << ", inv" << u << "[" << j * n + el << "], g[" << cols[j] << "]);\n";
+    }
+    o << "#pragma unroll\n    for (int a = 0; a < NAO; ++a) {\n      const double v = sao[" << e << " * NAO + a];\n"
+         "#pragma unroll\n      for (int m = 0; m < NM; ++m) dW[a][m] = fma(v, g[m], dW[a][m]);\n    }\n  }\n";
+  }
+  o << "  sig_out = sig;\n}\n";
   if (code) *code = o.str();
   return true;
 }
@@ -403,6 +450,8 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
 std::string prelude(const qmcb_plan *p, const Layout &L, Kind kind = KIND_THREAD) {
   const DevSys &S = p->sys;
   std::ostringstream o;
+  if (kind == KIND_THREAD)
+    o << "#define QMCB_ETAB_REP " << spec_etab_rep() << "\n#define SPEC_NAO " << S.nao << "\n#define SPEC_NCONF " << S.nconf << "\n";
   if (kind == KIND_TILE) {
     o << "#define SPEC_TILE 1\n#define SPEC_KPFX \"spect_\"\n#define SPEC_EEN_NTERM " << S.een_nterm
       << "\n#define SPEC_NAO " << S.nao << "\n#define SPEC_NCONF " << S.nconf << "\n#define SPEC_MOW_SMEM "
@@ -440,9 +489,9 @@ struct Module {
   std::vector<char> cubin;
   std::string log;
   CUmodule mod = nullptr;
-  CUfunction fn[4] = {nullptr, nullptr, nullptr, nullptr};   // psi, eloc, mh, grad
-  int occ[4] = {0, 0, 0, 0};
-  int smem[4] = {0, 0, 0, 0};
+  CUfunction fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // psi, eloc, mh, grad, backward
+  int occ[5] = {0, 0, 0, 0, 0};
+  int smem[5] = {0, 0, 0, 0, 0};
   bool loaded = false;
   bool from_disk = false;
 };
@@ -544,7 +593,16 @@ std::string drv_err(int rc) {
 }
 
 // dynamic shared memory of one CTA (doubles): etab | optional MO weights + CI | per-thread slices
+// register accumulators of the specialised backward: dW[nao][nmu] + CI + 2 Jastrow weights
+bool bwd_eligible(const DevSys &S) { return S.nao * S.nmu <= 48 && S.nconf <= 16; }
+
 size_t smem_doubles(const DevSys &S, int mode) {
+  if (mode == MODE_BWD) {
+    const int slice = (3 * S.nelec + S.nelec * S.nmu + S.nelec * S.nao) | 1;
+    const size_t red = (size_t)(SPEC_THREADS / 32) * (S.nao * S.nmu + S.nconf + 2);
+    const size_t body = (size_t)SPEC_THREADS * slice;
+    return (size_t)QMCB_ETAB * spec_etab_rep() + (body > red ? body : red);
+  }
   const bool deriv = mode == MODE_ELOC || mode == MODE_GRAD;
   const int nrow = mode == MODE_ELOC ? 2 : (mode == MODE_GRAD ? 4 : 1);
   const int ne3 = 3 * S.nelec;
@@ -553,7 +611,7 @@ size_t smem_doubles(const DevSys &S, int mode) {
       (mode == MODE_ELOC && def_value("SPEC_PREFETCH_ELOC", SPEC_DEFAULT_PREFETCH_ELOC)))
     slice += ne3 + (ne3 & 1);
   const int nmw = def_value("SPEC_MOW_SMEM", SPEC_DEFAULT_MOW_SMEM) ? ((S.nao * S.nmu + S.nconf + 1) & ~1) : 0;
-  return QMCB_ETAB + (size_t)nmw + (size_t)SPEC_THREADS * slice;
+  return (size_t)QMCB_ETAB * spec_etab_rep() + (size_t)nmw + (size_t)SPEC_THREADS * slice;
 }
 
 // warp-tile kernels (spec_tile.cuh): exp table | MO weights | CI | int tables | per-warp work areas
@@ -662,12 +720,13 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
     int rc = d.ModuleLoadData(&m.mod, m.cubin.data());
     if (rc != 0) return fail("cuModuleLoadData: " + drv_err(rc));
     const bool tile = kind == KIND_TILE;
-    const char *names[4] = {tile ? "spect_psi" : "spec_psi", tile ? "spect_eloc" : "spec_eloc",
-                            tile ? "spect_mh" : "spec_mh", tile ? nullptr : "spec_grad_psi"};
-    const int modes[4] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD};
+    const char *names[5] = {tile ? "spect_psi" : "spec_psi", tile ? "spect_eloc" : "spec_eloc",
+                            tile ? "spect_mh" : "spec_mh", tile ? nullptr : "spec_grad_psi",
+                            (tile || !bwd_eligible(p->sys)) ? nullptr : "spec_backward"};
+    const int modes[5] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD, MODE_BWD};
     const int threads = tile ? tile_threads(p->sys) : SPEC_THREADS;
-    for (int i = 0; i < 4; ++i) {
-      if (!names[i]) { m.fn[i] = nullptr; continue; }     // grad psi of tile structures: generic kernel
+    for (int i = 0; i < 5; ++i) {
+      if (!names[i]) { m.fn[i] = nullptr; continue; }     // grad psi / backward of tile structures: generic kernels
       rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
       if (rc != 0) return fail(std::string("cuModuleGetFunction ") + names[i] + ": " + drv_err(rc));
       m.smem[i] = (int)((tile ? tile_smem_doubles(p->sys, modes[i]) : smem_doubles(p->sys, modes[i])) * sizeof(double));
@@ -712,7 +771,8 @@ static void refresh_params(const qmcb_plan *p, qmcb_spec_state &st) {
 }
 
 int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *stream, int *grid_out) {
-  const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : (mode == MODE_GRAD ? 3 : -1)));
+  const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : (mode == MODE_GRAD ? 3 :
+                   (mode == MODE_BWD ? 4 : -1))));
   if (slot < 0 || p->device < 0) return QMCB_SPEC_SKIP;
   if (spec_prepare(p, true) != 0) {
     if (p->spec->level >= 2) {

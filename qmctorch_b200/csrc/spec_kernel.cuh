@@ -33,14 +33,16 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   constexpr int NROW = MODE == MODE_ELOC ? 2 : (MODE == MODE_GRAD ? 4 : 1);   // mo | B_kin or mo | d mo/dx,dy,dz
   constexpr int SLICE = (3 * Ne + (spec_deriv<MODE>() ? 4 * Ne : 0) + NROW * Ne * NM) | 1;
   extern __shared__ __align__(16) double smem[];
-  double *et = smem;
-  for (int i = threadIdx.x; i < QMCB_ETAB; i += blockDim.x) et[i] = P.etab_g[i];
+  // exp table, replicated QMCB_ETAB_REP times (device.cuh: exp_core); this thread reads replica lane % REP
+  double *et0 = smem;
+  for (int i = threadIdx.x; i < QMCB_ETAB * QMCB_ETAB_REP; i += blockDim.x) et0[i] = P.etab_g[i / QMCB_ETAB_REP];
+  const double *et = et0 + (threadIdx.x & (QMCB_ETAB_REP - 1));
   constexpr int NMW = SPEC_MOW_SMEM ? ((SPEC_NV - SPEC_OFF_MOW + 1) & ~1) : 0;   // MO weights + CI, even
-  double *mw = smem + QMCB_ETAB;
+  double *mw = smem + QMCB_ETAB * QMCB_ETAB_REP;
   for (int i = threadIdx.x; i < NMW; i += blockDim.x) mw[i] = i < SPEC_NV - SPEC_OFF_MOW ? P.v[SPEC_OFF_MOW + i] : 0.0;
   constexpr bool PF = SPEC_PREFETCH || (MODE == MODE_ELOC && SPEC_PREFETCH_ELOC);
   constexpr int SL = SLICE + (PF ? ne3 + (ne3 & 1) : 0);               // stays odd
-  double *spos = smem + QMCB_ETAB + NMW + (size_t)threadIdx.x * SL;
+  double *spos = smem + QMCB_ETAB * QMCB_ETAB_REP + NMW + (size_t)threadIdx.x * SL;
   double *jv = spos + ne3;
   double *smo = jv + (spec_deriv<MODE>() ? 4 * Ne : 0);
   double *sB = smo + Ne * NM;
@@ -194,7 +196,7 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
     __syncthreads();                     // every thread is done with its slice: reuse it
-    double *red = smem + QMCB_ETAB;
+    double *red = smem + QMCB_ETAB * QMCB_ETAB_REP;
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
       for (int k = 0; k < 4; ++k) red[(threadIdx.x >> 5) * 4 + k] = q[k];
@@ -229,6 +231,119 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// psi.backward(weight) for the parameters BASELINE config 3 trains (solver/solver.py:414-429; formulas:
+// SURVEY appendix A.6): MO weights of the occupied columns, CI coefficients, Pade Jastrow weights.
+// One walker per thread like the forward kernels: the walker's AO rows stay in its shared-memory slice,
+// the generated spec_bwd forms the inverses, the CI weights C_u and G[e][m] = w J sum_u C_u inv_u[j(m)][e]
+// with literal indices and adds AO[e][a] G[e][m] into REGISTER accumulators dW[a][m] that live for the
+// whole kernel; one fixed-order block reduction at the end -> one partial per CTA, summed in index order
+// by bwd_spec_reduce (backward.cu): bitwise reproducible.  The tile kernel backward_kernel (DMMA) remains
+// the path for basis-parameter gradients, three-body weights and larger structures.
+// ---------------------------------------------------------------------------------------
+#ifndef SPEC_NCONF
+#define SPEC_NCONF 1
+#endif
+__device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedArgs &a) {
+  constexpr int MODE = MODE_BWD;
+  constexpr int Ne = SPEC_NE, ne3 = 3 * SPEC_NE, NM = SPEC_NMUP, NAO = SPEC_NAO, NC = SPEC_NCONF;
+  constexpr int NACC = NAO * NM + NC + 2;
+  constexpr int SL = (ne3 + Ne * NM + Ne * NAO) | 1;
+  extern __shared__ __align__(16) double smem[];
+  double *et0 = smem;
+  for (int i = threadIdx.x; i < QMCB_ETAB * QMCB_ETAB_REP; i += blockDim.x) et0[i] = P.etab_g[i / QMCB_ETAB_REP];
+  const double *et = et0 + (threadIdx.x & (QMCB_ETAB_REP - 1));
+  double *spos = smem + QMCB_ETAB * QMCB_ETAB_REP + (size_t)threadIdx.x * SL;
+  double *smo = spos + ne3, *sao = smo + Ne * NM;
+  const SpecTab T{P};
+  __syncthreads();
+  double dW[NAO][NM], dci[NC], djee = 0.0, djen = 0.0;
+#pragma unroll
+  for (int i = 0; i < NAO; ++i)
+#pragma unroll
+    for (int j = 0; j < NM; ++j) dW[i][j] = 0.0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) dci[c] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.W; w += stride) {
+#pragma unroll
+    for (int i = 0; i < ne3; ++i) spos[i] = a.pos[w * ne3 + i];
+    // Jastrow exponent and its derivative w.r.t. the Pade weights (d/dw [w0 r / (1 + w r)] = -w0 r^2 / (1 + w r)^2)
+    double ks = 0.0, dkee = 0.0, dken = 0.0;
+#pragma unroll
+    for (int i = 0; i < Ne; ++i) {
+      const double xi = spos[3 * i], yi = spos[3 * i + 1], zi = spos[3 * i + 2];
+      const double ni = gram_norm(xi, yi, zi);
+      if (SPEC_USE_JEE) {
+#pragma unroll
+        for (int j = i + 1; j < Ne; ++j) {
+          const double xj = spos[3 * j], yj = spos[3 * j + 1], zj = spos[3 * j + 2];
+          const double d2 = gram_d2_ee(P, xi, yi, zi, ni, xj, yj, zj, gram_norm(xj, yj, zj));
+          const double r = d2 * fast_rsqrt(d2);
+          const double w0 = ((i < SPEC_NUP) == (j < SPEC_NUP)) ? 0.25 : 0.5;
+          const double den = fast_rcp(1.0 + P.jee_w * r);
+          const double t = w0 * r * den;
+          ks += t;
+          dkee -= t * r * den;
+        }
+      }
+      if (SPEC_USE_JEN) {
+#pragma unroll
+        for (int A = 0; A < SPEC_NATOM; ++A) {
+          const double xa = T.atoms()[4 * A], ya = T.atoms()[4 * A + 1], za = T.atoms()[4 * A + 2];
+          const double d2 = gram_d2_en(xi, yi, zi, ni, xa, ya, za, gram_norm(xa, ya, za));
+          const double r = d2 > 0.0 ? d2 * fast_rsqrt(d2) : 0.0;
+          const double den = fast_rcp(1.0 + P.jen_w * r);
+          ks += r * den;
+          dken -= r * r * den * den;
+        }
+      }
+    }
+    // AO rows (kept) and MO rows of the occupied columns
+    const FoldJ fj{0.0, 0.0, 0.0, 0.0};
+    double ven = 0.0;
+    for (int e = 0; e < Ne; ++e) {
+      double acc[1][NM];
+#pragma unroll
+      for (int j = 0; j < NM; ++j) acc[0][j] = 0.0;
+      spec_aos<MODE>(P, et, sao + e * NAO, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], fj, ven, acc);
+#pragma unroll
+      for (int j = 0; j < NM; ++j) smo[e * NM + j] = acc[0][j];
+    }
+    const double J = (SPEC_USE_JEE || SPEC_USE_JEN) ? exp_clamped(P, et, ks) : 1.0;
+    const double wJ = a.weight[w] * J;
+    double sig;
+    spec_bwd<MODE>(smo, sao, wJ, dW, dci, sig);
+    djee = fma(wJ * sig, dkee, djee);
+    djen = fma(wJ * sig, dken, djen);
+  }
+  // ---- fixed-order reduction over the CTA: warp butterflies, then the warps in order
+  double *red = smem + QMCB_ETAB * QMCB_ETAB_REP;       // [warps][NACC], reuses the slices
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  auto put = [&](int idx, double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * NACC + idx] = v;
+  };
+#pragma unroll
+  for (int i = 0; i < NAO; ++i)
+#pragma unroll
+    for (int j = 0; j < NM; ++j) put(i * NM + j, dW[i][j]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) put(NAO * NM + c, dci[c]);
+  put(NAO * NM + NC, djee);
+  put(NAO * NM + NC + 1, djen);
+  __syncthreads();
+  for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
+    double t = 0.0;
+    for (int wq = 0; wq < nwarp; ++wq) t += red[wq * NACC + i];
+    a.bwd_part[(size_t)blockIdx.x * NACC + i] = t;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB_ELOC)
+    spec_backward(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_bwd_body(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
     spec_psi(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_PSI>(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB_ELOC)

@@ -167,7 +167,7 @@ __device__ __forceinline__ void spect_body(const SpecParams &P, const FusedArgs 
     ElecTerms o;
     o.gx = o.gy = o.gz = o.lap = o.ks = o.ven = o.vee = 0.0;
     if (HASJ || WB) {
-      if (spec_deriv<MODE>() && Ne >= 2) {
+      if (spec_deriv<MODE>() && Ne >= 2 && SPEC_USE_JEE) {
         // every e-e pair once; partners exchange their contributions by shuffles (all lanes take part)
         electron_terms_paired<WB, false, SPEC_EEN_NTERM == 0>(P, T, sp, act ? e : 0, sub * Ne, act, o);
       } else if (act) {

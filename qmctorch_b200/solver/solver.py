@@ -5,7 +5,8 @@ low-variance ("manual") energy-gradient estimator.
 Orchestration stays Python; ``wf.local_energy``, ``wf(pos)`` and its backward are the fused
 CUDA kernels.  Under torch.distributed every rank owns a shard of the walkers and the
 statistics / gradients are summed with one all-reduce each (solver/distributed.py).
-HDF5 dumps (utils/hdf5_utils.py) are outside the hot path: results are returned, not written.
+Results are returned and - when an ``output`` file is named - dumped in the layout of the reference's
+``utils/hdf5_utils.py:dump_to_hdf5`` by the pure-Python writer ``utils/hdf5_write.py`` (rank 0 only).
 """
 import os
 from math import ceil
@@ -80,6 +81,9 @@ class Solver:
             if hasattr(self.sampler, "keep_on_device"):
                 self.sampler.keep_on_device = True
         self.hdf5file = output
+        # the reference always dumps to <molecule>_QMCTorch.hdf5 in the working directory; here a file is
+        # written only when the caller names one (solver.write_hdf5 can be switched on afterwards)
+        self.write_hdf5 = output is not None
         if output is None:
             base = os.path.basename(getattr(wf.mol, "hdf5file", "mol.hdf5")).split(".")[0]
             self.hdf5file = base + "_QMCTorch.hdf5"
@@ -275,11 +279,14 @@ class Solver:
         return res
 
     def _dump(self, kind, group, obj):
-        """HDF5 dump of a result (solver_base.py:381-385, solver.py:260,330); see utils/hdf5_write.py."""
-        if not getattr(self, "write_hdf5", False):
-            return
-        from ..utils.hdf5_write import dump_to_hdf5
-        dump_to_hdf5(obj, self.hdf5file, group)
+        """HDF5 dump of a result + its ``type`` attribute (solver_base.py:381-385,466-470, solver.py:255-263);
+        see utils/hdf5_write.py.  Rank 0 writes."""
+        if not getattr(self, "write_hdf5", False) or self.rank != 0:
+            return None
+        from ..utils.hdf5_write import add_group_attr, dump_to_hdf5
+        grp = dump_to_hdf5(obj, self.hdf5file, group)
+        add_group_attr(self.hdf5file, grp, {"type": kind})
+        return grp
 
     # -- optimisation (solver.py:186-431) --------------------------------------------------------
     def save_sampling_parameters(self):
@@ -298,6 +305,7 @@ class Solver:
         self.run_epochs(nepoch)
         self.restore_sampling_parameters()
         self.observable.models.last = dict(self.wf.state_dict())
+        self._dump("opt", hdf5_group, self.observable)
         return self.observable
 
     def prepare_optimization(self, batchsize, chkpt_every, tqdm=False):
@@ -372,9 +380,8 @@ class Solver:
         weight -= mean
         weight /= psi.detach().clone()
         weight *= 2.0 / ntot
-        mask = self.loss.get_clipping_mask(eloc)
-        if not bool(mask.all()):
-            weight = weight * mask
+        if self.loss.clip:          # (no mask, and no host read-back of it, when clipping is off)
+            weight = weight * self.loss.get_clipping_mask(eloc)
         psi.backward(weight)
         if allreduce:
             D.allreduce_gradients(self._trainable())
@@ -420,7 +427,9 @@ class Solver:
             for ip in p:
                 el.append(self.wf.local_energy(ip.to(self.device)).cpu().numpy())
         el = np.array(el).squeeze(-1)
-        return SimpleNamespace(local_energy=el, pos=pos)
+        obs = SimpleNamespace(local_energy=el, pos=pos)
+        self._dump("sampling_traj", hdf5_group, obs)
+        return obs
 
     def save_checkpoint(self, epoch, loss):
         """solver_base.py:389-405 (key spelling kept so checkpoints interchange)."""

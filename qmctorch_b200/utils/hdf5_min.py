@@ -18,6 +18,14 @@ _SIG = b"\x89HDF\r\n\x1a\n"
 _UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
+class Group(dict):
+    """A group: members by name, HDF5 attributes in ``.attrs``."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.attrs = {}
+
+
 class _File:
     def __init__(self, buf):
         self.b = buf
@@ -97,7 +105,15 @@ class _File:
             if mtype == 0x11:      # symbol table message: this object is a group
                 entries = []
                 self._btree_entries(self.u64(o), self.u64(o + 8), entries)
-                return {name: self.read_object(child) for name, child in entries}
+                grp = Group((name, self.read_object(child)) for name, child in entries)
+                for mt, _, ao, _ in msgs:
+                    if mt == 0x0C:
+                        try:
+                            name, val = self._attribute(ao)
+                            grp.attrs[name] = val
+                        except NotImplementedError:
+                            pass
+                return grp
         if any(m[0] == 0x02 or m[0] == 0x06 for m in msgs):
             raise NotImplementedError("link-message (new style) groups")
         return self._read_dataset(msgs)
@@ -149,6 +165,33 @@ class _File:
             self._gheaps[addr] = objs
         return self._gheaps[addr][index]
 
+    def _attribute(self, o):
+        """Version-1 attribute message -> (name, value)."""
+        if self.b[o] != 1:
+            raise NotImplementedError("attribute message version %d" % self.b[o])
+        nn, nt, ns = self.u16(o + 2), self.u16(o + 4), self.u16(o + 6)
+        p8 = lambda n: (n + 7) // 8 * 8
+        name = self.b[o + 8:o + 8 + nn].split(b"\0")[0].decode("utf-8")
+        t = o + 8 + p8(nn)
+        d = t + p8(nt)
+        raw = d + p8(ns)
+        shape, kind = self._dataspace(d), self._datatype(t)
+        count = int(np.prod(shape)) if shape else 1
+        return name, self._decode(kind, shape, count, self.b[raw:raw + count * (kind[1].itemsize if kind[0] == "num" else kind[1])])
+
+    def _decode(self, kind, shape, count, raw):
+        if kind[0] == "num":
+            arr = np.frombuffer(raw, dtype=kind[1], count=count).astype(kind[1].newbyteorder("="))
+            return arr.reshape(shape) if shape else arr[0]
+        if kind[0] == "str":
+            vals = [raw[i * kind[1]:(i + 1) * kind[1]].split(b"\0")[0].decode("utf-8") for i in range(count)]
+        else:  # vlen string: length (4) + global heap collection address (8) + object index (4)
+            vals = []
+            for i in range(count):
+                n, gaddr, gidx = struct.unpack_from("<IQI", raw, 16 * i)
+                vals.append(self._global_heap_object(gaddr, gidx)[:n].decode("utf-8") if n else "")
+        return np.array(vals).reshape(shape) if shape else vals[0]
+
     def _read_dataset(self, msgs):
         shape = kind = raw = None
         for mtype, _, o, msize in msgs:
@@ -173,17 +216,7 @@ class _File:
         if shape is None or kind is None or raw is None:
             raise ValueError("dataset without dataspace / datatype / layout")
         count = int(np.prod(shape)) if shape else 1
-        if kind[0] == "num":
-            arr = np.frombuffer(raw, dtype=kind[1], count=count).astype(kind[1].newbyteorder("="))
-            return arr.reshape(shape) if shape else arr[0]
-        if kind[0] == "str":
-            vals = [raw[i * kind[1]:(i + 1) * kind[1]].split(b"\0")[0].decode("utf-8") for i in range(count)]
-        else:  # vlen string: length (4) + global heap collection address (8) + object index (4)
-            vals = []
-            for i in range(count):
-                n, gaddr, gidx = struct.unpack_from("<IQI", raw, 16 * i)
-                vals.append(self._global_heap_object(gaddr, gidx)[:n].decode("utf-8") if n else "")
-        return np.array(vals).reshape(shape) if shape else vals[0]
+        return self._decode(kind, shape, count, raw)
 
 
 def read_hdf5(path):

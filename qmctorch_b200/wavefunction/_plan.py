@@ -69,14 +69,37 @@ class PlanHandle:
         self._sig = None
         self._content = None
 
-    def _system(self):
+    def _host(self, flat=None):
+        """Every tracked tensor on the host from ONE device-to-host copy (a plan update after opt.step()
+        otherwise pays one synchronising copy per tensor): list of numpy arrays in _tracked() order."""
+        ts = self._tracked()
+        if flat is None:
+            flat = self._flat()
+        h = flat.cpu().numpy()
+        out, off = [], 0
+        for t in ts:
+            n = t.numel()
+            out.append(h[off:off + n].reshape(tuple(t.shape)))
+            off += n
+        return out
+
+    def _system(self, flat=None):
         ao = self.ao
         nelec = self.nup + self.ndown
         nao = ao.norb
+        host = iter(self._host(flat))
+        h_atom, h_exp, h_coef = next(host), next(host), next(host)
         if self.mo is not None:
-            w = _cpu(self.mo.mo_scf * self.mo.mo_modifier)
+            h_mod, h_scf = next(host), next(host)
+            w = h_scf * h_mod
         else:
             w = np.eye(nao)
+        h_ci = next(host) if self.fc is not None else None
+        h_jee = next(host) if self.jee is not None else None
+        h_jen = next(host) if self.jen is not None else None
+        h_een = [next(host), next(host), next(host)] if self.jeen is not None else None
+        if getattr(self, "_norm_host", None) is None:
+            self._norm_host = _cpu(ao.norm_cst)            # frozen at construction (atomic_orbitals.py:90-94)
         nmo = w.shape[1]
         if self.configs is not None:
             cu = np.asarray(self.configs[0].cpu().numpy(), dtype=np.int32).reshape(-1, max(self.nup, 0))
@@ -86,7 +109,7 @@ class PlanHandle:
             cd = np.arange(self.ndown, dtype=np.int32)[None]
         nconf = cu.shape[0]
         if self.fc is not None:
-            ci = _cpu(self.fc.weight).reshape(-1)
+            ci = h_ci.reshape(-1)
         else:
             ci = np.zeros(nconf)
             ci[0] = 1.0
@@ -96,23 +119,23 @@ class PlanHandle:
         return _lib.SystemArrays(
             nelec=nelec, nup=self.nup, ndown=self.ndown, natom=ao.natoms, nbas=ao.nbas, nao=nao,
             nmo=nmo, radial_type=_lib.RADIAL[ao.radial_type], contract=int(ao.contract),
-            atom_coords=_cpu(ao.atom_coords), atomic_number=np.asarray(ao.atomic_number, dtype=np.float64),
-            bas_atom=ao.bas_atom_np, bas_exp=_cpu(ao.bas_exp), bas_coeffs=_cpu(ao.bas_coeffs),
-            bas_norm=_cpu(ao.norm_cst), bas_kx=ao.bas_kx_np, bas_ky=ao.bas_ky_np, bas_kz=ao.bas_kz_np,
+            atom_coords=h_atom, atomic_number=np.asarray(ao.atomic_number, dtype=np.float64),
+            bas_atom=ao.bas_atom_np, bas_exp=h_exp, bas_coeffs=h_coef,
+            bas_norm=self._norm_host, bas_kx=ao.bas_kx_np, bas_ky=ao.bas_ky_np, bas_kz=ao.bas_kz_np,
             bas_kr=ao.bas_kr_np, index_ctr=ao.index_ctr_np, mo=w, nconf=nconf, cfg_up=cu, cfg_down=cd,
             ci=ci,
             use_jee=int(self.jee is not None),
-            jee_w=float(_cpu(self.jee.jastrow_kernel.weight)[0]) if self.jee is not None else 0.0,
+            jee_w=float(h_jee.reshape(-1)[0]) if self.jee is not None else 0.0,
             use_jen=int(self.jen is not None),
-            jen_w=float(_cpu(self.jen.jastrow_kernel.weight)[0]) if self.jen is not None else 0.0,
-            gram_fma=gram_fma, **self._een_arrays())
+            jen_w=float(h_jen.reshape(-1)[0]) if self.jen is not None else 0.0,
+            gram_fma=gram_fma, **self._een_arrays(h_een))
 
-    def _een_arrays(self):
+    def _een_arrays(self, h_een):
         if self.jeen is None:
             return dict(een_nterm=0)
         k = self.jeen.jastrow_kernel
-        return dict(een_nterm=k.nterm, een_num=_cpu(k.weight_num).reshape(2, k.nterm),
-                    een_denom=_cpu(k.weight_denom).reshape(2, k.nterm), een_fc=_cpu(k.fc.weight).reshape(-1))
+        return dict(een_nterm=k.nterm, een_num=h_een[0].reshape(2, k.nterm),
+                    een_denom=h_een[1].reshape(2, k.nterm), een_fc=h_een[2].reshape(-1))
 
     def plan(self):
         """Returns the (up to date) ``qmcb_plan*``; rebuilds the tables if a parameter changed."""
@@ -131,7 +154,9 @@ class PlanHandle:
                     self._content.device == flat.device and torch.equal(self._content, flat):
                 return self._plan
         L = _lib.lib()
-        arrays = self._system()
+        if flat is None:
+            flat = self._flat()
+        arrays = self._system(flat)
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         if not self._plan:
             # make sure the primary context exists before the library's runtime touches it
@@ -146,7 +171,7 @@ class PlanHandle:
         self._arrays = arrays
         self._sig = sig
         if self.param_check == "content":
-            self._content = (self._flat() if flat is None else flat).clone()
+            self._content = flat.clone()
         return self._plan
 
     def host_plan_info(self):
