@@ -326,9 +326,10 @@ def plan_info(wf):
 
 def thermalised(C, mol, wf, spec, W, nbuf, therm, seed0):
     """nbuf independent ensembles: reference 'normal' start (drawn on the device), thermalised by the
-    fused Metropolis kernel."""
+    fused Metropolis kernel.  (QMCB_BENCH_THERM=<n> shortens the thermalisation for profiler runs.)"""
     import torch
     from qmctorch_b200.sampler import Metropolis
+    therm = int(os.environ.get("QMCB_BENCH_THERM", therm))
     ens = []
     for b in range(nbuf):
         torch.manual_seed(1234 + 17 * C.rank + b)

@@ -245,6 +245,84 @@ def main(only=None):
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def spherical_fixture():
+    """Spherical-harmonics bases (l <= 2, Slater and Gaussian radial parts with r^n; fixtures lih_sph,
+    lih_sph_gto).  The reference's Jacobi kinetic energy cannot run on them (spherical_harmonics.py:226-245
+    raises for derivative lists), so its wave function is built with kinetic="auto" (autograd Hessian of psi,
+    wf_base.py:142-182): psi, AO values, E_L, the manual-gradient estimator and Metropolis decisions are the
+    reference's; the oracle (spherical harmonics restated as cartesian monomials) is asserted against them
+    -> tests/golden/sph.npz."""
+    out = {}
+    for key, nw in (("lih_sph", 96), ("lih_sph_gto", 64)):
+        torch.manual_seed(2024)
+        np.random.seed(2024)
+        mol = fixture_molecule(key)
+        wf = SlaterJastrow(mol, configs="single_double(2,2)", kinetic="auto", include_all_mo=True)
+        sampler = Metropolis(nwalkers=nw, nstep=120, step_size=0.3, nelec=wf.nelec, ndim=3, init=mol.domain("normal"),
+                             move={"type": "all-elec", "proba": "normal"})
+        pos = sampler(wf.pdf, with_tqdm=False).detach().clone()
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            wf.mo.mo_modifier.mul_(1 + 0.05 * (torch.rand(wf.mo.mo_modifier.shape, generator=g) - 0.5))
+            wf.fc.weight.add_(0.2 * (torch.rand(wf.fc.weight.shape, generator=g) - 0.5))
+            wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+        P = orc.make_params(mol, wf.configs, jastrow_weight=0.8)
+        P.mo_modifier = wf.mo.mo_modifier.detach().clone()
+        P.ci = wf.fc.weight.detach().clone()
+        x = pos.clone().requires_grad_(True)
+        psi = wf(x).detach()
+        eloc = wf.local_energy(x).detach()
+        with torch.no_grad():
+            ao = wf.ao(pos)
+        errs = dict(ao=relmax(orc.ao_values(P, pos), ao), psi=rel(orc.psi(P, pos), psi),
+                    eloc=float(((orc.local_energy(P, pos) - eloc).abs() / eloc.abs().clamp(min=1.0)).max()))
+        # manual energy-gradient estimator, solver.py:414-429 applied by hand: Solver.evaluate_grad_manual wraps
+        # local_energy in no_grad, which kinetic="auto" cannot run under, so E_L above is reused
+        wf.zero_grad()
+        val = wf(pos)
+        weight = 2.0 / len(val) * (eloc - eloc.mean()) / val.detach()
+        val.backward(weight)
+        ref_g = dict(mo_modifier=wf.mo.mo_modifier.grad.clone(), ci=wf.fc.weight.grad.clone(),
+                     jastrow_weight=wf.jastrow.jastrow_kernel.weight.grad.clone())
+        og, _ = orc.param_grads(P, pos, eloc=eloc, names=tuple(ref_g))
+        for k, v in ref_g.items():
+            errs["g_" + k] = float((og[k] - v).abs().max() / max(float(v.abs().max()), 1e-6))
+        # Metropolis decisions, teacher forced
+        with torch.no_grad():
+            gen = torch.Generator().manual_seed(99)
+            sig = orc.proposal_sigma(0.3)
+            cur = pos.clone()
+            fx = wf.pdf(cur)
+            tr_disp, tr_tau, tr_acc, tr_pos = [], [], [], [cur.numpy().copy()]
+            for it in range(3):
+                disp = torch.randn(cur.shape, generator=gen, dtype=torch.float64) * np.sqrt(sig)
+                xn = cur + disp
+                fxn = wf.pdf(xn)
+                df = fxn / fx
+                torch.manual_seed(1000 + it)
+                idx = sampler._accept(df.clone())
+                torch.manual_seed(1000 + it)
+                tau = torch.rand_like(df)
+                npos, nfx, oacc, ofxn = orc.metropolis_step(P, cur, fx.clone(), disp, tau)
+                assert bool((oacc == idx).all()), "oracle accept mismatch"
+                cur[idx, :] = xn[idx, :]
+                fx[idx] = fxn[idx]
+                assert torch.equal(npos, cur)
+                tr_disp.append(disp.numpy()); tr_tau.append(tau.numpy()); tr_acc.append(idx.numpy())
+                tr_pos.append(cur.numpy().copy())
+        print("%-12s W=%3d " % (key, nw) + " ".join("%s=%.1e" % kv for kv in errs.items()))
+        bad = {k: v for k, v in errs.items() if not v < (2e-9 if k == "eloc" or k.startswith("g_") else 5e-11)}
+        assert not bad, "oracle does not reproduce the reference: %r" % bad
+        out.update({key + "_pos": pos.numpy(), key + "_psi": psi.numpy(), key + "_eloc": eloc.numpy(),
+                    key + "_ao": ao[:8].numpy(), key + "_mo_modifier": P.mo_modifier.numpy(), key + "_ci": P.ci.numpy(),
+                    key + "_cfg_up": wf.configs[0].numpy(), key + "_cfg_down": wf.configs[1].numpy(),
+                    key + "_mh_disp": np.stack(tr_disp), key + "_mh_tau": np.stack(tr_tau),
+                    key + "_mh_acc": np.stack(tr_acc), key + "_mh_pos": np.stack(tr_pos)})
+        for k, v in ref_g.items():
+            out[key + "_grad_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "sph.npz"), **out)
+
+
 def walker_init_fixture():
     """Initial ensembles of the reference's ``Walkers.initialize`` (sampler/walkers.py:41-150) for
     the four ``Molecule.domain`` methods, seeds 5/5 -> tests/golden/walkers_init.npz."""
@@ -337,7 +415,7 @@ def gto2sto_fixture():
 
 if __name__ == "__main__":
     special = {"walkers_init": walker_init_fixture, "gradient_samplers": gradient_sampler_fixture,
-               "gto2sto": gto2sto_fixture}
+               "gto2sto": gto2sto_fixture, "sph": spherical_fixture}
     args = sys.argv[1:]
     for name, fn in special.items():
         if not args or name in args:

@@ -67,9 +67,58 @@ def primitive_norms(basis):
     raise ValueError("radial_type")
 
 
+# Real spherical harmonics of the reference, l <= 2 (orbitals/spherical_harmonics.py:352-702; Y00 is the
+# truncated literal 0.2820948 of :363), written as sums of cartesian monomials over r^l:
+#   (l, m) -> [(coefficient, kx, ky, kz)]
+_SPH_MONOMIALS = {
+    (0, 0): [(0.2820948, 0, 0, 0)],
+    (1, -1): [(0.4886025119029199, 0, 1, 0)], (1, 0): [(0.4886025119029199, 0, 0, 1)],
+    (1, 1): [(0.4886025119029199, 1, 0, 0)],
+    (2, -2): [(1.0925484305920792, 1, 1, 0)], (2, -1): [(1.0925484305920792, 0, 1, 1)],
+    (2, 1): [(1.0925484305920792, 1, 0, 1)],
+    (2, 2): [(0.5462742152960396, 2, 0, 0), (-0.5462742152960396, 0, 2, 0)],
+    (2, 0): [(-0.31539156525252005, 2, 0, 0), (-0.31539156525252005, 0, 2, 0), (2 * 0.31539156525252005, 0, 0, 2)],
+}
+
+
+def spherical_as_cartesian(b):
+    """A spherical-harmonics basis (harmonics_type "sph": AO = N(n, alpha) r^n e^{-alpha r | r^2} Y_lm,
+    atomic_orbitals.py:56-64, radial_functions.py:6-238, norm_orbital.py:45-93) restated as the contracted
+    cartesian basis the rest of this oracle evaluates: r^n Y_lm = sum_t c_t x^a y^b z^c r^(n-l).  Returns
+    (cartesian namespace, per-primitive norm with the monomial coefficient folded in)."""
+    n = np.asarray(b.bas_n).astype(int)
+    lq, mq = np.asarray(b.bas_l).astype(int), np.asarray(b.bas_m).astype(int)
+    ex = np.asarray(b.bas_exp, dtype=np.float64)
+    if b.radial_type.startswith("sto"):
+        nfact = np.array([float(math.factorial(int(2 * k))) for k in n])
+        norm = (2 * ex) ** n * np.sqrt(2 * ex / nfact)
+    else:
+        n1 = n + 1.0
+        norm = np.sqrt(2 ** (2 * n1 + 1.5) / (np.array([_dfact(2 * int(k) - 1) for k in n1]) * np.pi ** 0.5)) \
+            * ex ** (0.25 * (2 * n1 + 1))
+    atom = np.repeat(np.arange(len(b.nshells)), np.asarray(b.nshells))
+    rows = []
+    for i in range(len(n)):
+        for c, a, bb, cc in _SPH_MONOMIALS[(int(lq[i]), int(mq[i]))]:
+            rows.append((i, c, a, bb, cc, n[i] - lq[i]))
+    ix = np.array([r[0] for r in rows])
+    out = SimpleNamespace(**vars(b))
+    out.harmonics_type = "cart"
+    out.nshells = [int((atom[ix] == a).sum()) for a in range(len(b.nshells))]
+    out.index_ctr = np.asarray(b.index_ctr)[ix]
+    out.bas_coeffs = np.asarray(b.bas_coeffs, dtype=np.float64)[ix]
+    out.bas_exp = ex[ix]
+    out.bas_kx = np.array([r[2] for r in rows]); out.bas_ky = np.array([r[3] for r in rows])
+    out.bas_kz = np.array([r[4] for r in rows]); out.bas_kr = np.array([r[5] for r in rows])
+    return out, norm[ix] * np.array([r[1] for r in rows]), ix
+
+
 def make_params(mol, configs, jastrow_weight=1.0, en_weight=None):
     """Collect every tensor the path reads.  Trainable leaves are plain tensors."""
     b = mol.basis
+    sph_norm = None
+    if b.harmonics_type == "sph":
+        b, sph_norm, _ = spherical_as_cartesian(b)
     p = SimpleNamespace()
     p.nelec, p.nup, p.ndown = mol.nelec, mol.nup, mol.ndown
     p.atom_coords = torch.tensor(np.asarray(b.atom_coords_internal), dtype=F64)
@@ -83,7 +132,9 @@ def make_params(mol, configs, jastrow_weight=1.0, en_weight=None):
     p.bas_n = torch.tensor(np.asarray(b.bas_kr), dtype=F64)
     p.bas_k = torch.tensor(np.stack([b.bas_kx, b.bas_ky, b.bas_kz], 1)).long()
     p.radial_type = b.radial_type
-    p.norm = torch.tensor(primitive_norms(b), dtype=F64)
+    p.norm = torch.tensor(primitive_norms(b) if sph_norm is None else sph_norm, dtype=F64)
+    if sph_norm is not None:
+        p.contract = True      # the monomials of an AO are summed by the contraction (index_add over index_ctr)
     p.mo_scf = torch.tensor(np.asarray(b.mos), dtype=F64)
     p.mo_modifier = torch.ones_like(p.mo_scf)
     p.configs = (torch.as_tensor(configs[0]).long(), torch.as_tensor(configs[1]).long())

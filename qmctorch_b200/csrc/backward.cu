@@ -37,6 +37,7 @@ struct BwdArgs {
   double *partial;
   const int *tiles;   // [ntile][2]
   int want_ao;
+  int multi;          // some AO is a sum of several monomial components: AO rows accumulate (plan.cu)
   int tw, rows, lda, ldg, ldx, ppad, ntile_mo, ntile_ao, nslot, lu_conc;
 };
 
@@ -126,7 +127,7 @@ __device__ __forceinline__ void jastrow_value_dw(const DevSys &S, const Tab &T, 
 template <int MOR>
 __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, double ex, double ey, double ez,
                                              double *ao, double *u, double *xr, int ppad, bool want_ao,
-                                             double *mo_row) {
+                                             double *mo_row, bool multi = false) {
   const double2 *rec = T.stream();
   const double *W = T.mow();
   const int nmup = S.nmup;
@@ -136,7 +137,7 @@ __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, doub
 #define BWD_EMIT(idx, val)                                             \
   do {                                                                 \
     const double v_ = (val);                                           \
-    ao[idx] = v_;                                                      \
+    if (multi) ao[idx] += v_; else ao[idx] = v_;                       \
     if (MOR > 0) {                                                     \
       _Pragma("unroll") for (int m = 0; m < MOR; ++m)                  \
         if (m < nmup) macc[m] = fma(v_, W[(idx)*nmup + m], macc[m]);   \
@@ -144,6 +145,8 @@ __device__ __forceinline__ void backward_row(const DevSys &S, const Tab &T, doub
   } while (0)
   const bool with_n = (S.radial_type == QMCB_GTO || S.radial_type == QMCB_STO);
   const bool gauss = (S.radial_type == QMCB_GTO || S.radial_type == QMCB_GTO_PURE);
+  if (multi)
+    for (int k = 0; k < S.nao; ++k) ao[k] = 0.0;
   int q = 0;
   for (int A = 0; A < S.natom; ++A) {
     const double x = ex - T.atoms()[4 * A], y = ey - T.atoms()[4 * A + 1], z = ez - T.atoms()[4 * A + 2];
@@ -248,16 +251,16 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
       jv[it] = ks; jv[TW * Ne + it] = dkee; jv[2 * TW * Ne + it] = dken;
       if (nmup <= 2)
         backward_row<2>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
-                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup);
+                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup, a.multi != 0);
       else if (nmup <= 4)
         backward_row<4>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
-                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup);
+                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup, a.multi != 0);
       else if (nmup <= 8)
         backward_row<8>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
-                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup);
+                        sx + it * ldx, a.ppad, a.want_ao != 0, smo + it * nmup, a.multi != 0);
       else
         backward_row<0>(S, T, sp[3 * e], sp[3 * e + 1], sp[3 * e + 2], sao + it * lda, su + it * lda,
-                        sx + it * ldx, a.ppad, a.want_ao != 0, nullptr);
+                        sx + it * ldx, a.ppad, a.want_ao != 0, nullptr, a.multi != 0);
     }
     // rows of a ragged last tile must not contribute
     for (int i = tid + nrow * ldg; i < rows * ldg; i += nthr) sg[i] = 0.0;
@@ -496,10 +499,16 @@ __global__ void backward_reduce(const DevSys S, const double *partial, int ngrid
 // [ngrid][nacc], nacc = nao * nmu + nconf + 2, summed in index order and scattered to the caller's layouts.
 __global__ void bwd_spec_reduce(const DevSys S, const double *partial, int ngrid, int nacc, int nmo_full, double *g_mo,
                                 double *g_ci, double *g_jee, double *g_jen) {
+  // one warp per accumulator: lane-strided sums over the CTAs, then a fixed butterfly (deterministic)
   const int *ib = S.iblob;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nacc; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < nacc; i += nwarp) {
     double v = 0.0;
-    for (int g = 0; g < ngrid; ++g) v += partial[(size_t)g * nacc + i];
+    for (int g = lane; g < ngrid; g += 32) v += partial[(size_t)g * nacc + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane != 0) continue;
     const int nw = S.nao * S.nmu;
     if (i < nw) {
       const int a = i / S.nmu, j = i - a * S.nmu;
@@ -603,6 +612,11 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
     return QMCB_EINVAL;
   }
   const int want_ao = (g_bas_exp || g_bas_coeffs) ? 1 : 0;
+  if (want_ao && p->multi_component) {
+    qmcb_set_error("qmcb_psi_backward: basis-parameter gradients are not available when an AO is a sum of several "
+                   "monomials (real spherical harmonics of l = 2); freeze 'ao'");
+    return QMCB_EINVAL;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // Jastrow / MO / CI gradients of a one-walker-per-thread structure (BASELINE config 3): the
   // structure-specialised backward, register accumulators, no tile staging (QMCB_BWD_SPEC=0 disables)
@@ -617,7 +631,7 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
     const int rc = qmcb_spec_launch(p, MODE_BWD, fa, stream, &grid);
     if (rc == 0) {
       const int nacc = p->sys.nao * p->sys.nmu + p->sys.nconf + 2;
-      bwd_spec_reduce<<<(nacc + 127) / 128, 128, 0, st>>>(p->sys, (const double *)workspace, grid, nacc, p->sys.nmo, g_mo,
+      bwd_spec_reduce<<<(nacc + 3) / 4, 128, 0, st>>>(p->sys, (const double *)workspace, grid, nacc, p->sys.nmo, g_mo,
                                                           g_ci, g_jee_w, g_jen_w);
       return qmcb_cuda_rc((int)cudaGetLastError(), "backward.cu spec reduce");
     }
@@ -631,6 +645,7 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
   BwdArgs a{};
   a.pos = pos; a.weight = weight; a.W = W; a.partial = (double *)workspace; a.tiles = p->d_bwd_tiles;
   a.want_ao = want_ao;
+  a.multi = p->multi_component ? 1 : 0;
   a.tw = b.tw; a.rows = b.rows; a.lda = b.lda; a.ldg = b.ldg; a.ldx = b.ldx; a.ppad = b.ppad;
   a.ntile_mo = b.ntile_mo; a.ntile_ao = b.ntile_ao; a.nslot = b.nslot; a.lu_conc = b.lu_conc;
   cudaError_t e = cudaFuncSetAttribute(backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem);

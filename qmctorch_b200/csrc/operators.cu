@@ -7,19 +7,29 @@
 #include "device.cuh"
 
 // ---- AtomicOrbitals.forward -----------------------------------------------------------
-template <int NCH>
+// MULTI: some AO is a sum of several cartesian monomials (real spherical harmonics of l = 2, plan.cu):
+// its components accumulate into a zeroed row instead of storing
+template <int NCH, bool MULTI>
 struct AoStoreSink {
   double *ao, *dao, *d2ao;   // already offset to this (walker, electron) row
   __device__ __forceinline__ void emit(int a, const double (&v)[NCH]) {
-    ao[a] = v[0];
-    if (NCH > 1) {
-      dao[3 * a] = v[1]; dao[3 * a + 1] = v[2]; dao[3 * a + 2] = v[3];
-      d2ao[a] = v[4];
+    if (MULTI) {
+      ao[a] += v[0];
+      if (NCH > 1) {
+        dao[3 * a] += v[1]; dao[3 * a + 1] += v[2]; dao[3 * a + 2] += v[3];
+        d2ao[a] += v[4];
+      }
+    } else {
+      ao[a] = v[0];
+      if (NCH > 1) {
+        dao[3 * a] = v[1]; dao[3 * a + 1] = v[2]; dao[3 * a + 2] = v[3];
+        d2ao[a] = v[4];
+      }
     }
   }
 };
 
-template <int NCH>
+template <int NCH, bool MULTI>
 __global__ void __launch_bounds__(256) ao_kernel(const DevSys S, const double *pos, int64_t rows, double *ao,
                                                  double *dao, double *d2ao) {
   extern __shared__ __align__(16) double smem[];
@@ -28,10 +38,16 @@ __global__ void __launch_bounds__(256) ao_kernel(const DevSys S, const double *p
   __syncthreads();
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows;
        row += (int64_t)gridDim.x * blockDim.x) {
-    AoStoreSink<NCH> sink;
+    AoStoreSink<NCH, MULTI> sink;
     sink.ao = ao + row * S.nao;
     sink.dao = NCH > 1 ? dao + row * S.nao * 3 : nullptr;
     sink.d2ao = NCH > 1 ? d2ao + row * S.nao : nullptr;
+    if (MULTI) {
+      for (int k = 0; k < S.nao; ++k) {
+        sink.ao[k] = 0.0;
+        if (NCH > 1) { sink.dao[3 * k] = 0.0; sink.dao[3 * k + 1] = 0.0; sink.dao[3 * k + 2] = 0.0; sink.d2ao[k] = 0.0; }
+      }
+    }
     eval_aos<NCH, 1>(S, T, pos[3 * row], pos[3 * row + 1], pos[3 * row + 2], sink);
   }
 }
@@ -48,12 +64,14 @@ extern "C" int qmcb_ao(const qmcb_plan *p, const double *pos, int64_t W, int one
   int64_t grid = (rows + 255) / 256;
   if (grid > (int64_t)p->sm_count * 8) grid = (int64_t)p->sm_count * 8;
   cudaStream_t st = (cudaStream_t)stream;
+  auto run = [&](auto kern, double *d1, double *d2) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<(unsigned)grid, 256, smem, st>>>(p->sys, pos, rows, ao, d1, d2);
+  };
   if (dao) {
-    cudaFuncSetAttribute(ao_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    ao_kernel<5><<<(unsigned)grid, 256, smem, st>>>(p->sys, pos, rows, ao, dao, d2ao);
+    if (p->multi_component) run(ao_kernel<5, true>, dao, d2ao); else run(ao_kernel<5, false>, dao, d2ao);
   } else {
-    cudaFuncSetAttribute(ao_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    ao_kernel<1><<<(unsigned)grid, 256, smem, st>>>(p->sys, pos, rows, ao, nullptr, nullptr);
+    if (p->multi_component) run(ao_kernel<1, true>, nullptr, nullptr); else run(ao_kernel<1, false>, nullptr, nullptr);
   }
   return qmcb_cuda_rc((int)cudaGetLastError(), "operators.cu launch");
 }

@@ -27,6 +27,7 @@ extern "C" int qmcb_abi_version(void) { return QMCB_ABI_VERSION; }
 namespace {
 
 struct AoDesc {
+  int ao = 0;           // AO index this component emits into
   int atom, kx, ky, kz;
   std::vector<double> alpha, pn, cn;   // per primitive
   std::vector<int> flat;
@@ -69,23 +70,36 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
     qmcb_set_error("qmcb_plan: unknown radial_type");
     return QMCB_EINVAL;
   }
-  // ---- AOs from flat primitives
-  std::vector<AoDesc> aos(s->nao);
+  // ---- AOs from flat primitives.  An AO is normally ONE cartesian monomial x^kx y^ky z^kz times a
+  // contracted radial function; real spherical harmonics of l = 2 (x^2 - y^2, 2z^2 - x^2 - y^2) arrive as
+  // several monomials with the same AO index (the host expands them, wavefunction/orbitals/atomic_orbitals.py).
+  // Every (AO, monomial) pair becomes a "component" of its own that EMITS INTO THE SAME AO: the projection
+  // onto the MOs is linear, so the fused kernels need nothing else.
+  std::vector<AoDesc> aos;
+  std::map<std::vector<int>, int> ao_key;           // (AO, kx, ky, kz) -> component descriptor
   std::vector<char> seen(s->nao, 0);
+  bool multi = false;
   for (int i = 0; i < s->nbas; ++i) {
     int a = s->index_ctr[i];
     if (a < 0 || a >= s->nao) {
       qmcb_set_error("qmcb_plan: index_ctr out of range");
       return QMCB_EINVAL;
     }
-    AoDesc &d = aos[a];
-    if (!seen[a]) {
+    const std::vector<int> key = {a, s->bas_kx[i], s->bas_ky[i], s->bas_kz[i]};
+    auto it = ao_key.find(key);
+    if (it == ao_key.end()) {
+      if (seen[a]) multi = true;
       seen[a] = 1;
-      d.atom = s->bas_atom[i];
-      d.kx = s->bas_kx[i]; d.ky = s->bas_ky[i]; d.kz = s->bas_kz[i];
-    } else if (d.atom != s->bas_atom[i] || d.kx != s->bas_kx[i] || d.ky != s->bas_ky[i] ||
-               d.kz != s->bas_kz[i]) {
-      qmcb_set_error("qmcb_plan: an AO mixes primitives of different centre/monomial (unsupported)");
+      it = ao_key.emplace(key, (int)aos.size()).first;
+      aos.emplace_back();
+      AoDesc &n = aos.back();
+      n.ao = a;
+      n.atom = s->bas_atom[i];
+      n.kx = s->bas_kx[i]; n.ky = s->bas_ky[i]; n.kz = s->bas_kz[i];
+    }
+    AoDesc &d = aos[it->second];
+    if (d.atom != s->bas_atom[i]) {
+      qmcb_set_error("qmcb_plan: an AO mixes primitives of different centres (unsupported)");
       return QMCB_EINVAL;
     }
     if (d.kx < 0 || d.ky < 0 || d.kz < 0 || d.kx > 15 || d.ky > 15 || d.kz > 15) {
@@ -110,10 +124,14 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
       qmcb_set_error("qmcb_plan: AO without primitives");
       return QMCB_EINVAL;
     }
+  p->multi_component = multi;
+  // components in AO order (stable: the monomials of one AO stay together)
+  std::stable_sort(aos.begin(), aos.end(), [](const AoDesc &x, const AoDesc &y) { return x.ao < y.ao; });
   // ---- shells
   std::vector<ShellDesc> shells;
-  for (int a = 0; a < s->nao; ++a) {
-    const AoDesc &d = aos[a];
+  for (size_t ic = 0; ic < aos.size(); ++ic) {
+    const AoDesc &d = aos[ic];
+    const int a = d.ao;
     bool placed = false;
     for (auto &sh : shells) {
       if (sh.atom != d.atom || sh.alpha != d.alpha || sh.pn != d.pn) continue;

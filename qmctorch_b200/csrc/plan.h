@@ -72,6 +72,7 @@ struct qmcb_spec_state;   // spec.cu
 
 struct qmcb_plan {
   int device = 0;
+  bool multi_component = false;                  // some AO is a sum of several cartesian monomials (sph l = 2)
   uint64_t version = 0;                          // bumped by every table rebuild
   mutable qmcb_spec_state *spec = nullptr;       // structure-specialised kernels (lazy)
   DevSys sys{};

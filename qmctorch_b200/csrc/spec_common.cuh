@@ -175,7 +175,8 @@ template <int MODE, int AO, int NCH>
 __device__ __forceinline__ void spec_emit(const double *mw, const double (&v)[NCH], double (&acc)[NCH][SPEC_NMUP]) {
   static_assert(NCH == spec_nch<MODE>(), "channel count");
   // parameter-gradient backward: the AO value of this electron is kept as well (mw = its AO row)
-  if constexpr (MODE == MODE_BWD) const_cast<double *>(mw)[AO] = v[0];
+  // (accumulated: an AO may be a sum of several monomial components; the row is zeroed by the caller)
+  if constexpr (MODE == MODE_BWD) const_cast<double *>(mw)[AO] += v[0];
   // (the MO weights of one AO are read once per column: SPEC_NMUP <= 8 one walker per thread, <= 16 warp tiles)
   double w[SPEC_NMUP];
   if (SPEC_MOW_SMEM && MODE != MODE_BWD) {

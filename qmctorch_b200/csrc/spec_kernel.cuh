@@ -306,6 +306,8 @@ __device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedAr
       double acc[1][NM];
 #pragma unroll
       for (int j = 0; j < NM; ++j) acc[0][j] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NAO; ++k) sao[e * NAO + k] = 0.0;
       spec_aos<MODE>(P, et, sao + e * NAO, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], fj, ven, acc);
 #pragma unroll
       for (int j = 0; j < NM; ++j) smo[e * NM + j] = acc[0][j];

@@ -144,6 +144,17 @@ _UNCONTRACTED = {
     },
 }
 
+# spherical-harmonics Slater / Gaussian bases (harmonics_type "sph": radial r^n exp(-zeta r) or r^n exp(-zeta r^2)
+# times the real Y_lm of spherical_harmonics.py:352-702): element -> list of (n, l, zeta); every m of a shell
+# is one AO.  Hand-built, "approximate" exponents: the reference reaches this path only through hand-built or
+# loaded bases (both of its calculators emit cartesian functions).
+_SPHERICAL = {
+    "sph-dz": {
+        "H": [(0, 0, 1.24), (1, 0, 0.90), (1, 1, 1.20)],
+        "Li": [(0, 0, 2.70), (1, 0, 0.65), (1, 1, 0.70), (2, 2, 0.90)],
+    },
+}
+
 _DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
@@ -237,6 +248,39 @@ def build_basis_uncontracted(atoms, atom_coords, basis_name, radial_type):
     return b
 
 
+def build_basis_spherical(atoms, atom_coords, basis_name, radial_type):
+    """Namespace of a spherical-harmonics basis (the fields atomic_orbitals.py:27-94 reads for
+    harmonics_type == "sph": bas_n, bas_l, bas_m instead of the cartesian powers)."""
+    table = _SPHERICAL[basis_name.lower()]
+    b = SimpleNamespace()
+    b.radial_type = radial_type
+    b.harmonics_type = "sph"
+    n, lq, mq, zeta, nshells = [], [], [], [], []
+    for el in atoms:
+        cnt = 0
+        for (ni, li, zi) in table[el]:
+            for m in range(-li, li + 1):
+                n.append(ni); lq.append(li); mq.append(m); zeta.append(zi)
+                cnt += 1
+        nshells.append(cnt)
+    nb = len(n)
+    b.nao = nb
+    b.nshells = nshells
+    b.nao_per_atom = nshells
+    b.index_ctr = np.arange(nb)
+    b.nctr_per_ao = np.ones(nb)
+    import torch
+    # (torch tensors: the reference's norm_slater_spherical mixes them with tensors, norm_orbital.py:61-67)
+    b.bas_n = torch.tensor(n, dtype=torch.int64)
+    b.bas_l = np.array(lq)
+    b.bas_m = np.array(mq)
+    b.bas_exp = torch.tensor(zeta, dtype=torch.float64)
+    b.bas_coeffs = np.ones(nb)
+    b.atom_coords_internal = [list(c) for c in atom_coords]
+    b.TotalEnergy = 0.0
+    return b
+
+
 def _seeded_mos(n, seed):
     """Deterministic, well-conditioned, diagonally dominant orthonormal matrix (test fixtures only)."""
     rng = np.random.RandomState(seed)
@@ -283,6 +327,10 @@ class Molecule:
             self.basis = build_basis_uncontracted(names, coords, basis, radial_type or "sto")
             if mos is None:
                 mos = _seeded_mos(self.basis.nao, 17)
+        elif basis.lower() in _SPHERICAL:
+            self.basis = build_basis_spherical(names, coords, basis, radial_type or "sto")
+            if mos is None:
+                mos = _seeded_mos(self.basis.nao, 23)
         else:
             self.basis = build_basis(names, coords, basis)
         if mos is None:
@@ -434,6 +482,9 @@ _SPECS = {
     "lih_sto_pure": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="sto-dz", name="LiH",
                          radial_type="sto_pure"),
     "lih_gto_kr": dict(atom="Li 0 0 0; H 0 0 3.015", unit="bohr", basis="sto-dz", name="LiH", radial_type="gto"),
+    # real spherical harmonics up to l = 2 (d shell on Li), Slater and Gaussian radial parts with r^n
+    "lih_sph": dict(atom="Li 0 0 0; H 0.3 -0.2 3.015", unit="bohr", basis="sph-dz", name="LiH", radial_type="sto"),
+    "lih_sph_gto": dict(atom="Li 0 0 0; H 0.3 -0.2 3.015", unit="bohr", basis="sph-dz", name="LiH", radial_type="gto"),
     "h2o": dict(atom="O 0 0 0; H 0.757 0.587 0; H -0.757 0.587 0", unit="angs",
                 basis="cc-pvdz", name="H2O"),
     "c4h6": dict(atom=None, unit="angs", basis="dzp", name="C4H6"),

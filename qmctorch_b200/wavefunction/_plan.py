@@ -100,6 +100,12 @@ class PlanHandle:
         h_een = [next(host), next(host), next(host)] if self.jeen is not None else None
         if getattr(self, "_norm_host", None) is None:
             self._norm_host = _cpu(ao.norm_cst)            # frozen at construction (atomic_orbitals.py:90-94)
+        h_norm = self._norm_host
+        if getattr(ao, "expand_index", None) is not None:
+            # spherical harmonics: one plan primitive per (primitive, cartesian monomial); the monomial's
+            # coefficient rides on the norm (an uncontracted basis keeps bas_coeffs = 1)
+            ix = ao.expand_index
+            h_exp, h_coef, h_norm = h_exp[ix], h_coef[ix], h_norm[ix] * ao.expand_scale
         nmo = w.shape[1]
         if self.configs is not None:
             cu = np.asarray(self.configs[0].cpu().numpy(), dtype=np.int32).reshape(-1, max(self.nup, 0))
@@ -117,11 +123,11 @@ class PlanHandle:
         # 3*Ne*Ne < 400, MKL (fma chain) otherwise - SURVEY.md section 7, hard part 1.
         gram_fma = 0 if 3 * nelec * nelec < 400 else 1
         return _lib.SystemArrays(
-            nelec=nelec, nup=self.nup, ndown=self.ndown, natom=ao.natoms, nbas=ao.nbas, nao=nao,
+            nelec=nelec, nup=self.nup, ndown=self.ndown, natom=ao.natoms, nbas=len(ao.index_ctr_np), nao=nao,
             nmo=nmo, radial_type=_lib.RADIAL[ao.radial_type], contract=int(ao.contract),
             atom_coords=h_atom, atomic_number=np.asarray(ao.atomic_number, dtype=np.float64),
             bas_atom=ao.bas_atom_np, bas_exp=h_exp, bas_coeffs=h_coef,
-            bas_norm=self._norm_host, bas_kx=ao.bas_kx_np, bas_ky=ao.bas_ky_np, bas_kz=ao.bas_kz_np,
+            bas_norm=h_norm, bas_kx=ao.bas_kx_np, bas_ky=ao.bas_ky_np, bas_kz=ao.bas_kz_np,
             bas_kr=ao.bas_kr_np, index_ctr=ao.index_ctr_np, mo=w, nconf=nconf, cfg_up=cu, cfg_down=cd,
             ci=ci,
             use_jee=int(self.jee is not None),

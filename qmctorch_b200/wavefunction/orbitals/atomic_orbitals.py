@@ -11,6 +11,43 @@ from .._plan import PlanHandle, as_walkers
 from .norm_orbital import atomic_orbital_norm
 
 
+# Real spherical harmonics up to l = 2 as the reference defines them (spherical_harmonics.py:352-702,
+# including its truncated literal for Y00): Y_lm = sum_t c_t x^a y^b z^c / r^l.  With the radial part
+# r^n exp(-alpha r) or r^n exp(-alpha r^2) (radial_functions.py:6-238) the primitive is a sum of CARTESIAN
+# monomials with radial power n - l, which is what the kernels evaluate:  (l, m) -> [(c, a, b, c)]
+_C1, _C20, _C22, _C2M = 0.4886025119029199, 0.31539156525252005, 0.5462742152960396, 1.0925484305920792
+_SPH = {
+    (0, 0): [(0.2820948, 0, 0, 0)],
+    (1, -1): [(_C1, 0, 1, 0)], (1, 0): [(_C1, 0, 0, 1)], (1, 1): [(_C1, 1, 0, 0)],
+    (2, -2): [(_C2M, 1, 1, 0)], (2, -1): [(_C2M, 0, 1, 1)], (2, 1): [(_C2M, 1, 0, 1)],
+    (2, 2): [(_C22, 2, 0, 0), (-_C22, 0, 2, 0)],
+    (2, 0): [(-_C20, 2, 0, 0), (-_C20, 0, 2, 0), (2.0 * _C20, 0, 0, 2)],
+}
+
+
+def _expand_spherical(basis):
+    """Flat primitives of a spherical-harmonics basis -> (index of the original primitive, monomial
+    coefficient, kx, ky, kz, radial power) of the equivalent cartesian primitives."""
+    n = np.asarray(basis.bas_n).astype(int)
+    lq = np.asarray(basis.bas_l).astype(int)
+    mq = np.asarray(basis.bas_m).astype(int)
+    if basis.radial_type.endswith("pure") and np.any(lq > 0):
+        raise NotImplementedError(
+            "spherical harmonics with l > 0 need a radial power n - l: use radial_type 'sto' or 'gto' "
+            "(the *_pure radial functions carry no r^n factor)")
+    idx, scale, kx, ky, kz, kr = [], [], [], [], [], []
+    for i, (ni, li, mi) in enumerate(zip(n, lq, mq)):
+        if (li, mi) not in _SPH:
+            raise NotImplementedError("spherical harmonics are implemented up to l = 2 (as in the reference); got "
+                                      "l = %d, m = %d" % (li, mi))
+        if ni < li:
+            raise NotImplementedError("radial power n = %d below l = %d: r^(n-l) Y_lm would be singular" % (ni, li))
+        for c, a, b, cz in _SPH[(li, mi)]:
+            idx.append(i); scale.append(c); kx.append(a); ky.append(b); kz.append(cz); kr.append(ni - li)
+    i32 = lambda v: np.asarray(v, dtype=np.int32)
+    return np.asarray(idx, dtype=np.int64), np.asarray(scale, dtype=np.float64), i32(kx), i32(ky), i32(kz), i32(kr)
+
+
 class AtomicOrbitals(nn.Module):
     def __init__(self, mol, cuda=False):
         super().__init__()
@@ -26,7 +63,7 @@ class AtomicOrbitals(nn.Module):
         self.atomic_number = mol.atomic_number
         self.nshells = torch.as_tensor(np.asarray(basis.nshells))
         self.nao_per_atom = torch.as_tensor(np.asarray(basis.nao_per_atom))
-        self.nbas = int(self.nshells.sum())
+        self.nbas = int(self.nshells.sum())          # the reference's flat primitives (len(bas_exp))
         self.index_ctr = torch.as_tensor(np.asarray(basis.index_ctr))
         self.nctr_per_ao = torch.as_tensor(np.asarray(basis.nctr_per_ao))
         self.contract = not len(torch.unique(self.index_ctr)) == len(self.index_ctr)
@@ -34,22 +71,31 @@ class AtomicOrbitals(nn.Module):
         self.bas_exp = nn.Parameter(torch.as_tensor(np.asarray(basis.bas_exp), dtype=dtype))
         self.bas_exp.requires_grad = True
         self.harmonics_type = basis.harmonics_type
-        if basis.harmonics_type != "cart":
-            raise NotImplementedError(
-                "harmonics_type='sph' (spherical_harmonics.py:202-702) is not on the CUDA path")
-        self.bas_n = torch.as_tensor(np.asarray(basis.bas_kr), dtype=dtype)
         self.radial_type = basis.radial_type
         if self.radial_type not in _lib.RADIAL:
             raise ValueError("unknown radial_type %r" % self.radial_type)
         with torch.no_grad():
             self.norm_cst = torch.as_tensor(atomic_orbital_norm(basis), dtype=dtype)
+        bas_atom = np.repeat(np.arange(self.natoms), np.asarray(basis.nshells)).astype(np.int32)
+        index_ctr = np.asarray(basis.index_ctr).astype(np.int32)
+        # primitives handed to the plan: one per (primitive, cartesian monomial).  expand_index maps them back
+        # to the reference's flat primitives, expand_scale is the monomial's coefficient (folded into the norm)
+        self.expand_index = None
+        self.expand_scale = None
+        if basis.harmonics_type == "cart":
+            self.bas_n = torch.as_tensor(np.asarray(basis.bas_kr), dtype=dtype)
+            kx, ky, kz, kr = (np.asarray(getattr(basis, k)).astype(np.int32) for k in ("bas_kx", "bas_ky", "bas_kz", "bas_kr"))
+        elif basis.harmonics_type == "sph":
+            self.bas_n = torch.as_tensor(np.asarray(basis.bas_n), dtype=dtype)
+            idx, scale, kx, ky, kz, kr = _expand_spherical(basis)
+            self.expand_index, self.expand_scale = idx, scale
+            bas_atom, index_ctr = bas_atom[idx], index_ctr[idx]
+        else:
+            raise ValueError("harmonics_type should be 'cart' or 'sph'")
         # host-side integer tables handed to the plan
-        self.bas_atom_np = np.repeat(np.arange(self.natoms), np.asarray(basis.nshells)).astype(np.int32)
-        self.bas_kx_np = np.asarray(basis.bas_kx).astype(np.int32)
-        self.bas_ky_np = np.asarray(basis.bas_ky).astype(np.int32)
-        self.bas_kz_np = np.asarray(basis.bas_kz).astype(np.int32)
-        self.bas_kr_np = np.asarray(basis.bas_kr).astype(np.int32)
-        self.index_ctr_np = np.asarray(basis.index_ctr).astype(np.int32)
+        self.bas_atom_np = bas_atom
+        self.bas_kx_np, self.bas_ky_np, self.bas_kz_np, self.bas_kr_np = kx, ky, kz, kr
+        self.index_ctr_np = index_ctr
         self.backflow_trans = None
         self.cuda = cuda
         self.device = torch.device("cpu")

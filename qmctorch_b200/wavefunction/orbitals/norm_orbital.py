@@ -16,11 +16,26 @@ def _odd_factorial(n):
     return out
 
 
+def _norm_spherical(basis):
+    """norm_slater_spherical / norm_gaussian_spherical (norm_orbital.py:45-93): functions of the radial
+    power ``bas_n`` and the exponent only."""
+    n = np.asarray(basis.bas_n, dtype=np.float64)
+    alpha = np.asarray(basis.bas_exp, dtype=np.float64)
+    if basis.radial_type.startswith("sto"):
+        nfact = np.array([float(math.factorial(int(2 * k))) for k in n])
+        return (2.0 * alpha) ** n * np.sqrt(2.0 * alpha / nfact)
+    if basis.radial_type.startswith("gto"):
+        n1 = n + 1.0
+        a = alpha ** (0.25 * (2.0 * n1 + 1.0))
+        b = 2.0 ** (2.0 * n1 + 1.5)
+        c = np.array([_odd_factorial(2 * int(k) - 1) for k in n1]) * math.pi ** 0.5
+        return np.sqrt(b / c) * a
+    raise ValueError("%s is not a valid radial_type" % basis.radial_type)
+
+
 def atomic_orbital_norm(basis):
-    if basis.harmonics_type != "cart":
-        raise NotImplementedError(
-            "spherical-harmonics bases (norm_orbital.py:45-93) are not on the CUDA path; "
-            "both reference calculators emit harmonics_type='cart'")
+    if basis.harmonics_type == "sph":
+        return _norm_spherical(basis)
     kx = np.asarray(basis.bas_kx).astype(int)
     ky = np.asarray(basis.bas_ky).astype(int)
     kz = np.asarray(basis.bas_kz).astype(int)

@@ -817,3 +817,65 @@ def test_specialised_backward_matches_tile_backward_and_oracle(name):
             err = float((a[k].cpu() - ref).abs().max() / max(float(ref.abs().max()), 1e-300))
             assert err < RTOL, (k, err)
     assert wf._handle.info(15) == 1
+
+
+@pytest.mark.parametrize("key", ["lih_sph", "lih_sph_gto"])
+def test_spherical_harmonics_basis_against_reference(key, monkeypatch):
+    """harmonics_type = "sph" (real spherical harmonics up to l = 2, d shell on Li; Slater and Gaussian radial
+    parts with r^n): AO values, psi, E_L, grad psi, accept decisions and the Jastrow / MO / CI gradients on the
+    CUDA path against the reference (tests/golden/sph.npz; its E_L is the autograd-Hessian kinetic energy - the
+    reference's Jacobi path raises on spherical harmonics) and against the oracle; generic and specialised
+    kernels; basis-parameter gradients are refused (an AO is a sum of several monomials)."""
+    from test_oracle_golden import _sph_case
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    g, mol, P = _sph_case(key)
+    pos = _dev(g[key + "_pos"])
+    el_ref = torch.tensor(g[key + "_eloc"])
+    for jit in ("0", "2"):
+        monkeypatch.setenv("QMCB_JIT", jit)
+        wf = SlaterJastrow(mol, configs="single_double(2,2)", cuda=True)
+        with torch.no_grad():
+            wf.mo.mo_modifier.copy_(torch.tensor(g[key + "_mo_modifier"]))
+            wf.fc.weight.copy_(torch.tensor(g[key + "_ci"]))
+            wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+        assert wf._handle.info(13) == (0 if jit == "0" else 1)
+        assert C.scaled_err(wf.ao(pos[:8]), g[key + "_ao"]) < RTOL
+        ao, dao, d2ao = wf.ao(pos[:8], derivative=[0, 1, 2])
+        o_ao, o_dao, o_d2 = orc.ao_all(P, pos[:8].cpu())
+        assert C.scaled_err(ao, o_ao) < RTOL and C.scaled_err(dao, o_dao) < RTOL and C.scaled_err(d2ao, o_d2) < RTOL
+        assert C.rel_err(wf(pos), g[key + "_psi"]) < RTOL
+        e = wf.local_energy(pos).cpu()
+        assert float(((e - el_ref).abs() / el_ref.abs().clamp(min=1.0)).max()) < 1e-9       # reference: autograd Hessian
+        eo = orc.local_energy(P, pos.cpu())
+        assert float(((e - eo).abs() / eo.abs().clamp(min=1.0)).max()) < RTOL               # oracle: Jacobi
+        assert C.scaled_err(wf.gradients_jacobi(pos), orc.grad_psi(P, pos.cpu())) < RTOL
+        # teacher-forced Metropolis decisions
+        L = _lib_mod().lib()
+        for it in range(g[key + "_mh_disp"].shape[0]):
+            x = _dev(g[key + "_mh_pos"][it])
+            disp, tau = _dev(g[key + "_mh_disp"][it]), _dev(g[key + "_mh_tau"][it])     # (kept alive until the sync)
+            fx = (wf(x).reshape(-1) ** 2).detach().contiguous()
+            acc = torch.zeros(x.shape[0], dtype=torch.uint8, device="cuda")
+            _lib_mod().check(L.qmcb_metropolis_step(
+                wf._handle.plan(), _lib_mod().ptr(x), _lib_mod().ptr(fx), x.shape[0], _lib_mod().ptr(disp),
+                _lib_mod().ptr(tau), None, -1, 1, 1.0, 1e-16, 0, 0, _lib_mod().ptr(acc), None,
+                _lib_mod().stream_ptr(x.device)), "qmcb_metropolis_step")
+            torch.cuda.synchronize()
+            assert np.array_equal(acc.cpu().numpy().astype(bool), g[key + "_mh_acc"][it])
+            assert np.array_equal(x.cpu().numpy(), g[key + "_mh_pos"][it + 1])
+        # psi.backward(weight) with the reference's weights
+        psi_ref = torch.tensor(g[key + "_psi"])
+        wgt = (2.0 / len(psi_ref) * (el_ref - el_ref.mean()) / psi_ref).reshape(-1).cuda()
+        got = wf._psi_backward(pos, wgt, {"mo_modifier", "ci", "jee_w"})
+        for k, ref in (("mo_modifier", g[key + "_grad_mo_modifier"]), ("ci", g[key + "_grad_ci"]),
+                       ("jee_w", g[key + "_grad_jastrow_weight"])):
+            ref = torch.tensor(ref)
+            err = float((got[k].cpu().reshape(ref.shape) - ref).abs().max() / ref.abs().max())
+            assert err < 1e-9, (k, err)
+        with pytest.raises(RuntimeError, match="monomials"):
+            wf._psi_backward(pos, wgt, None)
+
+
+def _lib_mod():
+    from qmctorch_b200 import _lib
+    return _lib

@@ -114,3 +114,40 @@ def test_oracle_gradient_samplers_reproduce_reference_chains(double_default):
     torch.manual_seed(int(f["hm_seed"][0]))
     out = orc.hamiltonian(P, start.clone(), nstep, float(f["hm_step"][0]), L, ntherm=ntherm, ndecor=ndecor)
     assert out.shape == f["hm_pos"].shape and C.scaled_err(out, f["hm_pos"]) < 1e-10
+
+
+def _sph_case(key):
+    """Oracle parameters of a spherical-harmonics fixture of tests/golden/sph.npz."""
+    import os
+    from qmctorch_b200.molecules import fixture_molecule
+    g = np.load(os.path.join(C.GOLDEN, "sph.npz"))
+    mol = fixture_molecule(key)
+    P = orc.make_params(mol, (g[key + "_cfg_up"], g[key + "_cfg_down"]), jastrow_weight=0.8)
+    P.mo_modifier = torch.tensor(g[key + "_mo_modifier"])
+    P.ci = torch.tensor(g[key + "_ci"])
+    return g, mol, P
+
+
+@pytest.mark.parametrize("key", ["lih_sph", "lih_sph_gto"])
+def test_oracle_spherical_harmonics_reproduce_reference(key):
+    """Real spherical harmonics l <= 2 (spherical_harmonics.py:352-702) with Slater / Gaussian radial parts
+    r^n e^{...}: the oracle evaluates them as sums of cartesian monomials with radial power n - l and
+    reproduces the reference's AO values, psi, E_L (the reference's autograd kinetic energy - its Jacobi
+    path cannot run on spherical harmonics), the manual gradient estimator and the accept decisions."""
+    g, mol, P = _sph_case(key)
+    pos = torch.tensor(g[key + "_pos"])
+    assert C.scaled_err(orc.ao_values(P, pos[:8]), g[key + "_ao"]) < TOL
+    assert C.rel_err(orc.psi(P, pos), g[key + "_psi"]) < TOL
+    el = torch.tensor(g[key + "_eloc"])
+    assert float(((orc.local_energy(P, pos) - el).abs() / el.abs().clamp(min=1.0)).max()) < 1e-10
+    og, _ = orc.param_grads(P, pos, eloc=el, names=("mo_modifier", "ci", "jastrow_weight"))
+    for k, v in og.items():
+        ref = torch.tensor(g[key + "_grad_" + k])
+        assert float((v - ref).abs().max() / ref.abs().max()) < 1e-10, k
+    for it in range(g[key + "_mh_disp"].shape[0]):
+        cur = torch.tensor(g[key + "_mh_pos"][it])
+        fx = (orc.psi(P, cur) ** 2).reshape(-1)
+        npos, nfx, acc, fxn = orc.metropolis_step(P, cur, fx, torch.tensor(g[key + "_mh_disp"][it]),
+                                                  torch.tensor(g[key + "_mh_tau"][it]))
+        assert np.array_equal(acc.numpy().astype(bool), g[key + "_mh_acc"][it])
+        assert np.array_equal(npos.numpy(), g[key + "_mh_pos"][it + 1])
