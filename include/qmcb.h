@@ -150,9 +150,10 @@ int qmcb_energy_stats(const double *eloc, int64_t W, double *out4, void *workspa
  * optional, out4 as qmcb_energy_stats.  One VMC energy step of Solver.single_point
  * (solver/solver_base.py:355-371: local_energy per batch, then mean / var).  Structure-specialised
  * kernels reduce their walkers inside the E_L kernel (no second pass over eloc, no second launch:
- * the CTA that arrives last adds the per-CTA partials in index order; the arrival counter belongs
- * to the plan, so concurrent calls on ONE plan must be ordered on a stream - use one plan per
- * concurrent stream).  workspace: qmcb_stats_workspace_bytes(W). */
+ * the CTA that arrives last adds the per-CTA partials in index order; the plan keeps one arrival
+ * counter per stream it has been called on (16; further streams take a separate second-stage
+ * launch), so concurrent streams may share a plan - each with its OWN workspace and out4).
+ * workspace: qmcb_stats_workspace_bytes(W). */
 int qmcb_local_energy_stats(const qmcb_plan *plan, const double *pos, int64_t W, double *eloc,
                             double *psi, double *ekin, double *out4, void *workspace, void *stream);
 

@@ -498,7 +498,7 @@ __global__ void backward_reduce(const DevSys S, const double *partial, int ngrid
 // Second stage of the structure-specialised backward (spec_kernel.cuh: spec_bwd_body): per-CTA partials
 // [ngrid][nacc], nacc = nao * nmu + nconf + 2, summed in index order and scattered to the caller's layouts.
 __global__ void bwd_spec_reduce(const DevSys S, const double *partial, int ngrid, int nacc, int nmo_full, double *g_mo,
-                                double *g_ci, double *g_jee, double *g_jen) {
+                                double *g_ci, double *g_jee, double *g_jen, double *g_coef, double *g_exp) {
   // one warp per accumulator: lane-strided sums over the CTAs, then a fixed butterfly (deterministic)
   const int *ib = S.iblob;
   const int lane = threadIdx.x & 31;
@@ -517,7 +517,13 @@ __global__ void bwd_spec_reduce(const DevSys S, const double *partial, int ngrid
       const int c = i - nw;
       if (c < S.nconf) { if (g_ci) g_ci[c] = v; }
       else if (c == S.nconf) { if (g_jee) g_jee[0] = v; }
-      else if (g_jen) g_jen[0] = v;
+      else if (c == S.nconf + 1) { if (g_jen) g_jen[0] = v; }
+      else {
+        // spec_backward_all: [nbas] d/d bas_coeffs, then [nbas] d/d bas_exp, by flat primitive
+        const int f = c - S.nconf - 2;
+        if (f < S.nbas) { if (g_coef) g_coef[f] = v; }
+        else if (g_exp) g_exp[f - S.nbas] = v;
+      }
     }
   }
 }
@@ -598,7 +604,7 @@ int qmcb_choose_backward(qmcb_plan *p) {
 extern "C" int64_t qmcb_backward_workspace_bytes(const qmcb_plan *p, int64_t) {
   if (!p) return 0;
   // tile kernel: 2 CTAs per SM x nslot;  specialised kernel: up to 8 CTAs per SM x (nao nmu + nconf + 2)
-  const int64_t spec = (int64_t)8 * p->sm_count * ((int64_t)p->sys.nao * p->sys.nmu + p->sys.nconf + 2);
+  const int64_t spec = (int64_t)8 * p->sm_count * ((int64_t)p->sys.nao * p->sys.nmu + p->sys.nconf + 2 + 2 * (int64_t)p->sys.nbas);
   const int64_t tile = (p->bwd.tw == 0 && p->bwd0.tw == 0) ? 0 : (int64_t)2 * p->sm_count * p->bwd.nslot;
   return (spec > tile ? spec : tile) * (int64_t)sizeof(double);
 }
@@ -620,19 +626,22 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
   cudaStream_t st = (cudaStream_t)stream;
   // Jastrow / MO / CI gradients of a one-walker-per-thread structure (BASELINE config 3): the
   // structure-specialised backward, register accumulators, no tile staging (QMCB_BWD_SPEC=0 disables)
-  static const bool spec_off = getenv("QMCB_BWD_SPEC") && atoi(getenv("QMCB_BWD_SPEC")) == 0;
-  if (!want_ao && !g_een && !spec_off) {
+  const char *env_spec = getenv("QMCB_BWD_SPEC");          // (read per call: tests switch between the two kernels)
+  const bool spec_off = env_spec && atoi(env_spec) == 0;
+  if (!g_een && !spec_off) {
+    // (with basis-parameter gradients: spec_backward_all - a second generated walk over the primitives and one
+    // register accumulator per flat primitive)
     cudaError_t e0;
     const size_t nmo_b = (size_t)p->sys.nao * p->sys.nmo * sizeof(double);
     if (g_mo && (e0 = cudaMemsetAsync(g_mo, 0, nmo_b, st)) != cudaSuccess) return qmcb_cuda_rc((int)e0, "backward.cu");
     FusedArgs fa{};
     fa.pos = pos; fa.W = W; fa.weight = weight; fa.bwd_part = (double *)workspace;
     int grid = 0;
-    const int rc = qmcb_spec_launch(p, MODE_BWD, fa, stream, &grid);
+    const int rc = qmcb_spec_launch(p, want_ao ? MODE_BWD_ALL : MODE_BWD, fa, stream, &grid);
     if (rc == 0) {
-      const int nacc = p->sys.nao * p->sys.nmu + p->sys.nconf + 2;
+      const int nacc = p->sys.nao * p->sys.nmu + p->sys.nconf + 2 + (want_ao ? 2 * p->sys.nbas : 0);
       bwd_spec_reduce<<<(nacc + 3) / 4, 128, 0, st>>>(p->sys, (const double *)workspace, grid, nacc, p->sys.nmo, g_mo,
-                                                          g_ci, g_jee_w, g_jen_w);
+                                                      g_ci, g_jee_w, g_jen_w, g_bas_coeffs, g_bas_exp);
       return qmcb_cuda_rc((int)cudaGetLastError(), "backward.cu spec reduce");
     }
     if (rc != QMCB_SPEC_SKIP) return rc;

@@ -2,7 +2,7 @@
 // only: this header is also compiled by NVRTC.
 #pragma once
 
-enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3, MODE_BWD = 4 };
+enum { MODE_PSI = 0, MODE_ELOC = 1, MODE_GRAD = 2, MODE_MH = 3, MODE_BWD = 4, MODE_BWD_ALL = 5 };
 
 // entries of the 2^(j/N) table of the exp() range reduction (device.cuh: exp_core); power of two
 #ifndef QMCB_ETAB_LOG2

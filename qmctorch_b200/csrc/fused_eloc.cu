@@ -28,7 +28,11 @@ extern "C" int qmcb_local_energy_stats(const qmcb_plan *p, const double *pos, in
   // the last CTA of the specialised kernel finishes the reduction (grid <= SMs x CTAs per SM, far
   // below QMCB_STATS_MAX_PARTIALS); QMCB_STATS_2STAGE=1 keeps the separate second-stage launch
   static const bool two_stage = getenv("QMCB_STATS_2STAGE") && atoi(getenv("QMCB_STATS_2STAGE")) > 0;
-  if (!two_stage && (int64_t)p->sm_count * 16 <= QMCB_STATS_MAX_PARTIALS) { a.stats_ticket = p->d_ticket; a.stats_out = out4; }
+  if (!two_stage && (int64_t)p->sm_count * 16 <= QMCB_STATS_MAX_PARTIALS) {
+    // one arrival counter per (plan, stream): concurrent streams on one plan do not share a counter
+    a.stats_ticket = qmcb_ticket_slot(p, stream);
+    if (a.stats_ticket) a.stats_out = out4;
+  }
   int grid = 0;
   rc = qmcb_spec_launch(p, MODE_ELOC, a, stream, &grid);
   if (rc == 0) {

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "plan.h"
 #include "spec.h"
@@ -22,6 +23,21 @@ int qmcb_cuda_rc(int cuda_error, const char *where) {
   return cuda_error;
 }
 extern "C" const char *qmcb_last_error(void) { return g_err.c_str(); }
+
+unsigned *qmcb_ticket_slot(const qmcb_plan *p, void *stream) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!p->d_ticket) return nullptr;
+  int free_slot = -1;
+  for (int i = 0; i < qmcb_plan::kTicketSlots; ++i) {
+    if (p->ticket_used[i] && p->ticket_owner[i] == stream) return p->d_ticket + 2 * i;
+    if (!p->ticket_used[i] && free_slot < 0) free_slot = i;
+  }
+  if (free_slot < 0) return nullptr;
+  p->ticket_used[free_slot] = true;
+  p->ticket_owner[free_slot] = stream;
+  return p->d_ticket + 2 * free_slot;
+}
 extern "C" int qmcb_abi_version(void) { return QMCB_ABI_VERSION; }
 
 namespace {
@@ -383,8 +399,9 @@ static int upload(qmcb_plan *p) {
   }
   if (nt && (e = cudaMemcpy(p->d_bwd_tiles, p->bwd_tiles.data(), nt, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   if (!p->d_ticket) {
-    if ((e = cudaMalloc(&p->d_ticket, 2 * sizeof(unsigned))) != cudaSuccess) return (int)e;
-    if ((e = cudaMemset(p->d_ticket, 0, 2 * sizeof(unsigned))) != cudaSuccess) return (int)e;
+    const size_t nb = 2 * qmcb_plan::kTicketSlots * sizeof(unsigned);
+    if ((e = cudaMalloc(&p->d_ticket, nb)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemset(p->d_ticket, 0, nb)) != cudaSuccess) return (int)e;
   }
   p->sys.dblob = p->d_dbl;
   p->sys.iblob = p->d_int;

@@ -98,9 +98,14 @@ struct qmcb_plan {
   // full MO matrix for the operator-level entry point
   double *d_mo_full = nullptr;
   size_t cap_mo_full = 0;
-  // arrival counter of the fused energy statistics (spec_eloc: the last CTA adds the partials);
-  // zero between launches (atomicInc wraps), so calls on one plan must be stream-ordered
+  // arrival counters of the fused energy statistics (the CTA of an E_L kernel that arrives last adds the
+  // partials); a counter is zero between launches (atomicInc wraps), so launches that share one must be
+  // stream-ordered: every stream gets its own slot (qmcb_ticket_slot), and a stream that finds no free
+  // slot takes the separate second-stage launch instead
   unsigned *d_ticket = nullptr;
+  static constexpr int kTicketSlots = 16;
+  mutable void *ticket_owner[kTicketSlots] = {};
+  mutable bool ticket_used[kTicketSlots] = {};
   // host copy of flat data needed by backward post-processing
   std::vector<int> index_ctr;
   std::vector<double> mo_full;
@@ -120,6 +125,8 @@ struct DeviceGuard {
   ~DeviceGuard() { if (active && prev >= 0) cudaSetDevice(prev); }
 };
 
+// device pointer of the arrival counter reserved for `stream` on this plan, or nullptr (all slots taken)
+unsigned *qmcb_ticket_slot(const qmcb_plan *p, void *stream);
 void qmcb_set_error(const std::string &msg);
 // maps a cudaError_t to the ABI return code and records its text for qmcb_last_error()
 int qmcb_cuda_rc(int cuda_error, const char *where);

@@ -52,7 +52,7 @@ constexpr int SPEC_DEFAULT_PREFETCH = 0;
 constexpr int SPEC_DEFAULT_PREFETCH_ELOC = 1;
 constexpr int SPEC_DEFAULT_MOW_SMEM = 0;
 constexpr size_t SPEC_SMEM_BUDGET = 100 * 1024;   // per CTA: at least two CTAs per SM
-constexpr int SPEC_MAX_VALUES = 448;   // doubles in the parameter block (keeps it under 4 KB)
+constexpr int SPEC_MAX_VALUES = 960;   // doubles in the parameter block (8 KB; sm_70+ take 32 KB of kernel parameters)
 
 // ---------------------------------------------------------------------------------------
 // dynamic bindings
@@ -243,6 +243,20 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
   o << "template <int MODE, int NCH>\n__device__ __forceinline__ void spec_aos(const SpecParams &P, const double *et, "
        "const double *mw, double ex, double ey, double ez, const FoldJ fj, double &ven, double (&acc)[NCH][SPEC_NMUP]) {\n";
   int nexp = 0;
+  // spec_aos_grad (MODE_BWD_ALL): second walk over the primitives for the basis-parameter gradients
+  std::ostringstream og;
+  og.precision(17);
+  og << "template <int MODE>\n__device__ __forceinline__ void spec_aos_grad(const SpecParams &P, const double *et, "
+        "const double *gao, double ex, double ey, double ez, double (&aC)[SPEC_NBAS], double (&aE)[SPEC_NBAS]) {\n";
+  int sidx = 0;      // running shell index (plan tables: o_spo, o_sco, o_pfo)
+  auto mono = [](int kx, int ky, int kz) {
+    std::string t;
+    const char *nm[3] = {"x", "y", "z"};
+    const int k[3] = {kx, ky, kz};
+    for (int c = 0; c < 3; ++c)
+      for (int i = 0; i < k[c]; ++i) t += (t.empty() ? "" : " * ") + std::string(nm[c]);
+    return t.empty() ? std::string("1.0") : t;
+  };
   for (int A = 0; A < S.natom; ++A) {
     const int ns = hi[S.o_ash + A + 1] - hi[S.o_ash + A];
     const int oa = L.off_atom + 4 * A;
@@ -261,6 +275,10 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     if (rt != QMCB_GTO_PURE) o << "    const double rinv = fast_rsqrt(r2), r = r2 * rinv;\n";
     else o << "    const double rinv = 0.0;\n";
     o << "    spec_ven<MODE, " << oa + 3 << ", " << rt << ">(r2, rinv, ven);\n";
+    og << "  {  // atom " << A << "\n    const double x = ex - spec_pv<MODE, " << oa << ">(), y = ey - spec_pv<MODE, " << oa + 1
+       << ">(), z = ez - spec_pv<MODE, " << oa + 2 << ">();\n    const double r2 = x * x + y * y + z * z;\n";
+    if (rt != QMCB_GTO_PURE) og << "    const double rinv = fast_rsqrt(r2), r = r2 * rinv;\n";
+    og << "    const double dfac = " << (arg_r2 ? "-r2" : "-r") << ";\n";
     // exponentials of this atom by exponent value: primitives with bitwise equal exponents (the s
     // and p functions of an SP shell) share one; a parameter update that separates them changes the
     // generated text and therefore selects (compiles) another module
@@ -285,8 +303,34 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
         if (it == known.end()) {
           it = known.emplace(bits, nexp++).first;
           o << "    const double e" << it->second << " = spec_exp<MODE, " << iv[q] << ">(P, et, " << (arg_r2 ? "r2" : "r") << ");\n";
+          og << "    const double e" << it->second << " = spec_exp<MODE, " << iv[q] << ">(P, et, " << (arg_r2 ? "r2" : "r") << ");\n";
         }
         ev[q] = it->second;
+      }
+      {
+        // basis-parameter gradients of this shell: R_q = r^n e_q, dR_q/dalpha = -(r^2 | r) R_q; per component
+        // X = Y_k Gao[a_k]; accumulators by FLAT primitive index (plan tables o_pfo / o_pflat)
+        const int k0 = hi[S.o_sco + sidx], ncomp_s = hi[S.o_sco + sidx + 1] - k0, pf0 = hi[S.o_pfo + sidx];
+        og << "    {\n";
+        for (int q = 0; q < nprim; ++q) {
+          og << "      const double R" << q << " = e" << ev[q];
+          if (with_n) {
+            const int pn = (int)prec[4 * q + 2];
+            for (int i = 0; i < pn; ++i) og << " * r";
+          }
+          og << ", D" << q << " = dfac * R" << q << ";\n";
+        }
+        for (int k = 0; k < ncomp_s; ++k) {
+          const int kk = hi[S.o_ck + k0 + k], ao = hi[S.o_cao + k0 + k];
+          og << "      { const double X = gao[" << ao << "] * (" << mono(kk & 255, (kk >> 8) & 255, (kk >> 16) & 255) << ");\n";
+          for (int q = 0; q < nprim; ++q) {
+            const int flat = hi[S.o_pflat + pf0 + q * ncomp_s + k];
+            og << "        aC[" << flat << "] = fma(R" << q << ", X, aC[" << flat << "]); aE[" << flat << "] = fma(D" << q
+               << ", X, aE[" << flat << "]);\n";
+          }
+          og << "      }\n";
+        }
+        og << "    }\n";
       }
       o << "    {\n      double S0 = 0.0, S1 = 0.0, S2 = 0.0, T2 = 0.0;\n";
       for (int q = 0; q < nprim; ++q) {
@@ -309,10 +353,13 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
         o << "(mw, x, y, z, S0, S1, Wf, fj, acc);\n";
       }
       o << "    }\n";
+      ++sidx;
     }
     o << "  }\n";
+    og << "  }\n";
   }
   o << "}\n\n";
+  og << "}\n\n";
   if ((int)(rec - (hd.data() + S.o_stream)) != 2 * S.nrec) return false;   // walked exactly the program
   // MO weights of the occupied columns only (the generic kernels pad the column count to a power of
   // two; a specialised kernel is compiled for the exact count)
@@ -333,7 +380,30 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
     for (int j = 0; j < S.nmu; ++j) push(hd[S.o_mow + a * S.nmup + j]);
   L.off_ci = nv;
   for (int c = 0; c < S.nconf; ++c) push(hd[S.o_ci + c]);
+  // basis-parameter gradient factors by flat primitive: norm (-> d/d bas_coeffs), coef_q * component scale (-> d/d bas_exp)
+  const int off_gfac = nv;
+  {
+    std::vector<double> fc(S.nbas, 0.0), fe(S.nbas, 0.0);
+    for (int sh = 0; sh < S.nshell; ++sh) {
+      const int q0 = hi[S.o_spo + sh], nq = hi[S.o_spo + sh + 1] - q0;
+      const int k0 = hi[S.o_sco + sh], nk = hi[S.o_sco + sh + 1] - k0, pf0 = hi[S.o_pfo + sh];
+      for (int q = 0; q < nq; ++q)
+        for (int k = 0; k < nk; ++k) {
+          const int flat = hi[S.o_pflat + pf0 + q * nk + k];
+          fc[flat] = hd[S.o_fnorm + flat];
+          fe[flat] = hd[S.o_coef + q0 + q] * hd[S.o_cscale + k0 + k];
+        }
+    }
+    for (int f = 0; f < S.nbas; ++f) push(fc[f]);
+    for (int f = 0; f < S.nbas; ++f) push(fe[f]);
+  }
   L.nv = nv;
+  o << og.str();
+  o << "template <int MODE>\n__device__ __forceinline__ void spec_grad_scale(double (&aC)[SPEC_NBAS], double (&aE)[SPEC_NBAS]) {\n";
+  for (int f = 0; f < S.nbas; ++f)
+    o << "  aC[" << f << "] *= spec_pv<MODE, " << off_gfac + f << ">(); aE[" << f << "] *= spec_pv<MODE, " << off_gfac + S.nbas + f
+      << ">();\n";
+  o << "}\n\n";
   // determinants of the unique occupations
   const int nun = S.nuu + S.nud;
   o << "template <bool WB>\n__device__ __forceinline__ void spec_dets(const double *A, const double *B, double (&det)["
@@ -440,7 +510,15 @@ bool walk(const qmcb_plan *p, std::string *code, std::vector<double> *vals, Layo
         o << "    g[" << cols[j] << "] = fma(cw" << u << ", inv" << u << "[" << j * n + el << "], g[" << cols[j] << "]);\n";
     }
     o << "#pragma unroll\n    for (int a = 0; a < NAO; ++a) {\n      const double v = sao[" << e << " * NAO + a];\n"
-         "#pragma unroll\n      for (int m = 0; m < NM; ++m) dW[a][m] = fma(v, g[m], dW[a][m]);\n    }\n  }\n";
+         "#pragma unroll\n      for (int m = 0; m < NM; ++m) dW[a][m] = fma(v, g[m], dW[a][m]);\n    }\n";
+    // MODE_BWD_ALL: the AO row has been consumed - it becomes Gao[e][a] = sum_m G[e][m] W[a][m]
+    o << "    if constexpr (MODE == MODE_BWD_ALL) {\n";
+    for (int a = 0; a < S.nao; ++a) {
+      o << "      const_cast<double *>(sao)[" << e << " * NAO + " << a << "] = ";
+      for (int m = 0; m < S.nmu; ++m) o << (m ? " + " : "") << "g[" << m << "] * spec_pv<MODE, " << L.off_mow + a * S.nmu + m << ">()";
+      o << ";\n";
+    }
+    o << "    }\n  }\n";
   }
   o << "  sig_out = sig;\n}\n";
   if (code) *code = o.str();
@@ -451,7 +529,7 @@ std::string prelude(const qmcb_plan *p, const Layout &L, Kind kind = KIND_THREAD
   const DevSys &S = p->sys;
   std::ostringstream o;
   if (kind == KIND_THREAD)
-    o << "#define QMCB_ETAB_REP " << spec_etab_rep() << "\n#define SPEC_NAO " << S.nao << "\n#define SPEC_NCONF " << S.nconf << "\n";
+    o << "#define QMCB_ETAB_REP " << spec_etab_rep() << "\n#define SPEC_NAO " << S.nao << "\n#define SPEC_NCONF " << S.nconf << "\n#define SPEC_NBAS " << S.nbas << "\n";
   if (kind == KIND_TILE) {
     o << "#define SPEC_TILE 1\n#define SPEC_KPFX \"spect_\"\n#define SPEC_EEN_NTERM " << S.een_nterm
       << "\n#define SPEC_NAO " << S.nao << "\n#define SPEC_NCONF " << S.nconf << "\n#define SPEC_MOW_SMEM "
@@ -489,9 +567,9 @@ struct Module {
   std::vector<char> cubin;
   std::string log;
   CUmodule mod = nullptr;
-  CUfunction fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // psi, eloc, mh, grad, backward
-  int occ[5] = {0, 0, 0, 0, 0};
-  int smem[5] = {0, 0, 0, 0, 0};
+  CUfunction fn[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // psi, eloc, mh, grad, backward, backward (all)
+  int occ[6] = {0, 0, 0, 0, 0, 0};
+  int smem[6] = {0, 0, 0, 0, 0, 0};
   bool loaded = false;
   bool from_disk = false;
 };
@@ -597,9 +675,9 @@ std::string drv_err(int rc) {
 bool bwd_eligible(const DevSys &S) { return S.nao * S.nmu <= 48 && S.nconf <= 16; }
 
 size_t smem_doubles(const DevSys &S, int mode) {
-  if (mode == MODE_BWD) {
-    const int slice = (3 * S.nelec + S.nelec * S.nmu + S.nelec * S.nao) | 1;
-    const size_t red = (size_t)(SPEC_THREADS / 32) * (S.nao * S.nmu + S.nconf + 2);
+  if (mode == MODE_BWD || mode == MODE_BWD_ALL) {
+    const int slice = (6 * S.nelec + S.nelec * S.nmu + S.nelec * S.nao) | 1;
+    const size_t red = (size_t)(SPEC_THREADS / 32) * (S.nao * S.nmu + S.nconf + 2 + (mode == MODE_BWD_ALL ? 2 * S.nbas : 0));
     const size_t body = (size_t)SPEC_THREADS * slice;
     return (size_t)QMCB_ETAB * spec_etab_rep() + (body > red ? body : red);
   }
@@ -720,12 +798,14 @@ static int spec_prepare(const qmcb_plan *p, bool load) {
     int rc = d.ModuleLoadData(&m.mod, m.cubin.data());
     if (rc != 0) return fail("cuModuleLoadData: " + drv_err(rc));
     const bool tile = kind == KIND_TILE;
-    const char *names[5] = {tile ? "spect_psi" : "spec_psi", tile ? "spect_eloc" : "spec_eloc",
+    const char *names[6] = {tile ? "spect_psi" : "spec_psi", tile ? "spect_eloc" : "spec_eloc",
                             tile ? "spect_mh" : "spec_mh", tile ? nullptr : "spec_grad_psi",
-                            (tile || !bwd_eligible(p->sys)) ? nullptr : "spec_backward"};
-    const int modes[5] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD, MODE_BWD};
+                            (tile || !bwd_eligible(p->sys)) ? nullptr : "spec_backward",
+                            (tile || !bwd_eligible(p->sys) || 2 * p->sys.nbas > 64 || p->multi_component) ? nullptr
+                                                                                                           : "spec_backward_all"};
+    const int modes[6] = {MODE_PSI, MODE_ELOC, MODE_MH, MODE_GRAD, MODE_BWD, MODE_BWD_ALL};
     const int threads = tile ? tile_threads(p->sys) : SPEC_THREADS;
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 6; ++i) {
       if (!names[i]) { m.fn[i] = nullptr; continue; }     // grad psi / backward of tile structures: generic kernels
       rc = d.ModuleGetFunction(&m.fn[i], m.mod, names[i]);
       if (rc != 0) return fail(std::string("cuModuleGetFunction ") + names[i] + ": " + drv_err(rc));
@@ -772,7 +852,7 @@ static void refresh_params(const qmcb_plan *p, qmcb_spec_state &st) {
 
 int qmcb_spec_launch(const qmcb_plan *p, int mode, const FusedArgs &a, void *stream, int *grid_out) {
   const int slot = mode == MODE_PSI ? 0 : (mode == MODE_ELOC ? 1 : (mode == MODE_MH ? 2 : (mode == MODE_GRAD ? 3 :
-                   (mode == MODE_BWD ? 4 : -1))));
+                   (mode == MODE_BWD ? 4 : (mode == MODE_BWD_ALL ? 5 : -1)))));
   if (slot < 0 || p->device < 0) return QMCB_SPEC_SKIP;
   if (spec_prepare(p, true) != 0) {
     if (p->spec->level >= 2) {

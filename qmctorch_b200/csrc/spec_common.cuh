@@ -56,6 +56,8 @@ __device__ __forceinline__ double spec_pv() {
     asm volatile("ld.param.f64 %0, [" SPEC_KPFX "grad_psi_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   else if constexpr (MODE == MODE_BWD)
     asm volatile("ld.param.f64 %0, [" SPEC_KPFX "backward_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
+  else if constexpr (MODE == MODE_BWD_ALL)
+    asm volatile("ld.param.f64 %0, [" SPEC_KPFX "backward_all_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   else
     asm volatile("ld.param.f64 %0, [" SPEC_KPFX "mh_param_0+%1];" : "=d"(v) : "n"(SPEC_V_BYTE0 + 8 * I));
   return v;
@@ -176,10 +178,10 @@ __device__ __forceinline__ void spec_emit(const double *mw, const double (&v)[NC
   static_assert(NCH == spec_nch<MODE>(), "channel count");
   // parameter-gradient backward: the AO value of this electron is kept as well (mw = its AO row)
   // (accumulated: an AO may be a sum of several monomial components; the row is zeroed by the caller)
-  if constexpr (MODE == MODE_BWD) const_cast<double *>(mw)[AO] += v[0];
+  if constexpr (MODE == MODE_BWD || MODE == MODE_BWD_ALL) const_cast<double *>(mw)[AO] += v[0];
   // (the MO weights of one AO are read once per column: SPEC_NMUP <= 8 one walker per thread, <= 16 warp tiles)
   double w[SPEC_NMUP];
-  if (SPEC_MOW_SMEM && MODE != MODE_BWD) {
+  if (SPEC_MOW_SMEM && MODE != MODE_BWD && MODE != MODE_BWD_ALL) {
     // shared-memory weights: row stride SPEC_MWLD; when it is even the rows are 16-byte aligned: two per LDS.128
     if constexpr (SPEC_MWLD % 2 == 0) {
       const double2 *wr = reinterpret_cast<const double2 *>(mw + AO * SPEC_MWLD);

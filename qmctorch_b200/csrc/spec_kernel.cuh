@@ -244,20 +244,42 @@ __device__ __forceinline__ void spec_body(const SpecParams &P, const FusedArgs &
 #ifndef SPEC_NCONF
 #define SPEC_NCONF 1
 #endif
+// MODE_BWD_ALL adds the basis parameters (bas_exp, bas_coeffs): after the dW accumulation the
+// AO row of an electron is overwritten by Gao[e][a] = sum_m G[e][m] W[a][m], and a second generated walk over
+// the primitives (spec_aos_grad) adds  R_q Y_k Gao[e][a_k]  and  dR_q/dalpha Y_k Gao[e][a_k]  into one
+// register accumulator per flat primitive; norms / coefficients are applied once at the end (spec_grad_scale).
+#ifndef SPEC_NBAS
+#define SPEC_NBAS 1
+#endif
+template <int MODE>
 __device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedArgs &a) {
-  constexpr int MODE = MODE_BWD;
+  constexpr bool ALL = MODE == MODE_BWD_ALL;
   constexpr int Ne = SPEC_NE, ne3 = 3 * SPEC_NE, NM = SPEC_NMUP, NAO = SPEC_NAO, NC = SPEC_NCONF;
-  constexpr int NACC = NAO * NM + NC + 2;
-  constexpr int SL = (ne3 + Ne * NM + Ne * NAO) | 1;
+  constexpr int NB = ALL ? SPEC_NBAS : 0;
+  constexpr int NACC = NAO * NM + NC + 2 + 2 * NB;
+  // slice: pos | mo rows | AO rows | landing zone of the next walker's coordinates (cp.async prefetch)
+  constexpr int SL = (ne3 + Ne * NM + Ne * NAO + ne3) | 1;
   extern __shared__ __align__(16) double smem[];
   double *et0 = smem;
   for (int i = threadIdx.x; i < QMCB_ETAB * QMCB_ETAB_REP; i += blockDim.x) et0[i] = P.etab_g[i / QMCB_ETAB_REP];
   const double *et = et0 + (threadIdx.x & (QMCB_ETAB_REP - 1));
   double *spos = smem + QMCB_ETAB * QMCB_ETAB_REP + (size_t)threadIdx.x * SL;
-  double *smo = spos + ne3, *sao = smo + Ne * NM;
+  double *smo = spos + ne3, *sao = smo + Ne * NM, *snext = sao + Ne * NAO;
+  auto prefetch = [&](int64_t wn) {
+    if (wn < a.W) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(snext);
+      const double *src = a.pos + wn * ne3;
+#pragma unroll
+      for (int i = 0; i < ne3; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * i), "l"(src + i) : "memory");
+    }
+  };
   const SpecTab T{P};
   __syncthreads();
   double dW[NAO][NM], dci[NC], djee = 0.0, djen = 0.0;
+  double aC[ALL ? SPEC_NBAS : 1], aE[ALL ? SPEC_NBAS : 1];
+#pragma unroll
+  for (int i = 0; i < (ALL ? SPEC_NBAS : 1); ++i) { aC[i] = 0.0; aE[i] = 0.0; }
 #pragma unroll
   for (int i = 0; i < NAO; ++i)
 #pragma unroll
@@ -265,9 +287,13 @@ __device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedAr
 #pragma unroll
   for (int c = 0; c < NC; ++c) dci[c] = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  prefetch((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.W; w += stride) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < ne3; ++i) spos[i] = a.pos[w * ne3 + i];
+    for (int i = 0; i < ne3; ++i) spos[i] = snext[i];
+    const double wgt = a.weight[w];
+    prefetch(w + stride);
     // Jastrow exponent and its derivative w.r.t. the Pade weights (d/dw [w0 r / (1 + w r)] = -w0 r^2 / (1 + w r)^2)
     double ks = 0.0, dkee = 0.0, dken = 0.0;
 #pragma unroll
@@ -313,12 +339,17 @@ __device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedAr
       for (int j = 0; j < NM; ++j) smo[e * NM + j] = acc[0][j];
     }
     const double J = (SPEC_USE_JEE || SPEC_USE_JEN) ? exp_clamped(P, et, ks) : 1.0;
-    const double wJ = a.weight[w] * J;
+    const double wJ = wgt * J;
     double sig;
     spec_bwd<MODE>(smo, sao, wJ, dW, dci, sig);
     djee = fma(wJ * sig, dkee, djee);
     djen = fma(wJ * sig, dken, djen);
+    if constexpr (ALL) {
+      for (int e = 0; e < Ne; ++e)
+        spec_aos_grad<MODE>(P, et, sao + e * NAO, spos[3 * e], spos[3 * e + 1], spos[3 * e + 2], aC, aE);
+    }
   }
+  if constexpr (ALL) spec_grad_scale<MODE>(aC, aE);
   // ---- fixed-order reduction over the CTA: warp butterflies, then the warps in order
   double *red = smem + QMCB_ETAB * QMCB_ETAB_REP;       // [warps][NACC], reuses the slices
   __syncthreads();
@@ -336,6 +367,10 @@ __device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedAr
   for (int c = 0; c < NC; ++c) put(NAO * NM + c, dci[c]);
   put(NAO * NM + NC, djee);
   put(NAO * NM + NC + 1, djen);
+  if constexpr (ALL) {
+#pragma unroll
+    for (int i = 0; i < SPEC_NBAS; ++i) { put(NAO * NM + NC + 2 + i, aC[i]); put(NAO * NM + NC + 2 + SPEC_NBAS + i, aE[i]); }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
     double t = 0.0;
@@ -345,7 +380,9 @@ __device__ __forceinline__ void spec_bwd_body(const SpecParams &P, const FusedAr
 }
 
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB_ELOC)
-    spec_backward(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_bwd_body(P, a); }
+    spec_backward(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_bwd_body<MODE_BWD>(P, a); }
+extern "C" __global__ void __launch_bounds__(SPEC_THREADS, 2)
+    spec_backward_all(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_bwd_body<MODE_BWD_ALL>(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB)
     spec_psi(const __grid_constant__ SpecParams P, const FusedArgs a) { spec_body<MODE_PSI>(P, a); }
 extern "C" __global__ void __launch_bounds__(SPEC_THREADS, SPEC_MINB_ELOC)

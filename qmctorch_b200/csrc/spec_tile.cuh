@@ -32,6 +32,9 @@ SPEC_GENERATED_CODE
 #ifndef SPEC_TILE_PREFETCH
 #define SPEC_TILE_PREFETCH 1
 #endif
+#ifndef SPEC_TILE_ALIGN
+#define SPEC_TILE_ALIGN 0     // 1: the warps of a CTA start every tile together (instruction-cache sharing experiment)
+#endif
 
 struct TileTab {
   const SpecParams &P;
@@ -106,7 +109,13 @@ __device__ __forceinline__ void spect_body(const SpecParams &P, const FusedArgs 
   int par = 0;
   prefetch(unit, 0);
 
-  for (int64_t tile = unit; tile < ntile; tile += nunit, par ^= 1) {
+  const int64_t nround = (ntile + nunit - 1) / nunit;     // the same trip count for every warp (SPEC_TILE_ALIGN)
+  int64_t tile = unit;
+  for (int64_t rnd = 0; SPEC_TILE_ALIGN ? rnd < nround : tile < ntile; ++rnd, tile += nunit, par ^= 1) {
+    if (SPEC_TILE_ALIGN) {
+      __syncthreads();
+      if (tile >= ntile) continue;
+    }
     const int64_t w0 = tile * PER;
     const int tw = (int)((a.W - w0) < PER ? (a.W - w0) : PER);
     const bool act = sub < tw;                       // (sub < PER follows: tw <= PER)

@@ -350,9 +350,13 @@ def _manual_grads(wf, pos):
     return out
 
 
+@pytest.mark.parametrize("bwd_spec", ["1", "0"])
 @pytest.mark.parametrize("name", C.CASES)
-def test_parameter_gradients_match_reference(name):
-    """psi.backward(weight) of the reference solver (golden) vs qmcb_psi_backward."""
+def test_parameter_gradients_match_reference(name, bwd_spec, monkeypatch):
+    """psi.backward(weight) of the reference solver (golden) vs qmcb_psi_backward: through the
+    structure-specialised backward where the structure has one (spec_backward_all: one walker per thread,
+    register accumulators) and through the DMMA tile kernel (QMCB_BWD_SPEC=0)."""
+    monkeypatch.setenv("QMCB_BWD_SPEC", bwd_spec)
     g = C.load(name)
     mol, wf = C.build_wf(g)
     grads = _manual_grads(wf, _dev(g["pos"]))
@@ -795,12 +799,23 @@ def test_specialised_backward_matches_tile_backward_and_oracle(name):
     want = {"mo_modifier", "ci", "jee_w", "jen_w"}
     a = wf._psi_backward(pos, wgt, want)
     b = wf._psi_backward(pos, wgt, want)
-    full = wf._psi_backward(pos, wgt, None)                 # all parameters: the tile kernel
+    all_spec = wf._psi_backward(pos, wgt, None)             # every parameter: spec_backward_all
+    all_spec2 = wf._psi_backward(pos, wgt, None)
+    os.environ["QMCB_BWD_SPEC"] = "0"
+    try:
+        full = wf._psi_backward(pos, wgt, None)             # the DMMA tile kernel
+    finally:
+        del os.environ["QMCB_BWD_SPEC"]
     keys = ["mo_modifier", "ci"] + (["jee_w"] if wf._jee is not None else []) + (["jen_w"] if wf._jen is not None else [])
     for k in keys:
         assert torch.equal(a[k], b[k]), k
         ref = full[k]
         err = float((a[k] - ref).abs().max() / max(float(ref.abs().max()), 1e-300))
+        assert err < 1e-11, (k, err)
+    for k in keys + ["bas_exp", "bas_coeffs"]:
+        assert torch.equal(all_spec[k], all_spec2[k]), k     # bitwise reproducible
+        ref = full[k]
+        err = float((all_spec[k] - ref).abs().max() / max(float(ref.abs().max()), 1e-300))
         assert err < 1e-11, (k, err)
     # the oracle: psi.backward(weight) by autograd on the CPU restatement
     leaves = {}
@@ -879,3 +894,74 @@ def test_spherical_harmonics_basis_against_reference(key, monkeypatch):
 def _lib_mod():
     from qmctorch_b200 import _lib
     return _lib
+
+
+@pytest.mark.parametrize("name,nw,jastrow", [("c4h6_ground", 4_000_000, None), ("h2o_cas44_een", 250_000, "een")])
+def test_full_size_properties_large_systems(name, nw, jastrow):
+    """BASELINE configs 5 (C4H6 DZP, 4e6 walkers) and 4 (H2O cas(4,4) + e-e-n Jastrow, 2.5e5 walkers) at
+    full size through the warp-tile kernels: size-independent properties - finite results, the E_L kernel's
+    psi equals the psi kernel's, antisymmetry under exchange of two same-spin electrons (psi flips sign, E_L
+    is unchanged), tiling independence (a ragged slice evaluated alone is BITWISE the slice of the full run),
+    bitwise determinism, and the oracle on a sample."""
+    g = C.load(name)
+    mol, wf = C.build_wf(g)
+    _, P = C.oracle_params(g)
+    assert wf._handle.info(15) == 2
+    pos, sampler = _thermalised(wf, mol, nw, nstep=12, step=float(g["step"]))
+    ne3 = 3 * wf.nelec
+    assert pos.shape == (nw, ne3)
+    e, p2, k = wf._eloc(pos, want_psi=True, want_ekin=True)
+    psi = wf(pos)
+    assert bool(torch.isfinite(e).all()) and bool(torch.isfinite(psi).all())
+    assert C.rel_err(p2, psi) < 1e-12
+    e2, _, _ = wf._eloc(pos)
+    assert torch.equal(e, e2)                                        # deterministic
+    lo, n = 12346, 1001                                              # ragged, and shifted against the warp tiles
+    es, ps, _ = wf._eloc(pos[lo:lo + n].contiguous(), want_psi=True)
+    assert torch.equal(es, e[lo:lo + n]) and torch.equal(ps, p2[lo:lo + n])
+    sub = pos[:200_000]
+    sw = sub.clone()
+    sw[:, 0:3], sw[:, 3:6] = sub[:, 3:6], sub[:, 0:3]                # two spin-up electrons
+    assert float(((wf(sw) + psi[:200_000]).abs() / psi[:200_000].abs()).max()) < 1e-8
+    d = (wf.local_energy(sw) - e[:200_000]).abs() / e[:200_000].abs().clamp(min=1.0)
+    assert float(d.max()) < 1e-6
+    ns = 24 if jastrow is None else 48
+    cpu = pos[:ns].cpu()
+    assert C.rel_err(psi[:ns], orc.psi(P, cpu)) < RTOL
+    eo = orc.local_energy(P, cpu)
+    assert float(((e[:ns].cpu() - eo).abs() / eo.abs().clamp(min=1.0)).max()) < RTOL
+
+
+def test_fused_statistics_on_concurrent_streams_share_a_plan():
+    """qmcb_local_energy_stats finishes its reduction in the CTA that arrives last (one kernel per E_L +
+    statistics step); the arrival counter is per (plan, stream), so two streams may drive ONE plan
+    concurrently (own workspace / outputs each): sums are bitwise those of sequential calls."""
+    from qmctorch_b200 import _lib
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    L = _lib.lib()
+    plan = wf._handle.plan()
+    W = 300_000
+    ens = [_thermalised(wf, mol, W, nstep=5, seed=s)[0] for s in (1, 2)]
+    ref = []
+    for x in ens:
+        e, o4 = wf.local_energy_stats(x)
+        torch.cuda.synchronize()
+        ref.append(o4.clone())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs = [(torch.empty(W, dtype=torch.float64, device="cuda"), torch.zeros(4, dtype=torch.float64, device="cuda"),
+             torch.empty(int(L.qmcb_stats_workspace_bytes(W)), dtype=torch.uint8, device="cuda")) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(25):
+        for k in range(2):
+            e, o4, ws = bufs[k]
+            _lib.check(L.qmcb_local_energy_stats(plan, _lib.ptr(ens[k]), W, _lib.ptr(e), None, None, _lib.ptr(o4),
+                                                 _lib.ptr(ws), ctypes_stream(streams[k])), "local_energy_stats")
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(bufs[k][1], ref[k]), (rep, k)
+
+
+def ctypes_stream(s):
+    import ctypes
+    return ctypes.c_void_p(s.cuda_stream)

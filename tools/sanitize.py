@@ -1,7 +1,8 @@
 """Small driver for compute-sanitizer (memcheck / racecheck / synccheck): a few hundred walkers
-through every fused entry point of the tile shapes in use (THREAD / specialised: LiH; CTA tiles with
-thread-per-block determinants: H2O cas(4,4); half-warp Gauss-Jordan + pair-once Jastrow + 16-column
-blocks: C4H6, triplet C2H4).
+through every fused entry point of the kernel kinds in use - one walker per thread (LiH: spec_* and
+spec_backward), warp tiles (spect_*: H2O cas(4,4) with thread-per-block determinants, H2O + three-body
+factor tables, C4H6 / triplet C2H4 with the half-warp Gauss-Jordan and the pair-once Jastrow, a
+spherical-harmonics basis) - and, with QMCB_JIT=0, the generic CTA-tile kernels of the same systems.
 
     compute-sanitizer --tool racecheck python tools/sanitize.py
 """
@@ -21,6 +22,8 @@ def systems():
     yield "lih", fixture_molecule("lih"), "ground_state", 700
     yield "h2o", fixture_molecule("h2o"), "cas(4,4)", 130
     yield "c4h6", fixture_molecule("c4h6"), "ground_state", 50
+    yield "lih_sph", fixture_molecule("lih_sph"), "single_double(2,2)", 300
+    yield "h2o_een", fixture_molecule("h2o"), "cas(2,2)", 100
     names, coords = _parse_atoms(C2H4, "angs")
     nao = build_basis(names, coords, "dzp").nao
     yield "c2h4_triplet", Molecule(C2H4, basis="dzp", unit="angs", spin=2, name="c2h4t", mos=_seeded_mos(nao, 5)), \
@@ -28,7 +31,12 @@ def systems():
 
 
 for name, mol, cfg, W in systems():
-    wf = SlaterJastrow(mol, configs=cfg, cuda=True)
+    jast = "default"
+    if name == "h2o_een":
+        from qmctorch_b200.wavefunction.jastrows.elec_elec import JastrowFactor as JEE, PadeJastrowKernel as PEE
+        from qmctorch_b200.wavefunction.jastrows.elec_elec_nuclei import JastrowFactor as JEEN, BoysHandyJastrowKernel as BH
+        jast = [JEE(mol, PEE, cuda=True), JEEN(mol, BH, cuda=True)]
+    wf = SlaterJastrow(mol, configs=cfg, jastrow=jast, cuda=True)
     g = torch.Generator().manual_seed(1)
     mean = torch.as_tensor(mol.domain("normal")["mean"])
     sig = torch.as_tensor(mol.domain("normal")["sigma"]).diagonal()
@@ -44,6 +52,8 @@ for name, mol, cfg, W in systems():
     x = pos.clone()
     _lib.check(L.qmcb_metropolis_step(plan, _lib.ptr(x), _lib.ptr(fx), W, None, None, None, -1, 1, 0.2, 1e-16, 3, 0,
                                       _lib.ptr(acc), None, sp), "mh")
+    wgt = torch.randn(W, dtype=torch.float64, device="cuda")
+    gb = wf._psi_backward(pos, wgt, {"mo_modifier", "ci", "jee_w"})
     torch.cuda.synchronize()
     print(name, "psi", float(psi.abs().mean()), "E", float(s4[0] / s4[2]), "grad", float(gr.abs().mean()),
-          "acc", float(acc.float().mean()), "spec", wf._handle.info(13), flush=True)
+          "acc", float(acc.float().mean()), "dW", float(gb["mo_modifier"].abs().sum()), "kind", wf._handle.info(15), flush=True)
