@@ -140,6 +140,25 @@ int qmcb_psi_backward(const qmcb_plan *plan, const double *pos, const double *we
                       double *g_mo, double *g_ci, double *g_bas_exp, double *g_bas_coeffs,
                       double *g_jee_w, double *g_jen_w, double *g_een, void *workspace, void *stream);
 
+/* Adjoint of the local energy (and of psi) w.r.t. the parameters AND the atom coordinates:
+ *   out_theta = sum_w  w_eloc[w] * d E_L(R_w) / d theta  +  w_psi[w] * d psi(R_w) / d theta .
+ * replaces the autograd backward THROUGH WaveFunction.local_energy in Solver.evaluate_grad_auto
+ * (solver/solver.py:352-370, loss.backward() with grad="auto") and the two autograd.grad calls of
+ * Solver.compute_forces (solver/solver.py:433-519: d E_L / d atom_coords, d log psi^2 / d atom_coords).
+ *   w_eloc, w_psi [W]: either may be NULL (taken as zero), not both.
+ *   g_mo [nao,nmo] (effective weights mo_scf*mo_modifier), g_ci [nconf], g_bas_exp [nbas],
+ *   g_bas_coeffs [nbas], g_jee_w [1], g_jen_w [1], g_atom_coords [natom,3] - through the AOs, V_en and
+ *   V_nn like the reference, whose Jastrow factors hold their own constant copy of the atom positions
+ *   (jastrow_factor_electron_nuclei.py:40-41).  Any output may be NULL; outputs are OVERWRITTEN.
+ *   The three-body (Boys-Handy) term contributes through grad J / J and lap J / J; its own weights
+ *   have no output here (the reference's graph drops the Laplacian's dependence on them).
+ *   workspace: qmcb_local_energy_backward_workspace_bytes(plan, W) bytes.  Deterministic. */
+int64_t qmcb_local_energy_backward_workspace_bytes(const qmcb_plan *plan, int64_t W);
+int qmcb_local_energy_backward(const qmcb_plan *plan, const double *pos, const double *w_eloc,
+                               const double *w_psi, int64_t W, double *g_mo, double *g_ci,
+                               double *g_bas_exp, double *g_bas_coeffs, double *g_jee_w, double *g_jen_w,
+                               double *g_atom_coords, void *workspace, void *stream);
+
 /* [sum E, sum E^2, count of finite, count of non-finite] -> out[4]; deterministic two-stage
  * reduction.  replaces torch.mean/var in SolverBase.single_point (solver/solver_base.py:371),
  * wf_base.py:217-229.  workspace: qmcb_stats_workspace_bytes(W). */

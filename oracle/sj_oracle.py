@@ -337,6 +337,13 @@ def jastrow_ee(p, pos, derivative=True):
     return J, dJ, d2J
 
 
+def _jastrow_atoms(p):
+    """The Jastrow factors keep their OWN copy of the atom positions, a plain tensor outside the autograd graph
+    (elec_nuclei/jastrow_factor_electron_nuclei.py:40-41, elec_elec_nuclei/...:46-47): derivatives w.r.t.
+    ao.atom_coords (forces) do not pass through them."""
+    return p.atom_coords.detach()
+
+
 def jastrow_en(p, pos, derivative=True):
     """Pade electron-nucleus Jastrow.  elec_nuclei/jastrow_factor_electron_nuclei.py:60-161,
     elec_nuclei/kernels/pade_jastrow_kernel.py:36-116, distance/electron_nuclei_distance.py:53-162."""
@@ -344,11 +351,12 @@ def jastrow_en(p, pos, derivative=True):
     Ne = p.nelec
     w = p.en_weight
     pos3 = pos.view(W, Ne, 3)
-    diff = pos3.unsqueeze(2) - p.atom_coords[None, None]      # [W,Ne,Nat,3]
+    atoms = _jastrow_atoms(p)
+    diff = pos3.unsqueeze(2) - atoms[None, None]              # [W,Ne,Nat,3]
     # Gram-form distance like the reference (electron_nuclei_distance.py:153-162)
     nrm = (pos3 ** 2).sum(-1).unsqueeze(-1)
-    nrm_at = (p.atom_coords ** 2).sum(-1).unsqueeze(-1).T
-    r = torch.sqrt(nrm + nrm_at - 2.0 * pos3 @ p.atom_coords.T)   # [W,Ne,Nat]
+    nrm_at = (atoms ** 2).sum(-1).unsqueeze(-1).T
+    r = torch.sqrt(nrm + nrm_at - 2.0 * pos3 @ atoms.T)       # [W,Ne,Nat]
     kern = r / (1.0 + w * r)                                  # w0 = 1
     J = torch.exp(kern.sum((-1, -2))).unsqueeze(-1)
     if not derivative:
@@ -396,10 +404,11 @@ def _een_logj(p, pos):
     pos3 = pos.view(W, Ne, 3)
     row, col = _tri_up(Ne)
     ree = ee_distance_gram(pos3)[:, row, col]                          # [W,Np]
+    atoms = _jastrow_atoms(p)
     nrm = (pos3 ** 2).sum(-1).unsqueeze(-1)
-    nrm_at = (p.atom_coords ** 2).sum(-1).unsqueeze(-1).T
-    ren = torch.sqrt(nrm + nrm_at - 2.0 * pos3 @ p.atom_coords.T)      # [W,Ne,Nat]
-    nat = p.atom_coords.shape[0]
+    nrm_at = (atoms ** 2).sum(-1).unsqueeze(-1).T
+    ren = torch.sqrt(nrm + nrm_at - 2.0 * pos3 @ atoms.T)              # [W,Ne,Nat]
+    nat = atoms.shape[0]
     r = torch.stack((ren[:, row, :].transpose(1, 2), ren[:, col, :].transpose(1, 2),
                      ree.unsqueeze(1).expand(W, nat, ree.shape[1])), dim=-1)   # [W,Nat,Np,3]
     return _een_kernel(p, r).reshape(W, -1).sum(-1)

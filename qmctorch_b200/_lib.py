@@ -47,6 +47,9 @@ _SIGS = {
                                        C.c_void_p]),
     "qmcb_backward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
     "qmcb_psi_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 9),
+    "qmcb_local_energy_backward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "qmcb_local_energy_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] +
+                                   [C.c_void_p] * 9),
     "qmcb_stats_workspace_bytes": (C.c_int64, [C.c_int64]),
     "qmcb_energy_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qmcb_local_energy_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1,0 +1,709 @@
+// Adjoint of the local energy: sum over walkers of
+//      wE_w * d E_L(R_w) / d theta   +   wP_w * d psi(R_w) / d theta
+// for every wave-function parameter theta AND the atom coordinates.  This is what the reference obtains by
+// back-propagating through WaveFunction.local_energy - Solver.evaluate_grad_auto (solver/solver.py:352-370:
+// loss.backward() through E_L) and Solver.compute_forces (solver/solver.py:433-519: autograd.grad of E_L and of
+// log psi^2 w.r.t. ao.atom_coords) - a second-order backward through the analytic AO derivatives, the
+// AO -> MO products, torch.inverse / torch.det of every spin block, the trace trick and the Jastrow
+// derivatives (wavefunction/slater_jastrow.py:312-344,449-482, pooling/slater_pooling.py:262-387).
+//
+// Here the adjoint is hand-derived for the dense middle of E_L and taken in FORWARD mode at the leaves:
+//
+//   leaves   AO channels (ao, d ao, lap ao)[e][a]        <- bas_exp, bas_coeffs, atom_coords
+//            g_e = grad_e J / J, l_e = lap_e J / J, J    <- Pade weights (e-e, e-n)
+//            V_en, V_nn                                   <- atom_coords
+//   middle   K[e][a]  = lap ao + 2 g_e . d ao + l_e ao                   (folded kinetic channel)
+//            MO = AO W,  B = -1/2 K W,   A_u = MO[rows_s, cols_u],  B_u likewise
+//            D_u = det A_u,  t_u = Tr(A_u^-1 B_u),  S = sum_c c_c Du Dd,  T = sum_c c_c Du Dd (tu + td)
+//            psi = J S,   E_L = T / S + V
+//
+//   reverse  S~ = wP J - wE T / S^2,  T~ = wE / S,  c~_c = S~ Du Dd + T~ Du Dd (tu + td),
+//            D~_u = sum_c (S~ + T~ (tu + td)) c_c D_other,   t~_u = sum_c T~ c_c Du Dd,
+//            A~_u = D~_u D_u A_u^-T - t~_u (A_u^-1 B_u A_u^-1)^T,   B~_u = t~_u A_u^-T,
+//            scattered into M0[e][m] (adjoint of MO from the determinants) and Q[e][m] = -1/2 B~[e][m];
+//            W~[a][m] = sum_e AO[e][a] M0[e][m] + K[e][a] Q[e][m];   QW = Q W^T,  MW = M0 W^T;
+//            adjoints of the AO channels: (MW + l_e QW, 2 g_e QW, QW);  g~_e = 2 sum_a d ao QW,  l~_e = sum_a ao QW.
+//
+// The Jacobian of the leaves is block diagonal - a primitive's exponent only moves its own AO, an atom only its
+// own shells, a Pade weight only its own term - so ONE dual-number evaluation per (electron, primitive) with
+// the tangent directions (u_x, u_y, u_z, alpha), contracted at once with the channel adjoints, yields every
+// basis-parameter and atom-coordinate derivative (third derivatives of the AOs included) without deriving them
+// by hand, and one Dual<2> pass over the Pade terms yields the Jastrow-weight derivatives.
+//
+// Mapping: one WARP per walker (lanes stride over (electron, AO) / (electron, MO) / matrix entries), per-warp
+// scratch in global memory (L1/L2 resident; sized for C4H6: 30 x 94 x 8 channels), phases separated by
+// __syncwarp().  Parameter sums go to per-warp accumulators with a fixed owner lane per entry; walkers are
+// assigned to warps by index and vjp_finish adds the per-warp partials in warp order: bitwise reproducible.
+// General in the structure (any radial type, cartesian monomials, CAS expansions, n x n spin blocks with
+// partial pivoting); the three-body Boys-Handy term enters through g_e, l_e, J (taken from the qmcb_jastrow
+// kernel) and its OWN weights get no E_L derivative - the reference's graph drops the Laplacian's dependence
+// on them too (jastrow_factor_electron_electron_nuclei.py:411-431: create_graph=False), so that gradient is
+// not defined there either; the host API refuses it.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "plan.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- dual numbers (forward-mode derivatives along N directions)
+template <int N>
+struct Dual {
+  double v;
+  double d[N];
+};
+template <int N> __device__ __forceinline__ Dual<N> mk(double v) {
+  Dual<N> r; r.v = v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = 0.0;
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual<N> seed(double v, int dir) {
+  Dual<N> r = mk<N>(v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) if (i == dir) r.d[i] = 1.0;
+  return r;
+}
+#define QMCB_DUAL_BIN(OP, VEXP, DEXP)                                                            \
+  template <int N> __device__ __forceinline__ Dual<N> operator OP(const Dual<N> &a, const Dual<N> &b) { \
+    Dual<N> r; r.v = VEXP;                                                                        \
+    _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = DEXP;                                  \
+    return r; }
+QMCB_DUAL_BIN(+, a.v + b.v, a.d[i] + b.d[i])
+QMCB_DUAL_BIN(-, a.v - b.v, a.d[i] - b.d[i])
+QMCB_DUAL_BIN(*, a.v * b.v, a.d[i] * b.v + a.v * b.d[i])
+#undef QMCB_DUAL_BIN
+template <int N> __device__ __forceinline__ Dual<N> operator*(double s, const Dual<N> &a) {
+  Dual<N> r; r.v = s * a.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i];
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, double s) { return s * a; }
+template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, double s) { Dual<N> r = a; r.v += s; return r; }
+template <int N> __device__ __forceinline__ Dual<N> operator+(double s, const Dual<N> &a) { return a + s; }
+template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, double s) { Dual<N> r = a; r.v -= s; return r; }
+template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a) { return -1.0 * a; }
+template <int N> __device__ __forceinline__ Dual<N> rcp(const Dual<N> &a) {
+  Dual<N> r; r.v = 1.0 / a.v;
+  const double m = -r.v * r.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = m * a.d[i];
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual<N> dsqrt(const Dual<N> &a) {
+  Dual<N> r; r.v = sqrt(a.v);
+  const double m = 0.5 / r.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = m * a.d[i];
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual<N> dexp(const Dual<N> &a) {
+  Dual<N> r; r.v = exp(a.v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = r.v * a.d[i];
+  return r;
+}
+__device__ __forceinline__ double rcp(double a) { return 1.0 / a; }
+__device__ __forceinline__ double dsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ double dexp(double a) { return exp(a); }
+
+template <class T> __device__ __forceinline__ T ipow(const T &x, int k) {   // k >= 1
+  T r = x;
+  for (int i = 1; i < k; ++i) r = r * x;
+  return r;
+}
+// x^k for any integer k given 1/x (k may be negative: r^(n-2) of the radial powers)
+template <class T> __device__ __forceinline__ T rpow(const T &x, const T &xinv, int k, const T &one) {
+  if (k == 0) return one;
+  return k > 0 ? ipow(x, k) : ipow(xinv, -k);
+}
+
+// ---- one primitive R(r) x^kx y^ky z^kz without coefficient / norm: value, gradient, Laplacian
+// (orbitals/radial_functions.py:6-406 and spherical_harmonics.py:102-199, the formulas of oracle/sj_oracle.py:
+// ao_all).  T = double or a dual number; out[0] value, out[1..3] gradient, out[4] Laplacian.
+template <class T>
+__device__ __forceinline__ void primitive5(int rt, int kx, int ky, int kz, int n, const T &x, const T &y, const T &z,
+                                           const T &al, const T &one, T (&out)[5]) {
+  const T r2 = x * x + y * y + z * z;
+  T R, R1, LR;     // R, (dR/dr)/r, lap R
+  if (rt == QMCB_GTO_PURE) {
+    R = dexp(-(al * r2));
+    R1 = -2.0 * (al * R);
+    LR = (al * R) * (4.0 * (al * r2) - 6.0);
+  } else {
+    const T r = dsqrt(r2);
+    const T rinv = rcp(r);
+    if (rt == QMCB_STO_PURE) {
+      R = dexp(-(al * r));
+      R1 = -(al * R) * rinv;
+      LR = (al * R) * (al - 2.0 * rinv);
+    } else {
+      const bool gto = rt == QMCB_GTO;
+      const T e = gto ? dexp(-(al * r2)) : dexp(-(al * r));
+      const T rn = rpow(r, rinv, n, one);
+      const T rnm2 = rpow(r, rinv, n - 2, one);
+      const double nn = (double)n;
+      R = rn * e;
+      if (gto) {
+        // R = r^n e^{-a r^2}:  R'/r = (n r^{n-2} - 2 a r^n) e,  lap R = (n(n+1) r^{n-2} - 2a(2n+3) r^n + 4 a^2 r^{n+2}) e
+        R1 = (nn * rnm2 - 2.0 * (al * rn)) * e;
+        LR = (nn * (nn + 1.0) * rnm2 - (2.0 * (2.0 * nn + 3.0)) * (al * rn) + 4.0 * ((al * al) * (rn * r2))) * e;
+      } else {
+        // R = r^n e^{-a r}:  R'/r = (n r^{n-2} - a r^{n-1}) e,  lap R = (n(n+1) r^{n-2} - 2a(n+1) r^{n-1} + a^2 r^n) e
+        const T rnm1 = rn * rinv;
+        R1 = (nn * rnm2 - al * rnm1) * e;
+        LR = (nn * (nn + 1.0) * rnm2 - (2.0 * (nn + 1.0)) * (al * rnm1) + (al * al) * rn) * e;
+      }
+    }
+  }
+  // cartesian monomial Y, its gradient and Laplacian
+  const T xk = kx ? ipow(x, kx) : one, yk = ky ? ipow(y, ky) : one, zk = kz ? ipow(z, kz) : one;
+  const T Y = xk * yk * zk;
+  T gx = one * 0.0, gy = gx, gz = gx, LY = gx;
+  if (kx) { const T xm = kx > 1 ? ipow(x, kx - 1) : one; gx = (double)kx * (xm * (yk * zk)); }
+  if (ky) { const T ym = ky > 1 ? ipow(y, ky - 1) : one; gy = (double)ky * (ym * (xk * zk)); }
+  if (kz) { const T zm = kz > 1 ? ipow(z, kz - 1) : one; gz = (double)kz * (zm * (xk * yk)); }
+  if (kx > 1) { const T xm = kx > 2 ? ipow(x, kx - 2) : one; LY = LY + (double)(kx * (kx - 1)) * (xm * (yk * zk)); }
+  if (ky > 1) { const T ym = ky > 2 ? ipow(y, ky - 2) : one; LY = LY + (double)(ky * (ky - 1)) * (ym * (xk * zk)); }
+  if (kz > 1) { const T zm = kz > 2 ? ipow(z, kz - 2) : one; LY = LY + (double)(kz * (kz - 1)) * (zm * (xk * yk)); }
+  const double L = (double)(kx + ky + kz);
+  const T R1Y = R1 * Y;
+  out[0] = R * Y;
+  out[1] = R1Y * x + R * gx;
+  out[2] = R1Y * y + R * gy;
+  out[3] = R1Y * z + R * gz;
+  out[4] = LR * Y + (2.0 * L) * R1Y + R * LY;      // u . grad Y = L Y (Euler)
+}
+
+// ---- device view of the system for this kernel
+struct VjpSys {
+  int nelec, nup, ndown, natom, nbas, nao, nmo, nmu, nmup, nconf, nuu, nud, radial_type, use_jee, use_jen, has_j;
+  double jee_w, jen_w;
+  const double *atoms;                   // [natom][4] x y z Z
+  const double *mow;                     // [nao][nmup] weights of the used MO columns
+  const double *ci;                      // [nconf]
+  const int *used, *ucu, *ucd, *ciu, *cid;
+  const double *alpha, *cn, *norm;       // [nbas] exponent, norm * coeff, norm
+  const int *patom, *pk, *pkr, *pao;     // [nbas] atom, kx | ky << 8 | kz << 16, radial power, AO
+  const int *ao_start, *ao_prim;         // CSR: AO -> its flat primitives
+};
+
+// accumulator layout (doubles, per warp): W~ [nao][nmu] | ci [nconf] | exp [nbas] | coef [nbas] | primR [nbas][3] |
+//                                         jee | jen | sum wE | V_en atoms [natom][3]
+struct AccLayout {
+  int o_w, o_ci, o_exp, o_coef, o_pr, o_jee, o_jen, o_sumE, o_ven, n;
+  __host__ __device__ explicit AccLayout(const VjpSys &S) {
+    o_w = 0; o_ci = o_w + S.nao * S.nmu; o_exp = o_ci + S.nconf; o_coef = o_exp + S.nbas; o_pr = o_coef + S.nbas;
+    o_jee = o_pr + 3 * S.nbas; o_jen = o_jee + 1; o_sumE = o_jen + 1; o_ven = o_sumE + 1; n = o_ven + 3 * S.natom;
+  }
+};
+// scratch layout (doubles, per warp)
+struct ScratchLayout {
+  int o_ao, o_kc, o_mo, o_bk, o_m0, o_q, o_mw, o_qw, o_g, o_gb, o_det, o_inv, o_gj, o_col, n;
+  __host__ __device__ explicit ScratchLayout(const VjpSys &S) {
+    const int ea = S.nelec * S.nao, em = S.nelec * S.nmu, nun = S.nuu + S.nud;
+    const int nmax = S.nup > S.ndown ? S.nup : S.ndown;
+    o_ao = 0; o_kc = o_ao + 5 * ea; o_mo = o_kc + ea; o_bk = o_mo + em; o_m0 = o_bk + em; o_q = o_m0 + em;
+    o_mw = o_q + em; o_qw = o_mw + ea; o_g = o_qw + ea;         // g: [4][Ne] (gx, gy, gz, l)
+    o_gb = o_g + 4 * S.nelec;                                    // adjoints of g, l: [4][Ne]
+    o_det = o_gb + 4 * S.nelec;                                  // D | t | D~ | t~ : [4][nun]
+    o_inv = o_det + 4 * nun;                                     // per unique block: A^-1 [n][n] | A^-1 B A^-1 [n][n]
+    o_gj = o_inv + 2 * (S.nuu * S.nup * S.nup + S.nud * S.ndown * S.ndown);
+    o_col = o_gj + 3 * nmax * nmax;                              // Gauss-Jordan work [n][3n], pivot column [n]
+    n = o_col + nmax;
+    n = (n + 1) & ~1;
+  }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// Warp-cooperative Gauss-Jordan on G [n][3n] = [A | I | B] with partial pivoting (first largest |entry|: the
+// pivot order does not depend on the lane count) -> [I | A^-1 | A^-1 B]; returns det A.
+__device__ double warp_gauss_jordan3(double *G, double *col, int n, int lane) {
+  const int ld = 3 * n;
+  double det = 1.0;
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0;
+    int bi = k;
+    for (int r = k + lane; r < n; r += 32) {
+      const double a = fabs(G[r * ld + k]);
+      if (a > best) { best = a; bi = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi != k) {
+      for (int c = lane; c < ld; c += 32) {
+        const double t = G[k * ld + c];
+        G[k * ld + c] = G[bi * ld + c];
+        G[bi * ld + c] = t;
+      }
+      det = -det;
+    }
+    __syncwarp();
+    const double p = G[k * ld + k];
+    det *= p;
+    const double pinv = 1.0 / p;
+    for (int r = lane; r < n; r += 32) col[r] = G[r * ld + k];
+    __syncwarp();
+    for (int c = lane; c < ld; c += 32) G[k * ld + c] *= pinv;
+    __syncwarp();
+    for (int i = lane; i < n * ld; i += 32) {
+      const int r = i / ld, c = i - r * ld;
+      if (r != k) G[i] = fma(-col[r], G[k * ld + c], G[i]);
+    }
+    __syncwarp();
+  }
+  return det;
+}
+
+// NDIR: tangent directions of the leaf pass over the primitives: 0 none, 1 (alpha), 4 (u_x, u_y, u_z, alpha)
+template <int NDIR>
+__device__ __forceinline__ void prim_leaf_pass(const VjpSys &S, const ScratchLayout &SL, const AccLayout &AL,
+                                               const double *x, double *sc, double *acc, int lane, bool want_coef) {
+  const int Ne = S.nelec, Na = S.nao;
+  const double *g = sc + SL.o_g;
+  const double *MW = sc + SL.o_mw, *QW = sc + SL.o_qw;
+  for (int q = lane; q < S.nbas; q += 32) {
+    const int A = S.patom[q], a = S.pao[q], pk = S.pk[q], n = S.pkr[q];
+    const int kx = pk & 255, ky = (pk >> 8) & 255, kz = (pk >> 16) & 255;
+    const double ax = S.atoms[4 * A], ay = S.atoms[4 * A + 1], az = S.atoms[4 * A + 2];
+    double sv = 0.0, sd[NDIR > 0 ? NDIR : 1] = {};
+    for (int e = 0; e < Ne; ++e) {
+      const double ux = x[3 * e] - ax, uy = x[3 * e + 1] - ay, uz = x[3 * e + 2] - az;
+      const double qw = QW[e * Na + a];
+      const double c0 = fma(g[3 * Ne + e], qw, MW[e * Na + a]);
+      const double c1 = 2.0 * g[e] * qw, c2 = 2.0 * g[Ne + e] * qw, c3 = 2.0 * g[2 * Ne + e] * qw;
+      if constexpr (NDIR == 0) {
+        double o[5];
+        primitive5<double>(S.radial_type, kx, ky, kz, n, ux, uy, uz, S.alpha[q], 1.0, o);
+        sv += c0 * o[0] + c1 * o[1] + c2 * o[2] + c3 * o[3] + qw * o[4];
+      } else {
+        typedef Dual<NDIR> T;
+        T o[5];
+        const T X = NDIR == 4 ? seed<NDIR>(ux, 0) : mk<NDIR>(ux), Y = NDIR == 4 ? seed<NDIR>(uy, 1) : mk<NDIR>(uy),
+                Z = NDIR == 4 ? seed<NDIR>(uz, 2) : mk<NDIR>(uz);
+        primitive5<T>(S.radial_type, kx, ky, kz, n, X, Y, Z, seed<NDIR>(S.alpha[q], NDIR - 1), mk<NDIR>(1.0), o);
+        sv += c0 * o[0].v + c1 * o[1].v + c2 * o[2].v + c3 * o[3].v + qw * o[4].v;
+#pragma unroll
+        for (int j = 0; j < NDIR; ++j)
+          sd[j] += c0 * o[0].d[j] + c1 * o[1].d[j] + c2 * o[2].d[j] + c3 * o[3].d[j] + qw * o[4].d[j];
+      }
+    }
+    if (want_coef) acc[AL.o_coef + q] += S.norm[q] * sv;
+    if constexpr (NDIR > 0) acc[AL.o_exp + q] += S.cn[q] * sd[NDIR - 1];
+    if constexpr (NDIR == 4) {
+      // d/dR_A = - d/du
+      acc[AL.o_pr + 3 * q] -= S.cn[q] * sd[0];
+      acc[AL.o_pr + 3 * q + 1] -= S.cn[q] * sd[1];
+      acc[AL.o_pr + 3 * q + 2] -= S.cn[q] * sd[2];
+    }
+  }
+}
+
+struct VjpArgs {
+  const double *pos;       // [W][3 Ne] (the whole ensemble)
+  const double *wE, *wP;   // [W] or nullptr
+  int64_t W, w0, w1;       // this launch handles walkers [w0, w1)
+  const double *J, *dJ, *d2J;   // Jastrow operator output of the chunk (index w - w0), or nullptr
+  double *scratch, *acc;   // per warp
+  int want_mo, want_ci, want_exp, want_coef, want_jee, want_jen, want_atom;
+};
+
+__global__ void __launch_bounds__(256, 1) eloc_vjp_kernel(const VjpSys S, const VjpArgs a) {
+  const ScratchLayout SL(S);
+  const AccLayout AL(S);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  double *sc = a.scratch + warp * SL.n;
+  double *acc = a.acc + warp * AL.n;
+  const int Ne = S.nelec, Na = S.nao, Nm = S.nmu, ld = S.nmup, nun = S.nuu + S.nud;
+  double *AO = sc + SL.o_ao, *KC = sc + SL.o_kc, *MO = sc + SL.o_mo, *BK = sc + SL.o_bk, *M0 = sc + SL.o_m0,
+         *Q = sc + SL.o_q, *MW = sc + SL.o_mw, *QW = sc + SL.o_qw, *g = sc + SL.o_g, *gb = sc + SL.o_gb,
+         *Dt = sc + SL.o_det, *INV = sc + SL.o_inv, *G = sc + SL.o_gj, *col = sc + SL.o_col;
+  // first walker of this warp such that the assignment walker -> warp is by GLOBAL index (chunked launches)
+  int64_t w = a.w0 + ((warp - a.w0 % nwarp) % nwarp + nwarp) % nwarp;
+  for (; w < a.w1; w += nwarp) {
+    const double *x = a.pos + w * 3 * Ne;
+    const double wE = a.wE ? a.wE[w] : 0.0, wP = a.wP ? a.wP[w] : 0.0;
+    // ---- Jastrow leaves of this walker: J, g = grad J / J, l = lap J / J
+    double J = 1.0;
+    if (S.has_j) {
+      const int64_t wl = w - a.w0;
+      J = a.J[wl];
+      const double Jinv = 1.0 / J;
+      for (int i = lane; i < 4 * Ne; i += 32)
+        g[i] = (i < 3 * Ne ? a.dJ[wl * 3 * Ne + i] : a.d2J[wl * Ne + (i - 3 * Ne)]) * Jinv;
+    } else {
+      for (int i = lane; i < 4 * Ne; i += 32) g[i] = 0.0;
+    }
+    __syncwarp();
+    // ---- AO channels and the folded kinetic channel
+    for (int it = lane; it < Ne * Na; it += 32) {
+      const int e = it / Na, ao = it - e * Na;
+      double s[5] = {0, 0, 0, 0, 0};
+      for (int k = S.ao_start[ao]; k < S.ao_start[ao + 1]; ++k) {
+        const int q = S.ao_prim[k], A = S.patom[q], pk = S.pk[q];
+        double o[5];
+        primitive5<double>(S.radial_type, pk & 255, (pk >> 8) & 255, (pk >> 16) & 255, S.pkr[q],
+                           x[3 * e] - S.atoms[4 * A], x[3 * e + 1] - S.atoms[4 * A + 1],
+                           x[3 * e + 2] - S.atoms[4 * A + 2], S.alpha[q], 1.0, o);
+        const double c = S.cn[q];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s[j] = fma(c, o[j], s[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) AO[j * Ne * Na + it] = s[j];
+      KC[it] = s[4] + 2.0 * (g[e] * s[1] + g[Ne + e] * s[2] + g[2 * Ne + e] * s[3]) + g[3 * Ne + e] * s[0];
+    }
+    __syncwarp();
+    // ---- MO = AO W, B = -1/2 K W (used columns)
+    for (int it = lane; it < Ne * Nm; it += 32) {
+      const int e = it / Nm, m = it - e * Nm;
+      double s0 = 0.0, s1 = 0.0;
+      for (int ao = 0; ao < Na; ++ao) {
+        const double wv = S.mow[ao * ld + m];
+        s0 = fma(AO[e * Na + ao], wv, s0);
+        s1 = fma(KC[e * Na + ao], wv, s1);
+      }
+      MO[it] = s0;
+      BK[it] = -0.5 * s1;
+    }
+    __syncwarp();
+    // ---- spin blocks: inverse, determinant, trace, A^-1 B A^-1
+    {
+      int off = 0;
+      for (int u = 0; u < nun; ++u) {
+        const bool up = u < S.nuu;
+        const int n = up ? S.nup : S.ndown, r0 = up ? 0 : S.nup;
+        const int *cols = up ? S.ucu + u * S.nup : S.ucd + (u - S.nuu) * S.ndown;
+        const int ldg = 3 * n;
+        for (int i = lane; i < n * n; i += 32) {
+          const int r = i / n, c = i - r * n;
+          G[r * ldg + c] = MO[(r0 + r) * Nm + cols[c]];
+          G[r * ldg + n + c] = r == c ? 1.0 : 0.0;
+          G[r * ldg + 2 * n + c] = BK[(r0 + r) * Nm + cols[c]];
+        }
+        __syncwarp();
+        const double det = warp_gauss_jordan3(G, col, n, lane);
+        double tr = 0.0;
+        for (int i = lane; i < n; i += 32) tr += G[i * ldg + 2 * n + i];
+        tr = warp_sum(tr);
+        double *Ai = INV + off, *Yv = Ai + n * n;
+        for (int i = lane; i < n * n; i += 32) {
+          const int r = i / n, c = i - r * n;
+          Ai[i] = G[r * ldg + n + c];
+          double s = 0.0;
+          for (int k = 0; k < n; ++k) s = fma(G[r * ldg + 2 * n + k], G[k * ldg + n + c], s);
+          Yv[i] = s;
+        }
+        if (lane == 0) { Dt[u] = det; Dt[nun + u] = tr; }
+        off += 2 * n * n;
+        __syncwarp();
+      }
+    }
+    // ---- CI sums
+    double Ssum = 0.0, Tsum = 0.0;
+    for (int c = lane; c < S.nconf; c += 32) {
+      const int iu = S.ciu[c], id = S.nuu + S.cid[c];
+      const double dd = S.ci[c] * Dt[iu] * Dt[id];
+      Ssum += dd;
+      Tsum = fma(dd, Dt[nun + iu] + Dt[nun + id], Tsum);
+    }
+    Ssum = warp_sum(Ssum);
+    Tsum = warp_sum(Tsum);
+    const double Sinv = 1.0 / Ssum;
+    const double Sb = wP * J - wE * Tsum * Sinv * Sinv, Tb = wE * Sinv;
+    if (a.want_ci)
+      for (int c = lane; c < S.nconf; c += 32) {
+        const int iu = S.ciu[c], id = S.nuu + S.cid[c];
+        const double dd = Dt[iu] * Dt[id];
+        acc[AL.o_ci + c] += dd * (Sb + Tb * (Dt[nun + iu] + Dt[nun + id]));
+      }
+    // adjoints of the determinants and traces of the unique blocks
+    for (int u = lane; u < nun; u += 32) {
+      const bool up = u < S.nuu;
+      double db = 0.0, tb = 0.0;
+      for (int c = 0; c < S.nconf; ++c) {
+        const int iu = S.ciu[c], id = S.nuu + S.cid[c];
+        if ((up ? iu : id) != u) continue;
+        const double other = Dt[up ? id : iu];
+        db = fma((Sb + Tb * (Dt[nun + iu] + Dt[nun + id])) * S.ci[c], other, db);
+        tb = fma(Tb * S.ci[c], Dt[iu] * Dt[id], tb);
+      }
+      Dt[2 * nun + u] = db;
+      Dt[3 * nun + u] = tb;
+    }
+    for (int i = lane; i < Ne * Nm; i += 32) { M0[i] = 0.0; Q[i] = 0.0; }
+    __syncwarp();
+    // ---- adjoint of MO (through the blocks) and Q = -1/2 adjoint of B
+    {
+      int off = 0;
+      for (int u = 0; u < nun; ++u) {
+        const bool up = u < S.nuu;
+        const int n = up ? S.nup : S.ndown, r0 = up ? 0 : S.nup;
+        const int *cols = up ? S.ucu + u * S.nup : S.ucd + (u - S.nuu) * S.ndown;
+        const double *Ai = INV + off, *Yv = Ai + n * n;
+        const double dD = Dt[2 * nun + u] * Dt[u], tb = Dt[3 * nun + u];
+        for (int i = lane; i < n * n; i += 32) {
+          const int r = i / n, c = i - r * n;
+          const int idx = (r0 + r) * Nm + cols[c];
+          M0[idx] += dD * Ai[c * n + r] - tb * Yv[c * n + r];
+          Q[idx] -= 0.5 * tb * Ai[c * n + r];
+        }
+        off += 2 * n * n;
+        __syncwarp();
+      }
+    }
+    // ---- back through the projections
+    for (int it = lane; it < Ne * Na; it += 32) {
+      const int e = it / Na, ao = it - e * Na;
+      double s0 = 0.0, s1 = 0.0;
+      for (int m = 0; m < Nm; ++m) {
+        const double wv = S.mow[ao * ld + m];
+        s0 = fma(M0[e * Nm + m], wv, s0);
+        s1 = fma(Q[e * Nm + m], wv, s1);
+      }
+      MW[it] = s0;
+      QW[it] = s1;
+    }
+    if (a.want_mo)
+      for (int it = lane; it < Na * Nm; it += 32) {
+        const int ao = it / Nm, m = it - ao * Nm;
+        double s = 0.0;
+        for (int e = 0; e < Ne; ++e)
+          s = fma(AO[e * Na + ao], M0[e * Nm + m], fma(KC[e * Na + ao], Q[e * Nm + m], s));
+        acc[AL.o_w + it] += s;
+      }
+    __syncwarp();
+    // ---- leaves: basis parameters and atom coordinates through the AO channels
+    if (a.want_atom) prim_leaf_pass<4>(S, SL, AL, x, sc, acc, lane, a.want_coef != 0);
+    else if (a.want_exp) prim_leaf_pass<1>(S, SL, AL, x, sc, acc, lane, a.want_coef != 0);
+    else if (a.want_coef) prim_leaf_pass<0>(S, SL, AL, x, sc, acc, lane, true);
+    // ---- leaves: Pade weights (e-e, e-n) through g, l and J
+    if ((a.want_jee && S.use_jee) || (a.want_jen && S.use_jen)) {
+      // adjoints of g_e, l_e from the kinetic channel: g~ = 2 sum_a d ao QW, l~ = sum_a ao QW
+      for (int i = lane; i < 4 * Ne; i += 32) {
+        const int k = i / Ne, e = i - k * Ne;
+        const double *ch = AO + (k < 3 ? (1 + k) : 0) * Ne * Na + e * Na;
+        double s = 0.0;
+        for (int ao = 0; ao < Na; ++ao) s = fma(ch[ao], QW[e * Na + ao], s);
+        gb[i] = k < 3 ? 2.0 * s : s;
+      }
+      __syncwarp();
+      typedef Dual<2> T;
+      const double Kb = wP * J * Ssum;          // adjoint of ln J: J~ J with J~ = wP S
+      double tj0 = 0.0, tj1 = 0.0;
+      for (int e = lane; e < Ne; e += 32) {
+        const double xe = x[3 * e], ye = x[3 * e + 1], ze = x[3 * e + 2];
+        const double lb = gb[3 * Ne + e];
+        // l = sum_b lap K_b + |g|^2  ->  adjoint of grad K picks up 2 l~ g
+        const double bx = fma(2.0 * lb, g[e], gb[e]), by = fma(2.0 * lb, g[Ne + e], gb[Ne + e]),
+                     bz = fma(2.0 * lb, g[2 * Ne + e], gb[2 * Ne + e]);
+        T ks = mk<2>(0.0), kx = ks, ky = ks, kz = ks, kl = ks, kn = ks;
+        if (S.use_jee) {
+          const T wj = seed<2>(S.jee_w, 0);
+          for (int j = 0; j < Ne; ++j) {
+            if (j == e) continue;
+            const double dx = xe - x[3 * j], dy = ye - x[3 * j + 1], dz = ze - x[3 * j + 2];
+            const double r = sqrt(dx * dx + dy * dy + dz * dz), rinv = 1.0 / r;
+            const double w0 = ((e < S.nup) == (j < S.nup)) ? 0.25 : 0.5;     // pade_jastrow_kernel.py:34-66
+            const T den = rcp(wj * r + 1.0);
+            const T k1 = w0 * (den * den);                   // k'
+            const T k2 = (-2.0 * w0) * (wj * (den * (den * den)));   // k''
+            ks = ks + (w0 * r) * den;
+            const T kr = k1 * rinv;
+            kx = kx + kr * dx; ky = ky + kr * dy; kz = kz + kr * dz;
+            kl = kl + k2 + 2.0 * kr;
+          }
+        }
+        if (S.use_jen) {
+          const T wn = seed<2>(S.jen_w, 1);
+          for (int A = 0; A < S.natom; ++A) {
+            const double dx = xe - S.atoms[4 * A], dy = ye - S.atoms[4 * A + 1], dz = ze - S.atoms[4 * A + 2];
+            const double r = sqrt(dx * dx + dy * dy + dz * dz), rinv = 1.0 / r;
+            const T den = rcp(wn * r + 1.0);
+            const T k1 = den * den;
+            const T k2 = -2.0 * (wn * (den * (den * den)));
+            kn = kn + r * den;
+            const T kr = k1 * rinv;
+            kx = kx + kr * dx; ky = ky + kr * dy; kz = kz + kr * dz;
+            kl = kl + k2 + 2.0 * kr;
+          }
+        }
+        // ln J = 1/2 sum_e sum_{j != e} k_ee + sum_e sum_A k_en
+        tj0 += Kb * 0.5 * ks.d[0] + bx * kx.d[0] + by * ky.d[0] + bz * kz.d[0] + lb * kl.d[0];
+        tj1 += Kb * kn.d[1] + bx * kx.d[1] + by * ky.d[1] + bz * kz.d[1] + lb * kl.d[1];
+      }
+      tj0 = warp_sum(tj0);
+      tj1 = warp_sum(tj1);
+      if (lane == 0) { acc[AL.o_jee] += tj0; acc[AL.o_jen] += tj1; }
+    }
+    // ---- potentials: d V_en / d R_A = -Z_A (r_e - R_A) / r^3 ; V_nn is added once by vjp_finish (sum of wE)
+    if (a.want_atom && a.wE) {
+      for (int i = lane; i < 3 * S.natom; i += 32) {
+        const int A = i / 3, k = i - 3 * A;
+        double s = 0.0;
+        for (int e = 0; e < Ne; ++e) {
+          const double dx = x[3 * e] - S.atoms[4 * A], dy = x[3 * e + 1] - S.atoms[4 * A + 1],
+                       dz = x[3 * e + 2] - S.atoms[4 * A + 2];
+          const double r2 = dx * dx + dy * dy + dz * dz, rinv = rsqrt(r2);
+          s -= S.atoms[4 * A + 3] * (k == 0 ? dx : (k == 1 ? dy : dz)) * rinv * rinv * rinv;
+        }
+        acc[AL.o_ven + i] += wE * s;
+      }
+      if (lane == 0) acc[AL.o_sumE] += wE;
+    }
+    __syncwarp();
+  }
+}
+
+struct VjpOut {
+  double *g_mo, *g_ci, *g_exp, *g_coef, *g_jee, *g_jen, *g_atom;
+};
+
+// Sums the per-warp accumulators in warp order and maps them onto the outputs.
+__global__ void vjp_finish(const VjpSys S, const double *acc, int nwarp, VjpOut o) {
+  const AccLayout AL(S);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  auto total = [&](int idx) {
+    double s = 0.0;
+    for (int w = 0; w < nwarp; ++w) s += acc[(size_t)w * AL.n + idx];
+    return s;
+  };
+  if (o.g_mo)
+    for (int i = tid; i < S.nao * S.nmo; i += nth) {
+      const int ao = i / S.nmo, m = i - ao * S.nmo;
+      int pos = -1;
+      for (int j = 0; j < S.nmu; ++j) if (S.used[j] == m) pos = j;
+      o.g_mo[i] = pos < 0 ? 0.0 : total(AL.o_w + ao * S.nmu + pos);
+    }
+  if (o.g_ci) for (int i = tid; i < S.nconf; i += nth) o.g_ci[i] = total(AL.o_ci + i);
+  if (o.g_exp) for (int i = tid; i < S.nbas; i += nth) o.g_exp[i] = total(AL.o_exp + i);
+  if (o.g_coef) for (int i = tid; i < S.nbas; i += nth) o.g_coef[i] = total(AL.o_coef + i);
+  if (o.g_jee && tid == 0) o.g_jee[0] = total(AL.o_jee);
+  if (o.g_jen && tid == 0) o.g_jen[0] = total(AL.o_jen);
+  if (o.g_atom)
+    for (int i = tid; i < 3 * S.natom; i += nth) {
+      const int A = i / 3, k = i - 3 * A;
+      double s = total(AL.o_ven + i);
+      for (int q = 0; q < S.nbas; ++q)
+        if (S.patom[q] == A) s += total(AL.o_pr + 3 * q + k);
+      // nuclear repulsion (wf_base.py:97-116): d V_nn / d R_A = - sum_B Z_A Z_B (R_A - R_B) / |R_A - R_B|^3
+      const double sE = total(AL.o_sumE);
+      double v = 0.0;
+      for (int B = 0; B < S.natom; ++B) {
+        if (B == A) continue;
+        const double dx = S.atoms[4 * A] - S.atoms[4 * B], dy = S.atoms[4 * A + 1] - S.atoms[4 * B + 1],
+                     dz = S.atoms[4 * A + 2] - S.atoms[4 * B + 2];
+        const double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2);
+        v -= S.atoms[4 * A + 3] * S.atoms[4 * B + 3] * (k == 0 ? dx : (k == 1 ? dy : dz)) / (r2 * r);
+      }
+      o.g_atom[i] = s + sE * v;
+    }
+}
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 1 << 17;      // walkers per Jastrow-operator chunk
+
+int grid_of(const qmcb_plan *p) { return p->sm_count * 2; }
+
+VjpSys make_sys(const qmcb_plan *p) {
+  const DevSys &D = p->sys;
+  VjpSys S{};
+  S.nelec = D.nelec; S.nup = D.nup; S.ndown = D.ndown; S.natom = D.natom; S.nbas = D.nbas; S.nao = D.nao; S.nmo = D.nmo;
+  S.nmu = D.nmu; S.nmup = D.nmup; S.nconf = D.nconf; S.nuu = D.nuu; S.nud = D.nud; S.radial_type = D.radial_type;
+  S.use_jee = D.use_jee; S.use_jen = D.use_jen;
+  S.has_j = D.use_jee || D.use_jen || D.een_nterm > 0;
+  S.jee_w = D.jee_w; S.jen_w = D.jen_w;
+  S.atoms = D.dblob + D.o_atoms; S.mow = D.dblob + D.o_mow; S.ci = D.dblob + D.o_ci;
+  S.used = D.iblob + D.o_used; S.ucu = D.iblob + D.o_ucu; S.ucd = D.iblob + D.o_ucd;
+  S.ciu = D.iblob + D.o_ciu; S.cid = D.iblob + D.o_cid;
+  const double *fd = p->d_flat_dbl;
+  const int *fi = p->d_flat_int;
+  const int nb = D.nbas;
+  S.alpha = fd; S.cn = fd + nb; S.norm = fd + 2 * nb;
+  S.patom = fi; S.pk = fi + nb; S.pkr = fi + 2 * nb; S.pao = fi + 3 * nb;
+  S.ao_start = fi + 4 * nb; S.ao_prim = fi + 4 * nb + D.nao + 1;
+  return S;
+}
+
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" int64_t qmcb_local_energy_backward_workspace_bytes(const qmcb_plan *p, int64_t W) {
+  if (!p || W < 0) return 0;
+  VjpSys S = make_sys(p);
+  const ScratchLayout SL(S);
+  const AccLayout AL(S);
+  const int64_t nwarp = (int64_t)grid_of(p) * (kThreads / 32);
+  const int64_t wc = W < kChunk ? W : kChunk;
+  size_t n = align256((size_t)nwarp * SL.n * 8) + align256((size_t)nwarp * AL.n * 8);
+  n += align256((size_t)wc * 8) + align256((size_t)wc * 3 * S.nelec * 8) + align256((size_t)wc * S.nelec * 8);
+  return (int64_t)n + 256;
+}
+
+extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos, const double *w_eloc,
+                                          const double *w_psi, int64_t W, double *g_mo, double *g_ci,
+                                          double *g_bas_exp, double *g_bas_coeffs, double *g_jee_w, double *g_jen_w,
+                                          double *g_atom_coords, void *workspace, void *stream) {
+  if (!p || !p->d_dbl || !p->d_flat_dbl || !pos || W < 0 || !workspace || (!w_eloc && !w_psi)) {
+    qmcb_set_error("qmcb_local_energy_backward: bad arguments");
+    return QMCB_EINVAL;
+  }
+  if (p->sys.nup > 64 || p->sys.ndown > 64) {
+    qmcb_set_error("qmcb_local_energy_backward: spin blocks larger than 64 x 64");
+    return QMCB_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const VjpSys S = make_sys(p);
+  const ScratchLayout SL(S);
+  const AccLayout AL(S);
+  const int grid = grid_of(p);
+  const int nwarp = grid * (kThreads / 32);
+  const int64_t wc = W < kChunk ? W : kChunk;
+  char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  double *scratch = (double *)ws; ws += align256((size_t)nwarp * SL.n * 8);
+  double *acc = (double *)ws; ws += align256((size_t)nwarp * AL.n * 8);
+  double *J = (double *)ws; ws += align256((size_t)wc * 8);
+  double *dJ = (double *)ws; ws += align256((size_t)wc * 3 * S.nelec * 8);
+  double *d2J = (double *)ws;
+  cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)nwarp * AL.n * 8, st);
+  if (e != cudaSuccess) return qmcb_cuda_rc((int)e, "qmcb_local_energy_backward memset");
+  VjpArgs a{};
+  a.pos = pos; a.wE = w_eloc; a.wP = w_psi; a.W = W;
+  a.scratch = scratch; a.acc = acc;
+  a.want_mo = g_mo != nullptr; a.want_ci = g_ci != nullptr; a.want_exp = g_bas_exp != nullptr;
+  a.want_coef = g_bas_coeffs != nullptr; a.want_jee = g_jee_w != nullptr; a.want_jen = g_jen_w != nullptr;
+  a.want_atom = g_atom_coords != nullptr;
+  for (int64_t w0 = 0; w0 < W; w0 += wc) {
+    const int64_t w1 = w0 + wc < W ? w0 + wc : W;
+    if (S.has_j) {
+      const int rc = qmcb_jastrow(p, pos + w0 * 3 * S.nelec, w1 - w0, 0, J, dJ, d2J, stream);
+      if (rc) return rc;
+      a.J = J; a.dJ = dJ; a.d2J = d2J;
+    }
+    a.w0 = w0; a.w1 = w1;
+    eloc_vjp_kernel<<<grid, kThreads, 0, st>>>(S, a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return qmcb_cuda_rc((int)e, "eloc_vjp_kernel launch");
+  }
+  VjpOut o{g_mo, g_ci, g_bas_exp, g_bas_coeffs, g_jee_w, g_jen_w, g_atom_coords};
+  vjp_finish<<<8, 256, 0, st>>>(S, acc, nwarp, o);
+  return qmcb_cuda_rc((int)cudaGetLastError(), "vjp_finish launch");
+}

@@ -361,6 +361,29 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   if (hi.size() & 1) hi.push_back(0);
   S.nint = (int)hi.size();
 
+  // flat primitive tables of the E_L adjoint (plan.h)
+  {
+    const int nb = s->nbas;
+    p->flat_dbl.assign(3 * (size_t)nb, 0.0);
+    p->flat_int.assign(5 * (size_t)nb + s->nao + 1, 0);
+    for (int i = 0; i < nb; ++i) {
+      p->flat_dbl[i] = s->bas_exp[i];
+      p->flat_dbl[nb + i] = s->bas_norm[i] * s->bas_coeffs[i];
+      p->flat_dbl[2 * nb + i] = s->bas_norm[i];
+      p->flat_int[i] = s->bas_atom[i];
+      p->flat_int[nb + i] = s->bas_kx[i] | (s->bas_ky[i] << 8) | (s->bas_kz[i] << 16);
+      p->flat_int[2 * nb + i] = s->bas_kr[i];
+      p->flat_int[3 * nb + i] = s->index_ctr[i];
+    }
+    int *start = p->flat_int.data() + 4 * nb, *list = start + s->nao + 1;
+    int o = 0;
+    for (int a = 0; a < s->nao; ++a) {
+      start[a] = o;
+      for (int i = 0; i < nb; ++i)
+        if (s->index_ctr[i] == a) list[o++] = i;
+    }
+    start[s->nao] = o;
+  }
   p->index_ctr.assign(s->index_ctr, s->index_ctr + s->nbas);
   p->mo_full.assign(s->mo, s->mo + (size_t)s->nao * s->nmo);
   return 0;
@@ -390,6 +413,21 @@ static int upload(qmcb_plan *p) {
   if ((e = cudaMemcpy(p->d_dbl, p->hd.data(), nd, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpy(p->d_int, p->hi.data(), ni, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpy(p->d_mo_full, p->mo_full.data(), nm, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  size_t nfd = p->flat_dbl.size() * sizeof(double), nfi = p->flat_int.size() * sizeof(int);
+  if (nfd > p->cap_flat_dbl) {
+    if (p->d_flat_dbl) cudaFree(p->d_flat_dbl);
+    p->d_flat_dbl = nullptr;
+    if ((e = cudaMalloc(&p->d_flat_dbl, nfd)) != cudaSuccess) return (int)e;
+    p->cap_flat_dbl = nfd;
+  }
+  if (nfi > p->cap_flat_int) {
+    if (p->d_flat_int) cudaFree(p->d_flat_int);
+    p->d_flat_int = nullptr;
+    if ((e = cudaMalloc(&p->d_flat_int, nfi)) != cudaSuccess) return (int)e;
+    p->cap_flat_int = nfi;
+  }
+  if ((e = cudaMemcpy(p->d_flat_dbl, p->flat_dbl.data(), nfd, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpy(p->d_flat_int, p->flat_int.data(), nfi, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
   size_t nt = p->bwd_tiles.size() * sizeof(int);
   if (nt > p->cap_bwd_tiles) {
     if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
@@ -464,6 +502,8 @@ extern "C" void qmcb_plan_destroy(qmcb_plan *p) {
   if (p->d_mo_full) cudaFree(p->d_mo_full);
   if (p->d_bwd_tiles) cudaFree(p->d_bwd_tiles);
   if (p->d_ticket) cudaFree(p->d_ticket);
+  if (p->d_flat_dbl) cudaFree(p->d_flat_dbl);
+  if (p->d_flat_int) cudaFree(p->d_flat_int);
   qmcb_spec_free(p);
   delete p;
 }

@@ -106,6 +106,14 @@ struct qmcb_plan {
   static constexpr int kTicketSlots = 16;
   mutable void *ticket_owner[kTicketSlots] = {};
   mutable bool ticket_used[kTicketSlots] = {};
+  // flat primitive list in the reference's own order (qmcb_system: one entry per primitive per cartesian
+  // monomial) for the adjoint of the local energy (eloc_vjp.cu): doubles alpha | norm*coeff | norm,
+  // ints atom | kx,ky,kz packed | radial power | AO | CSR AO -> primitives (start [nao+1], list [nbas])
+  std::vector<double> flat_dbl;
+  std::vector<int> flat_int;
+  double *d_flat_dbl = nullptr;
+  int *d_flat_int = nullptr;
+  size_t cap_flat_dbl = 0, cap_flat_int = 0;
   // host copy of flat data needed by backward post-processing
   std::vector<int> index_ctr;
   std::vector<double> mo_full;

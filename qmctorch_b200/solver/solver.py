@@ -21,18 +21,44 @@ from . import distributed as D
 
 
 class Loss:
-    """Clipping mask of qmctorch/solver/loss.py:93-110 (energy loss only on this path)."""
+    """qmctorch/solver/loss.py:7-153: energy or variance of the (sampling-weighted, clipped) local energies.
+    ``wf.local_energy`` and ``wf(pos)`` carry autograd nodes backed by qmcb_local_energy_backward /
+    qmcb_psi_backward, so ``loss.backward()`` (grad="auto") works like the reference's."""
 
     def __init__(self, wf, method="energy", clip=False, clip_threshold=5):
-        if method not in ("energy", "weighted-energy"):
-            raise NotImplementedError(
-                "only the energy loss with the manual gradient estimator is on the CUDA path")
+        if method not in ("energy", "variance", "weighted-energy", "weighted-variance"):
+            raise ValueError("loss method should be energy, variance, weighted-energy or weighted-variance")
         self.wf = wf
         self.method = method
         self.clip = clip
         self.clip_num_std = clip_threshold
         self.use_weight = False
+        # loss.py:43: only "energy" and "variance" index the reference's table (the weighted names raise a
+        # KeyError there); the weighted variants are the same reductions with use_weight switched on
+        self.loss_fn = torch.var if method.endswith("variance") else torch.mean
         self.weight = {"psi": None, "psi0": None}
+
+    def __call__(self, pos, no_grad=False, deactivate_weight=False):
+        """loss.py:49-82 -> (loss, local energies)."""
+        with (torch.no_grad() if no_grad else torch.enable_grad()):
+            local_energies = self.wf.local_energy(pos)
+            mask = self.get_clipping_mask(local_energies)
+            weight = self.get_sampling_weights(pos, deactivate_weight)
+            loss = self.loss_fn((weight * local_energies)[mask])
+        return loss, local_energies
+
+    forward = __call__
+
+    def get_sampling_weights(self, pos, deactivate_weight):
+        """loss.py:112-153: (psi / psi0)^2, normalised, when the walkers are not resampled every epoch."""
+        if not (self.use_weight and not deactivate_weight):
+            return torch.tensor(1.0, dtype=torch.float64, device=self.wf.ao.atom_coords.device)
+        self.weight["psi"] = self.wf(pos)
+        if self.weight["psi0"] is None:
+            self.weight["psi0"] = self.weight["psi"].detach().clone()
+            return torch.ones_like(self.weight["psi"])
+        w = (self.weight["psi"] / self.weight["psi0"]) ** 2
+        return w / w.sum()
 
     def get_clipping_mask(self, eloc):
         if not self.clip:
@@ -102,12 +128,10 @@ class Solver:
         if track is not None:
             self.track_observable(track)
         if grad is not None:
-            if grad != "manual":
-                raise NotImplementedError(
-                    "grad='auto' back-propagates through E_L (solver.py:352-370): second-order "
-                    "derivatives of the fused kernel are a later scope row (SURVEY.md 8f4)")
+            if grad not in ("manual", "auto"):
+                raise ValueError("grad should be 'auto' or 'manual'")
             self.grad_method = grad
-            self.evaluate_gradient = self.evaluate_grad_manual
+            self.evaluate_gradient = {"auto": self.evaluate_grad_auto, "manual": self.evaluate_grad_manual}[grad]
         if resampling is not None:
             self.configure_resampling(**resampling)
         if loss is not None:
@@ -346,7 +370,10 @@ class Solver:
                 if torch.isnan(eloc).any():
                     return cumulative_loss
                 self.store_observable(lpos, local_energy=eloc, ibatch=ibatch)
-            D.allreduce_gradients(self._trainable())
+            if self.grad_method == "auto":
+                self._average_auto_gradients()
+            else:
+                D.allreduce_gradients(self._trainable())
             self.optimization_step(lpos)
             if n == 0 or cumulative_loss < min_loss:
                 min_loss = cumulative_loss
@@ -358,6 +385,68 @@ class Solver:
                 self.scheduler.step()
             self.epoch_time = time() - tstart
         return cumulative_loss
+
+    def evaluate_grad_auto(self, lpos, allreduce=True):
+        """solver.py:352-370: loss.backward() through the local energies.  The backward of E_L is one call of
+        qmcb_local_energy_backward (adjoint of the Jacobi kinetic energy, csrc/eloc_vjp.cu).  Under
+        torch.distributed the loss of a rank is the loss of its shard; the gradients are averaged."""
+        bh = self.wf._jeen.jastrow_kernel if getattr(self.wf, "_jeen", None) is not None else None
+        if bh is not None and any(p.requires_grad for p in bh.parameters()):
+            raise NotImplementedError(
+                "grad='auto' with trainable three-body (Boys-Handy) weights: the reference's own graph drops the "
+                "dependence of the Jastrow Laplacian on them (jastrow_factor_electron_electron_nuclei.py:411-431, "
+                "create_graph=False), so its gradient is not the derivative of the loss; freeze ['jastrow'] or "
+                "use grad='manual'")
+        loss, eloc = self.loss(lpos)
+        loss.backward()
+        if allreduce:
+            self._average_auto_gradients()
+        return loss.detach(), eloc.detach()
+
+    def _average_auto_gradients(self):
+        """grad="auto": every rank differentiated the loss of its own shard -> mean over the ranks."""
+        if not D.is_distributed():
+            return
+        D.allreduce_gradients(self._trainable())
+        for p in self._trainable():
+            if p.grad is not None:
+                p.grad /= D.world()[1]
+
+    def compute_forces(self, lpos, batch_size=None, clip=None):
+        """F = -< grad_A E_L + (E_L - <E_L>) grad_A log psi^2 >  as returned (without the sign) by
+        solver.py:433-519: both gradients w.r.t. ``wf.ao.atom_coords`` come from qmcb_local_energy_backward
+        (the reference back-propagates through the local energy and through log pdf)."""
+        wf = self.wf
+        original_requires_grad = wf.ao.atom_coords.requires_grad
+        original_flag = wf.atom_coords_grad
+        wf.ao.atom_coords.requires_grad = True
+        wf.atom_coords_grad = True
+        try:
+            lpos = lpos.to(self.device)
+            if batch_size is None:
+                batch_size = lpos.shape[0]
+            nbatch = lpos.shape[0] // batch_size
+            forces = torch.zeros_like(wf.ao.atom_coords).requires_grad_(False)
+            for ibatch in range(nbatch):
+                batch = lpos[ibatch * batch_size: (ibatch + 1) * batch_size].detach()
+                with torch.enable_grad():
+                    local_energy = wf.local_energy(batch)
+                    if clip is not None:
+                        median = torch.median(local_energy)
+                        std = torch.std(local_energy)
+                        clip_mask = (torch.abs((local_energy - median) / std) < clip).to(local_energy.dtype)
+                    else:
+                        clip_mask = torch.ones_like(local_energy)
+                    grad_eloc = torch.autograd.grad(local_energy, wf.ao.atom_coords, grad_outputs=clip_mask)[0]
+                    proba = torch.log(wf.pdf(batch))
+                    grad_outputs = ((local_energy - local_energy.mean()) * clip_mask).detach().squeeze()
+                    grad_proba = torch.autograd.grad(proba, wf.ao.atom_coords,
+                                                     grad_outputs=grad_outputs.reshape(proba.shape))[0]
+                forces += 1.0 / batch_size * (grad_eloc + grad_proba)
+        finally:
+            wf.ao.atom_coords.requires_grad = original_requires_grad
+            wf.atom_coords_grad = original_flag
+        return forces
 
     def evaluate_grad_manual(self, lpos, allreduce=True):
         """dE/dk = < (dpsi/dk)/psi (E_L - <E_L>) > * 2   (solver.py:372-431); the mean and the

@@ -5,7 +5,8 @@ Same constructor, attributes, parameter names and method surface.  ``forward``,
 ``local_energy``, ``kinetic_energy``, ``gradients_jacobi`` and ``pdf`` each run one fused
 sm_100a kernel per call; ``forward`` is differentiable w.r.t. the wave-function
 parameters (``psi.backward(weight)`` as used by ``Solver.evaluate_grad_manual``) through
-``qmcb_psi_backward``.
+``qmcb_psi_backward``; ``local_energy`` is differentiable w.r.t. the parameters and the atom
+coordinates (``grad="auto"``, ``Solver.compute_forces``) through ``qmcb_local_energy_backward``.
 """
 import ctypes as C
 
@@ -27,7 +28,7 @@ class _PsiFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, wf, x, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w, een_num, een_denom, een_fc,
-                psi_value=None):
+                psi_value=None, atom_coords=None):
         ctx.wf = wf
         ctx.save_for_backward(x)
         # psi_value: psi of exactly these walkers, already produced by the E_L launch (out1)
@@ -48,6 +49,10 @@ class _PsiFunction(torch.autograd.Function):
             gx = wf._grad_psi(x, pdf=False) * grad_out.reshape(-1, 1)
         g = {k: g.get(k) for k in ("bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w", "jen_w", "een_num",
                                    "een_denom", "een_fc")}
+        g_atom = None
+        if need[12]:
+            # d psi / d atom_coords (Solver.compute_forces): the adjoint kernel of the local energy with a psi weight
+            g_atom = wf._eloc_backward(x, None, grad_out.reshape(-1).contiguous(), {"atom_coords"})["atom_coords"]
         return (None, gx,
                 g["bas_exp"] if need[2] else None,
                 # uncontracted bases: the reference never multiplies bas_coeffs into psi
@@ -60,7 +65,34 @@ class _PsiFunction(torch.autograd.Function):
                 g["een_num"] if need[8] else None,
                 g["een_denom"] if need[9] else None,
                 g["een_fc"] if need[10] else None,
-                None)
+                None, g_atom)
+
+
+class _ElocFunction(torch.autograd.Function):
+    """E_L(pos; theta) differentiable w.r.t. the parameters and the atom coordinates: the backward of
+    WaveFunction.local_energy that Solver.evaluate_grad_auto (solver/solver.py:352-370) and
+    Solver.compute_forces (:433-519) run through autograd, here one call of qmcb_local_energy_backward."""
+
+    NAMES = ("atom_coords", "bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w", "jen_w")
+
+    @staticmethod
+    def forward(ctx, wf, x, atom_coords, bas_exp, bas_coeffs, mo_modifier, ci, jee_w, jen_w):
+        ctx.wf = wf
+        ctx.save_for_backward(x)
+        return wf._eloc(x)[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        wf = ctx.wf
+        (x,) = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        if need[1]:
+            raise NotImplementedError("the local energy is not differentiable w.r.t. the walker positions here")
+        want = {n for n, flag in zip(_ElocFunction.NAMES, need[2:]) if flag}
+        if not wf.ao.contract:
+            want.discard("bas_coeffs")      # as for psi: an uncontracted basis never multiplies bas_coeffs in
+        g = wf._eloc_backward(x, grad_out.reshape(-1).contiguous(), None, want) if want else {}
+        return (None, None) + tuple(g.get(n) for n in _ElocFunction.NAMES)
 
 
 class SlaterJastrow(WaveFunction):
@@ -192,7 +224,7 @@ class SlaterJastrow(WaveFunction):
         dev = x.device
         W = x.shape[0]
         nao, nmo = self.mo.mo_scf.shape
-        nbas = self.ao.nbas
+        nbas = len(self.ao.index_ctr_np)         # plan primitives (one per cartesian monomial)
         g_mo = torch.empty(nao, nmo, dtype=torch.float64, device=dev)
         g_ci = torch.empty(1, self.nci, dtype=torch.float64, device=dev)
         g_exp = torch.empty(nbas, dtype=torch.float64, device=dev)
@@ -213,11 +245,59 @@ class SlaterJastrow(WaveFunction):
                                        out("jee_w", g_jee), out("jen_w", g_jen),
                                        out("een", g_een) if nt else None, _lib.ptr(ws), _lib.stream_ptr(dev)),
                    "qmcb_psi_backward")
+        g_exp, g_cf = self._fold_primitives(g_exp), self._fold_primitives(g_cf)
         return {"mo_modifier": g_mo * self.mo.mo_scf, "ci": g_ci, "bas_exp": g_exp, "bas_coeffs": g_cf,
                 "jee_w": g_jee, "jen_w": g_jen,
                 "een_num": g_een[: 2 * nt].view(1, 2, nt) if nt else None,
                 "een_denom": g_een[2 * nt: 4 * nt].view(1, 2, nt) if nt else None,
                 "een_fc": g_een[4 * nt: 5 * nt].view(1, nt) if nt else None}
+
+    def _fold_primitives(self, g):
+        """Plan primitives -> the reference's flat primitives: the cartesian monomials of a spherical
+        harmonic share one (exponent, coefficient), so their derivatives add up."""
+        ix = getattr(self.ao, "expand_index", None)
+        if ix is None:
+            return g
+        ix = torch.as_tensor(ix, dtype=torch.long, device=g.device)
+        return torch.zeros(self.ao.nbas, dtype=g.dtype, device=g.device).index_add_(0, ix, g)
+
+    def _eloc_backward(self, x, w_eloc, w_psi, want):
+        """sum_w w_eloc d E_L / d theta + w_psi d psi / d theta for the names in ``want`` (a subset of
+        _ElocFunction.NAMES) through qmcb_local_energy_backward; returns {name: tensor shaped like the leaf}."""
+        L = _lib.lib()
+        plan = self._handle.plan()
+        dev = x.device
+        W = x.shape[0]
+        nao, nmo = self.mo.mo_scf.shape
+        nbas = len(self.ao.index_ctr_np)
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float64, device=dev)
+        bufs = {"mo_modifier": new(nao, nmo), "ci": new(1, self.nci), "bas_exp": new(nbas), "bas_coeffs": new(nbas),
+                "jee_w": new(1), "jen_w": new(1), "atom_coords": new(self.natom, 3)}
+        if self._jee is None:
+            want = set(want) - {"jee_w"}
+        if self._jen is None:
+            want = set(want) - {"jen_w"}
+        nbytes = L.qmcb_local_energy_backward_workspace_bytes(plan, W)
+        ws = self._ws.get("vjp")
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = self._ws["vjp"] = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
+        out = lambda name: _lib.ptr(bufs[name]) if name in want else None
+        _lib.check(L.qmcb_local_energy_backward(
+            plan, _lib.ptr(x), _lib.ptr(w_eloc), _lib.ptr(w_psi), W, out("mo_modifier"), out("ci"), out("bas_exp"),
+            out("bas_coeffs"), out("jee_w"), out("jen_w"), out("atom_coords"), _lib.ptr(ws), _lib.stream_ptr(dev)),
+            "qmcb_local_energy_backward")
+        g = {n: bufs[n] for n in want}
+        if "mo_modifier" in g:
+            g["mo_modifier"] = g["mo_modifier"] * self.mo.mo_scf
+        for n in ("bas_exp", "bas_coeffs"):
+            if n in g:
+                g[n] = self._fold_primitives(g[n])
+        return g
+
+    # atom coordinates join the autograd graphs of psi and E_L only on request (Solver.compute_forces switches
+    # this on): ao.atom_coords requires grad by default like the reference's, and every psi.backward() of an
+    # optimisation would otherwise pay for a derivative nobody reads
+    atom_coords_grad = False
 
     # -- public API (reference signatures) ---------------------------------------------------
     def forward(self, x, ao=None, _psi_value=None):
@@ -231,14 +311,15 @@ class SlaterJastrow(WaveFunction):
         leaves = [self.ao.bas_exp, self.ao.bas_coeffs, self.mo.mo_modifier, self.fc.weight, jw, nw,
                   bh.weight_num if bh is not None else None, bh.weight_denom if bh is not None else None,
                   bh.fc.weight if bh is not None else None]
+        atom = self.ao.atom_coords if (self.atom_coords_grad and self.ao.atom_coords.requires_grad) else None
         track = torch.is_grad_enabled() and (
-            any(t is not None and t.requires_grad for t in leaves) or x.requires_grad)
+            any(t is not None and t.requires_grad for t in leaves) or x.requires_grad or atom is not None)
         if not track:
             return self._psi(xd) if _psi_value is None else _psi_value
         if x.requires_grad:
             xd = x if (x.device == xd.device and x.dtype == torch.float64 and x.is_contiguous()) else \
                 x.to(device=xd.device, dtype=torch.float64).contiguous()
-        return _PsiFunction.apply(self, xd, *leaves, _psi_value)
+        return _PsiFunction.apply(self, xd, *leaves, _psi_value, atom)
 
     def local_energy_and_psi(self, pos):
         """(E_L [W,1] without graph, psi [W,1] in the autograd graph of the parameters) from ONE
@@ -260,7 +341,18 @@ class SlaterJastrow(WaveFunction):
     def local_energy(self, pos):
         """E_L [W,1]  (wf_base.py:184-215 + slater_jastrow.py:312-344).  A host tensor is streamed
         to the device in chunks so that the H2D copy of chunk k+1 overlaps the kernel on chunk k."""
-        if pos.device.type == "cpu" and pos.shape[0] >= self.host_chunk_min:
+        streamed = pos.device.type == "cpu" and pos.shape[0] >= self.host_chunk_min
+        if torch.is_grad_enabled() and not streamed:
+            # differentiable w.r.t. the parameters (grad="auto", forces): one autograd node around the E_L kernel
+            # (a large HOST ensemble is streamed through the device in chunks and carries no graph: its device
+            # copy does not outlive the call)
+            jw = self._jee.jastrow_kernel.weight if self._jee is not None else None
+            nw = self._jen.jastrow_kernel.weight if self._jen is not None else None
+            atom = self.ao.atom_coords if self.atom_coords_grad else None
+            leaves = [atom, self.ao.bas_exp, self.ao.bas_coeffs, self.mo.mo_modifier, self.fc.weight, jw, nw]
+            if any(t is not None and t.requires_grad for t in leaves):
+                return _ElocFunction.apply(self, self._x(pos), *leaves)
+        if streamed:
             return self._eloc_from_host(pos)
         return self._eloc(self._x(pos))[0]
 
