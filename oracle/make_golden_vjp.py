@@ -82,17 +82,7 @@ def leaves_of(wf, jt):
 def oracle_adjoint(g, pos, wE):
     """The same adjoint by autograd through the oracle (no three-body term: the oracle detaches it)."""
     mol, P = C.oracle_params(g)
-    names = ["atom_coords", "bas_exp", "bas_coeffs", "mo_modifier", "ci"]
-    if P.jastrow_weight is not None:
-        names.append("jastrow_weight")
-    if P.en_weight is not None:
-        names.append("en_weight")
-    for n in names:
-        setattr(P, n, getattr(P, n).detach().clone().requires_grad_(True))
-    e = orc.local_energy(P, pos)
-    gr = torch.autograd.grad((e.reshape(-1) * wE).sum(), [getattr(P, n) for n in names], allow_unused=True)
-    ren = {"jastrow_weight": "jee_w", "en_weight": "jen_w"}
-    return {ren.get(n, n): v for n, v in zip(names, gr)}
+    return orc.local_energy_adjoint(P, pos, w_eloc=wE)
 
 
 def main():

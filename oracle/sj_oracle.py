@@ -747,6 +747,33 @@ def param_grads(p, pos, eloc=None, names=("jastrow_weight", "mo_modifier", "ci",
     return out, eloc
 
 
+def local_energy_adjoint(p, pos, w_eloc=None, w_psi=None):
+    """sum_w w_eloc d E_L / d theta + w_psi d psi / d theta by autograd through this restatement: what the
+    reference's loss.backward() (solver/solver.py:352-370, grad="auto") and compute_forces (:433-519) obtain.
+    Leaves: atom_coords (through the AOs and potentials only - the Jastrow factors hold a constant copy,
+    _jastrow_atoms), bas_exp, bas_coeffs, mo_modifier, ci and the Pade weights.  Without the three-body term
+    (its derivatives are detached here, partially detached in the reference).  Returns dict name -> gradient."""
+    assert getattr(p, "een", None) is None
+    names = ["atom_coords", "bas_exp", "bas_coeffs", "mo_modifier", "ci"]
+    if p.jastrow_weight is not None:
+        names.append("jastrow_weight")
+    if p.en_weight is not None:
+        names.append("en_weight")
+    old = {n: getattr(p, n) for n in names}
+    for n in names:
+        setattr(p, n, old[n].detach().clone().requires_grad_(True))
+    total = 0.0
+    if w_eloc is not None:
+        total = total + (local_energy(p, pos).reshape(-1) * w_eloc).sum()
+    if w_psi is not None:
+        total = total + (psi(p, pos).reshape(-1) * w_psi).sum()
+    gr = torch.autograd.grad(total, [getattr(p, n) for n in names], allow_unused=True)
+    for n in names:
+        setattr(p, n, old[n])
+    ren = {"jastrow_weight": "jee_w", "en_weight": "jen_w"}
+    return {ren.get(n, n): v for n, v in zip(names, gr)}
+
+
 def energy_stats(eloc):
     """wf_base.py:217-229, solver_base.py:371: mean, unbiased variance, sqrt(var/N)."""
     e = eloc.mean()

@@ -43,6 +43,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,7 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int kThreads = 128;        // 4 walkers (warps) per CTA
 
 // ---- dual numbers (forward-mode derivatives along N directions)
 template <int N>
@@ -202,6 +204,7 @@ struct AccLayout {
   __host__ __device__ explicit AccLayout(const VjpSys &S) {
     o_w = 0; o_ci = o_w + S.nao * S.nmu; o_exp = o_ci + S.nconf; o_coef = o_exp + S.nbas; o_pr = o_coef + S.nbas;
     o_jee = o_pr + 3 * S.nbas; o_jen = o_jee + 1; o_sumE = o_jen + 1; o_ven = o_sumE + 1; n = o_ven + 3 * S.natom;
+    n = (n + 1) & ~1;
   }
 };
 // scratch layout (doubles, per warp)
@@ -321,17 +324,27 @@ struct VjpArgs {
   int64_t W, w0, w1;       // this launch handles walkers [w0, w1)
   const double *J, *dJ, *d2J;   // Jastrow operator output of the chunk (index w - w0), or nullptr
   double *scratch, *acc;   // per warp
+  int smem;                // 1: scratch and accumulators of a warp live in shared memory (small systems)
   int want_mo, want_ci, want_exp, want_coef, want_jee, want_jen, want_atom;
 };
 
-__global__ void __launch_bounds__(256, 1) eloc_vjp_kernel(const VjpSys S, const VjpArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S, const VjpArgs a) {
+  extern __shared__ __align__(16) double vjp_smem[];
   const ScratchLayout SL(S);
   const AccLayout AL(S);
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-  double *sc = a.scratch + warp * SL.n;
-  double *acc = a.acc + warp * AL.n;
+  // per-warp work area: shared memory when the system is small enough (an L2 round trip per phase otherwise
+  // dominates: the phases of one walker are a chain of ~30 dependent steps), global scratch for large ones
+  double *sc = a.smem ? vjp_smem + (threadIdx.x >> 5) * (SL.n + AL.n) : a.scratch + warp * SL.n;
+  double *gacc = a.acc + warp * AL.n;
+  double *acc = a.smem ? sc + SL.n : gacc;
+  if (a.smem) {
+    for (int i = lane; i < AL.n; i += 32) acc[i] = 0.0;
+    __syncwarp();
+  }
   const int Ne = S.nelec, Na = S.nao, Nm = S.nmu, ld = S.nmup, nun = S.nuu + S.nud;
   double *AO = sc + SL.o_ao, *KC = sc + SL.o_kc, *MO = sc + SL.o_mo, *BK = sc + SL.o_bk, *M0 = sc + SL.o_m0,
          *Q = sc + SL.o_q, *MW = sc + SL.o_mw, *QW = sc + SL.o_qw, *g = sc + SL.o_g, *gb = sc + SL.o_gb,
@@ -571,6 +584,8 @@ __global__ void __launch_bounds__(256, 1) eloc_vjp_kernel(const VjpSys S, const 
     }
     __syncwarp();
   }
+  if (a.smem)
+    for (int i = lane; i < AL.n; i += 32) gacc[i] += acc[i];
 }
 
 struct VjpOut {
@@ -618,10 +633,31 @@ __global__ void vjp_finish(const VjpSys S, const double *acc, int nwarp, VjpOut 
     }
 }
 
-constexpr int kThreads = 256;
 constexpr int kChunk = 1 << 17;      // walkers per Jastrow-operator chunk
 
-int grid_of(const qmcb_plan *p) { return p->sm_count * 2; }
+// launch shape: CTAs of kThreads; shared-memory work areas when 2 CTAs per SM fit, else global scratch
+struct VjpLaunch { int grid, smem_bytes, use_smem, minb; };
+int env_minb() {
+  const char *e = getenv("QMCB_VJP_MINB");       // CTAs per SM the kernel is compiled for (register budget)
+  const int v = e ? atoi(e) : 3;
+  return v < 2 ? 2 : (v > 4 ? 4 : v);
+}
+VjpLaunch launch_of(const qmcb_plan *p, const VjpSys &S) {
+  const ScratchLayout SL(S);
+  const AccLayout AL(S);
+  const size_t per_cta = (size_t)(kThreads / 32) * (SL.n + AL.n) * 8;
+  VjpLaunch L{};
+  const size_t budget = (size_t)p->smem_optin - 1024;
+  if (per_cta <= budget) {
+    int per_sm = (int)(((size_t)227 * 1024) / (per_cta + 1024));
+    const int cap = env_minb();
+    per_sm = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
+    L.use_smem = 1; L.smem_bytes = (int)per_cta; L.grid = p->sm_count * per_sm; L.minb = per_sm < 2 ? 2 : per_sm;
+  } else {
+    L.use_smem = 0; L.smem_bytes = 0; L.minb = env_minb(); L.grid = p->sm_count * L.minb;
+  }
+  return L;
+}
 
 VjpSys make_sys(const qmcb_plan *p) {
   const DevSys &D = p->sys;
@@ -652,7 +688,7 @@ extern "C" int64_t qmcb_local_energy_backward_workspace_bytes(const qmcb_plan *p
   VjpSys S = make_sys(p);
   const ScratchLayout SL(S);
   const AccLayout AL(S);
-  const int64_t nwarp = (int64_t)grid_of(p) * (kThreads / 32);
+  const int64_t nwarp = (int64_t)launch_of(p, S).grid * (kThreads / 32);
   const int64_t wc = W < kChunk ? W : kChunk;
   size_t n = align256((size_t)nwarp * SL.n * 8) + align256((size_t)nwarp * AL.n * 8);
   n += align256((size_t)wc * 8) + align256((size_t)wc * 3 * S.nelec * 8) + align256((size_t)wc * S.nelec * 8);
@@ -675,8 +711,15 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
   const VjpSys S = make_sys(p);
   const ScratchLayout SL(S);
   const AccLayout AL(S);
-  const int grid = grid_of(p);
+  const VjpLaunch LC = launch_of(p, S);
+  const int grid = LC.grid;
   const int nwarp = grid * (kThreads / 32);
+  void (*kern)(const VjpSys, const VjpArgs) =
+      LC.minb == 2 ? eloc_vjp_kernel<2> : (LC.minb == 3 ? eloc_vjp_kernel<3> : eloc_vjp_kernel<4>);
+  if (LC.use_smem) {
+    cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LC.smem_bytes);
+    if (ea != cudaSuccess) return qmcb_cuda_rc((int)ea, "qmcb_local_energy_backward smem");
+  }
   const int64_t wc = W < kChunk ? W : kChunk;
   char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   double *scratch = (double *)ws; ws += align256((size_t)nwarp * SL.n * 8);
@@ -688,7 +731,7 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
   if (e != cudaSuccess) return qmcb_cuda_rc((int)e, "qmcb_local_energy_backward memset");
   VjpArgs a{};
   a.pos = pos; a.wE = w_eloc; a.wP = w_psi; a.W = W;
-  a.scratch = scratch; a.acc = acc;
+  a.scratch = scratch; a.acc = acc; a.smem = LC.use_smem;
   a.want_mo = g_mo != nullptr; a.want_ci = g_ci != nullptr; a.want_exp = g_bas_exp != nullptr;
   a.want_coef = g_bas_coeffs != nullptr; a.want_jee = g_jee_w != nullptr; a.want_jen = g_jen_w != nullptr;
   a.want_atom = g_atom_coords != nullptr;
@@ -700,7 +743,7 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
       a.J = J; a.dJ = dJ; a.d2J = d2J;
     }
     a.w0 = w0; a.w1 = w1;
-    eloc_vjp_kernel<<<grid, kThreads, 0, st>>>(S, a);
+    kern<<<grid, kThreads, LC.smem_bytes, st>>>(S, a);
     if ((e = cudaGetLastError()) != cudaSuccess) return qmcb_cuda_rc((int)e, "eloc_vjp_kernel launch");
   }
   VjpOut o{g_mo, g_ci, g_bas_exp, g_bas_coeffs, g_jee_w, g_jen_w, g_atom_coords};

@@ -131,30 +131,40 @@ def test_solver_forces_and_grad_auto_match_reference(name):
         assert seen >= 4
 
 
-def test_grad_auto_descends_the_variance_on_fixed_walkers():
-    """Variance minimisation with grad='auto' (what the manual estimator cannot do): on a FIXED ensemble the
-    loss is a deterministic function of the parameters, so a few small Adam steps along the adjoint's gradient
-    must lower it."""
-    g = C.load("lih_ground")
+@pytest.mark.parametrize("loss", ["energy", "variance"])
+def test_grad_auto_is_the_derivative_of_the_loss(loss):
+    """grad='auto' on a FIXED ensemble of 4096 LiH walkers: the loss is a deterministic function of the
+    parameters, so a small step against the gradient the Solver left in .grad must change the loss by
+    -eps |g| to first order (central finite difference of the loss along the gradient direction)."""
+    g = C.load("lih_een")
     mol, wf = C.build_wf(g)
     from qmctorch_b200.sampler import Metropolis
-    from qmctorch_b200.solver import Solver
     torch.manual_seed(0)
     sampler = Metropolis(nwalkers=4096, nstep=300, step_size=0.3, nelec=wf.nelec, ndim=3, init=mol.domain("normal"),
                          move={"type": "all-elec", "proba": "normal"}, cuda=True, seed=3)
     pos = sampler(wf.pdf, with_tqdm=False).detach()
-    opt = torch.optim.Adam(wf.parameters(), lr=2e-3)
-    solver = Solver(wf=wf, sampler=sampler, optimizer=opt)
-    solver.configure(track=["local_energy"], freeze=["ao"], loss="variance", grad="auto", clip_loss=True,
+    solver = _solver(wf, mol, 4096)
+    solver.configure(track=["local_energy"], loss=loss, grad="auto",
                      resampling={"mode": "never", "resample_every": 1, "nstep_update": 25})
-    losses = []
-    for _ in range(10):
-        opt.zero_grad()
-        loss, _ = solver.evaluate_gradient(pos)
-        losses.append(float(loss))
-        opt.step()
-    assert np.isfinite(losses).all()
-    assert losses[-1] < 0.9 * losses[0], losses
+    wf.zero_grad()
+    solver.evaluate_gradient(pos)
+    params = [p for p in wf.parameters() if p.grad is not None]
+    assert len(params) >= 4
+    grads = [p.grad.detach().clone() for p in params]
+    norm = float(torch.sqrt(sum((x ** 2).sum() for x in grads)))
+    eps = 1e-5
+
+    def loss_at(step):
+        with torch.no_grad():
+            for p, x in zip(params, grads):
+                p.add_(x, alpha=step / norm)
+            val = float(solver.loss(pos, no_grad=True)[0])
+            for p, x in zip(params, grads):
+                p.sub_(x, alpha=step / norm)
+        return val
+
+    slope = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
+    assert abs(slope - norm) < 1e-5 * norm, (slope, norm)
 
 
 def test_three_body_weights_are_refused_by_grad_auto():

@@ -151,3 +151,31 @@ def test_oracle_spherical_harmonics_reproduce_reference(key):
                                                   torch.tensor(g[key + "_mh_tau"][it]))
         assert np.array_equal(acc.numpy().astype(bool), g[key + "_mh_acc"][it])
         assert np.array_equal(npos.numpy(), g[key + "_mh_pos"][it + 1])
+
+
+VJP_CASES = ["h2_single22", "lih_cas24", "lih_een", "h2o_cas44", "lih_sto", "lih_gto_kr", "lih_adf_sd22"]
+
+
+@pytest.mark.parametrize("name", VJP_CASES)
+def test_oracle_local_energy_adjoint(name):
+    """Autograd through the oracle's E_L and psi reproduces the reference's (tests/golden/vjp.npz, written by
+    oracle/make_golden_vjp.py from the unmodified reference): pins the oracle for grad="auto" and the forces."""
+    import os
+    gold = np.load(os.path.join(C.GOLDEN, "vjp.npz"))
+    g = C.load(name)
+    mol, P = C.oracle_params(g)
+    n = int(gold[name + "/n"][0])
+    pos = torch.tensor(g["pos"][:n])
+    gE = orc.local_energy_adjoint(P, pos, w_eloc=torch.tensor(gold[name + "/wE"]))
+    gP = orc.local_energy_adjoint(P, pos, w_psi=torch.tensor(gold[name + "/wP"]))
+    checked = 0
+    for leaf in ("atom_coords", "bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w", "jen_w"):
+        for tag, got in (("gE_", gE), ("gP_", gP)):
+            key = name + "/" + tag + leaf
+            if key not in gold.files or got.get(leaf) is None:
+                continue
+            ref = torch.tensor(gold[key])
+            err = float((got[leaf] - ref).abs().max() / ref.abs().max().clamp(min=1e-4))
+            assert err < 1e-10, (key, err)
+            checked += 1
+    assert checked >= 10
