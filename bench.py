@@ -569,6 +569,66 @@ def run_opt_config(C, steps, warmup, with_cpu):
     return ent
 
 
+def run_adjoint(C, with_cpu):
+    """grad="auto" / forces: the adjoint of the local energy (qmcb_local_energy_backward) on the LiH ensemble -
+    every wave-function parameter, the Jastrow + MO set of BASELINE config 3, and the atom coordinates - next
+    to the reference back-propagating through its own wf.local_energy on the host cores (bounded sample)."""
+    import torch
+    spec = WORKLOADS["lih"]
+    W = spec["walkers"]
+    mol, wf = build_wf(spec)
+    pos = thermalised(C, mol, wf, spec, W, 1, spec["therm"], 77)[0]
+    wgt = torch.randn(W, dtype=torch.float64, device=C.dev)
+    stream = torch.cuda.current_stream(C.dev)
+    sets = {"all_parameters": {"bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w"},
+            "jastrow+mo": {"mo_modifier", "jee_w"}, "atom_coordinates": {"atom_coords"}}
+    out = {"workload": "LiH 6-31G ground_state, %d walkers/GPU: sum_w w d E_L / d theta (backward of "
+                       "wf.local_energy: Solver grad='auto', compute_forces)" % W, "walkers_per_gpu": W, "ms": {}}
+    for name, want in sets.items():
+        wf._eloc_backward(pos, wgt, None, want)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            wf._eloc_backward(pos, wgt, None, want)
+        e1.record(stream)
+        torch.cuda.synchronize(C.dev)
+        out["ms"][name] = C.max_over_ranks(e0.elapsed_time(e1) / 3)
+    out["walkers_per_s_all_parameters"] = C.world * W / (out["ms"]["all_parameters"] * 1e-3)
+    if with_cpu:
+        try:
+            kind, rmol, rwf, _, sample = _reference_wf(spec)
+            nw = 5000
+            rpos = sample(nw, 10)
+            cores = torch.get_num_threads()
+            times = []
+            if kind == "reference":
+                leaves = [p_ for p_ in rwf.parameters() if p_.requires_grad]
+
+                def step():
+                    e = rwf.local_energy(rpos)
+                    torch.autograd.grad(e.sum(), leaves, allow_unused=True)
+            else:
+                import sj_oracle as orc
+
+                def step():
+                    orc.local_energy_adjoint(rwf, rpos, w_eloc=torch.ones(nw, dtype=torch.float64))
+            t_all = time.perf_counter()
+            for i in range(4):
+                t0 = time.perf_counter()
+                step()
+                if i:
+                    times.append(time.perf_counter() - t0)
+                if time.perf_counter() - t_all > 15.0 and times:
+                    break
+            med = statistics.median(times)
+            out["cpu_baseline"] = {"value": nw / med, "unit": "walkers/s", "cores": cores, "kind": kind,
+                                   "sample": "%d walkers x %d backward passes through wf.local_energy (autograd), "
+                                             "torch CPU FP64, median" % (nw, len(times)), "ms_per_step": med * 1e3}
+        except Exception as ex:
+            out["cpu_baseline"] = {"error": repr(ex)[:200]}
+    return out
+
+
 def run_strong(C, steps, warmup):
     """BASELINE config 2 as written: 1e6 LiH walkers in TOTAL, contiguous shards over the N GPUs, the
     4-double all-reduce every step.  The step (kernel + all-reduce) is replayed from a CUDA graph of
@@ -906,6 +966,13 @@ def main():
             strong = run_strong(C, max(args.steps, 20), 3)
         except Exception as ex:
             strong = {"error": repr(ex)[:300]}
+    adjoint = None
+    if args.configs == "all":
+        try:
+            adjoint = run_adjoint(C, with_cpu)
+        except Exception as ex:
+            adjoint = {"error": repr(ex)[:300]}
+            torch.cuda.synchronize(dev)
     sp_e2e = None
     if e2e is not None and args.configs != "none":
         try:
@@ -927,7 +994,7 @@ def main():
         "config": cfg, "result": {k: main_ent.get(k) for k in ("energy_hartree", "n_nonfinite", "specialised_kernel",
                                                                "tile_walkers", "threads_per_cta", "smem_bytes")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
-        "configs": entries, "strong": strong, "single_point_e2e": sp_e2e, "notes": C.notes,
+        "configs": entries, "strong": strong, "single_point_e2e": sp_e2e, "adjoint": adjoint, "notes": C.notes,
     }
     if with_cpu:
         line["cpu_baseline"] = main_ent.get("cpu_baseline")

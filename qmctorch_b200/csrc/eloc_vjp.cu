@@ -52,7 +52,8 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kThreads = 128;        // 4 walkers (warps) per CTA
+constexpr int kThreads = 128;        // 4 warps per CTA
+constexpr int kMinBlocks = 3;        // CTAs per SM the kernel is compiled for: 168 registers (measured: 2 -> 20.6, 3 -> 14.7 ms per 1e6 LiH walkers)
 
 // ---- dual numbers (forward-mode derivatives along N directions)
 template <int N>
@@ -225,95 +226,138 @@ struct ScratchLayout {
   }
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
+// ---- lane groups.  G lanes (a power of two, 4 ... 32) own one walker, a warp works on 32 / G walkers at
+// once; every loop below strides by G with the lane's position in its group and every reduction stays inside
+// the group, so the groups of a warp run the same phases in lockstep and __syncwarp() separates them.
+template <int G> __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// sum over the groups of the warp of the value each group holds on the same group lane (fixed butterfly)
+template <int G> __device__ __forceinline__ double across_groups(double v) {
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// Per-warp accumulators: for idx0 .. idx0 + n, entry i is owned by group lane i % G; the groups' values are
+// added across the warp and group 0 adds the sum to acc (one owner lane per entry: no atomics, fixed order).
+// `f(i)` returns this group's contribution to entry i.
+template <int G, class F>
+__device__ __forceinline__ void accumulate(double *acc, int idx0, int n, int sub, bool first_group, F f) {
+  for (int i0 = 0; i0 < n; i0 += G) {
+    const int i = i0 + sub;
+    double v = i < n ? f(i) : 0.0;
+    v = across_groups<G>(v);
+    if (first_group && i < n) acc[idx0 + i] += v;
+  }
+}
 
-// Warp-cooperative Gauss-Jordan on G [n][3n] = [A | I | B] with partial pivoting (first largest |entry|: the
-// pivot order does not depend on the lane count) -> [I | A^-1 | A^-1 B]; returns det A.
-__device__ double warp_gauss_jordan3(double *G, double *col, int n, int lane) {
+// Group-cooperative Gauss-Jordan on M [n][3n] = [A | I | B] with partial pivoting (first largest |entry|: the
+// pivot order does not depend on G) -> [I | A^-1 | A^-1 B]; returns det A.
+template <int G>
+__device__ double group_gauss_jordan3(double *M, double *col, int n, int sub) {
   const int ld = 3 * n;
   double det = 1.0;
   for (int k = 0; k < n; ++k) {
     double best = -1.0;
     int bi = k;
-    for (int r = k + lane; r < n; r += 32) {
-      const double a = fabs(G[r * ld + k]);
+    for (int r = k + sub; r < n; r += G) {
+      const double a = fabs(M[r * ld + k]);
       if (a > best) { best = a; bi = r; }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = G / 2; o > 0; o >>= 1) {
       const double ob = __shfl_xor_sync(FULL, best, o);
       const int oi = __shfl_xor_sync(FULL, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
     if (bi != k) {
-      for (int c = lane; c < ld; c += 32) {
-        const double t = G[k * ld + c];
-        G[k * ld + c] = G[bi * ld + c];
-        G[bi * ld + c] = t;
+      for (int c = sub; c < ld; c += G) {
+        const double t = M[k * ld + c];
+        M[k * ld + c] = M[bi * ld + c];
+        M[bi * ld + c] = t;
       }
       det = -det;
     }
     __syncwarp();
-    const double p = G[k * ld + k];
+    const double p = M[k * ld + k];
     det *= p;
     const double pinv = 1.0 / p;
-    for (int r = lane; r < n; r += 32) col[r] = G[r * ld + k];
+    for (int r = sub; r < n; r += G) col[r] = M[r * ld + k];
     __syncwarp();
-    for (int c = lane; c < ld; c += 32) G[k * ld + c] *= pinv;
+    for (int c = sub; c < ld; c += G) M[k * ld + c] *= pinv;
     __syncwarp();
-    for (int i = lane; i < n * ld; i += 32) {
+    for (int i = sub; i < n * ld; i += G) {
       const int r = i / ld, c = i - r * ld;
-      if (r != k) G[i] = fma(-col[r], G[k * ld + c], G[i]);
+      if (r != k) M[i] = fma(-col[r], M[k * ld + c], M[i]);
     }
     __syncwarp();
   }
   return det;
 }
 
-// NDIR: tangent directions of the leaf pass over the primitives: 0 none, 1 (alpha), 4 (u_x, u_y, u_z, alpha)
+// One flat primitive q against all electrons of the walker: sum_e (channel adjoints) . (channels of q and their
+// tangents).  NDIR: tangent directions: 0 none, 1 (alpha), 4 (u_x, u_y, u_z, alpha).  Returns through sv
+// (value part: the bas_coeffs derivative) and sd[NDIR].
 template <int NDIR>
-__device__ __forceinline__ void prim_leaf_pass(const VjpSys &S, const ScratchLayout &SL, const AccLayout &AL,
-                                               const double *x, double *sc, double *acc, int lane, bool want_coef) {
+__device__ __forceinline__ void prim_leaf(const VjpSys &S, const ScratchLayout &SL, const double *x, const double *sc,
+                                          int q, double &sv, double (&sd)[4]) {
   const int Ne = S.nelec, Na = S.nao;
   const double *g = sc + SL.o_g;
   const double *MW = sc + SL.o_mw, *QW = sc + SL.o_qw;
-  for (int q = lane; q < S.nbas; q += 32) {
-    const int A = S.patom[q], a = S.pao[q], pk = S.pk[q], n = S.pkr[q];
-    const int kx = pk & 255, ky = (pk >> 8) & 255, kz = (pk >> 16) & 255;
-    const double ax = S.atoms[4 * A], ay = S.atoms[4 * A + 1], az = S.atoms[4 * A + 2];
-    double sv = 0.0, sd[NDIR > 0 ? NDIR : 1] = {};
-    for (int e = 0; e < Ne; ++e) {
-      const double ux = x[3 * e] - ax, uy = x[3 * e + 1] - ay, uz = x[3 * e + 2] - az;
-      const double qw = QW[e * Na + a];
-      const double c0 = fma(g[3 * Ne + e], qw, MW[e * Na + a]);
-      const double c1 = 2.0 * g[e] * qw, c2 = 2.0 * g[Ne + e] * qw, c3 = 2.0 * g[2 * Ne + e] * qw;
-      if constexpr (NDIR == 0) {
-        double o[5];
-        primitive5<double>(S.radial_type, kx, ky, kz, n, ux, uy, uz, S.alpha[q], 1.0, o);
-        sv += c0 * o[0] + c1 * o[1] + c2 * o[2] + c3 * o[3] + qw * o[4];
-      } else {
-        typedef Dual<NDIR> T;
-        T o[5];
-        const T X = NDIR == 4 ? seed<NDIR>(ux, 0) : mk<NDIR>(ux), Y = NDIR == 4 ? seed<NDIR>(uy, 1) : mk<NDIR>(uy),
-                Z = NDIR == 4 ? seed<NDIR>(uz, 2) : mk<NDIR>(uz);
-        primitive5<T>(S.radial_type, kx, ky, kz, n, X, Y, Z, seed<NDIR>(S.alpha[q], NDIR - 1), mk<NDIR>(1.0), o);
-        sv += c0 * o[0].v + c1 * o[1].v + c2 * o[2].v + c3 * o[3].v + qw * o[4].v;
+  const int A = S.patom[q], a = S.pao[q], pk = S.pk[q], n = S.pkr[q];
+  const int kx = pk & 255, ky = (pk >> 8) & 255, kz = (pk >> 16) & 255;
+  const double ax = S.atoms[4 * A], ay = S.atoms[4 * A + 1], az = S.atoms[4 * A + 2];
+  sv = 0.0;
+  sd[0] = sd[1] = sd[2] = sd[3] = 0.0;
+  for (int e = 0; e < Ne; ++e) {
+    const double ux = x[3 * e] - ax, uy = x[3 * e + 1] - ay, uz = x[3 * e + 2] - az;
+    const double qw = QW[e * Na + a];
+    const double c0 = fma(g[3 * Ne + e], qw, MW[e * Na + a]);
+    const double c1 = 2.0 * g[e] * qw, c2 = 2.0 * g[Ne + e] * qw, c3 = 2.0 * g[2 * Ne + e] * qw;
+    if constexpr (NDIR == 0) {
+      double o[5];
+      primitive5<double>(S.radial_type, kx, ky, kz, n, ux, uy, uz, S.alpha[q], 1.0, o);
+      sv += c0 * o[0] + c1 * o[1] + c2 * o[2] + c3 * o[3] + qw * o[4];
+    } else {
+      typedef Dual<NDIR> T;
+      T o[5];
+      const T X = NDIR == 4 ? seed<NDIR>(ux, 0) : mk<NDIR>(ux), Y = NDIR == 4 ? seed<NDIR>(uy, 1) : mk<NDIR>(uy),
+              Z = NDIR == 4 ? seed<NDIR>(uz, 2) : mk<NDIR>(uz);
+      primitive5<T>(S.radial_type, kx, ky, kz, n, X, Y, Z, seed<NDIR>(S.alpha[q], NDIR - 1), mk<NDIR>(1.0), o);
+      sv += c0 * o[0].v + c1 * o[1].v + c2 * o[2].v + c3 * o[3].v + qw * o[4].v;
 #pragma unroll
-        for (int j = 0; j < NDIR; ++j)
-          sd[j] += c0 * o[0].d[j] + c1 * o[1].d[j] + c2 * o[2].d[j] + c3 * o[3].d[j] + qw * o[4].d[j];
-      }
+      for (int j = 0; j < NDIR; ++j)
+        sd[j] += c0 * o[0].d[j] + c1 * o[1].d[j] + c2 * o[2].d[j] + c3 * o[3].d[j] + qw * o[4].d[j];
     }
-    if (want_coef) acc[AL.o_coef + q] += S.norm[q] * sv;
-    if constexpr (NDIR > 0) acc[AL.o_exp + q] += S.cn[q] * sd[NDIR - 1];
+  }
+}
+
+template <int G, int NDIR>
+__device__ __forceinline__ void prim_leaf_pass(const VjpSys &S, const ScratchLayout &SL, const AccLayout &AL,
+                                               const double *x, const double *sc, double *acc, int sub, bool first_group,
+                                               bool want_coef) {
+  for (int q0 = 0; q0 < S.nbas; q0 += G) {
+    const int q = q0 + sub;
+    const bool on = q < S.nbas;
+    double sv = 0.0, sd[4] = {0.0, 0.0, 0.0, 0.0};
+    if (on) prim_leaf<NDIR>(S, SL, x, sc, q, sv, sd);
+    const double cn = on ? S.cn[q] : 0.0;
+    if (want_coef) {
+      const double v = across_groups<G>(on ? S.norm[q] * sv : 0.0);
+      if (first_group && on) acc[AL.o_coef + q] += v;
+    }
+    if constexpr (NDIR > 0) {
+      const double v = across_groups<G>(cn * sd[NDIR - 1]);
+      if (first_group && on) acc[AL.o_exp + q] += v;
+    }
     if constexpr (NDIR == 4) {
-      // d/dR_A = - d/du
-      acc[AL.o_pr + 3 * q] -= S.cn[q] * sd[0];
-      acc[AL.o_pr + 3 * q + 1] -= S.cn[q] * sd[1];
-      acc[AL.o_pr + 3 * q + 2] -= S.cn[q] * sd[2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double v = across_groups<G>(cn * sd[k]);
+        if (first_group && on) acc[AL.o_pr + 3 * q + k] -= v;      // d/dR_A = - d/du
+      }
     }
   }
 }
@@ -323,24 +367,29 @@ struct VjpArgs {
   const double *wE, *wP;   // [W] or nullptr
   int64_t W, w0, w1;       // this launch handles walkers [w0, w1)
   const double *J, *dJ, *d2J;   // Jastrow operator output of the chunk (index w - w0), or nullptr
-  double *scratch, *acc;   // per warp
-  int smem;                // 1: scratch and accumulators of a warp live in shared memory (small systems)
+  double *scratch, *acc;   // global: scratch per group (large systems), accumulators per warp
+  int smem;                // 1: the work areas and accumulators of a warp live in shared memory
   int want_mo, want_ci, want_exp, want_coef, want_jee, want_jen, want_atom;
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S, const VjpArgs a) {
+template <int G>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const VjpSys S, const VjpArgs a) {
   extern __shared__ __align__(16) double vjp_smem[];
+  constexpr int GPW = 32 / G;                       // walkers (groups) per warp
   const ScratchLayout SL(S);
   const AccLayout AL(S);
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
+  const bool first_group = grp == 0;
+  const int wic = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wic;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-  // per-warp work area: shared memory when the system is small enough (an L2 round trip per phase otherwise
-  // dominates: the phases of one walker are a chain of ~30 dependent steps), global scratch for large ones
-  double *sc = a.smem ? vjp_smem + (threadIdx.x >> 5) * (SL.n + AL.n) : a.scratch + warp * SL.n;
+  // work area of the group and accumulators of the warp: shared memory when the system is small enough (the
+  // phases of one walker are a chain of ~30 dependent steps: an L2 round trip per step otherwise dominates),
+  // global scratch for large ones
+  double *wbase = vjp_smem + (size_t)wic * (GPW * SL.n + AL.n);
+  double *sc = a.smem ? wbase + grp * SL.n : a.scratch + (warp * GPW + grp) * SL.n;
   double *gacc = a.acc + warp * AL.n;
-  double *acc = a.smem ? sc + SL.n : gacc;
+  double *acc = a.smem ? wbase + GPW * SL.n : gacc;
   if (a.smem) {
     for (int i = lane; i < AL.n; i += 32) acc[i] = 0.0;
     __syncwarp();
@@ -348,26 +397,29 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
   const int Ne = S.nelec, Na = S.nao, Nm = S.nmu, ld = S.nmup, nun = S.nuu + S.nud;
   double *AO = sc + SL.o_ao, *KC = sc + SL.o_kc, *MO = sc + SL.o_mo, *BK = sc + SL.o_bk, *M0 = sc + SL.o_m0,
          *Q = sc + SL.o_q, *MW = sc + SL.o_mw, *QW = sc + SL.o_qw, *g = sc + SL.o_g, *gb = sc + SL.o_gb,
-         *Dt = sc + SL.o_det, *INV = sc + SL.o_inv, *G = sc + SL.o_gj, *col = sc + SL.o_col;
-  // first walker of this warp such that the assignment walker -> warp is by GLOBAL index (chunked launches)
-  int64_t w = a.w0 + ((warp - a.w0 % nwarp) % nwarp + nwarp) % nwarp;
-  for (; w < a.w1; w += nwarp) {
+         *Dt = sc + SL.o_det, *INV = sc + SL.o_inv, *GJ = sc + SL.o_gj, *col = sc + SL.o_col;
+  // walkers of this launch go to (warp, group) slots by their index: a fixed assignment, so the sums are
+  // bitwise reproducible.  The loop bound is warp uniform; a group past the end re-evaluates the last walker
+  // with zero weights (every adjoint is proportional to them).
+  for (int64_t wb = a.w0 + warp * GPW; wb < a.w1; wb += nwarp * GPW) {
+    const bool live = wb + grp < a.w1;
+    const int64_t w = live ? wb + grp : a.w1 - 1;
     const double *x = a.pos + w * 3 * Ne;
-    const double wE = a.wE ? a.wE[w] : 0.0, wP = a.wP ? a.wP[w] : 0.0;
+    const double wE = (live && a.wE) ? a.wE[w] : 0.0, wP = (live && a.wP) ? a.wP[w] : 0.0;
     // ---- Jastrow leaves of this walker: J, g = grad J / J, l = lap J / J
     double J = 1.0;
     if (S.has_j) {
       const int64_t wl = w - a.w0;
       J = a.J[wl];
       const double Jinv = 1.0 / J;
-      for (int i = lane; i < 4 * Ne; i += 32)
+      for (int i = sub; i < 4 * Ne; i += G)
         g[i] = (i < 3 * Ne ? a.dJ[wl * 3 * Ne + i] : a.d2J[wl * Ne + (i - 3 * Ne)]) * Jinv;
     } else {
-      for (int i = lane; i < 4 * Ne; i += 32) g[i] = 0.0;
+      for (int i = sub; i < 4 * Ne; i += G) g[i] = 0.0;
     }
     __syncwarp();
     // ---- AO channels and the folded kinetic channel
-    for (int it = lane; it < Ne * Na; it += 32) {
+    for (int it = sub; it < Ne * Na; it += G) {
       const int e = it / Na, ao = it - e * Na;
       double s[5] = {0, 0, 0, 0, 0};
       for (int k = S.ao_start[ao]; k < S.ao_start[ao + 1]; ++k) {
@@ -386,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
     }
     __syncwarp();
     // ---- MO = AO W, B = -1/2 K W (used columns)
-    for (int it = lane; it < Ne * Nm; it += 32) {
+    for (int it = sub; it < Ne * Nm; it += G) {
       const int e = it / Nm, m = it - e * Nm;
       double s0 = 0.0, s1 = 0.0;
       for (int ao = 0; ao < Na; ++ao) {
@@ -406,50 +458,49 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
         const int n = up ? S.nup : S.ndown, r0 = up ? 0 : S.nup;
         const int *cols = up ? S.ucu + u * S.nup : S.ucd + (u - S.nuu) * S.ndown;
         const int ldg = 3 * n;
-        for (int i = lane; i < n * n; i += 32) {
+        for (int i = sub; i < n * n; i += G) {
           const int r = i / n, c = i - r * n;
-          G[r * ldg + c] = MO[(r0 + r) * Nm + cols[c]];
-          G[r * ldg + n + c] = r == c ? 1.0 : 0.0;
-          G[r * ldg + 2 * n + c] = BK[(r0 + r) * Nm + cols[c]];
+          GJ[r * ldg + c] = MO[(r0 + r) * Nm + cols[c]];
+          GJ[r * ldg + n + c] = r == c ? 1.0 : 0.0;
+          GJ[r * ldg + 2 * n + c] = BK[(r0 + r) * Nm + cols[c]];
         }
         __syncwarp();
-        const double det = warp_gauss_jordan3(G, col, n, lane);
+        const double det = group_gauss_jordan3<G>(GJ, col, n, sub);
         double tr = 0.0;
-        for (int i = lane; i < n; i += 32) tr += G[i * ldg + 2 * n + i];
-        tr = warp_sum(tr);
+        for (int i = sub; i < n; i += G) tr += GJ[i * ldg + 2 * n + i];
+        tr = group_sum<G>(tr);
         double *Ai = INV + off, *Yv = Ai + n * n;
-        for (int i = lane; i < n * n; i += 32) {
+        for (int i = sub; i < n * n; i += G) {
           const int r = i / n, c = i - r * n;
-          Ai[i] = G[r * ldg + n + c];
+          Ai[i] = GJ[r * ldg + n + c];
           double s = 0.0;
-          for (int k = 0; k < n; ++k) s = fma(G[r * ldg + 2 * n + k], G[k * ldg + n + c], s);
+          for (int k = 0; k < n; ++k) s = fma(GJ[r * ldg + 2 * n + k], GJ[k * ldg + n + c], s);
           Yv[i] = s;
         }
-        if (lane == 0) { Dt[u] = det; Dt[nun + u] = tr; }
+        if (sub == 0) { Dt[u] = det; Dt[nun + u] = tr; }
         off += 2 * n * n;
         __syncwarp();
       }
     }
     // ---- CI sums
     double Ssum = 0.0, Tsum = 0.0;
-    for (int c = lane; c < S.nconf; c += 32) {
+    for (int c = sub; c < S.nconf; c += G) {
       const int iu = S.ciu[c], id = S.nuu + S.cid[c];
       const double dd = S.ci[c] * Dt[iu] * Dt[id];
       Ssum += dd;
       Tsum = fma(dd, Dt[nun + iu] + Dt[nun + id], Tsum);
     }
-    Ssum = warp_sum(Ssum);
-    Tsum = warp_sum(Tsum);
+    Ssum = group_sum<G>(Ssum);
+    Tsum = group_sum<G>(Tsum);
     const double Sinv = 1.0 / Ssum;
     const double Sb = wP * J - wE * Tsum * Sinv * Sinv, Tb = wE * Sinv;
     if (a.want_ci)
-      for (int c = lane; c < S.nconf; c += 32) {
+      accumulate<G>(acc, AL.o_ci, S.nconf, sub, first_group, [&](int c) {
         const int iu = S.ciu[c], id = S.nuu + S.cid[c];
-        const double dd = Dt[iu] * Dt[id];
-        acc[AL.o_ci + c] += dd * (Sb + Tb * (Dt[nun + iu] + Dt[nun + id]));
-      }
+        return Dt[iu] * Dt[id] * (Sb + Tb * (Dt[nun + iu] + Dt[nun + id]));
+      });
     // adjoints of the determinants and traces of the unique blocks
-    for (int u = lane; u < nun; u += 32) {
+    for (int u = sub; u < nun; u += G) {
       const bool up = u < S.nuu;
       double db = 0.0, tb = 0.0;
       for (int c = 0; c < S.nconf; ++c) {
@@ -462,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
       Dt[2 * nun + u] = db;
       Dt[3 * nun + u] = tb;
     }
-    for (int i = lane; i < Ne * Nm; i += 32) { M0[i] = 0.0; Q[i] = 0.0; }
+    for (int i = sub; i < Ne * Nm; i += G) { M0[i] = 0.0; Q[i] = 0.0; }
     __syncwarp();
     // ---- adjoint of MO (through the blocks) and Q = -1/2 adjoint of B
     {
@@ -473,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
         const int *cols = up ? S.ucu + u * S.nup : S.ucd + (u - S.nuu) * S.ndown;
         const double *Ai = INV + off, *Yv = Ai + n * n;
         const double dD = Dt[2 * nun + u] * Dt[u], tb = Dt[3 * nun + u];
-        for (int i = lane; i < n * n; i += 32) {
+        for (int i = sub; i < n * n; i += G) {
           const int r = i / n, c = i - r * n;
           const int idx = (r0 + r) * Nm + cols[c];
           M0[idx] += dD * Ai[c * n + r] - tb * Yv[c * n + r];
@@ -484,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
       }
     }
     // ---- back through the projections
-    for (int it = lane; it < Ne * Na; it += 32) {
+    for (int it = sub; it < Ne * Na; it += G) {
       const int e = it / Na, ao = it - e * Na;
       double s0 = 0.0, s1 = 0.0;
       for (int m = 0; m < Nm; ++m) {
@@ -496,22 +547,22 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
       QW[it] = s1;
     }
     if (a.want_mo)
-      for (int it = lane; it < Na * Nm; it += 32) {
+      accumulate<G>(acc, AL.o_w, Na * Nm, sub, first_group, [&](int it) {
         const int ao = it / Nm, m = it - ao * Nm;
         double s = 0.0;
         for (int e = 0; e < Ne; ++e)
           s = fma(AO[e * Na + ao], M0[e * Nm + m], fma(KC[e * Na + ao], Q[e * Nm + m], s));
-        acc[AL.o_w + it] += s;
-      }
+        return s;
+      });
     __syncwarp();
     // ---- leaves: basis parameters and atom coordinates through the AO channels
-    if (a.want_atom) prim_leaf_pass<4>(S, SL, AL, x, sc, acc, lane, a.want_coef != 0);
-    else if (a.want_exp) prim_leaf_pass<1>(S, SL, AL, x, sc, acc, lane, a.want_coef != 0);
-    else if (a.want_coef) prim_leaf_pass<0>(S, SL, AL, x, sc, acc, lane, true);
+    if (a.want_atom) prim_leaf_pass<G, 4>(S, SL, AL, x, sc, acc, sub, first_group, a.want_coef != 0);
+    else if (a.want_exp) prim_leaf_pass<G, 1>(S, SL, AL, x, sc, acc, sub, first_group, a.want_coef != 0);
+    else if (a.want_coef) prim_leaf_pass<G, 0>(S, SL, AL, x, sc, acc, sub, first_group, true);
     // ---- leaves: Pade weights (e-e, e-n) through g, l and J
     if ((a.want_jee && S.use_jee) || (a.want_jen && S.use_jen)) {
       // adjoints of g_e, l_e from the kinetic channel: g~ = 2 sum_a d ao QW, l~ = sum_a ao QW
-      for (int i = lane; i < 4 * Ne; i += 32) {
+      for (int i = sub; i < 4 * Ne; i += G) {
         const int k = i / Ne, e = i - k * Ne;
         const double *ch = AO + (k < 3 ? (1 + k) : 0) * Ne * Na + e * Na;
         double s = 0.0;
@@ -522,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
       typedef Dual<2> T;
       const double Kb = wP * J * Ssum;          // adjoint of ln J: J~ J with J~ = wP S
       double tj0 = 0.0, tj1 = 0.0;
-      for (int e = lane; e < Ne; e += 32) {
+      for (int e = sub; e < Ne; e += G) {
         const double xe = x[3 * e], ye = x[3 * e + 1], ze = x[3 * e + 2];
         const double lb = gb[3 * Ne + e];
         // l = sum_b lap K_b + |g|^2  ->  adjoint of grad K picks up 2 l~ g
@@ -563,13 +614,13 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
         tj0 += Kb * 0.5 * ks.d[0] + bx * kx.d[0] + by * ky.d[0] + bz * kz.d[0] + lb * kl.d[0];
         tj1 += Kb * kn.d[1] + bx * kx.d[1] + by * ky.d[1] + bz * kz.d[1] + lb * kl.d[1];
       }
-      tj0 = warp_sum(tj0);
-      tj1 = warp_sum(tj1);
+      tj0 = across_groups<G>(group_sum<G>(tj0));
+      tj1 = across_groups<G>(group_sum<G>(tj1));
       if (lane == 0) { acc[AL.o_jee] += tj0; acc[AL.o_jen] += tj1; }
     }
     // ---- potentials: d V_en / d R_A = -Z_A (r_e - R_A) / r^3 ; V_nn is added once by vjp_finish (sum of wE)
     if (a.want_atom && a.wE) {
-      for (int i = lane; i < 3 * S.natom; i += 32) {
+      accumulate<G>(acc, AL.o_ven, 3 * S.natom, sub, first_group, [&](int i) {
         const int A = i / 3, k = i - 3 * A;
         double s = 0.0;
         for (int e = 0; e < Ne; ++e) {
@@ -578,9 +629,10 @@ __global__ void __launch_bounds__(kThreads, MINB) eloc_vjp_kernel(const VjpSys S
           const double r2 = dx * dx + dy * dy + dz * dz, rinv = rsqrt(r2);
           s -= S.atoms[4 * A + 3] * (k == 0 ? dx : (k == 1 ? dy : dz)) * rinv * rinv * rinv;
         }
-        acc[AL.o_ven + i] += wE * s;
-      }
-      if (lane == 0) acc[AL.o_sumE] += wE;
+        return wE * s;
+      });
+      const double sE = across_groups<G>(sub == 0 ? wE : 0.0);
+      if (lane == 0) acc[AL.o_sumE] += sE;
     }
     __syncwarp();
   }
@@ -592,35 +644,37 @@ struct VjpOut {
   double *g_mo, *g_ci, *g_exp, *g_coef, *g_jee, *g_jen, *g_atom;
 };
 
-// Sums the per-warp accumulators in warp order and maps them onto the outputs.
-__global__ void vjp_finish(const VjpSys S, const double *acc, int nwarp, VjpOut o) {
+// Sums the per-warp accumulators in warp order (thread = entry: coalesced rows, fixed order) ...
+__global__ void vjp_reduce(const double *acc, int nwarp, int n, double *tot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int w = 0; w < nwarp; ++w) s += acc[(size_t)w * n + i];
+  tot[i] = s;
+}
+// ... and maps the totals onto the outputs.
+__global__ void vjp_finish(const VjpSys S, const double *tot, VjpOut o) {
   const AccLayout AL(S);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  auto total = [&](int idx) {
-    double s = 0.0;
-    for (int w = 0; w < nwarp; ++w) s += acc[(size_t)w * AL.n + idx];
-    return s;
-  };
   if (o.g_mo)
     for (int i = tid; i < S.nao * S.nmo; i += nth) {
       const int ao = i / S.nmo, m = i - ao * S.nmo;
       int pos = -1;
       for (int j = 0; j < S.nmu; ++j) if (S.used[j] == m) pos = j;
-      o.g_mo[i] = pos < 0 ? 0.0 : total(AL.o_w + ao * S.nmu + pos);
+      o.g_mo[i] = pos < 0 ? 0.0 : tot[AL.o_w + ao * S.nmu + pos];
     }
-  if (o.g_ci) for (int i = tid; i < S.nconf; i += nth) o.g_ci[i] = total(AL.o_ci + i);
-  if (o.g_exp) for (int i = tid; i < S.nbas; i += nth) o.g_exp[i] = total(AL.o_exp + i);
-  if (o.g_coef) for (int i = tid; i < S.nbas; i += nth) o.g_coef[i] = total(AL.o_coef + i);
-  if (o.g_jee && tid == 0) o.g_jee[0] = total(AL.o_jee);
-  if (o.g_jen && tid == 0) o.g_jen[0] = total(AL.o_jen);
+  if (o.g_ci) for (int i = tid; i < S.nconf; i += nth) o.g_ci[i] = tot[AL.o_ci + i];
+  if (o.g_exp) for (int i = tid; i < S.nbas; i += nth) o.g_exp[i] = tot[AL.o_exp + i];
+  if (o.g_coef) for (int i = tid; i < S.nbas; i += nth) o.g_coef[i] = tot[AL.o_coef + i];
+  if (o.g_jee && tid == 0) o.g_jee[0] = tot[AL.o_jee];
+  if (o.g_jen && tid == 0) o.g_jen[0] = tot[AL.o_jen];
   if (o.g_atom)
     for (int i = tid; i < 3 * S.natom; i += nth) {
       const int A = i / 3, k = i - 3 * A;
-      double s = total(AL.o_ven + i);
+      double s = tot[AL.o_ven + i];
       for (int q = 0; q < S.nbas; ++q)
-        if (S.patom[q] == A) s += total(AL.o_pr + 3 * q + k);
+        if (S.patom[q] == A) s += tot[AL.o_pr + 3 * q + k];
       // nuclear repulsion (wf_base.py:97-116): d V_nn / d R_A = - sum_B Z_A Z_B (R_A - R_B) / |R_A - R_B|^3
-      const double sE = total(AL.o_sumE);
       double v = 0.0;
       for (int B = 0; B < S.natom; ++B) {
         if (B == A) continue;
@@ -629,33 +683,44 @@ __global__ void vjp_finish(const VjpSys S, const double *acc, int nwarp, VjpOut 
         const double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2);
         v -= S.atoms[4 * A + 3] * S.atoms[4 * B + 3] * (k == 0 ? dx : (k == 1 ? dy : dz)) / (r2 * r);
       }
-      o.g_atom[i] = s + sE * v;
+      o.g_atom[i] = s + tot[AL.o_sumE] * v;
     }
 }
 
 constexpr int kChunk = 1 << 17;      // walkers per Jastrow-operator chunk
 
-// launch shape: CTAs of kThreads; shared-memory work areas when 2 CTAs per SM fit, else global scratch
-struct VjpLaunch { int grid, smem_bytes, use_smem, minb; };
-int env_minb() {
-  const char *e = getenv("QMCB_VJP_MINB");       // CTAs per SM the kernel is compiled for (register budget)
-  const int v = e ? atoi(e) : 3;
-  return v < 2 ? 2 : (v > 4 ? 4 : v);
-}
+// launch shape: CTAs of kThreads; G lanes per walker by the size of the system (items per phase ~ nelec * nao);
+// shared-memory work areas when at least one CTA fits, else global scratch with a whole warp per walker
+struct VjpLaunch { int grid, threads, smem_bytes, use_smem, G; };
 VjpLaunch launch_of(const qmcb_plan *p, const VjpSys &S) {
   const ScratchLayout SL(S);
   const AccLayout AL(S);
-  const size_t per_cta = (size_t)(kThreads / 32) * (SL.n + AL.n) * 8;
+  const char *eg = getenv("QMCB_VJP_G");           // tuning: force the group size
+  int G = 4;
+  while (G < 32 && G * 6 < S.nelec * S.nao) G *= 2;
+  if (eg && (atoi(eg) == 4 || atoi(eg) == 8 || atoi(eg) == 16 || atoi(eg) == 32)) G = atoi(eg);
   VjpLaunch L{};
-  const size_t budget = (size_t)p->smem_optin - 1024;
-  if (per_cta <= budget) {
-    int per_sm = (int)(((size_t)227 * 1024) / (per_cta + 1024));
-    const int cap = env_minb();
-    per_sm = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
-    L.use_smem = 1; L.smem_bytes = (int)per_cta; L.grid = p->sm_count * per_sm; L.minb = per_sm < 2 ? 2 : per_sm;
-  } else {
-    L.use_smem = 0; L.smem_bytes = 0; L.minb = env_minb(); L.grid = p->sm_count * L.minb;
-  }
+  const size_t budget = (size_t)p->smem_optin - 1024, sm_total = (size_t)227 * 1024;
+  const int reg_warps = 65536 / (168 * 32);          // resident warps the register file allows
+  // candidates: (G, warps per CTA); keep the one with the most resident warps per SM, then the smaller G
+  int best_warps = 0;
+  for (int g = G; g <= 32; g *= 2)
+    for (int wpc = kThreads / 32; wpc >= 1; wpc /= 2) {
+      const size_t per_cta = (size_t)wpc * ((size_t)(32 / g) * SL.n + AL.n) * 8;
+      if (per_cta > budget) continue;
+      int per_sm = (int)(sm_total / (per_cta + 1024));
+      if (per_sm * wpc > reg_warps) per_sm = reg_warps / wpc;
+      if (per_sm > 16) per_sm = 16;
+      if (per_sm < 1) continue;
+      // walkers in flight weigh more than warps: a smaller group wins ties
+      if (per_sm * wpc > best_warps) {
+        best_warps = per_sm * wpc;
+        L.use_smem = 1; L.smem_bytes = (int)per_cta; L.grid = p->sm_count * per_sm; L.G = g; L.threads = 32 * wpc;
+      }
+    }
+  if (best_warps >= 6) return L;
+  // large systems: a whole warp per walker on global (L2-resident) scratch
+  L.use_smem = 0; L.smem_bytes = 0; L.G = 32; L.threads = kThreads; L.grid = p->sm_count * kMinBlocks;
   return L;
 }
 
@@ -688,9 +753,11 @@ extern "C" int64_t qmcb_local_energy_backward_workspace_bytes(const qmcb_plan *p
   VjpSys S = make_sys(p);
   const ScratchLayout SL(S);
   const AccLayout AL(S);
-  const int64_t nwarp = (int64_t)launch_of(p, S).grid * (kThreads / 32);
+  const VjpLaunch LC = launch_of(p, S);
+  const int64_t nwarp = (int64_t)LC.grid * (LC.threads / 32);
   const int64_t wc = W < kChunk ? W : kChunk;
-  size_t n = align256((size_t)nwarp * SL.n * 8) + align256((size_t)nwarp * AL.n * 8);
+  size_t n = align256((size_t)nwarp * (32 / LC.G) * SL.n * 8) + align256((size_t)nwarp * AL.n * 8) +
+             align256((size_t)AL.n * 8);
   n += align256((size_t)wc * 8) + align256((size_t)wc * 3 * S.nelec * 8) + align256((size_t)wc * S.nelec * 8);
   return (int64_t)n + 256;
 }
@@ -713,17 +780,18 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
   const AccLayout AL(S);
   const VjpLaunch LC = launch_of(p, S);
   const int grid = LC.grid;
-  const int nwarp = grid * (kThreads / 32);
+  const int nwarp = grid * (LC.threads / 32);
   void (*kern)(const VjpSys, const VjpArgs) =
-      LC.minb == 2 ? eloc_vjp_kernel<2> : (LC.minb == 3 ? eloc_vjp_kernel<3> : eloc_vjp_kernel<4>);
+      LC.G == 4 ? eloc_vjp_kernel<4> : (LC.G == 8 ? eloc_vjp_kernel<8> : (LC.G == 16 ? eloc_vjp_kernel<16> : eloc_vjp_kernel<32>));
   if (LC.use_smem) {
     cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LC.smem_bytes);
     if (ea != cudaSuccess) return qmcb_cuda_rc((int)ea, "qmcb_local_energy_backward smem");
   }
   const int64_t wc = W < kChunk ? W : kChunk;
   char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  double *scratch = (double *)ws; ws += align256((size_t)nwarp * SL.n * 8);
+  double *scratch = (double *)ws; ws += align256((size_t)nwarp * (32 / LC.G) * SL.n * 8);
   double *acc = (double *)ws; ws += align256((size_t)nwarp * AL.n * 8);
+  double *tot = (double *)ws; ws += align256((size_t)AL.n * 8);
   double *J = (double *)ws; ws += align256((size_t)wc * 8);
   double *dJ = (double *)ws; ws += align256((size_t)wc * 3 * S.nelec * 8);
   double *d2J = (double *)ws;
@@ -743,10 +811,11 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
       a.J = J; a.dJ = dJ; a.d2J = d2J;
     }
     a.w0 = w0; a.w1 = w1;
-    kern<<<grid, kThreads, LC.smem_bytes, st>>>(S, a);
+    kern<<<grid, LC.threads, LC.smem_bytes, st>>>(S, a);
     if ((e = cudaGetLastError()) != cudaSuccess) return qmcb_cuda_rc((int)e, "eloc_vjp_kernel launch");
   }
   VjpOut o{g_mo, g_ci, g_bas_exp, g_bas_coeffs, g_jee_w, g_jen_w, g_atom_coords};
-  vjp_finish<<<8, 256, 0, st>>>(S, acc, nwarp, o);
+  vjp_reduce<<<(AL.n + 127) / 128, 128, 0, st>>>(acc, nwarp, AL.n, tot);
+  vjp_finish<<<8, 256, 0, st>>>(S, tot, o);
   return qmcb_cuda_rc((int)cudaGetLastError(), "vjp_finish launch");
 }
