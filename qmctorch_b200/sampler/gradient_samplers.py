@@ -17,6 +17,10 @@ from the textbook, so that the same ``torch.manual_seed`` gives the reference's 
 
 Random draws are made on the CPU generator in the reference's order and shipped to the device of
 the walkers.
+
+Deliberate restatements: ``GeneralizedMetropolis.__call__/move/_move/trans`` and ``Hamiltonian.__call__`` track
+generalized_metropolis.py:60-186 and hamiltonian.py:68-150 variable for variable for that reason; what is new
+here is ``_density_and_gradient`` (the analytic gradient through the CUDA path).
 """
 import numpy as np
 import torch

@@ -7,6 +7,11 @@ and the ensemble never leaves the GPU.  Draws come from an in-kernel Philox gene
 (``rng="philox"``, default) or, for parity runs, from the same torch generator calls the
 reference makes (``rng="torch"``: MultivariateNormal on the CPU generator, ``rand`` for the
 acceptance draw).  For any other callable the reference's generic torch loop is used.
+
+Deliberate restatements of the reference (they fix the ORDER of the generator calls, which is what makes
+``rng="torch"`` chains and the arbitrary-callable fallback reproduce the reference's from the same seed):
+``configure_move``, ``move``, ``_move``, ``_accept`` and ``_call_generic`` follow metropolis.py:179-298
+statement by statement, print strings included.  The fused path inside ``__call__`` and ``_torch_draws`` are original.
 """
 import math
 from time import time

@@ -459,7 +459,8 @@ class SlaterJastrow(WaveFunction):
         are tabulated on ``torch.linspace(-5, 5, 501)`` (default dtype, as there) and fitted
         with ``scipy.optimize.curve_fit``; norms of the new basis are recomputed by ``AtomicOrbitals``
         (``bas_norm`` is ignored, atomic_orbitals.py:90).  The returned object evaluates on the CUDA
-        path like any other."""
+        path like any other.  (A deliberate restatement of slater_jastrow.py:649-733: grid, dtype and fit call must
+        be the reference's for the fitted exponents to come out bit-identical.)"""
         from copy import deepcopy
         import numpy as np
         from scipy.optimize import curve_fit
