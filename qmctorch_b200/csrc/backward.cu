@@ -601,12 +601,16 @@ int qmcb_choose_backward(qmcb_plan *p) {
   return 0;
 }
 
-extern "C" int64_t qmcb_backward_workspace_bytes(const qmcb_plan *p, int64_t) {
+extern "C" int64_t qmcb_backward_workspace_bytes(const qmcb_plan *p, int64_t W) {
   if (!p) return 0;
+  // bases with multi-monomial AOs (real spherical harmonics, l = 2): the basis-parameter gradients come from the
+  // flat-primitive adjoint kernel (eloc_vjp.cu), which brings its own work areas
+  const int64_t vjp = p->multi_component ? qmcb_local_energy_backward_workspace_bytes(p, W) : 0;
   // tile kernel: 2 CTAs per SM x nslot;  specialised kernel: up to 8 CTAs per SM x (nao nmu + nconf + 2)
   const int64_t spec = (int64_t)8 * p->sm_count * ((int64_t)p->sys.nao * p->sys.nmu + p->sys.nconf + 2 + 2 * (int64_t)p->sys.nbas);
   const int64_t tile = (p->bwd.tw == 0 && p->bwd0.tw == 0) ? 0 : (int64_t)2 * p->sm_count * p->bwd.nslot;
-  return (spec > tile ? spec : tile) * (int64_t)sizeof(double);
+  const int64_t own = (spec > tile ? spec : tile) * (int64_t)sizeof(double);
+  return own > vjp ? own : vjp;
 }
 
 extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const double *weight, int64_t W,
@@ -617,12 +621,18 @@ extern "C" int qmcb_psi_backward(const qmcb_plan *p, const double *pos, const do
     qmcb_set_error("qmcb_psi_backward: bad arguments");
     return QMCB_EINVAL;
   }
-  const int want_ao = (g_bas_exp || g_bas_coeffs) ? 1 : 0;
-  if (want_ao && p->multi_component) {
-    qmcb_set_error("qmcb_psi_backward: basis-parameter gradients are not available when an AO is a sum of several "
-                   "monomials (real spherical harmonics of l = 2); freeze 'ao'");
-    return QMCB_EINVAL;
+  if ((g_bas_exp || g_bas_coeffs) && p->multi_component) {
+    // An AO that is a sum of several monomials (real spherical harmonics of l = 2) does not fit the shell /
+    // component staging of the kernels below; the adjoint kernel works on the flat primitive list and serves
+    // any AO composition: basis-parameter gradients from there (psi weight only), the rest as usual.
+    int rc = qmcb_local_energy_backward(p, pos, nullptr, weight, W, nullptr, nullptr, g_bas_exp, g_bas_coeffs, nullptr,
+                                        nullptr, nullptr, workspace, stream);
+    if (rc) return rc;
+    if (!g_mo && !g_ci && !g_jee_w && !g_jen_w && !g_een) return 0;
+    g_bas_exp = nullptr;
+    g_bas_coeffs = nullptr;
   }
+  const int want_ao = (g_bas_exp || g_bas_coeffs) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   // Jastrow / MO / CI gradients of a one-walker-per-thread structure (BASELINE config 3): the
   // structure-specialised backward, register accumulators, no tile staging (QMCB_BWD_SPEC=0 disables)

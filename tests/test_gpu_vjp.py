@@ -95,6 +95,47 @@ def test_local_energy_is_differentiable_through_autograd(name):
         assert not wf.local_energy(pos).requires_grad
 
 
+@pytest.mark.parametrize("key", ["lih_sph", "lih_sph_gto"])
+def test_spherical_harmonics_adjoint_against_oracle(key):
+    """Real spherical harmonics (l = 2: an AO is a sum of several monomials).  The reference's Jacobi kinetic energy
+    raises on such bases, so the checker is autograd through the oracle (pinned on the cartesian cases by
+    test_oracle_local_energy_adjoint); exponent derivatives of the monomials of one primitive add up.  The same
+    kernel serves the basis-parameter gradients of psi.backward for these bases (qmcb_psi_backward)."""
+    import sj_oracle as orc
+    from test_oracle_golden import _sph_case
+    from qmctorch_b200.wavefunction import SlaterJastrow
+    g, mol, P = _sph_case(key)
+    pos = torch.as_tensor(g[key + "_pos"][:12]).cuda()
+    wf = SlaterJastrow(mol, configs="single_double(2,2)", cuda=True)
+    with torch.no_grad():
+        wf.mo.mo_modifier.copy_(torch.tensor(g[key + "_mo_modifier"]))
+        wf.fc.weight.copy_(torch.tensor(g[key + "_ci"]))
+        wf.jastrow.jastrow_kernel.weight.fill_(0.8)
+    gen = torch.Generator().manual_seed(5)
+    wE = torch.rand(12, generator=gen, dtype=torch.float64) - 0.3
+    wP = torch.rand(12, generator=gen, dtype=torch.float64) - 0.3
+    want = {"atom_coords", "bas_exp", "mo_modifier", "ci", "jee_w"}
+    ix = torch.as_tensor(wf.ao.expand_index, dtype=torch.long)
+
+    def fold(d):
+        d = dict(d)
+        d["bas_exp"] = torch.zeros(wf.ao.nbas, dtype=torch.float64).index_add_(0, ix, d["bas_exp"])
+        return d
+    for we, wp in ((wE, None), (None, wP), (wE, wP)):
+        got = wf._eloc_backward(pos, None if we is None else we.cuda(), None if wp is None else wp.cuda(), want)
+        ref = fold(orc.local_energy_adjoint(P, pos.cpu(), w_eloc=we, w_psi=wp))
+        for n in sorted(want):
+            assert got[n].shape == _leaf(wf, n).shape
+            assert _err(got[n], ref[n]) < RTOL, (n, _err(got[n], ref[n]))
+    # psi.backward with the basis exponents trainable
+    wf.ao.bas_exp.requires_grad = True
+    psi = wf(pos)
+    psi.backward(wP.cuda().reshape(psi.shape))
+    ref = fold(orc.local_energy_adjoint(P, pos.cpu(), w_psi=wP))
+    assert _err(wf.ao.bas_exp.grad, ref["bas_exp"]) < RTOL
+    assert _err(wf.mo.mo_modifier.grad, ref["mo_modifier"]) < RTOL
+
+
 def _solver(wf, mol, nw):
     from qmctorch_b200.sampler import Metropolis
     from qmctorch_b200.solver import Solver
