@@ -840,7 +840,7 @@ def test_spherical_harmonics_basis_against_reference(key, monkeypatch):
     parts with r^n): AO values, psi, E_L, grad psi, accept decisions and the Jastrow / MO / CI gradients on the
     CUDA path against the reference (tests/golden/sph.npz; its E_L is the autograd-Hessian kinetic energy - the
     reference's Jacobi path raises on spherical harmonics) and against the oracle; generic and specialised
-    kernels; basis-parameter gradients are refused (an AO is a sum of several monomials)."""
+    kernels; basis-parameter gradients go through the flat-primitive adjoint kernel (an AO is a sum of several monomials)."""
     from test_oracle_golden import _sph_case
     from qmctorch_b200.wavefunction import SlaterJastrow
     g, mol, P = _sph_case(key)
@@ -887,8 +887,12 @@ def test_spherical_harmonics_basis_against_reference(key, monkeypatch):
             ref = torch.tensor(ref)
             err = float((got[k].cpu().reshape(ref.shape) - ref).abs().max() / ref.abs().max())
             assert err < 1e-9, (k, err)
-        with pytest.raises(RuntimeError, match="monomials"):
-            wf._psi_backward(pos, wgt, None)
+        # every gradient at once: the basis-parameter part of a multi-monomial basis comes from the flat-primitive
+        # adjoint kernel (checked against the oracle in tests/test_gpu_vjp.py), the rest must not change
+        full = wf._psi_backward(pos, wgt, None)
+        assert full["bas_exp"].shape == wf.ao.bas_exp.shape and bool(torch.isfinite(full["bas_exp"]).all())
+        for k in ("mo_modifier", "ci", "jee_w"):
+            assert torch.equal(full[k], got[k])
 
 
 def _lib_mod():
