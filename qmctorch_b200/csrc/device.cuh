@@ -105,7 +105,13 @@ template <class SYS>
 __device__ __forceinline__ double exp_core(const SYS &S, const double *etab, double x) {
   const double t = fma(x, S.expc[0], S.expc[1]);
   const int ki = __double2loint(t);
-  const double kd = t - S.expc[1];
+#ifndef QMCB_EXP_I2F
+#define QMCB_EXP_I2F 1
+#endif
+  // kd = the integer just read from the low word of t.  Converted back with I2F.F64.S32 it costs a slot of the
+  // conversion (XU) pipe instead of a DADD on the FP64 pipe, which is the pipe these kernels are bound by
+  // (QMCB_EXP_I2F=0: kd = t - 1.5 * 2^52, the classical form).
+  const double kd = QMCB_EXP_I2F ? (double)ki : t - S.expc[1];
   const double r = fma(kd, S.expc[2], x);
   double p;
   if (QMCB_ETAB_LOG2 >= 10) {
