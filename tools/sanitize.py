@@ -2,7 +2,7 @@
 through every fused entry point of the kernel kinds in use - one walker per thread (LiH: spec_* and
 spec_backward), warp tiles (spect_*: H2O cas(4,4) with thread-per-block determinants, H2O + three-body
 factor tables, C4H6 / triplet C2H4 with the half-warp Gauss-Jordan and the pair-once Jastrow, a
-spherical-harmonics basis) - and, with QMCB_JIT=0, the generic CTA-tile kernels of the same systems.
+spherical-harmonics basis), the adjoint kernel of the local energy on each of them - and, with QMCB_JIT=0, the generic CTA-tile kernels of the same systems.
 
     compute-sanitizer --tool racecheck python tools/sanitize.py
 """
@@ -54,6 +54,14 @@ for name, mol, cfg, W in systems():
                                       _lib.ptr(acc), None, sp), "mh")
     wgt = torch.randn(W, dtype=torch.float64, device="cuda")
     gb = wf._psi_backward(pos, wgt, {"mo_modifier", "ci", "jee_w"})
+    # adjoint of the local energy (eloc_vjp.cu): every leaf, E_L and psi weights, lane groups / shared or global
+    # work areas as the launch heuristic picks them for this structure
+    nv = min(W, 96)
+    want = {"mo_modifier", "ci", "bas_exp", "bas_coeffs", "jee_w", "atom_coords"}
+    if not wf.ao.contract:
+        want.discard("bas_coeffs")
+    ga = wf._eloc_backward(pos[:nv].contiguous(), wgt[:nv].contiguous(), wgt[:nv].contiguous(), want)
     torch.cuda.synchronize()
+    print(name, "adjoint dR", float(ga["atom_coords"].abs().sum()), "dexp", float(ga["bas_exp"].abs().sum()), flush=True)
     print(name, "psi", float(psi.abs().mean()), "E", float(s4[0] / s4[2]), "grad", float(gr.abs().mean()),
           "acc", float(acc.float().mean()), "dW", float(gb["mo_modifier"].abs().sum()), "kind", wf._handle.info(15), flush=True)
