@@ -65,6 +65,8 @@ class Metropolis(SamplerBase):
         self._step_counter = 0
         self.acceptance_rate = None
 
+    host_work = None        # optional callable run between the launch of the moves and the first device wait
+
     def configure_move(self, move):
         """metropolis.py:179-225."""
         self.movedict = move
@@ -143,6 +145,10 @@ class Metropolis(SamplerBase):
                     if idecor % self.ndecor == 0:
                         kept.append(x.clone() if self.keep_on_device else x.to("cpu"))
                     idecor += 1
+            if self.host_work is not None:
+                # host-side work of the caller (Solver: turning the previous E_L batch into its numpy observable)
+                # while the moves queued above run on the device; the counter read-back below is the first wait
+                self.host_work()
             self.acceptance_rate = float(naccept.item()) / max(W * self._move_per_iter * max(self.nstep, 1), 1)
             self.sampling_time = time() - tstart
         out = self.symmetry(torch.cat(kept))

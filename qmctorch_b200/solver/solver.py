@@ -226,6 +226,16 @@ class Solver:
             elif obs == "local_energy":
                 if local_energy is None:
                     continue
+                if (ibatch is None or ibatch == 0) and self._defer_observables and local_energy.is_cuda \
+                        and local_energy.numel() >= 65536:
+                    # large device tensor inside run_epochs: start the D2H into a pinned ring slot now, turn it
+                    # into the numpy array the list holds while the GPU runs the resampling kernels
+                    # (Metropolis calls _flush_observables before it waits for the acceptance counter)
+                    self._flush_observables()
+                    self.observable.local_energy.append(None)
+                    self._stage(local_energy, self.observable.local_energy, len(self.observable.local_energy) - 1)
+                    continue
+                self._flush_observables()
                 data = self._to_numpy(local_energy)
                 if ibatch is None or ibatch == 0:
                     self.observable.local_energy.append(data)
@@ -251,6 +261,34 @@ class Solver:
                     getattr(self.observable, obs)[-1] = np.append(getattr(self.observable, obs)[-1], data)
 
     # -- device -> numpy for tracked observables ------------------------------------------------
+    _defer_observables = False       # set by run_epochs for the duration of the epoch loop
+    _pending = None
+
+    def _stage(self, t, target, index):
+        """Asynchronous D2H of ``t`` into a slot of a two-deep pinned ring; ``target[index]`` receives the numpy
+        array when _flush_observables runs."""
+        ring = getattr(self, "_ring", None)
+        if ring is None or ring[0].numel() < t.numel() or ring[0].dtype != t.dtype:
+            ring = self._ring = [torch.empty(t.numel(), dtype=t.dtype).pin_memory() for _ in range(2)]
+            self._ring_next = 0
+        k = self._ring_next
+        self._ring_next = 1 - k
+        view = ring[k][: t.numel()].view(t.shape)
+        view.copy_(t.detach(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        self._pending = (ev, view, target, index)
+
+    def _flush_observables(self):
+        """Completes a staged observable (waits for its copy, which finished long ago when this runs behind the
+        resampling kernels, and copies it out of the ring)."""
+        if self._pending is None:
+            return
+        ev, view, target, index = self._pending
+        self._pending = None
+        ev.synchronize()
+        target[index] = view.numpy().copy()
+
     def _to_numpy(self, t):
         """Tracked observables are numpy arrays (solver_base.py:166-248).  Large device tensors go
         through a reused pinned staging buffer: one DMA + one host memcpy instead of a pageable D2H
@@ -355,6 +393,18 @@ class Solver:
         self.chkpt_every = chkpt_every
 
     def run_epochs(self, nepoch, with_tqdm=False, verbose=True):
+        self._defer_observables = True
+        if hasattr(self.sampler, "host_work"):
+            self.sampler.host_work = self._flush_observables
+        try:
+            return self._run_epochs(nepoch)
+        finally:
+            self._defer_observables = False
+            if hasattr(self.sampler, "host_work"):
+                self.sampler.host_work = None
+            self._flush_observables()
+
+    def _run_epochs(self, nepoch):
         cumulative_loss = 0
         min_loss = 0
         for n in range(nepoch):

@@ -409,6 +409,28 @@ def test_solver_optimisation_lowers_energy_and_matches_oracle_step():
     assert hasattr(obs.models, "best") and "mo.mo_modifier" in obs.models.best
 
 
+def test_solver_tracked_local_energies_are_staged_behind_the_resampling():
+    """Large ensembles: the per-epoch local energies reach the host through a pinned ring while the resampling
+    kernels run (Solver._stage / _flush_observables, Metropolis.host_work).  The observable must be what the
+    blocking path stores: one float64 numpy array per epoch whose mean is the tracked energy of that epoch."""
+    from qmctorch_b200.sampler import Metropolis
+    from qmctorch_b200.solver import Solver
+    g = C.load("lih_ground")
+    mol, wf = C.build_wf(g)
+    sampler = Metropolis(nwalkers=70000, nstep=60, step_size=0.3, nelec=wf.nelec, ndim=3,
+                         init=mol.domain("normal"), move={"type": "all-elec", "proba": "normal"}, cuda=True, seed=2)
+    solver = Solver(wf=wf, sampler=sampler, optimizer=torch.optim.SGD(wf.parameters(), lr=0.01))
+    solver.configure(track=["local_energy"], freeze=["ci", "ao"], loss="energy", grad="manual",
+                     resampling={"mode": "update", "resample_every": 1, "nstep_update": 10})
+    obs = solver.run(4, tqdm=False)
+    assert solver._pending is None and sampler.host_work is None and not solver._defer_observables
+    assert len(obs.local_energy) == 4 and len(obs.energy) == 5
+    for k, e in enumerate(obs.local_energy):
+        assert isinstance(e, np.ndarray) and e.dtype == np.float64 and e.shape == (70000, 1)
+        assert abs(float(e.mean()) - obs.energy[k + 1]) < 1e-9 * abs(obs.energy[k + 1])
+    assert not np.array_equal(obs.local_energy[0], obs.local_energy[1])          # ring slots were copied out
+
+
 @pytest.mark.parametrize("move_type,proba", [("one-elec", "normal"), ("all-elec-iter", "normal"),
                                              ("all-elec", "uniform"), ("one-elec", "uniform")])
 def test_sampler_move_types_replay_reference_draws(move_type, proba):
