@@ -136,6 +136,40 @@ def test_spherical_harmonics_adjoint_against_oracle(key):
     assert _err(wf.mo.mo_modifier.grad, ref["mo_modifier"]) < RTOL
 
 
+@pytest.mark.parametrize("name,nw", [("lih_een", 300_001), ("h2o_cas44", 20_011)])
+def test_adjoint_is_additive_over_walkers_at_full_size(name, nw):
+    """Size-independent property at sizes the oracle cannot reach: the adjoint is a sum over walkers, so any
+    split of a large ensemble (several Jastrow-operator chunks of 131072 walkers, ragged tails, several trips of
+    the persistent walker loop, partially filled lane groups) must add up to the adjoint of the whole - and the
+    first walkers, evaluated alone, must reproduce the reference-pinned small case."""
+    g, wf, pos0 = _setup(name)
+    n0 = pos0.shape[0]
+    gen = torch.Generator().manual_seed(11)
+    reps = -(-nw // g["pos"].shape[0])
+    base = torch.as_tensor(g["pos"]).repeat(reps, 1)[:nw]
+    pos = (base + 0.05 * torch.randn(base.shape, generator=gen, dtype=torch.float64)).cuda()
+    pos[:n0] = pos0
+    wE = (torch.rand(nw, generator=gen, dtype=torch.float64) - 0.3).cuda()
+    wP = (torch.rand(nw, generator=gen, dtype=torch.float64) - 0.3).cuda()
+    wE[:n0] = torch.as_tensor(GOLD[name + "/wE"]).cuda()
+    wP[:n0] = torch.as_tensor(GOLD[name + "/wP"]).cuda()
+    want = {"atom_coords", "bas_exp", "bas_coeffs", "mo_modifier", "ci", "jee_w", "jen_w"}
+    whole = wf._eloc_backward(pos, wE, wP, want)
+    cuts = [0, n0, 131072 + 5, nw] if nw > 140000 else [0, n0, 7777, nw]
+    parts = [wf._eloc_backward(pos[a:b].contiguous(), wE[a:b].contiguous(), wP[a:b].contiguous(), want)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    for n in sorted(want):
+        total = sum(p[n] for p in parts)
+        scale = sum(p[n].abs() for p in parts).max().clamp(min=1e-300)
+        assert bool(torch.isfinite(whole[n]).all()), n
+        assert float((whole[n] - total).abs().max() / scale) < 1e-12, n
+        ref = GOLD[name + "/gE_" + n] + GOLD[name + "/gP_" + n]
+        assert _err(parts[0][n], ref) < 2 * RTOL, n
+    again = wf._eloc_backward(pos, wE, wP, want)
+    for n in want:
+        assert torch.equal(again[n], whole[n])
+
+
 def _solver(wf, mol, nw):
     from qmctorch_b200.sampler import Metropolis
     from qmctorch_b200.solver import Solver
