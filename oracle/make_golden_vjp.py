@@ -147,7 +147,21 @@ def main():
             for pn, p in wf.named_parameters():
                 if p.grad is not None:
                     out[name + "/auto_%s/%s" % (loss, pn)] = p.grad.detach().numpy().copy()
-        print("%-16s solver: forces, grad=auto (energy, variance)" % name)
+        # sampling weights (loss.py:112-153): walkers kept for two epochs -> the second loss is weighted by
+        # (psi / psi0)^2 / sum, and its gradient passes through psi as well as through E_L
+        solver.configure(track=["local_energy"], loss="energy", grad="auto",
+                         resampling={"mode": "update", "resample_every": 2, "nstep_update": 5})
+        assert solver.loss.use_weight
+        wf.zero_grad()
+        solver.evaluate_gradient(pos.clone())          # records psi0, weights = 1
+        opt.step()                                     # SGD, lr = 1e-3: psi now differs from psi0
+        wf.zero_grad()
+        val, _ = solver.evaluate_gradient(pos.clone())
+        out[name + "/auto_weighted_loss"] = np.array([float(val)])
+        for pn, p in wf.named_parameters():
+            if p.grad is not None:
+                out[name + "/auto_weighted/%s" % pn] = p.grad.detach().numpy().copy()
+        print("%-16s solver: forces, grad=auto (energy, variance, weighted energy)" % name)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "%.0f KB" % (os.path.getsize(OUT) / 1024))
 

@@ -204,6 +204,25 @@ def test_solver_forces_and_grad_auto_match_reference(name):
                 assert _err(p.grad, GOLD[key]) < RTOL, (loss, pn, _err(p.grad, GOLD[key]))
                 seen += 1
         assert seen >= 4
+    # sampling weights: walkers kept for two epochs - the second loss is weighted by (psi / psi0)^2 / sum and its
+    # gradient passes through psi (qmcb_psi_backward) as well as through E_L (qmcb_local_energy_backward)
+    solver.configure(track=["local_energy"], loss="energy", grad="auto",
+                     resampling={"mode": "update", "resample_every": 2, "nstep_update": 5})
+    assert solver.loss.use_weight
+    wf.zero_grad()
+    solver.evaluate_gradient(pos)
+    solver.opt.step()
+    wf.zero_grad()
+    val, _ = solver.evaluate_gradient(pos)
+    ref = float(GOLD[name + "/auto_weighted_loss"][0])
+    assert abs(float(val) - ref) < 1e-9 * max(1.0, abs(ref))
+    seen = 0
+    for pn, p in wf.named_parameters():
+        key = name + "/auto_weighted/%s" % pn
+        if key in GOLD:
+            assert _err(p.grad, GOLD[key]) < 10 * RTOL, (pn, _err(p.grad, GOLD[key]))
+            seen += 1
+    assert seen >= 4
 
 
 @pytest.mark.parametrize("loss", ["energy", "variance"])
