@@ -61,11 +61,7 @@ WORKLOADS = {
 # sm__inst_executed_pipe_fp64 (% of peak) of the dominant kernel from the `ncu --set full` captures under
 # profiles/ (static: a number measured under a profiler is evidence, never a bench value), and the DRAM
 # traffic per launch of the same capture: (workload, walkers) -> (pipe %, bytes, file)
-NCU = {
-    ("lih", 1_000_000): (68.2, 96.036608e6 + 4.964608e6, "profiles/r1_fold_ncu_raw.csv"),
-    ("c4h6", 20_000): (37.6, None, "profiles/r1_fold_ncu_raw.csv"),
-    ("h2o-cas44", 100_000): (36.5, None, "profiles/r1_fold_ncu_raw.csv"),
-}
+NCU = {}      # (workload, walkers) -> (FP64 pipe % under ncu, DRAM bytes per launch, file); profiles/ncu_summary.json
 try:
     with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as _f:
         for _k, _v in json.load(_f).items():

@@ -32,6 +32,27 @@ def load(path):
     return {h: (u, v) for h, u, v in zip(hdr, units, vals)}, (vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "")
 
 
+# ncu scales every value of a capture on its own (Kbyte here, Mbyte there; us / ms; Gbyte/s / Tbyte/s): one
+# unit per row, values of the other captures converted
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-9, "us": 1e-6, "ms": 1e-3,
+         "s": 1.0, "second": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9}
+
+
+def convert(item, unit):
+    u, v = item
+    if u == unit or not v:
+        return v
+    num, den = (u.split("/") + [""])[:2], None
+    tnum = (unit.split("/") + [""])[:2]
+    try:
+        f = SCALE[num[0]] / SCALE[tnum[0]]
+        if num[1] != tnum[1]:
+            f *= SCALE[tnum[1]] / SCALE[num[1]]
+        return "%.6f" % (float(v.replace(",", "")) * f)
+    except (KeyError, ValueError):
+        return v + " " + u          # unknown unit pair: keep the value with its own unit
+
+
 def main():
     out = sys.argv[1]
     cols = [a.split("=", 1) for a in sys.argv[2:]]
@@ -43,7 +64,7 @@ def main():
         w.writerow(["kernel", ""] + [k for _, _, k in data])
         for h in names:
             unit = next((d[h][0] for _, d, _ in data if h in d), "")
-            w.writerow([h, unit] + [d.get(h, ("", ""))[1] for _, d, _ in data])
+            w.writerow([h, unit] + [convert(d.get(h, ("", "")), unit) for _, d, _ in data])
 
 
 if __name__ == "__main__":
