@@ -170,6 +170,34 @@ def test_adjoint_is_additive_over_walkers_at_full_size(name, nw):
         assert torch.equal(again[n], whole[n])
 
 
+def test_adjoint_entry_point_error_behaviour_and_empty_input():
+    """C ABI contract of qmcb_local_energy_backward: both weights NULL or no workspace -> QMCB_EINVAL with a
+    message, outputs untouched; W = 0 -> success and zero sums (V_nn contributes sum(w_eloc) = 0)."""
+    import ctypes
+    from qmctorch_b200 import _lib
+    g, wf, pos = _setup("lih_een")
+    L = _lib.lib()
+    plan = wf._handle.plan()
+    W = pos.shape[0]
+    ws = torch.empty(int(L.qmcb_local_energy_backward_workspace_bytes(plan, W)), dtype=torch.uint8, device="cuda")
+    wgt = torch.ones(W, dtype=torch.float64, device="cuda")
+    out = torch.full((wf.natom, 3), 7.0, dtype=torch.float64, device="cuda")
+    sp = _lib.stream_ptr(pos.device)
+    args = lambda we, wp, n, w_: (plan, _lib.ptr(pos), we, wp, n, None, None, None, None, None, None, _lib.ptr(out),
+                                  w_, sp)
+    assert L.qmcb_local_energy_backward(*args(None, None, W, _lib.ptr(ws))) == -1
+    assert b"qmcb_local_energy_backward" in L.qmcb_last_error()
+    assert L.qmcb_local_energy_backward(*args(_lib.ptr(wgt), None, W, None)) == -1
+    torch.cuda.synchronize()
+    assert float(out.min()) == 7.0 and float(out.max()) == 7.0
+    assert L.qmcb_local_energy_backward(*args(_lib.ptr(wgt), None, 0, _lib.ptr(ws))) == 0
+    torch.cuda.synchronize()
+    assert float(out.abs().max()) == 0.0
+    assert L.qmcb_local_energy_backward_workspace_bytes(plan, 0) > 0
+    with pytest.raises(RuntimeError):
+        wf._eloc_backward(pos, None, None, {"ci"})
+
+
 def _solver(wf, mol, nw):
     from qmctorch_b200.sampler import Metropolis
     from qmctorch_b200.solver import Solver
