@@ -3,7 +3,8 @@
  * config 1 by hand (public STO-3G table; MOs (phi1 +- phi2)/sqrt2, column-normalised like
  * scf/calculator/calculator_base.py:35-46), creates a host-only plan (device -1: table grouping only)
  * and - when a CUDA device is present - a device plan, evaluates psi and E_L on four walkers through
- * qmcb_psi / qmcb_local_energy and checks them against the closed form evaluated right here.
+ * qmcb_psi / qmcb_local_energy and checks them against the closed form evaluated right here, and the atom-coordinate
+ * derivative of psi from qmcb_local_energy_backward against a finite difference of that closed form.
  * Exit code 0 = pass (prints "ABI_OK host" or "ABI_OK device").
  */
 #include <math.h>
@@ -18,6 +19,25 @@
 #define NW 4
 
 static double dfact(int n) { double r = 1.0; for (; n > 1; n -= 2) r *= n; return r; }
+
+/* closed form of the H2 STO-3G wave function of one walker for the given atom positions:
+ * psi = J * sigma_g(r1) * sigma_g(r2), sigma_g = (phi_A + phi_B)/sqrt2, J = exp(0.5 r12 / (1 + r12)) */
+static double psi_closed_form(const double *x, const double *atoms, const double *expo, const double *coef) {
+  const double pi = 3.14159265358979323846, s = 1.0 / sqrt(2.0);
+  double mo_e[2];
+  for (int e = 0; e < 2; ++e) {
+    double v = 0.0;
+    for (int a = 0; a < 2; ++a) {
+      const double dx = x[3 * e] - atoms[3 * a], dy = x[3 * e + 1] - atoms[3 * a + 1], dz = x[3 * e + 2] - atoms[3 * a + 2];
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      for (int q = 0; q < 3; ++q) v += s * coef[q] * pow(2.0 * expo[q] / pi, 0.75) * exp(-expo[q] * r2);
+    }
+    mo_e[e] = v;
+  }
+  const double dx = x[0] - x[3], dy = x[1] - x[4], dz = x[2] - x[5];
+  const double r12 = sqrt(dx * dx + dy * dy + dz * dz);
+  return exp(0.5 * r12 / (1.0 + r12)) * mo_e[0] * mo_e[1];
+}
 
 int main(void) {
   const double expo[3] = {3.42525091, 0.62391373, 0.16885540};
@@ -76,23 +96,34 @@ int main(void) {
   cudaMemcpy(psi, d_psi, sizeof(psi), cudaMemcpyDeviceToHost);
   cudaMemcpy(el, d_el, sizeof(el), cudaMemcpyDeviceToHost);
   for (int w = 0; w < NW; ++w) {
-    /* psi = J * sigma_g(r1) * sigma_g(r2), sigma_g = (phi_A + phi_B)/sqrt2, J = exp(0.5 r12 / (1 + r12)) */
-    double mo_e[2];
-    for (int e = 0; e < 2; ++e) {
-      double v = 0.0;
-      for (int a = 0; a < 2; ++a) {
-        const double dx = pos[w * 6 + 3 * e] - atom_coords[3 * a], dy = pos[w * 6 + 3 * e + 1] - atom_coords[3 * a + 1],
-                     dz = pos[w * 6 + 3 * e + 2] - atom_coords[3 * a + 2];
-        const double r2 = dx * dx + dy * dy + dz * dz;
-        for (int q = 0; q < 3; ++q) v += s * coef[q] * pow(2.0 * expo[q] / pi, 0.75) * exp(-expo[q] * r2);
-      }
-      mo_e[e] = v;
-    }
-    const double dx = pos[w * 6] - pos[w * 6 + 3], dy = pos[w * 6 + 1] - pos[w * 6 + 4], dz = pos[w * 6 + 2] - pos[w * 6 + 5];
-    const double r12 = sqrt(dx * dx + dy * dy + dz * dz);
-    const double ref = exp(0.5 * r12 / (1.0 + r12)) * mo_e[0] * mo_e[1];
+    const double ref = psi_closed_form(pos + w * 6, atom_coords, expo, coef);
     if (fabs(psi[w] - ref) > 1e-12 * fabs(ref)) { fprintf(stderr, "psi[%d] = %.17g, expected %.17g\n", w, psi[w], ref); return 10; }
     if (!(el[w] == el[w]) || fabs(el[w]) > 1e3) { fprintf(stderr, "E_L[%d] = %g\n", w, el[w]); return 11; }
+  }
+  /* adjoint entry point (grad="auto" / forces): d/dR_A of sum_w psi_w against a central finite difference of the
+   * closed form (the e-e Jastrow factor does not depend on the atoms) */
+  {
+    double *d_w, *d_ga, *d_ws, ones[NW] = {1, 1, 1, 1}, ga[6];
+    const int64_t nb = qmcb_local_energy_backward_workspace_bytes(plan, NW);
+    cudaMalloc((void **)&d_w, sizeof(ones)); cudaMalloc((void **)&d_ga, sizeof(ga)); cudaMalloc((void **)&d_ws, (size_t)nb);
+    cudaMemcpy(d_w, ones, sizeof(ones), cudaMemcpyHostToDevice);
+    if (qmcb_local_energy_backward(plan, d_pos, NULL, d_w, NW, NULL, NULL, NULL, NULL, NULL, NULL, d_ga, d_ws, NULL) != 0) {
+      fprintf(stderr, "qmcb_local_energy_backward: %s\n", qmcb_last_error()); return 12;
+    }
+    cudaMemcpy(ga, d_ga, sizeof(ga), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < 6; ++i) {
+      const double h = 1e-5;
+      double ap[6], am[6], fp = 0.0, fm = 0.0;
+      memcpy(ap, atom_coords, sizeof(ap)); memcpy(am, atom_coords, sizeof(am));
+      ap[i] += h; am[i] -= h;
+      for (int w = 0; w < NW; ++w) { fp += psi_closed_form(pos + w * 6, ap, expo, coef); fm += psi_closed_form(pos + w * 6, am, expo, coef); }
+      const double fd = (fp - fm) / (2.0 * h);
+      if (fabs(ga[i] - fd) > 1e-7 * (fabs(fd) + 1e-3)) { fprintf(stderr, "d psi / d R[%d] = %.12g, finite difference %.12g\n", i, ga[i], fd); return 13; }
+    }
+    if (qmcb_local_energy_backward(plan, d_pos, NULL, NULL, NW, NULL, NULL, NULL, NULL, NULL, NULL, d_ga, d_ws, NULL) == 0) {
+      fprintf(stderr, "adjoint without weights accepted\n"); return 14;
+    }
+    cudaFree(d_w); cudaFree(d_ga); cudaFree(d_ws);
   }
   cudaFree(d_pos); cudaFree(d_psi); cudaFree(d_el);
   qmcb_plan_destroy(plan);
