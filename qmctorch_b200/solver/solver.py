@@ -149,6 +149,9 @@ class Solver:
             for p in self.wf.jastrow.parameters():
                 p.requires_grad = wf_params
         self.wf.ao.atom_coords.requires_grad = geo_params
+        # geometry optimisation (ase/optimizer/torch_optim.py:126-133: geo_params=True + evaluate_grad_auto): the atom
+        # coordinates join the autograd graph of E_L / psi (qmcb_local_energy_backward) only when asked for
+        self.wf.atom_coords_grad = bool(geo_params)
 
     def freeze_parameters(self, freeze):
         if freeze is None:
@@ -569,6 +572,40 @@ class Solver:
         obs = SimpleNamespace(local_energy=el, pos=pos)
         self._dump("sampling_traj", hdf5_group, obs)
         return obs
+
+    # -- small host-side helpers of the reference Solver (solver_base.py:250-271,473-517) --------------------
+    def print_observable(self, cumulative_loss, verbose=False):
+        """solver_base.py:250-271 (plain print instead of the twiggy logger)."""
+        self._flush_observables()
+        for k in self.observable.__dict__.keys():
+            if k == "local_energy" and self.observable.local_energy:
+                eloc = self.observable.local_energy[-1]
+                e, v = np.mean(eloc), np.var(eloc)
+                print("  energy   : %f +/- %f" % (e, np.sqrt(v / len(eloc))))
+                print("  variance : %f" % np.sqrt(v))
+            elif verbose and k not in ("qmctorch_version", "models") and getattr(self.observable, k):
+                print(k + " : ", getattr(self.observable, k)[-1])
+                print("loss %f" % cumulative_loss)
+
+    def print_parameters(self, grad=False):
+        """solver_base.py:473-484."""
+        for p in self.wf.parameters():
+            if p.requires_grad:
+                print(p.grad if grad else p)
+
+    def save_traj(self, fname, obs):
+        """xyz trajectory of a geometry optimisation (solver_base.py:498-517; ``obs.geometry`` in bohr)."""
+        nm2bohr = 1.88973
+        with open(fname, "w") as f:
+            for snap in obs.geometry:
+                f.write("%d \n\n" % len(snap))
+                for i, pos in enumerate(snap):
+                    f.write("%s % 7.5f % 7.5f %7.5f\n" % (self.wf.atoms[i][0], pos[0] / nm2bohr, pos[1] / nm2bohr,
+                                                        pos[2] / nm2bohr))
+                f.write("\n")
+
+    def log_data(self):
+        pass
 
     def save_checkpoint(self, epoch, loss):
         """solver_base.py:389-405 (key spelling kept so checkpoints interchange)."""

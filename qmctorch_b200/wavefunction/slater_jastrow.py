@@ -444,10 +444,12 @@ class SlaterJastrow(WaveFunction):
                 vnn = vnn + self.ao.atomic_number[a] * self.ao.atomic_number[b] / (c[a] - c[b]).norm()
         return vnn
 
-    def geometry(self, pos=None):
+    def geometry(self, pos=None, convert_to_angs=False):
+        """slater_jastrow.py:629-647."""
         d = []
+        convert = 0.529177 if convert_to_angs else 1
         for iat in range(self.natom):
-            xyz = self.ao.atom_coords[iat, :].detach().cpu().numpy().tolist()
+            xyz = (self.ao.atom_coords[iat, :].detach().cpu().numpy() * convert).tolist()
             d.append(xyz)
         return d
 

@@ -31,7 +31,7 @@ def _err(a, ref, floor=1e-4):
     """max |a - ref| / max |ref|; ``floor`` bounds the denominator from below for gradients that vanish
     analytically (the CI coefficient of a one-determinant expansion: two O(10) terms cancel to round-off)."""
     a = torch.as_tensor(a).detach().cpu().double().reshape(-1)
-    ref = torch.as_tensor(ref).double().reshape(-1)
+    ref = torch.as_tensor(ref).detach().cpu().double().reshape(-1)
     return float((a - ref).abs().max() / ref.abs().max().clamp(min=floor))
 
 
@@ -287,6 +287,39 @@ def test_grad_auto_is_the_derivative_of_the_loss(loss):
 
     slope = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
     assert abs(slope - norm) < 1e-5 * norm, (slope, norm)
+
+
+def test_geometry_step_through_the_solver():
+    """The geometry-optimisation step of the reference's ASE optimiser (ase/optimizer/torch_optim.py:126-133):
+    set_params_requires_grad(wf_params=False, geo_params=True) + evaluate_grad_auto leaves d<E_L>/dR in
+    ao.atom_coords.grad and nothing else; an SGD step moves the atoms and the device tables follow."""
+    g = C.load("lih_een")
+    mol, wf = C.build_wf(g)
+    n = int(GOLD["lih_een/n"][0])
+    pos = torch.as_tensor(g["pos"][:n]).cuda()
+    solver = _solver(wf, mol, n)
+    solver.configure(track=["local_energy"], loss="energy", grad="auto",
+                     resampling={"mode": "update", "resample_every": 1, "nstep_update": 5})
+    solver.set_params_requires_grad(wf_params=False, geo_params=True)
+    assert wf.atom_coords_grad and wf.ao.atom_coords.requires_grad and not wf.mo.mo_modifier.requires_grad
+    opt = torch.optim.SGD(wf.parameters(), lr=1e-2)
+    solver.opt = opt
+    wf.zero_grad()
+    loss, eloc = solver.evaluate_gradient(pos)
+    grad = wf.ao.atom_coords.grad.clone()
+    ref = wf._eloc_backward(pos, torch.full((n,), 1.0 / n, dtype=torch.float64, device="cuda"), None,
+                            {"atom_coords"})["atom_coords"]
+    assert _err(grad, ref) < 1e-12 and wf.mo.mo_modifier.grad is None
+    e0 = wf.local_energy(pos).detach().clone()
+    before = wf.geometry(None)
+    opt.step()
+    after = wf.geometry(None, convert_to_angs=True)
+    assert before != wf.geometry(None) and abs(after[0][2] - wf.geometry(None)[0][2] * 0.529177) < 1e-12
+    with torch.no_grad():
+        e1 = wf.local_energy(pos)
+    assert float((e1 - e0).abs().max()) > 1e-6          # the plan follows the moved atoms
+    solver.set_params_requires_grad(wf_params=True, geo_params=False)
+    assert not wf.atom_coords_grad
 
 
 def test_three_body_weights_are_refused_by_grad_auto():
