@@ -297,6 +297,104 @@ __device__ double group_gauss_jordan3(double *M, double *col, int n, int sub) {
   return det;
 }
 
+// Small spin blocks (n <= 6: CAS expansions have many of them): ONE LANE per block, everything in registers -
+// LU with partial pivoting (row swaps as selects: no dynamic register indexing), the inverse by one forward / back
+// substitution per unit vector (written to Ai as it is formed), then X = A^-1 B row by row with its trace and
+// Y = X A^-1.  The cooperative Gauss-Jordan spends ~10^4 cycles of dependent shared-memory round trips on a 5 x 5
+// block; here the blocks of a walker are done side by side on different lanes.
+template <int N>
+__device__ __noinline__ void lane_block(const double *MO, const double *BK, int Nm, int r0, const int *cols, double *Ai,
+                                        double *Yv, double &det_out, double &tr_out) {
+  double a[N][N];
+  int perm[N], cj[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    cj[j] = cols[j];
+    perm[j] = j;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i][j] = MO[(r0 + i) * Nm + cj[j]];
+  }
+  double det = 1.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double best = fabs(a[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(a[i][k]);
+      if (v > best) { best = v; piv = i; }
+    }
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const bool sw = piv == i;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double t = a[k][j];
+        a[k][j] = sw ? a[i][j] : t;
+        a[i][j] = sw ? t : a[i][j];
+      }
+      const int tp = perm[k];
+      perm[k] = sw ? perm[i] : tp;
+      perm[i] = sw ? tp : perm[i];
+    }
+    if (piv != k) det = -det;
+    det *= a[k][k];
+    const double ip = 1.0 / a[k][k];
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double l = a[i][k] * ip;
+      a[i][k] = l;
+#pragma unroll
+      for (int j = k + 1; j < N; ++j) a[i][j] = fma(-l, a[k][j], a[i][j]);
+    }
+  }
+  double inv_d[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) inv_d[i] = 1.0 / a[i][i];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {                     // forward: L y = P e_j
+      double v = perm[i] == j ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < i; ++q) v = fma(-a[i][q], x[q], v);
+      x[i] = v;
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {                // backward: U x = y
+      double v = x[i];
+#pragma unroll
+      for (int q = i + 1; q < N; ++q) v = fma(-a[i][q], x[q], v);
+      x[i] = v * inv_d[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) Ai[i * N + j] = x[i];
+  }
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double xr[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) v = fma(Ai[i * N + k], BK[(r0 + k) * Nm + cj[j]], v);
+      xr[j] = v;
+    }
+    tr += xr[i];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) v = fma(xr[k], Ai[k * N + j], v);
+      Yv[i * N + j] = v;
+    }
+  }
+  det_out = det;
+  tr_out = tr;
+}
+
 // One flat primitive q against all electrons of the walker: sum_e (channel adjoints) . (channels of q and their
 // tangents).  NDIR: tangent directions: 0 none, 1 (alpha), 4 (u_x, u_y, u_z, alpha).  Returns through sv
 // (value part: the bas_coeffs derivative) and sd[NDIR].
@@ -369,6 +467,7 @@ struct VjpArgs {
   const double *J, *dJ, *d2J;   // Jastrow operator output of the chunk (index w - w0), or nullptr
   double *scratch, *acc;   // global: scratch per group (large systems), accumulators per warp
   int smem;                // 1: the work areas and accumulators of a warp live in shared memory
+  int stop;                // profiling only (QMCB_VJP_STOP=k): leave the walker after phase k; 0 = full pass
   int want_mo, want_ci, want_exp, want_coef, want_jee, want_jen, want_atom;
 };
 
@@ -437,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
       KC[it] = s[4] + 2.0 * (g[e] * s[1] + g[Ne + e] * s[2] + g[2 * Ne + e] * s[3]) + g[3 * Ne + e] * s[0];
     }
     __syncwarp();
+    if (a.stop == 1) continue;
     // ---- MO = AO W, B = -1/2 K W (used columns)
     for (int it = sub; it < Ne * Nm; it += G) {
       const int e = it / Nm, m = it - e * Nm;
@@ -450,8 +550,31 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
       BK[it] = -0.5 * s1;
     }
     __syncwarp();
+    if (a.stop == 2) continue;
     // ---- spin blocks: inverse, determinant, trace, A^-1 B A^-1
-    {
+    if (S.nup <= 6 && S.ndown <= 6) {
+      // small blocks: one lane per unique block (lane_block), the blocks of the walker side by side
+      for (int u = sub; u < nun; u += G) {
+        const bool up = u < S.nuu;
+        const int n = up ? S.nup : S.ndown, r0 = up ? 0 : S.nup;
+        const int *cols = up ? S.ucu + u * S.nup : S.ucd + (u - S.nuu) * S.ndown;
+        double *Ai = INV + (up ? 2 * S.nup * S.nup * u : 2 * S.nup * S.nup * S.nuu + 2 * S.ndown * S.ndown * (u - S.nuu));
+        double *Yv = Ai + n * n;
+        double det = 1.0, tr = 0.0;
+        switch (n) {
+          case 1: lane_block<1>(MO, BK, Nm, r0, cols, Ai, Yv, det, tr); break;
+          case 2: lane_block<2>(MO, BK, Nm, r0, cols, Ai, Yv, det, tr); break;
+          case 3: lane_block<3>(MO, BK, Nm, r0, cols, Ai, Yv, det, tr); break;
+          case 4: lane_block<4>(MO, BK, Nm, r0, cols, Ai, Yv, det, tr); break;
+          case 5: lane_block<5>(MO, BK, Nm, r0, cols, Ai, Yv, det, tr); break;
+          case 6: lane_block<6>(MO, BK, Nm, r0, cols, Ai, Yv, det, tr); break;
+          default: break;                               // n = 0: empty spin block, det = 1
+        }
+        Dt[u] = det;
+        Dt[nun + u] = tr;
+      }
+      __syncwarp();
+    } else {
       int off = 0;
       for (int u = 0; u < nun; ++u) {
         const bool up = u < S.nuu;
@@ -482,6 +605,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
         __syncwarp();
       }
     }
+    if (a.stop == 3) continue;
     // ---- CI sums
     double Ssum = 0.0, Tsum = 0.0;
     for (int c = sub; c < S.nconf; c += G) {
@@ -534,6 +658,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
         __syncwarp();
       }
     }
+    if (a.stop == 4) continue;
     // ---- back through the projections
     for (int it = sub; it < Ne * Na; it += G) {
       const int e = it / Na, ao = it - e * Na;
@@ -555,10 +680,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
         return s;
       });
     __syncwarp();
+    if (a.stop == 5) continue;
     // ---- leaves: basis parameters and atom coordinates through the AO channels
     if (a.want_atom) prim_leaf_pass<G, 4>(S, SL, AL, x, sc, acc, sub, first_group, a.want_coef != 0);
     else if (a.want_exp) prim_leaf_pass<G, 1>(S, SL, AL, x, sc, acc, sub, first_group, a.want_coef != 0);
     else if (a.want_coef) prim_leaf_pass<G, 0>(S, SL, AL, x, sc, acc, sub, first_group, true);
+    if (a.stop == 6) continue;
     // ---- leaves: Pade weights (e-e, e-n) through g, l and J
     if ((a.want_jee && S.use_jee) || (a.want_jen && S.use_jen)) {
       // adjoints of g_e, l_e from the kinetic channel: g~ = 2 sum_a d ao QW, l~ = sum_a ao QW
@@ -800,6 +927,7 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
   VjpArgs a{};
   a.pos = pos; a.wE = w_eloc; a.wP = w_psi; a.W = W;
   a.scratch = scratch; a.acc = acc; a.smem = LC.use_smem;
+  { const char *es = getenv("QMCB_VJP_STOP"); a.stop = es ? atoi(es) : 0; }
   a.want_mo = g_mo != nullptr; a.want_ci = g_ci != nullptr; a.want_exp = g_bas_exp != nullptr;
   a.want_coef = g_bas_coeffs != nullptr; a.want_jee = g_jee_w != nullptr; a.want_jen = g_jen_w != nullptr;
   a.want_atom = g_atom_coords != nullptr;
