@@ -166,7 +166,22 @@ __device__ __forceinline__ void primitive5(int rt, int kx, int ky, int kz, int n
       }
     }
   }
-  // cartesian monomial Y, its gradient and Laplacian
+  // cartesian monomial Y, its gradient and Laplacian; s and p functions (most of every basis) without the
+  // general power code
+  const int Lk = kx + ky + kz;
+  if (Lk == 0) {
+    out[0] = R; out[1] = R1 * x; out[2] = R1 * y; out[3] = R1 * z; out[4] = LR;
+    return;
+  }
+  if (Lk == 1) {
+    const T &u = kx ? x : (ky ? y : z);
+    const T R1u = R1 * u;
+    out[0] = R * u;
+    out[1] = R1u * x; out[2] = R1u * y; out[3] = R1u * z;
+    if (kx) out[1] = out[1] + R; else if (ky) out[2] = out[2] + R; else out[3] = out[3] + R;
+    out[4] = LR * u + 2.0 * R1u;
+    return;
+  }
   const T xk = kx ? ipow(x, kx) : one, yk = ky ? ipow(y, ky) : one, zk = kz ? ipow(z, kz) : one;
   const T Y = xk * yk * zk;
   T gx = one * 0.0, gy = gx, gz = gx, LY = gx;
@@ -196,6 +211,7 @@ struct VjpSys {
   const double *alpha, *cn, *norm;       // [nbas] exponent, norm * coeff, norm
   const int *patom, *pk, *pkr, *pao;     // [nbas] atom, kx | ky << 8 | kz << 16, radial power, AO
   const int *ao_start, *ao_prim;         // CSR: AO -> its flat primitives
+  const int *ao_order;                   // AOs by decreasing contraction length (lockstep lanes get equal work)
 };
 
 // accumulator layout (doubles, per warp): W~ [nao][nmu] | ci [nconf] | exp [nbas] | coef [nbas] | primR [nbas][3] |
@@ -517,9 +533,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
       for (int i = sub; i < 4 * Ne; i += G) g[i] = 0.0;
     }
     __syncwarp();
+    if (a.stop == 7) continue;
     // ---- AO channels and the folded kinetic channel
-    for (int it = sub; it < Ne * Na; it += G) {
-      const int e = it / Na, ao = it - e * Na;
+    for (int it0 = sub; it0 < Ne * Na; it0 += G) {
+      // items AO-major, AOs by decreasing contraction length: the lanes of a round (and the groups of the warp,
+      // which run in lockstep) evaluate AOs of (nearly) the same length
+      const int ko = it0 / Ne, e = it0 - ko * Ne, ao = S.ao_order[ko], it = e * Na + ao;
       double s[5] = {0, 0, 0, 0, 0};
       for (int k = S.ao_start[ao]; k < S.ao_start[ao + 1]; ++k) {
         const int q = S.ao_prim[k], A = S.patom[q], pk = S.pk[q];
@@ -867,7 +886,7 @@ VjpSys make_sys(const qmcb_plan *p) {
   const int nb = D.nbas;
   S.alpha = fd; S.cn = fd + nb; S.norm = fd + 2 * nb;
   S.patom = fi; S.pk = fi + nb; S.pkr = fi + 2 * nb; S.pao = fi + 3 * nb;
-  S.ao_start = fi + 4 * nb; S.ao_prim = fi + 4 * nb + D.nao + 1;
+  S.ao_start = fi + 4 * nb; S.ao_prim = fi + 4 * nb + D.nao + 1; S.ao_order = fi + 5 * nb + D.nao + 1;
   return S;
 }
 

@@ -365,7 +365,7 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
   {
     const int nb = s->nbas;
     p->flat_dbl.assign(3 * (size_t)nb, 0.0);
-    p->flat_int.assign(5 * (size_t)nb + s->nao + 1, 0);
+    p->flat_int.assign(5 * (size_t)nb + 2 * (size_t)s->nao + 1, 0);
     for (int i = 0; i < nb; ++i) {
       p->flat_dbl[i] = s->bas_exp[i];
       p->flat_dbl[nb + i] = s->bas_norm[i] * s->bas_coeffs[i];
@@ -383,6 +383,10 @@ int qmcb_build_tables(const qmcb_system *s, qmcb_plan *p) {
         if (s->index_ctr[i] == a) list[o++] = i;
     }
     start[s->nao] = o;
+    // AOs by decreasing contraction length (stable): lockstep lanes of the adjoint kernel get equal work
+    int *order = list + nb;
+    for (int a = 0; a < s->nao; ++a) order[a] = a;
+    std::stable_sort(order, order + s->nao, [&](int x, int y) { return start[x + 1] - start[x] > start[y + 1] - start[y]; });
   }
   p->index_ctr.assign(s->index_ctr, s->index_ctr + s->nbas);
   p->mo_full.assign(s->mo, s->mo + (size_t)s->nao * s->nmo);

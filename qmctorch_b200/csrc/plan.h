@@ -108,7 +108,8 @@ struct qmcb_plan {
   mutable bool ticket_used[kTicketSlots] = {};
   // flat primitive list in the reference's own order (qmcb_system: one entry per primitive per cartesian
   // monomial) for the adjoint of the local energy (eloc_vjp.cu): doubles alpha | norm*coeff | norm,
-  // ints atom | kx,ky,kz packed | radial power | AO | CSR AO -> primitives (start [nao+1], list [nbas])
+  // ints atom | kx,ky,kz packed | radial power | AO | CSR AO -> primitives (start [nao+1], list [nbas]) |
+  // AOs by decreasing contraction length [nao]
   std::vector<double> flat_dbl;
   std::vector<int> flat_int;
   double *d_flat_dbl = nullptr;
