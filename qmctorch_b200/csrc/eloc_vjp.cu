@@ -523,12 +523,48 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const Vj
     const double wE = (live && a.wE) ? a.wE[w] : 0.0, wP = (live && a.wP) ? a.wP[w] : 0.0;
     // ---- Jastrow leaves of this walker: J, g = grad J / J, l = lap J / J
     double J = 1.0;
-    if (S.has_j) {
+    if (S.has_j && a.J) {
+      // (three-body term present: the product of all factors from the jastrow_kernel launch of this chunk)
       const int64_t wl = w - a.w0;
       J = a.J[wl];
       const double Jinv = 1.0 / J;
       for (int i = sub; i < 4 * Ne; i += G)
         g[i] = (i < 3 * Ne ? a.dJ[wl * 3 * Ne + i] : a.d2J[wl * Ne + (i - 3 * Ne)]) * Jinv;
+    } else if (S.has_j) {
+      // Pade factors only: ln J = K, grad J / J = grad K, lap J / J = lap K + |grad K|^2 evaluated here (the same
+      // kernels the derivative pass below differentiates) - no operator launch, no J / dJ / d2J round trip
+      double ksum = 0.0;
+      for (int e = sub; e < Ne; e += G) {
+        const double xe = x[3 * e], ye = x[3 * e + 1], ze = x[3 * e + 2];
+        double kx = 0.0, ky = 0.0, kz = 0.0, kl = 0.0;
+        if (S.use_jee) {
+          for (int j = 0; j < Ne; ++j) {
+            if (j == e) continue;
+            const double dx = xe - x[3 * j], dy = ye - x[3 * j + 1], dz = ze - x[3 * j + 2];
+            const double r = sqrt(dx * dx + dy * dy + dz * dz), rinv = 1.0 / r;
+            const double w0 = ((e < S.nup) == (j < S.nup)) ? 0.25 : 0.5;
+            const double den = 1.0 / (S.jee_w * r + 1.0);
+            const double k1 = w0 * den * den, kr = k1 * rinv;
+            ksum = fma(0.5 * w0 * r, den, ksum);
+            kx = fma(kr, dx, kx); ky = fma(kr, dy, ky); kz = fma(kr, dz, kz);
+            kl += -2.0 * S.jee_w * k1 * den + 2.0 * kr;
+          }
+        }
+        if (S.use_jen) {
+          for (int A = 0; A < S.natom; ++A) {
+            const double dx = xe - S.atoms[4 * A], dy = ye - S.atoms[4 * A + 1], dz = ze - S.atoms[4 * A + 2];
+            const double r = sqrt(dx * dx + dy * dy + dz * dz), rinv = 1.0 / r;
+            const double den = 1.0 / (S.jen_w * r + 1.0);
+            const double k1 = den * den, kr = k1 * rinv;
+            ksum = fma(r, den, ksum);
+            kx = fma(kr, dx, kx); ky = fma(kr, dy, ky); kz = fma(kr, dz, kz);
+            kl += -2.0 * S.jen_w * k1 * den + 2.0 * kr;
+          }
+        }
+        g[e] = kx; g[Ne + e] = ky; g[2 * Ne + e] = kz;
+        g[3 * Ne + e] = kl + kx * kx + ky * ky + kz * kz;
+      }
+      J = exp(group_sum<G>(ksum));
     } else {
       for (int i = sub; i < 4 * Ne; i += G) g[i] = 0.0;
     }
@@ -952,7 +988,7 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
   a.want_atom = g_atom_coords != nullptr;
   for (int64_t w0 = 0; w0 < W; w0 += wc) {
     const int64_t w1 = w0 + wc < W ? w0 + wc : W;
-    if (S.has_j) {
+    if (S.has_j && p->sys.een_nterm > 0) {
       const int rc = qmcb_jastrow(p, pos + w0 * 3 * S.nelec, w1 - w0, 0, J, dJ, d2J, stream);
       if (rc) return rc;
       a.J = J; a.dJ = dJ; a.d2J = d2J;
