@@ -1009,6 +1009,81 @@ __device__ __noinline__ void det_trace_reg(const double *A, const double *B, int
   tr_out = tr;
 }
 
+// Register-resident inverse for N = 4..6 (grad psi of CAS expansions: every unique spin block needs A^-1):
+// the LU of det_trace_reg, then one forward/back substitution per unit vector.  inv(i,j) is written to
+// m[(i * ldw + N + j) * es] - the [A | I] layout the shared-memory Gauss-Jordan leaves behind, so the
+// epilogue reads either.  Returns det(A).
+template <int N>
+__device__ __noinline__ double inverse_reg(const double *A, int ld, const int *cols, double *m, int ldw, int es) {
+  double a[N][N];
+  int perm[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const int cj = cols[j];
+    perm[j] = j;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i][j] = A[i * ld + cj];
+  }
+  double det = 1.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double best = fabs(a[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(a[i][k]);
+      if (v > best) { best = v; piv = i; }
+    }
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const bool sw = piv == i;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double t = a[k][j];
+        a[k][j] = sw ? a[i][j] : t;
+        a[i][j] = sw ? t : a[i][j];
+      }
+      const int tp = perm[k];
+      perm[k] = sw ? perm[i] : tp;
+      perm[i] = sw ? tp : perm[i];
+    }
+    if (piv != k) det = -det;
+    det *= a[k][k];
+    const double ip = fast_rcp(a[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double l = a[i][k] * ip;
+      a[i][k] = l;
+#pragma unroll
+      for (int j = k + 1; j < N; ++j) a[i][j] -= l * a[k][j];
+    }
+  }
+  double inv_d[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) inv_d[i] = fast_rcp(a[i][i]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {                     // forward: L y = P e_j
+      double v = perm[i] == j ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < i; ++q) v -= a[i][q] * x[q];
+      x[i] = v;
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {                // backward: U x = y
+      double v = x[i];
+#pragma unroll
+      for (int q = i + 1; q < N; ++q) v -= a[i][q] * x[q];
+      x[i] = v * inv_d[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) m[(i * ldw + N + j) * es] = x[i];
+  }
+  return det;
+}
+
 // Row-owner Gauss-Jordan for spin blocks of order n <= 16: TWO blocks per warp, one per half-warp.
 // Lane hl of a half owns ROW hl of [A | R]: A in a[0..15], R in r[0..15].  The pivot COLUMN k is a
 // compile-time loop index and the pivot ROW is a lane id, so no register is ever indexed dynamically

@@ -391,6 +391,9 @@ __global__ void __launch_bounds__(TILE == 1 ? QMCB_WARP_CTA : (TILE == 2 ? QMCB_
           } else if (MODE == MODE_GRAD) {
             double *m = scr + it;   // element stride = conc
             if (n <= 3) det = inverse_small(n, A, ldm, cols, m, conc);
+            else if (TILE == 0 && n == 4) det = inverse_reg<4>(A, ldm, cols, m, 2 * n, conc);
+            else if (TILE == 0 && n == 5) det = inverse_reg<5>(A, ldm, cols, m, 2 * n, conc);
+            else if (TILE == 0 && n == 6) det = inverse_reg<6>(A, ldm, cols, m, 2 * n, conc);
             else {
               const int ldw = 2 * n;
               for (int i = 0; i < n; ++i)
