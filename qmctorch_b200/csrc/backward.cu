@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(512, 1) backward_kernel(const DevSys S, const 
         const double *A = smo + ((size_t)wl * Ne + (up ? 0 : S.nup)) * nmup;
         double det = 1.0;
         if (n > 0 && n <= 3) det = inverse_small(n, A, nmup, cols, scr + it, conc);
+        else if (n == 4) det = inverse_reg<4>(A, nmup, cols, scr + it, 2 * n, conc);   // register LU + unit-vector
+        else if (n == 5) det = inverse_reg<5>(A, nmup, cols, scr + it, 2 * n, conc);   // solves (device.cuh): CAS
+        else if (n == 6) det = inverse_reg<6>(A, nmup, cols, scr + it, 2 * n, conc);   // blocks, same scratch layout
         else if (n > 3) {
           double *m = scr + it;
           const int ldw = 2 * n;
