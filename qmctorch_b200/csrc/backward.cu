@@ -583,7 +583,7 @@ int qmcb_choose_backward(qmcb_plan *p) {
       const int ntile_act = b.ntile_mo + (wao ? b.ntile_ao : 0);
       const int need_warps = (ntile_act + BWD_MAXT - 1) / BWD_MAXT;
       if (threads < 32 * need_warps) threads = 32 * need_warps;
-      if (threads < 128) threads = 128;
+      { const char *em = getenv("QMCB_BWD_MINTHREADS"); const int mt = em ? atoi(em) : 256; if (threads < mt) threads = mt; }   // measured (ms, J+MO / all): H2O 1e5 walkers 128: 1.60 / 5.28, 256: 1.51 / 4.97, 384: 2.81 / 4.90; C4H6 2e4: 2.13 / 13.5, 256: 2.01 / 13.1
       if (threads > 512) continue;
       const int conc = tw * nun;
       size_t d = (size_t)table_doubles(S) + (size_t)tw * 3 * S.nelec +
