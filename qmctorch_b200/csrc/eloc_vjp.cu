@@ -488,9 +488,27 @@ struct VjpArgs {
 };
 
 template <int G>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const VjpSys S, const VjpArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) eloc_vjp_kernel(const VjpSys S_in, const VjpArgs a) {
   extern __shared__ __align__(16) double vjp_smem[];
   constexpr int GPW = 32 / G;                       // walkers (groups) per warp
+  VjpSys S = S_in;
+  if (!a.smem) {
+    // large systems: the work areas stream through L1 and evict the small read-only tables every primitive
+    // evaluation touches (7 loads per primitive went to L2); shared memory is unused in this mode, so the
+    // tables live there: atoms | MO weights | alpha, norm*coeff, norm | int tables
+    const int nb = S.nbas, nfi = 5 * nb + 2 * S.nao + 1;
+    double *t_atoms = vjp_smem, *t_mow = t_atoms + 4 * S.natom, *t_fd = t_mow + S.nao * S.nmup;
+    int *t_fi = reinterpret_cast<int *>(t_fd + 3 * nb);
+    for (int i = threadIdx.x; i < 4 * S.natom; i += blockDim.x) t_atoms[i] = S_in.atoms[i];
+    for (int i = threadIdx.x; i < S.nao * S.nmup; i += blockDim.x) t_mow[i] = S_in.mow[i];
+    for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) t_fd[i] = S_in.alpha[i];
+    for (int i = threadIdx.x; i < nfi; i += blockDim.x) t_fi[i] = S_in.patom[i];
+    __syncthreads();
+    S.atoms = t_atoms; S.mow = t_mow;
+    S.alpha = t_fd; S.cn = t_fd + nb; S.norm = t_fd + 2 * nb;
+    S.patom = t_fi; S.pk = t_fi + nb; S.pkr = t_fi + 2 * nb; S.pao = t_fi + 3 * nb;
+    S.ao_start = t_fi + 4 * nb; S.ao_prim = t_fi + 4 * nb + S.nao + 1; S.ao_order = t_fi + 5 * nb + S.nao + 1;
+  }
   const ScratchLayout SL(S);
   const AccLayout AL(S);
   const int lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
@@ -902,7 +920,10 @@ VjpLaunch launch_of(const qmcb_plan *p, const VjpSys &S) {
     }
   if (best_warps >= 6) return L;
   // large systems: a whole warp per walker on global (L2-resident) scratch
-  L.use_smem = 0; L.smem_bytes = 0; L.G = 32; L.threads = kThreads; L.grid = p->sm_count * kMinBlocks;
+  // (shared memory then holds the read-only tables, see the kernel prologue)
+  const size_t tab = ((size_t)4 * S.natom + (size_t)S.nao * S.nmup + 3 * (size_t)S.nbas) * 8 +
+                     ((size_t)5 * S.nbas + 2 * (size_t)S.nao + 1) * 4 + 16;
+  L.use_smem = 0; L.smem_bytes = tab <= budget ? (int)tab : -1; L.G = 32; L.threads = kThreads; L.grid = p->sm_count * kMinBlocks;
   return L;
 }
 
@@ -965,7 +986,11 @@ extern "C" int qmcb_local_energy_backward(const qmcb_plan *p, const double *pos,
   const int nwarp = grid * (LC.threads / 32);
   void (*kern)(const VjpSys, const VjpArgs) =
       LC.G == 4 ? eloc_vjp_kernel<4> : (LC.G == 8 ? eloc_vjp_kernel<8> : (LC.G == 16 ? eloc_vjp_kernel<16> : eloc_vjp_kernel<32>));
-  if (LC.use_smem) {
+  if (LC.smem_bytes < 0) {
+    qmcb_set_error("qmcb_local_energy_backward: basis tables exceed the shared memory of an SM");
+    return QMCB_ESMEM;
+  }
+  {
     cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LC.smem_bytes);
     if (ea != cudaSuccess) return qmcb_cuda_rc((int)ea, "qmcb_local_energy_backward smem");
   }
