@@ -53,7 +53,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kThreads = 128;        // 4 warps per CTA
-constexpr int kMinBlocks = 3;        // CTAs per SM the kernel is compiled for: 168 registers (measured: 2 -> 20.6, 3 -> 14.7 ms per 1e6 LiH walkers)
+constexpr int kMinBlocks = 3;        // CTAs per SM the kernel is compiled for: 168 registers (measured, first version: 2 -> 20.6, 3 -> 14.7 ms per 1e6 LiH walkers; final version: 3 -> 4.5, 4 (128 registers, spills) -> 5.5 ms)
 
 // ---- dual numbers (forward-mode derivatives along N directions)
 template <int N>
@@ -901,7 +901,7 @@ VjpLaunch launch_of(const qmcb_plan *p, const VjpSys &S) {
   if (eg && (atoi(eg) == 4 || atoi(eg) == 8 || atoi(eg) == 16 || atoi(eg) == 32)) G = atoi(eg);
   VjpLaunch L{};
   const size_t budget = (size_t)p->smem_optin - 1024, sm_total = (size_t)227 * 1024;
-  const int reg_warps = 65536 / (168 * 32);          // resident warps the register file allows
+  const int reg_warps = 4 * kMinBlocks;              // resident warps the register budget of __launch_bounds__ allows
   // candidates: (G, warps per CTA); keep the one with the most resident warps per SM, then the smaller G
   int best_warps = 0;
   for (int g = G; g <= 32; g *= 2)
