@@ -513,7 +513,7 @@ class Solver:
         if D.is_distributed():
             buf = torch.stack([eloc.sum(), torch.tensor(float(len(psi)), dtype=torch.float64, device=eloc.device)])
             D.allreduce_sum_(buf)
-            ntot = float(buf[1])
+            ntot = buf[1]              # stays on the device: no host read-back between the two collectives
             mean = buf[0] / ntot
         else:
             ntot = float(len(psi))
